@@ -1,0 +1,123 @@
+/*
+ * rlsolver_b200 -- C ABI of the B200-native max-cut / QUBO environment hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The
+ * reference (Open-Finance-Lab/RLSolver) is 100% Python with no FFI of its own;
+ * each entry point below names the reference function (file:line, relative to
+ * the reference checkout) whose work it replaces.  INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 (RLSB_OK) or a positive error code; the message
+ *     for the calling thread's last error is rlsb_last_error().
+ *   - pointers are DEVICE pointers unless the parameter name starts with `h_`.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - spins ("xs") at the API surface are the reference's layout: row-major
+ *     bool/uint8 [E][N], one byte per (environment, node).
+ *   - packed spins are uint32 [W][Np], W = ceil(E/32) env tiles, Np =
+ *     rlsb_graph_padded_nodes(): word [t][i] holds node i of envs 32t..32t+31
+ *     (bit b <-> env 32t+b).  Padding bits/words are zero on pack.
+ *   - objective values ("vs") are int64 [E] as in the reference (th.long).
+ *   - nothing here allocates device memory except rlsb_graph_create.
+ */
+#ifndef RLSOLVER_B200_H
+#define RLSOLVER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLSB_OK 0
+#define RLSB_ERR_INVALID 1     /* bad argument (reference would raise IndexError/ValueError/assert) */
+#define RLSB_ERR_CUDA 2        /* CUDA runtime error, see rlsb_last_error() */
+#define RLSB_ERR_UNSUPPORTED 3 /* shape outside what the kernels are built for */
+#define RLSB_ERR_NODEVICE 4    /* graph was built host-only (device < 0) */
+
+typedef struct rlsb_graph rlsb_graph_t;
+
+int rlsb_version(void);
+const char* rlsb_last_error(void);
+
+/* ---- graph store: replaces EnvMaxcut.__init__ (rlsolver/envs/env_L2A.py:25-52),
+ * build_adjacency_indies (rlsolver/methods/util_read_data.py:144-187) and
+ * calc_num_nodes_in_mygraph (rlsolver/methods/util.py:35-40).
+ * h_n0/h_n1 are HOST arrays of 0-based endpoints in file order; h_w (nullable)
+ * integer weights.  num_nodes <= 0 -> number of distinct endpoints (reference
+ * quirk); ids must then be < that number.  device < 0 builds host-side only. */
+int rlsb_graph_create(int32_t num_nodes, int64_t num_edges, const int32_t* h_n0, const int32_t* h_n1,
+                      const int32_t* h_w, int32_t bidirectional, int32_t device, rlsb_graph_t** out);
+int rlsb_graph_destroy(rlsb_graph_t* g);
+int32_t rlsb_graph_num_nodes(const rlsb_graph_t* g);
+int32_t rlsb_graph_padded_nodes(const rlsb_graph_t* g);
+int64_t rlsb_graph_num_edges(const rlsb_graph_t* g);      /* len(mygraph) */
+int64_t rlsb_graph_num_listed(const rlsb_graph_t* g);     /* Md: M or 2M */
+int64_t rlsb_graph_num_full(const rlsb_graph_t* g);       /* undirected neighbour slots, self loops dropped */
+int32_t rlsb_graph_num_levels(const rlsb_graph_t* g);     /* Gauss-Seidel dependency levels of the sweep */
+int32_t rlsb_graph_max_listed_degree(const rlsb_graph_t* g);
+int32_t rlsb_graph_max_full_degree(const rlsb_graph_t* g);
+/* copy host-side arrays out (each pointer nullable).  listed_*: sorted listed-neighbour
+ * CSR (== n0_ids/n1_ids, n0_num_n1 of the reference); full_*: undirected CSR;
+ * level_*: nodes grouped by dependency level. */
+int rlsb_graph_export(const rlsb_graph_t* g, int32_t* h_listed_ptr, int32_t* h_listed_col, int32_t* h_full_ptr,
+                      int32_t* h_full_col, int32_t* h_level_ptr, int32_t* h_level_nodes);
+
+/* ---- spin (de)packing: layout change only, no reference counterpart */
+int rlsb_pack_spins(const uint8_t* xs, int64_t num_envs, int32_t num_nodes, int32_t padded_nodes, uint32_t* packed,
+                    void* stream);
+int rlsb_unpack_spins(const uint32_t* packed, int64_t num_envs, int32_t num_nodes, int32_t padded_nodes, uint8_t* xs,
+                      void* stream);
+
+/* ---- objective: replaces EnvMaxcut.calculate_obj_values (env_L2A.py:54-66)
+ * cut_eval: bool [E][N] in, int64 [E] out (if_sum=True; '//2' of the bidirectional
+ * listing is folded in).  cut_eval_packed: same on packed spins.
+ * cut_edges: if_sum=False, uint8 [E][Md] per-listed-edge indicators. */
+int rlsb_cut_eval(const rlsb_graph_t* g, const uint8_t* xs, int64_t num_envs, int64_t* vs, void* stream);
+int rlsb_cut_eval_packed(const rlsb_graph_t* g, const uint32_t* packed, int64_t num_envs, int64_t* vs, void* stream);
+int rlsb_cut_edges(const rlsb_graph_t* g, const uint8_t* xs, int64_t num_envs, uint8_t* out, void* stream);
+
+/* ---- per-node cross counts: integer core of calculate_obj_values_for_loop
+ * (env_L2A.py:68-80).  cross is uint16 [E][Np] (row-major, rows padded to Np):
+ * number of LISTED neighbours of node i on the other side in env e.
+ * col_min/col_max (nullable, int32 [N]) receive min/max over envs per node --
+ * the cross-env coupling `ws_std` of env_L2A.py:93 / LocalSearch.py:65. */
+int rlsb_node_cross_counts(const rlsb_graph_t* g, const uint32_t* packed, int64_t num_envs, uint16_t* cross,
+                           int32_t* col_min, int32_t* col_max, void* stream);
+
+/* ---- noisy multi-flip local search, env_L2A.py:92-107 / LocalSearch.py:62-75.
+ * ws[e][i] = listed_degree[i] - ws_mult * cross[e][i]   (ws_mult: 1 = local_search_inplace,
+ *            2 = LocalSearch.random_search), rd_std[i] = float(ws_mult*(col_max-col_min)) * noise_std,
+ * spin_rand = ws + noise*rd_std in float32 with one rounding per op.
+ * ls_thresh: thresh[e] = kth smallest of spin_rand[e][:], k = N - num_spin  (torch.kthvalue).
+ * ls_noisy_iters: for each of num_iters noise tensors (h_noise_ptrs: HOST array of device
+ * pointers, float32 [E][N] each): flip where spin_rand > thresh, evaluate, keep rows with vs' >= vs.
+ * packed and vs are updated in place. */
+int rlsb_ls_thresh(const rlsb_graph_t* g, const uint16_t* cross, const int32_t* col_min, const int32_t* col_max,
+                   int32_t ws_mult, float noise_std, const float* noise, int32_t num_spin, int64_t num_envs,
+                   float* thresh, void* stream);
+int rlsb_ls_noisy_iters(const rlsb_graph_t* g, uint32_t* packed, int64_t* vs, const uint16_t* cross,
+                        const int32_t* col_min, const int32_t* col_max, int32_t ws_mult, float noise_std,
+                        const float* const* h_noise_ptrs, int32_t num_iters, const float* thresh,
+                        int64_t num_envs, void* stream);
+
+/* ---- exhaustive single-flip pass, env_L2A.py:110-115 / LocalSearch.py:78-83:
+ * for node 0..N-1 in order, flip it where the cut does not get worse (gain >= 0),
+ * Gauss-Seidel.  O(2M) word operations per 32 envs instead of N full evaluations;
+ * the per-flip gain rule is the batched form of S2V_PPO/env.py:197-206. */
+int rlsb_flip_sweep(const rlsb_graph_t* g, uint32_t* packed, int64_t* vs, int64_t num_envs, void* stream);
+
+/* ---- select ops on the reference's bool layout
+ * select_rows: update_xs_by_vs (util_read_data.py:190-202): rows of (xs1,vs1) replace
+ *   rows of (xs0,vs0) where vs1 >= vs0 (<= when maximize == 0).
+ * pick_best: pick_xs_by_vs (util_read_data.py:204-216): input viewed [R][S][N];
+ *   per sim the repeat with the best value, lowest repeat index on ties. */
+int rlsb_select_rows(uint8_t* xs0, int64_t* vs0, const uint8_t* xs1, const int64_t* vs1, int64_t num_envs,
+                     int32_t num_nodes, int32_t maximize, void* stream);
+int rlsb_pick_best(const uint8_t* xs, const int64_t* vs, int32_t num_repeats, int64_t num_sims, int32_t num_nodes,
+                   int32_t maximize, uint8_t* out_xs, int64_t* out_vs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLSOLVER_B200_H */

@@ -1,0 +1,108 @@
+// Objective evaluation: replaces EnvMaxcut.calculate_obj_values (rlsolver/envs/env_L2A.py:54-66).
+// The reference gathers xs through three int64 [E][Md] index tensors (~27 B per env-edge);
+// here one CTA owns a tile of 32 envs: it bit-packs the 32 bool rows into shared memory
+// (coalesced row reads, the only HBM traffic: N bytes per env) and streams the edge list
+// once for all 32 envs.  Algorithmic bytes per env-eval: N + 8 + 8M/E (bool API) or
+// N/8 + 8 + 8M/E (packed).
+#include "tile_ops.cuh"
+
+namespace rlsb {
+
+constexpr int kCutThreads = 512;
+
+template <int VEC, bool PACKED_IN>
+__global__ void __launch_bounds__(kCutThreads) cut_eval_kernel(GraphDev g, const uint8_t* __restrict__ xs,
+                                                               const uint32_t* __restrict__ packed,
+                                                               int64_t num_envs, int64_t* __restrict__ vs) {
+  extern __shared__ uint32_t sP[];
+  __shared__ int sCnt[kTileEnvs];
+  const int64_t tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
+    if (PACKED_IN) {
+      for (int i = threadIdx.x; i < g.np; i += blockDim.x) sP[i] = __ldg(packed + tile * g.np + i);
+    } else {
+      pack_tile_to_smem<VEC>(xs, num_envs, g.n, g.np, tile, sP);
+    }
+    __syncthreads();
+    const int cnt = tile_cut_partial(g, sP);
+    if (cnt) atomicAdd(&sCnt[threadIdx.x & 31], cnt);
+    __syncthreads();
+    const int64_t env = tile * kTileEnvs + threadIdx.x;
+    if (threadIdx.x < kTileEnvs && env < num_envs) vs[env] = sCnt[threadIdx.x];
+    __syncthreads();
+  }
+}
+
+// if_sum=False: one indicator byte per (env, listed edge), in the reference's n0/n1 order.
+__global__ void __launch_bounds__(256) cut_edges_kernel(GraphDev g, const uint8_t* __restrict__ xs, int64_t num_envs,
+                                                        uint8_t* __restrict__ out) {
+  const int64_t env = blockIdx.y;
+  const uint8_t* row = xs + env * (int64_t)g.n;
+  uint8_t* orow = out + env * (int64_t)g.md;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < g.md; k += gridDim.x * blockDim.x)
+    orow[k] = (uint8_t)((row[__ldg(g.listed_row + k)] != 0) ^ (row[__ldg(g.listed_col + k)] != 0));
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) RLSB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return RLSB_OK;
+}
+
+}  // namespace rlsb
+
+extern "C" {
+
+static int cut_eval_common(const rlsb_graph_t* gh, const uint8_t* xs, const uint32_t* packed, int64_t num_envs,
+                           int64_t* vs, void* stream) {
+  using namespace rlsb;
+  const GraphDev* g = graph_dev(gh);
+  RLSB_REQUIRE(gh != nullptr, RLSB_ERR_INVALID, "cut_eval: null graph");
+  RLSB_REQUIRE(g != nullptr, RLSB_ERR_NODEVICE, "cut_eval: graph has no device image");
+  RLSB_REQUIRE(num_envs >= 0, RLSB_ERR_INVALID, "cut_eval: negative num_envs");
+  if (num_envs == 0) return RLSB_OK;
+  RLSB_REQUIRE((xs || packed) && vs, RLSB_ERR_INVALID, "cut_eval: null pointer");
+  const size_t smem = (size_t)g->np * sizeof(uint32_t);
+  RLSB_REQUIRE(smem <= 200 * 1024, RLSB_ERR_UNSUPPORTED, "cut_eval: %d nodes exceed the shared-memory tile", g->n);
+  const int64_t tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;
+  const unsigned grid = (unsigned)(tiles < 8 * kNumSMs ? tiles : 8 * kNumSMs);
+  auto st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if (packed) {
+    if ((rc = set_smem(cut_eval_kernel<1, true>, smem))) return rc;
+    cut_eval_kernel<1, true><<<grid, kCutThreads, smem, st>>>(*g, nullptr, packed, num_envs, vs);
+  } else if (rows_vec4_ok(xs, g->n)) {
+    if ((rc = set_smem(cut_eval_kernel<4, false>, smem))) return rc;
+    cut_eval_kernel<4, false><<<grid, kCutThreads, smem, st>>>(*g, xs, nullptr, num_envs, vs);
+  } else {
+    if ((rc = set_smem(cut_eval_kernel<1, false>, smem))) return rc;
+    cut_eval_kernel<1, false><<<grid, kCutThreads, smem, st>>>(*g, xs, nullptr, num_envs, vs);
+  }
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+int rlsb_cut_eval(const rlsb_graph_t* g, const uint8_t* xs, int64_t num_envs, int64_t* vs, void* stream) {
+  return cut_eval_common(g, xs, nullptr, num_envs, vs, stream);
+}
+
+int rlsb_cut_eval_packed(const rlsb_graph_t* g, const uint32_t* packed, int64_t num_envs, int64_t* vs, void* stream) {
+  return cut_eval_common(g, nullptr, packed, num_envs, vs, stream);
+}
+
+int rlsb_cut_edges(const rlsb_graph_t* gh, const uint8_t* xs, int64_t num_envs, uint8_t* out, void* stream) {
+  using namespace rlsb;
+  const GraphDev* g = graph_dev(gh);
+  RLSB_REQUIRE(gh != nullptr, RLSB_ERR_INVALID, "cut_edges: null graph");
+  RLSB_REQUIRE(g != nullptr, RLSB_ERR_NODEVICE, "cut_edges: graph has no device image");
+  if (num_envs <= 0 || g->md == 0) return RLSB_OK;
+  RLSB_REQUIRE(xs && out, RLSB_ERR_INVALID, "cut_edges: null pointer");
+  RLSB_REQUIRE(num_envs <= 65535, RLSB_ERR_UNSUPPORTED, "cut_edges: more than 65535 envs per call");
+  dim3 grid((unsigned)((g->md + 1023) / 1024), (unsigned)num_envs);
+  cut_edges_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*g, xs, num_envs, out);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+// Row-select operators on the reference's bool [E][N] layout.
+//   select_rows : update_xs_by_vs   rlsolver/methods/util_read_data.py:190-202
+//                 (the reference uses boolean-mask index_put, which syncs the host for nonzero())
+//   pick_best   : pick_xs_by_vs     rlsolver/methods/util_read_data.py:204-216
+// Both are pure data movement (HBM-bound: at most 2*N bytes per selected row).
+#include "common.cuh"
+
+namespace rlsb {
+
+__device__ __forceinline__ void copy_row(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int n, int tid,
+                                         int nthreads) {
+  const bool vec = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0;
+  if (vec) {
+    const int n16 = n >> 4;
+    for (int i = tid; i < n16; i += nthreads)
+      reinterpret_cast<uint4*>(dst)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    for (int i = (n16 << 4) + tid; i < n; i += nthreads) dst[i] = src[i];
+  } else {
+    for (int i = tid; i < n; i += nthreads) dst[i] = src[i];
+  }
+}
+
+// one warp per row
+__global__ void __launch_bounds__(256) select_rows_kernel(uint8_t* __restrict__ xs0, int64_t* __restrict__ vs0,
+                                                          const uint8_t* __restrict__ xs1,
+                                                          const int64_t* __restrict__ vs1, int64_t num_envs, int n,
+                                                          int maximize) {
+  const int lane = threadIdx.x & 31;
+  const int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (env >= num_envs) return;
+  const int64_t a = vs0[env], b = vs1[env];
+  const bool take = maximize ? (b >= a) : (b <= a);
+  if (!take) return;
+  copy_row(xs0 + env * (int64_t)n, xs1 + env * (int64_t)n, n, lane, 32);
+  if (lane == 0) vs0[env] = b;
+}
+
+// one CTA per sim: warp 0 finds the best repeat (lowest index on ties), all threads copy the row
+__global__ void __launch_bounds__(128) pick_best_kernel(const uint8_t* __restrict__ xs, const int64_t* __restrict__ vs,
+                                                        int num_repeats, int64_t num_sims, int n, int maximize,
+                                                        uint8_t* __restrict__ out_xs, int64_t* __restrict__ out_vs) {
+  __shared__ int sBest;
+  const int64_t sim = blockIdx.x;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int64_t best = 0;
+    int arg = -1;
+    for (int r = lane; r < num_repeats; r += 32) {     // ascending r per lane: strict compare keeps the lowest index
+      const int64_t v = vs[(int64_t)r * num_sims + sim];
+      if (arg < 0 || (maximize ? v > best : v < best)) best = v, arg = r;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const int64_t ob = __shfl_xor_sync(kFull, best, off);
+      const int oa = __shfl_xor_sync(kFull, arg, off);
+      const bool better = oa >= 0 && (arg < 0 || (maximize ? ob > best : ob < best) || (ob == best && oa < arg));
+      if (better) best = ob, arg = oa;
+    }
+    if (lane == 0) {
+      sBest = arg;
+      out_vs[sim] = best;
+    }
+  }
+  __syncthreads();
+  const int r = sBest;
+  copy_row(out_xs + sim * (int64_t)n, xs + ((int64_t)r * num_sims + sim) * (int64_t)n, n, threadIdx.x, blockDim.x);
+}
+
+}  // namespace rlsb
+
+extern "C" {
+
+int rlsb_select_rows(uint8_t* xs0, int64_t* vs0, const uint8_t* xs1, const int64_t* vs1, int64_t num_envs,
+                     int32_t num_nodes, int32_t maximize, void* stream) {
+  using namespace rlsb;
+  RLSB_REQUIRE(num_envs >= 0 && num_nodes >= 0, RLSB_ERR_INVALID, "select_rows: negative size");
+  if (num_envs == 0) return RLSB_OK;
+  RLSB_REQUIRE(xs0 && vs0 && xs1 && vs1, RLSB_ERR_INVALID, "select_rows: null pointer");
+  select_rows_kernel<<<(unsigned)((num_envs + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      xs0, vs0, xs1, vs1, num_envs, num_nodes, maximize);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+int rlsb_pick_best(const uint8_t* xs, const int64_t* vs, int32_t num_repeats, int64_t num_sims, int32_t num_nodes,
+                   int32_t maximize, uint8_t* out_xs, int64_t* out_vs, void* stream) {
+  using namespace rlsb;
+  RLSB_REQUIRE(num_repeats >= 1 && num_sims >= 0 && num_nodes >= 0, RLSB_ERR_INVALID, "pick_best: bad shape");
+  if (num_sims == 0) return RLSB_OK;
+  RLSB_REQUIRE(xs && vs && out_xs && out_vs, RLSB_ERR_INVALID, "pick_best: null pointer");
+  pick_best_kernel<<<(unsigned)num_sims, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      xs, vs, num_repeats, num_sims, num_nodes, maximize, out_xs, out_vs);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+}  // extern "C"

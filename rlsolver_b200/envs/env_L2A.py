@@ -1,0 +1,125 @@
+"""Drop-in for `rlsolver.envs.env_L2A.EnvMaxcut` (rlsolver/envs/env_L2A.py:24-116; the same
+class is `rlsolver.envs.env_MCPG.EnvMaxcut`, env_MCPG.py:24-116).
+
+Same constructor, attributes, method names, argument meaning, in-place mutation and RNG call
+sequence as the reference; the tensor work runs in the sm_100a kernels behind the C ABI
+(include/rlsolver_b200.h).  CUDA only -- constructing it on a CPU device raises.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch as th
+
+from ..graph_store import GraphStore, require_cuda
+from ..methods.config import MyGraph
+from ..methods.util import build_adjacency_bool
+from ..methods.util_read_data import load_mygraph2, update_xs_by_vs
+
+TEN = th.Tensor
+
+# noise tensors handed to one fused ls_noisy_iters launch are capped to this many bytes so a
+# huge E*N batch does not hold every draw of a call alive at once
+_NOISE_BYTES_PER_LAUNCH = 4 << 30
+
+
+class EnvMaxcut:
+    def __init__(self, sim_name: str = 'max_cut', mygraph: MyGraph = (),
+                 device=th.device('cpu'), if_bidirectional: bool = False):
+        self.device = require_cuda(device)
+        self.sim_name = sim_name
+        self.int_type = th.long
+        self.if_maximize = True
+        self.if_bidirectional = if_bidirectional
+
+        mygraph = mygraph if mygraph else load_mygraph2(graph_name=sim_name)
+        self._mygraph = mygraph
+        self.store = GraphStore(mygraph, if_bidirectional, device=self.device)
+        self.num_nodes = self.store.num_nodes
+        self.num_edges = self.store.num_edges
+
+        arrs = self.store.export()
+        ptr, col = arrs["listed_ptr"].astype(np.int64), arrs["listed_col"].astype(np.int64)
+        self._listed_ptr, self._listed_col = ptr, col
+        n0 = np.repeat(np.arange(self.num_nodes, dtype=np.int64), np.diff(ptr))
+        self.n0_ids = th.from_numpy(n0).to(self.device)[None, :]
+        self.n1_ids = th.from_numpy(col.copy()).to(self.device)[None, :]
+        self.sim_ids = th.zeros((1, self.store.num_listed), dtype=th.long, device=self.device)
+        self.n0_num_n1 = th.from_numpy(np.diff(ptr)).to(self.device)[None, :]
+        self._adjacency_bool: Optional[TEN] = None
+        self._adjacency_indies: Optional[List[TEN]] = None
+
+    # the two O(N^2) / O(N)-tensor attributes are only read by a few callers: built on first use
+    @property
+    def adjacency_bool(self) -> TEN:
+        if self._adjacency_bool is None:
+            self._adjacency_bool = build_adjacency_bool(self._mygraph, if_bidirectional=True).to(self.device)
+        return self._adjacency_bool
+
+    @property
+    def adjacency_indies(self) -> List[TEN]:
+        if self._adjacency_indies is None:
+            flat = th.from_numpy(self._listed_col.copy()).to(self.device)
+            self._adjacency_indies = list(th.split(flat, np.diff(self._listed_ptr).tolist()))
+        return self._adjacency_indies
+
+    # ------------------------------------------------------------------ objective
+    def calculate_obj_values(self, xs: TEN, if_sum: bool = True) -> TEN:
+        if if_sum:
+            return self.store.cut_eval(xs)
+        values = self.store.cut_edges(xs)
+        if self.if_bidirectional:     # reference: bool // 2 -> int64 zeros
+            values = values.to(th.long) // 2
+        return values
+
+    def calculate_obj_values_for_loop(self, xs: TEN, if_sum: bool = True) -> TEN:
+        num_sims = xs.shape[0]
+        packed = self.store.pack(xs)
+        cross, _, _ = self.store.cross_counts(packed, num_sims, want_minmax=False)
+        values = cross[:, :self.num_nodes].to(th.long) & 0xFFFF       # uint16 payload
+        if if_sum:
+            values = values.sum(dim=1)
+        if self.if_bidirectional:
+            values = values.float() / 2
+        return values
+
+    def generate_xs_randomly(self, num_sims):
+        xs = th.randint(0, 2, size=(num_sims, self.num_nodes), dtype=th.bool, device=self.device)
+        xs[:, 0] = 0
+        return xs
+
+    # ------------------------------------------------------------------ local search
+    def local_search_inplace(self, good_xs: TEN, good_vs: TEN,
+                             num_iters: int = 8, num_spin: int = 8, noise_std: float = 0.3):
+        """env_L2A.py:87-116.  RNG: 1 + num_iters draws of randn [E, N] float32 on self.device,
+        in the reference's order, so the flip sequence matches the reference's for a given seed."""
+        st = self.store
+        num_sims = good_xs.shape[0]
+        if not good_xs.is_contiguous():
+            raise RuntimeError("local_search_inplace mutates good_xs in place: it must be contiguous")
+        packed = st.pack(good_xs)
+        cross, cmin, cmax = st.cross_counts(packed, num_sims)
+        if good_vs.shape == ():
+            good_vs = st.cut_eval_packed(packed, num_sims)
+        else:
+            good_vs = good_vs.long()
+            if not good_vs.is_contiguous():
+                good_vs = good_vs.contiguous()
+        shape = (num_sims, self.num_nodes)
+        noise0 = th.randn(shape, dtype=th.float32, device=self.device)
+        thresh = st.ls_thresh(cross, cmin, cmax, 1, noise_std, noise0, num_spin)
+        del noise0
+        per_launch = max(1, min(16, _NOISE_BYTES_PER_LAUNCH // max(1, 4 * num_sims * self.num_nodes)))
+        done = 0
+        while done < num_iters:
+            now = min(per_launch, num_iters - done)
+            noises = [th.randn(shape, dtype=th.float32, device=self.device) for _ in range(now)]
+            st.ls_noisy_iters(packed, good_vs, cross, cmin, cmax, 1, noise_std, noises, thresh)
+            done += now
+        st.flip_sweep(packed, good_vs)
+        st.unpack(packed, num_sims, out=good_xs)
+        return good_xs, good_vs
+
+
+__all__ = ["EnvMaxcut", "update_xs_by_vs"]

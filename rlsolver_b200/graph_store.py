@@ -1,0 +1,214 @@
+"""Python handle of the native graph store (csrc/graph_store.cu) plus thin op wrappers.
+
+Everything here is plumbing: torch owns device memory and streams, the C-ABI library does
+the work.  No op has a CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch as th
+
+from . import _lib
+
+TEN = th.Tensor
+
+
+def _stream_ptr(device: th.device) -> C.c_void_p:
+    return C.c_void_p(th.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[TEN]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def require_cuda(device) -> th.device:
+    device = th.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(
+            f"rlsolver_b200 runs on CUDA (sm_100a) only; got device '{device}'. There is no CPU fallback.")
+    if device.index is None:
+        device = th.device("cuda", th.cuda.current_device())
+    return device
+
+
+class GraphStore:
+    """CSR + edge list + sweep levels, built natively from a reference-style MyGraph
+    (list of (n0, n1, weight), 0-based).  `device=None` keeps it host-only (no CUDA needed)."""
+
+    def __init__(self, mygraph: Sequence[Tuple[int, int, int]], if_bidirectional: bool = False,
+                 device: Optional[th.device] = None, num_nodes: int = 0):
+        self._lib = _lib.lib()
+        arr = np.asarray(list(mygraph), dtype=np.int64).reshape(-1, 3) if len(mygraph) else np.zeros((0, 3), np.int64)
+        if arr.size and (arr[:, :2].max() >= 2 ** 31 or arr[:, :2].min() < 0):
+            raise IndexError("node ids must be in [0, 2^31)")
+        n0 = np.ascontiguousarray(arr[:, 0], dtype=np.int32)
+        n1 = np.ascontiguousarray(arr[:, 1], dtype=np.int32)
+        w = np.ascontiguousarray(arr[:, 2], dtype=np.int32)
+        self.device = None if device is None else require_cuda(device)
+        handle = C.c_void_p()
+        st = self._lib.rlsb_graph_create(int(num_nodes), int(arr.shape[0]), n0.ctypes.data, n1.ctypes.data,
+                                         w.ctypes.data, int(bool(if_bidirectional)),
+                                         -1 if self.device is None else self.device.index, C.byref(handle))
+        if st == 1 and "IndexError" in self._lib.rlsb_last_error().decode():
+            raise IndexError(self._lib.rlsb_last_error().decode())
+        _lib.check(st, "graph_create")
+        self._h = handle
+        L = self._lib
+        self.num_nodes = int(L.rlsb_graph_num_nodes(handle))
+        self.padded_nodes = int(L.rlsb_graph_padded_nodes(handle))
+        self.num_edges = int(L.rlsb_graph_num_edges(handle))
+        self.num_listed = int(L.rlsb_graph_num_listed(handle))
+        self.num_full = int(L.rlsb_graph_num_full(handle))
+        self.num_levels = int(L.rlsb_graph_num_levels(handle))
+        self.max_listed_degree = int(L.rlsb_graph_max_listed_degree(handle))
+        self.max_full_degree = int(L.rlsb_graph_max_full_degree(handle))
+        self.if_bidirectional = bool(if_bidirectional)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._lib.rlsb_graph_destroy(h)
+            except Exception:
+                pass
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    def export(self) -> Dict[str, np.ndarray]:
+        """Host copies of the built arrays (listed CSR == the reference's n0_ids/n1_ids order)."""
+        n = self.num_nodes
+        out = {
+            "listed_ptr": np.zeros(n + 1, np.int32), "listed_col": np.zeros(self.num_listed, np.int32),
+            "full_ptr": np.zeros(n + 1, np.int32), "full_col": np.zeros(self.num_full, np.int32),
+            "level_ptr": np.zeros(self.num_levels + 1, np.int32), "level_nodes": np.zeros(n, np.int32),
+        }
+        _lib.check(self._lib.rlsb_graph_export(self._h, *[out[k].ctypes.data for k in (
+            "listed_ptr", "listed_col", "full_ptr", "full_col", "level_ptr", "level_nodes")]), "graph_export")
+        return out
+
+    # ------------------------------------------------------------------ layout helpers
+    def tiles(self, num_envs: int) -> int:
+        return (num_envs + 31) // 32
+
+    def new_packed(self, num_envs: int) -> TEN:
+        return th.empty((self.tiles(num_envs), self.padded_nodes), dtype=th.int32, device=self.device)
+
+    def _check_xs(self, xs: TEN) -> TEN:
+        if xs.dtype != th.bool:
+            raise TypeError(f"xs must be torch.bool, got {xs.dtype}")
+        if xs.dim() != 2 or xs.shape[1] != self.num_nodes:
+            raise IndexError(f"xs must be [num_envs, {self.num_nodes}], got {tuple(xs.shape)}")
+        if xs.device != self.device:
+            raise RuntimeError(f"xs is on {xs.device}, the simulator is on {self.device}")
+        return xs if xs.is_contiguous() else xs.contiguous()
+
+    # ------------------------------------------------------------------ ops (device tensors in/out)
+    def pack(self, xs: TEN, out: Optional[TEN] = None) -> TEN:
+        xs = self._check_xs(xs)
+        e = xs.shape[0]
+        out = self.new_packed(e) if out is None else out
+        _lib.check(self._lib.rlsb_pack_spins(_ptr(xs), e, self.num_nodes, self.padded_nodes, _ptr(out),
+                                             _stream_ptr(self.device)), "pack_spins")
+        return out
+
+    def unpack(self, packed: TEN, num_envs: int, out: Optional[TEN] = None) -> TEN:
+        if out is None:
+            out = th.empty((num_envs, self.num_nodes), dtype=th.bool, device=self.device)
+        elif not out.is_contiguous():
+            raise RuntimeError("unpack target must be contiguous")
+        _lib.check(self._lib.rlsb_unpack_spins(_ptr(packed), num_envs, self.num_nodes, self.padded_nodes, _ptr(out),
+                                               _stream_ptr(self.device)), "unpack_spins")
+        return out
+
+    def cut_eval(self, xs: TEN) -> TEN:
+        xs = self._check_xs(xs)
+        vs = th.empty((xs.shape[0],), dtype=th.int64, device=self.device)
+        _lib.check(self._lib.rlsb_cut_eval(self._h, _ptr(xs), xs.shape[0], _ptr(vs), _stream_ptr(self.device)),
+                   "cut_eval")
+        return vs
+
+    def cut_eval_packed(self, packed: TEN, num_envs: int, out: Optional[TEN] = None) -> TEN:
+        vs = th.empty((num_envs,), dtype=th.int64, device=self.device) if out is None else out
+        _lib.check(self._lib.rlsb_cut_eval_packed(self._h, _ptr(packed), num_envs, _ptr(vs),
+                                                  _stream_ptr(self.device)), "cut_eval_packed")
+        return vs
+
+    def cut_edges(self, xs: TEN) -> TEN:
+        xs = self._check_xs(xs)
+        out = th.empty((xs.shape[0], self.num_listed), dtype=th.bool, device=self.device)
+        for lo in range(0, xs.shape[0], 32768):
+            part = xs[lo:lo + 32768]
+            _lib.check(self._lib.rlsb_cut_edges(self._h, _ptr(part), part.shape[0], _ptr(out[lo:lo + 32768]),
+                                                _stream_ptr(self.device)), "cut_edges")
+        return out
+
+    def cross_counts(self, packed: TEN, num_envs: int, want_minmax: bool = True):
+        """uint16 counts as an int16 tensor [E, Np] (+ int32 [N] min / max over envs)."""
+        cross = th.empty((num_envs, self.padded_nodes), dtype=th.int16, device=self.device)
+        cmin = cmax = None
+        if want_minmax:
+            cmin = th.empty((self.num_nodes,), dtype=th.int32, device=self.device)
+            cmax = th.empty((self.num_nodes,), dtype=th.int32, device=self.device)
+        _lib.check(self._lib.rlsb_node_cross_counts(self._h, _ptr(packed), num_envs, _ptr(cross), _ptr(cmin),
+                                                    _ptr(cmax), _stream_ptr(self.device)), "node_cross_counts")
+        return cross, cmin, cmax
+
+    def ls_thresh(self, cross: TEN, cmin: TEN, cmax: TEN, ws_mult: int, noise_std: float, noise: TEN,
+                  num_spin: int) -> TEN:
+        e = noise.shape[0]
+        thresh = th.empty((e,), dtype=th.float32, device=self.device)
+        _lib.check(self._lib.rlsb_ls_thresh(self._h, _ptr(cross), _ptr(cmin), _ptr(cmax), ws_mult, float(noise_std),
+                                            _ptr(noise), int(num_spin), e, _ptr(thresh), _stream_ptr(self.device)),
+                   "ls_thresh")
+        return thresh
+
+    def ls_noisy_iters(self, packed: TEN, vs: TEN, cross: TEN, cmin: TEN, cmax: TEN, ws_mult: int, noise_std: float,
+                       noises: Sequence[TEN], thresh: TEN) -> None:
+        if not noises:
+            return
+        e = vs.shape[0]
+        ptrs = (C.c_void_p * len(noises))(*[t.data_ptr() for t in noises])
+        _lib.check(self._lib.rlsb_ls_noisy_iters(self._h, _ptr(packed), _ptr(vs), _ptr(cross), _ptr(cmin), _ptr(cmax),
+                                                 ws_mult, float(noise_std), ptrs, len(noises), _ptr(thresh), e,
+                                                 _stream_ptr(self.device)), "ls_noisy_iters")
+
+    def flip_sweep(self, packed: TEN, vs: TEN) -> None:
+        _lib.check(self._lib.rlsb_flip_sweep(self._h, _ptr(packed), _ptr(vs), vs.shape[0],
+                                             _stream_ptr(self.device)), "flip_sweep")
+
+
+def select_rows(xs0: TEN, vs0: TEN, xs1: TEN, vs1: TEN, if_maximize: bool = True) -> None:
+    """In-place update_xs_by_vs on device tensors (bool [E,N] contiguous, int64 [E])."""
+    lib = _lib.lib()
+    dev = require_cuda(xs0.device)
+    if not (xs0.is_contiguous() and vs0.is_contiguous()):
+        raise RuntimeError("select_rows mutates xs0 / vs0 in place: they must be contiguous")
+    if xs0.dtype != th.bool or xs1.dtype != th.bool or xs0.shape != xs1.shape:
+        raise TypeError("select_rows: xs0/xs1 must be bool tensors of one shape")
+    if vs0.dtype != th.int64:
+        raise TypeError("select_rows: vs0 must be int64")
+    vs1 = vs1.to(th.int64)
+    _lib.check(lib.rlsb_select_rows(_ptr(xs0), _ptr(vs0), _ptr(xs1.contiguous()), _ptr(vs1.contiguous()),
+                                    xs0.shape[0], xs0.shape[1], int(bool(if_maximize)), _stream_ptr(dev)),
+               "select_rows")
+
+
+def pick_best(xs: TEN, vs: TEN, num_repeats: int, if_maximize: bool = True) -> Tuple[TEN, TEN]:
+    lib = _lib.lib()
+    dev = require_cuda(xs.device)
+    if xs.dtype != th.bool:
+        raise TypeError("pick_best: xs must be bool")
+    n = xs.shape[1]
+    sims = xs.shape[0] // num_repeats
+    xs = xs.contiguous()
+    vs64 = vs.to(th.int64).contiguous()
+    out_xs = th.empty((sims, n), dtype=th.bool, device=dev)
+    out_vs = th.empty((sims,), dtype=th.int64, device=dev)
+    _lib.check(lib.rlsb_pick_best(_ptr(xs), _ptr(vs64), int(num_repeats), sims, n, int(bool(if_maximize)),
+                                  _ptr(out_xs), _ptr(out_vs), _stream_ptr(dev)), "pick_best")
+    return out_xs, out_vs.to(vs.dtype)

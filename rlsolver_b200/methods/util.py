@@ -1,0 +1,40 @@
+"""Graph helpers of rlsolver/methods/util.py used on the hot path:
+calc_num_nodes_in_mygraph (35-40), evolutionary_replacement (87-94), build_adjacency_bool (343-370)."""
+from __future__ import annotations
+
+import numpy as np
+import torch as th
+
+from .config import MyGraph
+
+TEN = th.Tensor
+
+
+def calc_num_nodes_in_mygraph(mygraph: MyGraph) -> int:
+    """Number of distinct endpoints -- isolated nodes do not count (reference behaviour)."""
+    if len(mygraph) == 0:
+        return 0
+    arr = np.asarray([(a, b) for a, b, _ in mygraph], dtype=np.int64)
+    return int(np.unique(arr).size)
+
+
+def build_adjacency_bool(mygraph: MyGraph, num_nodes: int = 0, if_bidirectional: bool = False) -> TEN:
+    if num_nodes == 0:
+        num_nodes = calc_num_nodes_in_mygraph(mygraph)
+    adj = np.zeros((num_nodes, num_nodes), dtype=bool)
+    arr = np.asarray([(a, b) for a, b, _ in mygraph], dtype=np.int64)
+    adj[arr[:, 0], arr[:, 1]] = True
+    if if_bidirectional:
+        adj |= adj.T
+    return th.from_numpy(adj)
+
+
+def evolutionary_replacement(xs: TEN, vs: TEN, low_k: int, if_maximize: bool):
+    """Overwrite `low_k` random non-elite rows with the `low_k` best rows (in place).
+    Same RNG call as the reference: one randperm(E - low_k) on xs.device."""
+    num_sims = xs.shape[0]
+    ids = vs.argsort()
+    top_ids, low_ids = (ids[:-low_k], ids[-low_k:]) if if_maximize else (ids[:low_k], ids[low_k:])
+    replace_ids = top_ids[th.randperm(num_sims - low_k, device=xs.device)[:low_k]]
+    xs[replace_ids] = xs[low_ids]
+    vs[replace_ids] = vs[low_ids]

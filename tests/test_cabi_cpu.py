@@ -1,0 +1,88 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol the header
+declares, and its native graph builder agrees with the oracle / the reference goldens.
+No device compute here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_files
+from oracle import maxcut as om
+from synth import gset_like
+
+import rlsolver_b200
+from rlsolver_b200 import _lib
+from rlsolver_b200.graph_store import GraphStore
+
+
+@pytest.fixture(scope="module")
+def lib():
+    rlsolver_b200.build()
+    return rlsolver_b200.lib()
+
+
+def test_header_symbols_exported(lib):
+    header = open(os.path.join(ROOT, "include", "rlsolver_b200.h")).read()
+    declared = set(re.findall(r"\b(rlsb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/rlsolver_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes signature table and header drifted"
+    assert lib.rlsb_version() >= 100
+
+
+@pytest.mark.parametrize("path", golden_files("maxcut_"), ids=os.path.basename)
+def test_graph_builder_matches_reference(lib, path):
+    z = np.load(path)
+    edges = [tuple(int(t) for t in row) for row in z["edges"]]
+    bidir = bool(z["bidirectional"])
+    st = GraphStore(edges, bidir, device=None)
+    assert st.num_nodes == int(z["num_nodes"]) and st.num_edges == int(z["num_edges"])
+    arrs = st.export()
+    n0 = np.repeat(np.arange(st.num_nodes), np.diff(arrs["listed_ptr"]))
+    assert np.array_equal(n0, z["n0_ids"]) and np.array_equal(arrs["listed_col"], z["n1_ids"])
+    assert np.array_equal(np.diff(arrs["listed_ptr"]), z["n0_num_n1"])
+    g = om.build_graph_store(edges, bidir)
+    fptr, fcol = om.full_neighbourhood(g)
+    assert np.array_equal(arrs["full_ptr"], fptr) and np.array_equal(arrs["full_col"], fcol)
+
+
+@pytest.mark.parametrize("name", ["G14", "G22", "G70"])
+def test_levels_are_a_valid_schedule(lib, name):
+    edges = gset_like(name)
+    st = GraphStore(edges, True, device=None)
+    a = st.export()
+    level_of = np.empty(st.num_nodes, np.int64)
+    for l in range(st.num_levels):
+        nodes = a["level_nodes"][a["level_ptr"][l]:a["level_ptr"][l + 1]]
+        assert np.all(np.diff(nodes) > 0)
+        level_of[nodes] = l
+    assert sorted(a["level_nodes"].tolist()) == list(range(st.num_nodes))
+    src = np.repeat(np.arange(st.num_nodes), np.diff(a["full_ptr"]))
+    dst = a["full_col"]
+    lo = src > dst          # every edge: the later node sits on a strictly later level
+    assert np.all(level_of[src[lo]] > level_of[dst[lo]])
+    assert np.all(level_of[src] != level_of[dst])
+
+
+def test_builder_errors(lib):
+    with pytest.raises(IndexError):      # isolated node shrinks N below the largest id (reference IndexError)
+        GraphStore([(0, 1, 1), (1, 5, 1)], False, device=None)
+    st = GraphStore([], False, device=None)
+    assert st.num_nodes == 0 and st.num_edges == 0
+
+
+def test_device_ops_refuse_host_only_graph(lib):
+    st = GraphStore([(0, 1, 1), (1, 2, 1)], False, device=None)
+    out = (C.c_int64 * 4)()
+    rc = lib.rlsb_cut_eval(st.handle, C.c_void_p(1), 4, out, None)
+    assert rc == 4 and b"no device image" in lib.rlsb_last_error()
+
+
+def test_no_cpu_fallback():
+    import torch as th
+    from rlsolver_b200.envs.env_L2A import EnvMaxcut
+    with pytest.raises(RuntimeError, match="CUDA"):
+        EnvMaxcut(mygraph=[(0, 1, 1)], device=th.device("cpu"))
