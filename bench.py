@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""Benchmark of the max-cut environment hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1]): G22-shaped max-cut (2000 nodes, 19990 edges, synthetic,
+seed 74), 4096 environments per GPU, one dREINFORCE sampling step of local search =
+`EnvMaxcut.local_search_inplace(xs, ())` with the reference defaults (8 noisy multi-flip
+iterations + the 2000-node single-flip pass).  1 env-step = one (environment, candidate move)
+whose cut value is produced: E * (1 + num_iters + N) per step.
+
+One JSON line on rank 0.  `value` = env-steps/s with inputs resident in HBM, CUDA-event timed,
+L2 flushed between steps; `e2e` = the same through the public API from pinned HOST buffers
+(H2D of the spins, D2H of spins + values inside the timed region).  `--impl reference` times
+the CPU restatement of the reference's own algorithm (oracle/torch_port.py) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "maxcut_env_steps_per_sec"
+UNIT = "env-steps/s"
+GRAPH, NUM_ENVS, NUM_ITERS, NUM_SPIN, NOISE_STD = "G22", 4096, 8, 8, 0.3
+
+
+def workload_name(envs):
+    return (f"G22-shaped maxcut (2000 nodes, 19990 edges, synthetic seed 74), {envs} envs/GPU, "
+            f"local_search_inplace: {NUM_ITERS} noisy multi-flip iters + full single-flip pass (dREINFORCE sampling step)")
+
+
+def env_steps_per_call(envs, n, num_iters, sweep_nodes):
+    return envs * (1 + num_iters + sweep_nodes)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def cpu_reference_run(steps, warmup, budget_s=3.0):
+    """The reference's algorithm on the host cores: torch restatement (index-gather objective,
+    one full re-evaluation per candidate flip).  Each step is a bounded sample of the workload:
+    256 of the envs, all noisy iterations, and the first `sweep_nodes` nodes of the single-flip
+    pass, sized so a step takes about `budget_s` seconds."""
+    import torch as th
+    from oracle import torch_port as tp
+    from synth import gset_like
+
+    th.set_num_threads(os.cpu_count() or 1)
+    edges = gset_like(GRAPH)
+    sim = tp.TorchSim(edges, True, device="cpu")
+    envs = 256
+    th.manual_seed(74)
+    xs0 = sim.random_xs(envs)
+    sim.objective(xs0)                                   # builds the [E, Md] index tensors
+    t = time.perf_counter()
+    for _ in range(3):
+        sim.objective(xs0)
+    t_eval = (time.perf_counter() - t) / 3
+    sweep_nodes = int(max(8, min(sim.num_nodes, budget_s / max(t_eval * 1.3, 1e-4) - (2 + NUM_ITERS))))
+    per_call = env_steps_per_call(envs, sim.num_nodes, NUM_ITERS, sweep_nodes)
+    times = []
+    for it in range(warmup + steps):
+        xs = xs0.clone()
+        t = time.perf_counter()
+        sim.local_search_inplace(xs, None, NUM_ITERS, NUM_SPIN, NOISE_STD, sweep_nodes=sweep_nodes)
+        dt = time.perf_counter() - t
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    value = per_call * len(times) / total
+    sample = (f"{envs} envs of the same graph, {NUM_ITERS} noisy iters + first {sweep_nodes} of 2000 sweep nodes "
+              f"per step ({per_call} env-steps), torch CPU ops as the reference uses them")
+    return {"value": value, "unit": UNIT, "cores": th.get_num_threads(), "kind": "port", "sample": sample,
+            "ms_per_step": 1e3 * total / len(times), "steps": len(times)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    warm = min(args.warmup, 1) if args.warmup else 0
+    r = cpu_reference_run(args.steps, warm)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": workload_name(NUM_ENVS), "cpu_sample": r["sample"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch as th
+    import torch.distributed as dist
+    from synth import gset_like
+
+    import rlsolver_b200
+    from rlsolver_b200.dist import best_allreduce
+    from rlsolver_b200.envs.env_L2A import EnvMaxcut
+    from rlsolver_b200.graph_store import OpTimer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not th.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (rlsolver_b200 has no CPU fallback)")
+    th.cuda.set_device(local)
+    dev = th.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rlsolver_b200.build()
+
+    envs = args.envs
+    edges = gset_like(GRAPH)
+    sim = EnvMaxcut(mygraph=edges, device=dev, if_bidirectional=True)
+    n = sim.num_nodes
+    th.manual_seed(74 + rank)
+    xs0 = sim.generate_xs_randomly(envs)
+    xs = xs0.clone()
+    sentinel = th.empty(())
+    flush = th.empty(256 << 20, dtype=th.uint8, device=dev)       # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        th.cuda.synchronize()
+
+    def one_step():
+        gx, gv = sim.local_search_inplace(xs, sentinel, NUM_ITERS, NUM_SPIN, NOISE_STD)
+        if world > 1:     # the path's only exchange: best cut + its argmax + the winner's spins
+            best_allreduce(gv, gx, rank, world, envs)
+        return gx, gv
+
+    def timed_steps(k):
+        evs = []
+        for _ in range(k):
+            xs.copy_(xs0)
+            flush.zero_()                                           # evict L2 between steps (untimed)
+            a, b = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+            a.record()
+            one_step()
+            b.record()
+            evs.append((a, b))
+        th.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    # warm-up: at least W steps and at least ~1.5 s of load so the clocks settle
+    t_w = time.time()
+    done = 0
+    while done < max(3, args.warmup) or time.time() - t_w < 1.5:
+        timed_steps(1)
+        done += 1
+    barrier()
+    launches0 = sim.store.launch_count
+    t0 = time.time()
+    ms = timed_steps(args.steps)
+    barrier()
+    t1 = time.time()
+    launches = sim.store.launch_count - launches0
+    total_ms = th.tensor([sum(ms)], dtype=th.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    per_call = env_steps_per_call(envs, n, NUM_ITERS, n)
+    value = per_call * world * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end from pinned host buffers through the public API
+    h_xs = xs0.cpu().pin_memory()
+    h_out_xs = th.empty_like(h_xs).pin_memory()
+    h_out_vs = th.empty((envs,), dtype=th.int64).pin_memory()
+
+    def e2e_step():
+        d_xs = h_xs.to(dev, non_blocking=True)
+        gx, gv = sim.local_search_inplace(d_xs, sentinel, NUM_ITERS, NUM_SPIN, NOISE_STD)
+        if world > 1:
+            best_allreduce(gv, gx, rank, world, envs)
+        h_out_xs.copy_(gx, non_blocking=True)
+        h_out_vs.copy_(gv, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e2e_ms = []
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        a.record()
+        e2e_step()
+        b.record()
+        th.cuda.synchronize()
+        e2e_ms.append(a.elapsed_time(b))
+    barrier()
+    e2e_total = th.tensor([sum(e2e_ms)], dtype=th.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
+    e2e_value = per_call * world * args.steps / (float(e2e_total.item()) * 1e-3)
+    clock_info = clocks.stop(t_w, time.time()) if clocks else None
+
+    # ---- per-kernel pass (CUDA events around every launch of this library) for the roofline
+    sim.store.timer = OpTimer()
+    timed_steps(args.steps)
+    spans = sim.store.timer.summary()
+    sim.store.timer = None
+    step_ms_prof = sum(v[1] for v in spans.values()) / args.steps
+    share = {k: round(v[1] / args.steps / max(step_ms_prof, 1e-9), 4) for k, v in spans.items()}
+    kernel_ms = {k: v[1] / v[0] for k, v in spans.items()}
+    dom = max(spans, key=lambda k: spans[k][1])
+    np_ = sim.store.padded_nodes
+    alg_bytes = {   # algorithmic bytes per launch, DESIGN.md "Kernels"
+        "ls_noisy_iters": NUM_ITERS * (4 * envs * n + 2 * envs * np_) + 2 * envs * np_ // 8 + 20 * envs
+                          + 8 * sim.num_edges + 12 * n,
+        "flip_sweep": 2 * envs * np_ // 8 + 16 * envs + 4 * (n + 1) + 4 * sim.store.num_full + 4 * n,
+        "ls_thresh": 4 * envs * n + 2 * envs * np_ + 4 * envs + 12 * n,
+        "node_cross_counts": envs * np_ // 8 + 2 * envs * np_ + 4 * (n + 1) + 4 * sim.store.num_listed + 8 * n,
+        "pack_spins": envs * n + envs * np_ // 8,
+        "unpack_spins": envs * n + envs * np_ // 8,
+        "cut_eval_packed": envs * np_ // 8 + 8 * envs + 8 * sim.num_edges,
+    }
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = alg_bytes[dom] / (kernel_ms[dom] * 1e-3) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "ms_per_launch": kernel_ms[dom], "algorithmic_bytes_per_launch": alg_bytes[dom],
+                "share_of_step": share,
+                "all_kernels_gbs": {k: alg_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9 for k in kernel_ms if k in alg_bytes},
+                "pass": "separate K-step pass with CUDA events around each launch of this library"}
+    traffic_path = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(traffic_path):
+        roofline["traffic"] = json.load(open(traffic_path)).get(dom)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(steps=3, warmup=1, budget_s=4.0)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-packed spins / int64 values / f32 noise",
+                "data": "synthetic",
+                "config": {"workload": workload_name(envs), "envs_per_gpu": envs, "nodes": n, "edges": sim.num_edges,
+                           "env_steps_per_step_per_gpu": per_call, "l2": "flushed between steps (256 MiB write)",
+                           "rng": "torch CUDA Philox randn, 1+8 draws of [E,N] f32 per step inside the timed region",
+                           "multi_gpu": "env batch sharded, graph replicated, best-cut allreduce per step"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": envs * n,
+                        "d2h_bytes_per_step": envs * n + 8 * envs, "ms_per_step": float(e2e_total.item()) / args.steps},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=NUM_ENVS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

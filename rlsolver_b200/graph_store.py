@@ -34,6 +34,47 @@ def require_cuda(device) -> th.device:
     return device
 
 
+class OpTimer:
+    """Optional per-op CUDA-event timing (bench.py's roofline pass).  Events are recorded on
+    the stream the kernels are launched on (torch's current stream)."""
+
+    def __init__(self):
+        self.spans = {}
+        self.launches = 0
+
+    def begin(self, name):
+        ev = th.cuda.Event(enable_timing=True)
+        ev.record()
+        return name, ev
+
+    def end(self, tok, launches=1):
+        name, start = tok
+        stop = th.cuda.Event(enable_timing=True)
+        stop.record()
+        self.spans.setdefault(name, []).append((start, stop))
+        self.launches += launches
+
+    def summary(self):
+        th.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.spans.items()}
+
+
+class _Span:
+    __slots__ = ("timer", "name", "launches", "tok")
+
+    def __init__(self, timer, name, launches):
+        self.timer, self.name, self.launches = timer, name, launches
+
+    def __enter__(self):
+        if self.timer is not None:
+            self.tok = self.timer.begin(self.name)
+
+    def __exit__(self, *exc):
+        if self.timer is not None:
+            self.timer.end(self.tok, self.launches)
+        return False
+
+
 class GraphStore:
     """CSR + edge list + sweep levels, built natively from a reference-style MyGraph
     (list of (n0, n1, weight), 0-based).  `device=None` keeps it host-only (no CUDA needed)."""
@@ -66,6 +107,12 @@ class GraphStore:
         self.max_listed_degree = int(L.rlsb_graph_max_listed_degree(handle))
         self.max_full_degree = int(L.rlsb_graph_max_full_degree(handle))
         self.if_bidirectional = bool(if_bidirectional)
+        self.timer: Optional[OpTimer] = None      # set by bench.py for the per-kernel pass
+        self.launch_count = 0                     # kernels of this library launched through this store
+
+    def _op(self, name: str, launches: int = 1) -> _Span:
+        self.launch_count += launches
+        return _Span(self.timer, name, launches)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -112,8 +159,9 @@ class GraphStore:
         xs = self._check_xs(xs)
         e = xs.shape[0]
         out = self.new_packed(e) if out is None else out
-        _lib.check(self._lib.rlsb_pack_spins(_ptr(xs), e, self.num_nodes, self.padded_nodes, _ptr(out),
-                                             _stream_ptr(self.device)), "pack_spins")
+        with self._op("pack_spins"):
+            _lib.check(self._lib.rlsb_pack_spins(_ptr(xs), e, self.num_nodes, self.padded_nodes, _ptr(out),
+                                                 _stream_ptr(self.device)), "pack_spins")
         return out
 
     def unpack(self, packed: TEN, num_envs: int, out: Optional[TEN] = None) -> TEN:
@@ -121,21 +169,24 @@ class GraphStore:
             out = th.empty((num_envs, self.num_nodes), dtype=th.bool, device=self.device)
         elif not out.is_contiguous():
             raise RuntimeError("unpack target must be contiguous")
-        _lib.check(self._lib.rlsb_unpack_spins(_ptr(packed), num_envs, self.num_nodes, self.padded_nodes, _ptr(out),
-                                               _stream_ptr(self.device)), "unpack_spins")
+        with self._op("unpack_spins"):
+            _lib.check(self._lib.rlsb_unpack_spins(_ptr(packed), num_envs, self.num_nodes, self.padded_nodes,
+                                                   _ptr(out), _stream_ptr(self.device)), "unpack_spins")
         return out
 
     def cut_eval(self, xs: TEN) -> TEN:
         xs = self._check_xs(xs)
         vs = th.empty((xs.shape[0],), dtype=th.int64, device=self.device)
-        _lib.check(self._lib.rlsb_cut_eval(self._h, _ptr(xs), xs.shape[0], _ptr(vs), _stream_ptr(self.device)),
-                   "cut_eval")
+        with self._op("cut_eval"):
+            _lib.check(self._lib.rlsb_cut_eval(self._h, _ptr(xs), xs.shape[0], _ptr(vs), _stream_ptr(self.device)),
+                       "cut_eval")
         return vs
 
     def cut_eval_packed(self, packed: TEN, num_envs: int, out: Optional[TEN] = None) -> TEN:
         vs = th.empty((num_envs,), dtype=th.int64, device=self.device) if out is None else out
-        _lib.check(self._lib.rlsb_cut_eval_packed(self._h, _ptr(packed), num_envs, _ptr(vs),
-                                                  _stream_ptr(self.device)), "cut_eval_packed")
+        with self._op("cut_eval_packed"):
+            _lib.check(self._lib.rlsb_cut_eval_packed(self._h, _ptr(packed), num_envs, _ptr(vs),
+                                                      _stream_ptr(self.device)), "cut_eval_packed")
         return vs
 
     def cut_edges(self, xs: TEN) -> TEN:
@@ -154,17 +205,19 @@ class GraphStore:
         if want_minmax:
             cmin = th.empty((self.num_nodes,), dtype=th.int32, device=self.device)
             cmax = th.empty((self.num_nodes,), dtype=th.int32, device=self.device)
-        _lib.check(self._lib.rlsb_node_cross_counts(self._h, _ptr(packed), num_envs, _ptr(cross), _ptr(cmin),
-                                                    _ptr(cmax), _stream_ptr(self.device)), "node_cross_counts")
+        with self._op("node_cross_counts", 3 if want_minmax else 1):
+            _lib.check(self._lib.rlsb_node_cross_counts(self._h, _ptr(packed), num_envs, _ptr(cross), _ptr(cmin),
+                                                        _ptr(cmax), _stream_ptr(self.device)), "node_cross_counts")
         return cross, cmin, cmax
 
     def ls_thresh(self, cross: TEN, cmin: TEN, cmax: TEN, ws_mult: int, noise_std: float, noise: TEN,
                   num_spin: int) -> TEN:
         e = noise.shape[0]
         thresh = th.empty((e,), dtype=th.float32, device=self.device)
-        _lib.check(self._lib.rlsb_ls_thresh(self._h, _ptr(cross), _ptr(cmin), _ptr(cmax), ws_mult, float(noise_std),
-                                            _ptr(noise), int(num_spin), e, _ptr(thresh), _stream_ptr(self.device)),
-                   "ls_thresh")
+        with self._op("ls_thresh"):
+            _lib.check(self._lib.rlsb_ls_thresh(self._h, _ptr(cross), _ptr(cmin), _ptr(cmax), ws_mult,
+                                                float(noise_std), _ptr(noise), int(num_spin), e, _ptr(thresh),
+                                                _stream_ptr(self.device)), "ls_thresh")
         return thresh
 
     def ls_noisy_iters(self, packed: TEN, vs: TEN, cross: TEN, cmin: TEN, cmax: TEN, ws_mult: int, noise_std: float,
@@ -173,13 +226,15 @@ class GraphStore:
             return
         e = vs.shape[0]
         ptrs = (C.c_void_p * len(noises))(*[t.data_ptr() for t in noises])
-        _lib.check(self._lib.rlsb_ls_noisy_iters(self._h, _ptr(packed), _ptr(vs), _ptr(cross), _ptr(cmin), _ptr(cmax),
-                                                 ws_mult, float(noise_std), ptrs, len(noises), _ptr(thresh), e,
-                                                 _stream_ptr(self.device)), "ls_noisy_iters")
+        with self._op("ls_noisy_iters", (len(noises) + 15) // 16):
+            _lib.check(self._lib.rlsb_ls_noisy_iters(self._h, _ptr(packed), _ptr(vs), _ptr(cross), _ptr(cmin),
+                                                     _ptr(cmax), ws_mult, float(noise_std), ptrs, len(noises),
+                                                     _ptr(thresh), e, _stream_ptr(self.device)), "ls_noisy_iters")
 
     def flip_sweep(self, packed: TEN, vs: TEN) -> None:
-        _lib.check(self._lib.rlsb_flip_sweep(self._h, _ptr(packed), _ptr(vs), vs.shape[0],
-                                             _stream_ptr(self.device)), "flip_sweep")
+        with self._op("flip_sweep"):
+            _lib.check(self._lib.rlsb_flip_sweep(self._h, _ptr(packed), _ptr(vs), vs.shape[0],
+                                                 _stream_ptr(self.device)), "flip_sweep")
 
 
 def select_rows(xs0: TEN, vs0: TEN, xs1: TEN, vs1: TEN, if_maximize: bool = True) -> None:
