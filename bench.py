@@ -258,15 +258,18 @@ def run_b200(args):
     kernel_ms = {k: v[1] / v[0] for k, v in spans.items()}
     dom = max(spans, key=lambda k: spans[k][1])
     np_ = sim.store.padded_nodes
-    alg_bytes = {   # algorithmic bytes per launch, DESIGN.md "Kernels"
-        "ls_noisy_iters": NUM_ITERS * (4 * envs * n + 2 * envs * np_) + 2 * envs * np_ // 8 + 20 * envs
-                          + 8 * sim.num_edges + 12 * n,
-        "flip_sweep": 2 * envs * np_ // 8 + 16 * envs + 4 * (n + 1) + 4 * sim.store.num_full + 4 * n,
-        "ls_thresh": 4 * envs * n + 2 * envs * np_ + 4 * envs + 12 * n,
-        "node_cross_counts": envs * np_ // 8 + 2 * envs * np_ + 4 * (n + 1) + 4 * sim.store.num_listed + 8 * n,
+    cb = 1 if max(sim.store.max_listed_degree, sim.store.max_full_degree) <= 255 else 2   # cross-count bytes
+    graph_b = 4 * sim.num_edges + 2 * sim.store.num_full + 12 * np_
+    alg_bytes = {   # algorithmic bytes per launch group, DESIGN.md "Kernels"
+        # noise + cross counts per iteration; packed tile in/out, bool rows + values out, graph once
+        "ls_search": NUM_ITERS * (4 * envs * n + cb * envs * np_) + 2 * envs * np_ // 8 + envs * n + 16 * envs
+                     + graph_b,
+        "ls_thresh": 4 * envs * n + cb * envs * np_ + 4 * envs + 8 * np_,
+        "ls_begin": envs * n + envs * np_ // 8 + cb * envs * np_ + 8 * envs + graph_b,
         "pack_spins": envs * n + envs * np_ // 8,
         "unpack_spins": envs * n + envs * np_ // 8,
-        "cut_eval_packed": envs * np_ // 8 + 8 * envs + 8 * sim.num_edges,
+        "cut_eval_packed": envs * np_ // 8 + 8 * envs + 4 * sim.num_edges,
+        "cut_eval": envs * n + 8 * envs + 4 * sim.num_edges,
     }
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):

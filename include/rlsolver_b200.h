@@ -63,6 +63,16 @@ int32_t rlsb_graph_max_full_degree(const rlsb_graph_t* g);
 int rlsb_graph_export(const rlsb_graph_t* g, int32_t* h_listed_ptr, int32_t* h_listed_col, int32_t* h_full_ptr,
                       int32_t* h_full_col, int32_t* h_level_ptr, int32_t* h_level_nodes);
 
+/* The tile kernels read neighbour lists as SELL-32 slices (32 node slots per slice, column ids
+ * round-major, short rows padded with the node's own id, unused slots = 0xFFFF).  which = 0:
+ * listed neighbours, slot == node over the padded node range; which = 1: full neighbours in
+ * sweep order (dependency level, then degree-descending), `half` = floor(degree/2), and
+ * level_slice[l] .. level_slice[l+1] = the slices of level l.  sizes: out3 = {num_slices,
+ * column entries, levels + 1}.  Host-side copies for tests and tools. */
+int rlsb_graph_sell_sizes(const rlsb_graph_t* g, int32_t which, int64_t* out3);
+int rlsb_graph_sell_export(const rlsb_graph_t* g, int32_t which, int32_t* h_off, uint16_t* h_node, uint16_t* h_half,
+                           uint16_t* h_col, int32_t* h_level_slice);
+
 /* ---- spin (de)packing: layout change only, no reference counterpart */
 int rlsb_pack_spins(const uint8_t* xs, int64_t num_envs, int32_t num_nodes, int32_t padded_nodes, uint32_t* packed,
                     void* stream);
@@ -81,30 +91,46 @@ int rlsb_cut_edges(const rlsb_graph_t* g, const uint8_t* xs, int64_t num_envs, u
  * (env_L2A.py:68-80).  cross is uint16 [E][Np] (row-major, rows padded to Np):
  * number of LISTED neighbours of node i on the other side in env e.
  * col_min/col_max (nullable, int32 [N]) receive min/max over envs per node --
- * the cross-env coupling `ws_std` of env_L2A.py:93 / LocalSearch.py:65. */
+ * the cross-env coupling `ws_std` of env_L2A.py:93 / LocalSearch.py:65.  Listed degree <= 4095. */
 int rlsb_node_cross_counts(const rlsb_graph_t* g, const uint32_t* packed, int64_t num_envs, uint16_t* cross,
                            int32_t* col_min, int32_t* col_max, void* stream);
 
-/* ---- noisy multi-flip local search, env_L2A.py:92-107 / LocalSearch.py:62-75.
- * ws[e][i] = listed_degree[i] - ws_mult * cross[e][i]   (ws_mult: 1 = local_search_inplace,
- *            2 = LocalSearch.random_search), rd_std[i] = float(ws_mult*(col_max-col_min)) * noise_std,
- * spin_rand = ws + noise*rd_std in float32 with one rounding per op.
- * ls_thresh: thresh[e] = kth smallest of spin_rand[e][:], k = N - num_spin  (torch.kthvalue).
- * ls_noisy_iters: for each of num_iters noise tensors (h_noise_ptrs: HOST array of device
- * pointers, float32 [E][N] each): flip where spin_rand > thresh, evaluate, keep rows with vs' >= vs.
- * packed and vs are updated in place. */
-int rlsb_ls_thresh(const rlsb_graph_t* g, const uint16_t* cross, const int32_t* col_min, const int32_t* col_max,
-                   int32_t ws_mult, float noise_std, const float* noise, int32_t num_spin, int64_t num_envs,
-                   float* thresh, void* stream);
-int rlsb_ls_noisy_iters(const rlsb_graph_t* g, uint32_t* packed, int64_t* vs, const uint16_t* cross,
-                        const int32_t* col_min, const int32_t* col_max, int32_t ws_mult, float noise_std,
-                        const float* const* h_noise_ptrs, int32_t num_iters, const float* thresh,
-                        int64_t num_envs, void* stream);
+/* ---- local search: EnvMaxcut.local_search_inplace (env_L2A.py:87-116) and
+ * LocalSearch.random_search (LocalSearch.py:53-86) in four calls on one stream.  State between
+ * the calls lives in a caller-provided, 256-byte aligned device workspace of
+ * rlsb_ls_workspace_bytes(g, E) bytes (returns -1 on a bad handle).
+ *
+ *   ws[e][i]  = listed_degree[i] - ws_mult * cross[e][i]   (ws_mult: 1 = local_search_inplace,
+ *               2 = LocalSearch.random_search), rd_std[i] = float(ws_mult*(max_e cross - min_e cross)) * noise_std,
+ *   spin_rand = ws + noise * rd_std in float32, one rounding per op (as the reference's torch kernels).
+ *
+ * ls_begin : bool xs [E][N] -> packed tiles, per-node cross counts, their max/min over the env
+ *            batch (the `ws_std` coupling, env_L2A.py:92-93), rd_std; if compute_vs != 0 also
+ *            vs[e] = cut (the `()` sentinel of env_L2A.py:91), else vs is left as given.
+ * ls_thresh: thresh[e] = kth smallest of spin_rand[e][:], k = N - num_spin (torch.kthvalue,
+ *            env_L2A.py:94-96) from one noise tensor float32 [E][N].
+ * ls_search: for each of num_iters noise tensors (h_noise_ptrs: HOST array of device pointers,
+ *            float32 [E][N]): flip where spin_rand > thresh, evaluate, keep rows with vs' >= vs
+ *            (env_L2A.py:97-107).  If finish != 0 it then runs the exhaustive single-flip pass
+ *            (env_L2A.py:110-115: node 0..N-1 in order, flip where the cut does not get worse,
+ *            Gauss-Seidel; O(2M) word operations per 32 envs instead of N full evaluations; the
+ *            gain rule is the batched form of S2V_PPO/env.py:197-206), writes the bool rows to
+ *            xs_out [E][N] and the final cut values to vs.  vs must be consistent with the state
+ *            (vs[e] == cut of row e) when ls_begin was called with compute_vs == 0. */
+int64_t rlsb_ls_workspace_bytes(const rlsb_graph_t* g, int64_t num_envs);
+/* byte offset of a workspace section (tests / debugging): 0 packed u32 [W][Np], 1 cross counts
+ * (uint8, or uint16 when a degree exceeds 255) [E][Np], 2 col_min i32 [Np], 3 col_max i32 [Np],
+ * 4 listed degree + 0x4B400000 i32 [Np], 5 rd_std f32 [Np], 6 thresh f32 [E]; -1 on error. */
+int64_t rlsb_ls_workspace_offset(const rlsb_graph_t* g, int64_t num_envs, int32_t section);
+int rlsb_ls_begin(const rlsb_graph_t* g, const uint8_t* xs, int64_t num_envs, int64_t* vs, int32_t compute_vs,
+                  int32_t ws_mult, float noise_std, void* workspace, void* stream);
+int rlsb_ls_thresh(const rlsb_graph_t* g, int64_t num_envs, int32_t ws_mult, const float* noise, int32_t num_spin,
+                   void* workspace, void* stream);
+int rlsb_ls_search(const rlsb_graph_t* g, int64_t num_envs, int64_t* vs, int32_t ws_mult,
+                   const float* const* h_noise_ptrs, int32_t num_iters, int32_t finish, uint8_t* xs_out,
+                   void* workspace, void* stream);
 
-/* ---- exhaustive single-flip pass, env_L2A.py:110-115 / LocalSearch.py:78-83:
- * for node 0..N-1 in order, flip it where the cut does not get worse (gain >= 0),
- * Gauss-Seidel.  O(2M) word operations per 32 envs instead of N full evaluations;
- * the per-flip gain rule is the batched form of S2V_PPO/env.py:197-206. */
+/* ---- the exhaustive single-flip pass alone, on packed tiles (vs is recomputed) */
 int rlsb_flip_sweep(const rlsb_graph_t* g, uint32_t* packed, int64_t* vs, int64_t num_envs, void* stream);
 
 /* ---- select ops on the reference's bool layout

@@ -93,14 +93,19 @@ SIGNATURES = {
     "rlsb_graph_max_listed_degree": (_i32, [_vp]),
     "rlsb_graph_max_full_degree": (_i32, [_vp]),
     "rlsb_graph_export": (C.c_int, [_vp] * 7),
+    "rlsb_graph_sell_sizes": (C.c_int, [_vp, _i32, _vp]),
+    "rlsb_graph_sell_export": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "rlsb_pack_spins": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "rlsb_unpack_spins": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "rlsb_cut_eval": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "rlsb_cut_eval_packed": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "rlsb_cut_edges": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "rlsb_node_cross_counts": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
-    "rlsb_ls_thresh": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _f32, _vp, _i32, _i64, _vp, _vp]),
-    "rlsb_ls_noisy_iters": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _i32, _vp, _i64, _vp]),
+    "rlsb_ls_workspace_bytes": (_i64, [_vp, _i64]),
+    "rlsb_ls_workspace_offset": (_i64, [_vp, _i64, _i32]),
+    "rlsb_ls_begin": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _f32, _vp, _vp]),
+    "rlsb_ls_thresh": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp]),
+    "rlsb_ls_search": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
     "rlsb_flip_sweep": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "rlsb_select_rows": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "rlsb_pick_best": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),

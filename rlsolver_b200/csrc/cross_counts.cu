@@ -1,72 +1,141 @@
-// Per-node cross counts: integer core of EnvMaxcut.calculate_obj_values_for_loop
-// (rlsolver/envs/env_L2A.py:68-80), which the reference runs as N Python iterations of
-// three tiny kernels.  One CTA per tile of 32 envs; one warp per node: lanes take the
-// node's listed neighbours, XOR their packed words with the node's word, and a 32x32 bit
-// transpose turns "bit = env" into "lane = env" so a POPC yields the count for env == lane.
-// Rows are staged through shared memory so the uint16 [E][Np] output is written coalesced.
-// Also produces the cross-env min / max per node that `ws_std` needs (env_L2A.py:93).
+// Tile "prepare" kernel: everything the reference computes from a batch of states before it
+// starts flipping -- EnvMaxcut.calculate_obj_values_for_loop (rlsolver/envs/env_L2A.py:68-80,
+// N Python iterations of three tiny kernels there), its cross-env max/min (`ws_std`,
+// env_L2A.py:93 / LocalSearch.py:65) and the objective (env_L2A.py:54-66).
+//
+// One CTA per tile of 32 envs, spins bit-packed in shared memory.  One LANE per node: the lane
+// walks its node's listed neighbours (SELL-32 slice, coalesced uint16 ids), XORs the
+// neighbour word with its own and adds the result into bit-sliced counters, so a LOP3 serves
+// 32 environments and there are no shuffles in the counting loop.  The planes are expanded to
+// one byte (or halfword) per env only when the counts leave the chip.
 #include <limits.h>
 
 #include "tile_ops.cuh"
 
 namespace rlsb {
 
-constexpr int kCCThreads = 512;
-constexpr int kCCChunk = 256;            // nodes per staging pass
-constexpr int kCCRow = kCCChunk + 2;     // halfwords per staged row: odd word stride -> conflict-free
+constexpr int kPrepThreads = 512;
 
-__global__ void __launch_bounds__(kCCThreads) cross_counts_kernel(GraphDev g, const uint32_t* __restrict__ packed,
-                                                                  int64_t num_envs, uint16_t* __restrict__ cross,
-                                                                  int32_t* col_min, int32_t* col_max) {
-  extern __shared__ uint32_t smem[];
-  uint32_t* sP = smem;
-  uint16_t* sOut = reinterpret_cast<uint16_t*>(smem + g.np);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int64_t tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int valid = (int)min((int64_t)kTileEnvs, num_envs - tile * kTileEnvs);
-    for (int i = threadIdx.x; i < g.np; i += blockDim.x) sP[i] = __ldg(packed + tile * g.np + i);
-    __syncthreads();
-    for (int base = 0; base < g.n; base += kCCChunk) {
-      const int stop = min(base + kCCChunk, g.n);
-      for (int i = base + warp; i < stop; i += nwarps) {
-        const int rb = __ldg(g.listed_ptr + i), re = __ldg(g.listed_ptr + i + 1);
-        const uint32_t pi = sP[i];
-        int cnt = 0;
-        for (int c = rb; c < re; c += 32) {
-          const int k = c + lane;
-          uint32_t x = 0;
-          if (k < re) x = sP[__ldg(g.listed_col + k)] ^ pi;
-          cnt += __popc(transpose32(x, lane));
-        }
-        sOut[lane * kCCRow + (i - base)] = (uint16_t)cnt;
-        if (col_min) {
-          const unsigned mn = __reduce_min_sync(kFull, lane < valid ? (unsigned)cnt : 0xffffffffu);
-          const unsigned mx = __reduce_max_sync(kFull, lane < valid ? (unsigned)cnt : 0u);
-          if (lane == 0) {
-            atomicMin(col_min + i, (int)mn);
-            atomicMax(col_max + i, (int)mx);
-          }
-        }
-      }
-      __syncthreads();
-      const int width = stop - base;              // base is a multiple of 256 -> even
-      for (int e = warp; e < valid; e += nwarps) {
-        uint16_t* dst = cross + (tile * kTileEnvs + e) * (int64_t)g.np + base;
-        const uint16_t* src = sOut + e * kCCRow;
-        for (int j = 2 * lane; j < width; j += 64) {
-          if (j + 1 < width) *reinterpret_cast<uint32_t*>(dst + j) = *reinterpret_cast<const uint32_t*>(src + j);
-          else dst[j] = src[j];
-        }
-      }
-      __syncthreads();
+template <int P, typename CrossT>
+__device__ __forceinline__ void store_cross(const VCount<P>& vc, CrossT* __restrict__ cross, int64_t env0, int valid,
+                                            int np, int i) {
+  CrossT* base = cross + env0 * (int64_t)np + i;
+  if (sizeof(CrossT) == 1) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t b = vc.bytes4(q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (4 * q + j < valid) base[(int64_t)(4 * q + j) * np] = (CrossT)((b >> (8 * j)) & 0xffu);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const uint32_t h = vc.halves2(q);
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (2 * q + j < valid) base[(int64_t)(2 * q + j) * np] = (CrossT)((h >> (16 * j)) & 0xffffu);
     }
   }
 }
 
-__global__ void fill_i32_kernel(int32_t* p, int32_t v, int n) {
+// VEC: 0 = packed input, 1 / 4 = bool rows read bytewise / as 4-byte words
+template <int P, typename CrossT, int VEC>
+__global__ void __launch_bounds__(kPrepThreads) prepare_kernel(GraphDev g, const uint8_t* __restrict__ xs,
+                                                               const uint32_t* __restrict__ packed_in,
+                                                               int64_t num_envs, uint32_t* __restrict__ packed_out,
+                                                               CrossT* __restrict__ cross, int32_t* col_min,
+                                                               int32_t* col_max, int64_t* __restrict__ vs,
+                                                               int cut_warps) {
+  extern __shared__ uint32_t sP[];
+  __shared__ int sCnt[kTileEnvs];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int64_t tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t env0 = tile * kTileEnvs;
+    const int valid = (int)min((int64_t)kTileEnvs, num_envs - env0);
+    const uint32_t vmask = valid == 32 ? kFull : ((1u << valid) - 1u);
+    if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
+    if (VEC == 0) {
+      for (int i = threadIdx.x; i < g.np; i += blockDim.x) sP[i] = __ldg(packed_in + tile * g.np + i);
+    } else {
+      pack_tile_to_smem<(VEC == 0 ? 1 : VEC)>(xs, num_envs, g.n, g.np, tile, sP);
+    }
+    __syncthreads();
+    if (VEC != 0 && packed_out)
+      for (int i = threadIdx.x; i < g.np; i += blockDim.x) packed_out[tile * g.np + i] = sP[i];
+    if (vs) {
+      const int cnt = tile_cut_partial(g, sP, cut_warps);
+      if (cnt) atomicAdd(&sCnt[lane], cnt);
+    }
+    if (cross || col_min) {
+      for (int slice = warp; slice * 32 < g.np; slice += nwarps) {
+        const int i = slice * 32 + lane;
+        VCount<P> vc;
+        sell_cross<P, false>(g.listed, slice, lane, sP, sP[i], vc);
+        if (cross) store_cross<P, CrossT>(vc, cross, env0, valid, g.np, i);
+        if (col_min && i < g.n) {
+          atomicMin(col_min + i, (int)vc.min_over(vmask));
+          atomicMax(col_max + i, (int)vc.max_over(vmask));
+        }
+      }
+    }
+    __syncthreads();
+    if (vs && threadIdx.x < valid) vs[env0 + threadIdx.x] = sCnt[threadIdx.x];
+    __syncthreads();
+  }
+}
+
+__global__ void fill_minmax_kernel(int32_t* mn, int32_t* mx, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
+  if (i < n) mn[i] = INT_MAX, mx[i] = 0;
+}
+
+template <int P, typename CrossT, int VEC>
+static int launch_prepare(const GraphDev& g, const uint8_t* xs, const uint32_t* packed_in, int64_t num_envs,
+                          uint32_t* packed_out, CrossT* cross, int32_t* col_min, int32_t* col_max, int64_t* vs,
+                          cudaStream_t st) {
+  const size_t smem = (size_t)g.np * sizeof(uint32_t);
+  auto kernel = prepare_kernel<P, CrossT, VEC>;
+  if (smem > 48 * 1024)
+    RLSB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;
+  const unsigned grid = (unsigned)(tiles < 8 * kNumSMs ? tiles : 8 * kNumSMs);
+  kernel<<<grid, kPrepThreads, smem, st>>>(g, xs, packed_in, num_envs, packed_out, cross, col_min, col_max, vs,
+                                           cut_warps_for(g.m, kPrepThreads / 32));
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+template <typename CrossT, int VEC>
+static int dispatch_planes(const GraphDev& g, const uint8_t* xs, const uint32_t* packed_in, int64_t num_envs,
+                           uint32_t* packed_out, CrossT* cross, int32_t* col_min, int32_t* col_max, int64_t* vs,
+                           cudaStream_t st) {
+  if (g.max_listed_deg <= 63)
+    return launch_prepare<6, CrossT, VEC>(g, xs, packed_in, num_envs, packed_out, cross, col_min, col_max, vs, st);
+  if (g.max_listed_deg <= 255)
+    return launch_prepare<8, CrossT, VEC>(g, xs, packed_in, num_envs, packed_out, cross, col_min, col_max, vs, st);
+  if (sizeof(CrossT) == 1) {
+    set_error("prepare: listed degree %d needs uint16 counts", g.max_listed_deg);
+    return RLSB_ERR_INVALID;
+  }
+  return launch_prepare<12, CrossT, VEC>(g, xs, packed_in, num_envs, packed_out, cross, col_min, col_max, vs, st);
+}
+
+// Used by rlsb_ls_begin (local_search.cu).  cross_is_u8 selects the element type of `cross`.
+int prepare_tiles(const GraphDev& g, const uint8_t* xs, const uint32_t* packed_in, int64_t num_envs,
+                  uint32_t* packed_out, void* cross, bool cross_is_u8, int32_t* col_min, int32_t* col_max, int64_t* vs,
+                  cudaStream_t st) {
+  if (col_min && g.n > 0) {
+    fill_minmax_kernel<<<(g.n + 255) / 256, 256, 0, st>>>(col_min, col_max, g.n);
+    RLSB_LAUNCH_OK();
+  }
+  if (num_envs == 0 || g.n == 0) return RLSB_OK;
+#define RLSB_PREP(T, V) dispatch_planes<T, V>(g, xs, packed_in, num_envs, packed_out, (T*)cross, col_min, col_max, vs, st)
+  if (packed_in) return cross_is_u8 ? RLSB_PREP(uint8_t, 0) : RLSB_PREP(uint16_t, 0);
+  if (rows_vec4_ok(xs, g.n)) return cross_is_u8 ? RLSB_PREP(uint8_t, 4) : RLSB_PREP(uint16_t, 4);
+  return cross_is_u8 ? RLSB_PREP(uint8_t, 1) : RLSB_PREP(uint16_t, 1);
+#undef RLSB_PREP
 }
 
 }  // namespace rlsb
@@ -74,29 +143,12 @@ __global__ void fill_i32_kernel(int32_t* p, int32_t v, int n) {
 extern "C" int rlsb_node_cross_counts(const rlsb_graph_t* gh, const uint32_t* packed, int64_t num_envs,
                                       uint16_t* cross, int32_t* col_min, int32_t* col_max, void* stream) {
   using namespace rlsb;
-  const GraphDev* g = graph_dev(gh);
-  RLSB_REQUIRE(gh != nullptr, RLSB_ERR_INVALID, "node_cross_counts: null graph");
-  RLSB_REQUIRE(g != nullptr, RLSB_ERR_NODEVICE, "node_cross_counts: graph has no device image");
+  const GraphDev* g;
+  if (int rc = graph_check(gh, &g, "node_cross_counts")) return rc;
   RLSB_REQUIRE(num_envs >= 0, RLSB_ERR_INVALID, "node_cross_counts: negative num_envs");
   RLSB_REQUIRE((col_min == nullptr) == (col_max == nullptr), RLSB_ERR_INVALID,
                "node_cross_counts: col_min and col_max must both be given or both be null");
-  RLSB_REQUIRE(rlsb_graph_max_listed_degree(gh) <= 65535, RLSB_ERR_UNSUPPORTED,
-               "node_cross_counts: listed degree above 65535 does not fit the uint16 counts");
-  auto st = static_cast<cudaStream_t>(stream);
-  if (col_min && g->n > 0) {
-    fill_i32_kernel<<<(g->n + 255) / 256, 256, 0, st>>>(col_min, INT_MAX, g->n);
-    fill_i32_kernel<<<(g->n + 255) / 256, 256, 0, st>>>(col_max, 0, g->n);
-  }
-  if (num_envs == 0 || g->n == 0) return RLSB_OK;
-  RLSB_REQUIRE(packed && cross, RLSB_ERR_INVALID, "node_cross_counts: null pointer");
-  const size_t smem = (size_t)g->np * sizeof(uint32_t) + (size_t)kTileEnvs * kCCRow * sizeof(uint16_t);
-  RLSB_REQUIRE(smem <= 220 * 1024, RLSB_ERR_UNSUPPORTED, "node_cross_counts: %d nodes exceed the shared-memory tile",
-               g->n);
-  if (smem > 48 * 1024)
-    RLSB_CUDA_OK(cudaFuncSetAttribute(cross_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;
-  const unsigned grid = (unsigned)(tiles < 8 * kNumSMs ? tiles : 8 * kNumSMs);
-  cross_counts_kernel<<<grid, kCCThreads, smem, st>>>(*g, packed, num_envs, cross, col_min, col_max);
-  RLSB_LAUNCH_OK();
-  return RLSB_OK;
+  RLSB_REQUIRE(num_envs == 0 || g->n == 0 || (packed && cross), RLSB_ERR_INVALID, "node_cross_counts: null pointer");
+  return prepare_tiles(*g, nullptr, packed, num_envs, nullptr, cross, false, col_min, col_max, nullptr,
+                       static_cast<cudaStream_t>(stream));
 }

@@ -2,18 +2,19 @@
 // The reference gathers xs through three int64 [E][Md] index tensors (~27 B per env-edge);
 // here one CTA owns a tile of 32 envs: it bit-packs the 32 bool rows into shared memory
 // (coalesced row reads, the only HBM traffic: N bytes per env) and streams the edge list
-// once for all 32 envs.  Algorithmic bytes per env-eval: N + 8 + 8M/E (bool API) or
-// N/8 + 8 + 8M/E (packed).
+// once for all 32 envs, each lane adding its edges' XOR words into bit-sliced counters
+// (vcount.cuh).  Algorithmic bytes per env-eval: N + 8 + 4M/E (bool API) or N/8 + 8 + 4M/E (packed).
 #include "tile_ops.cuh"
 
 namespace rlsb {
 
-constexpr int kCutThreads = 512;
+constexpr int kCutThreads = 256;
 
 template <int VEC, bool PACKED_IN>
 __global__ void __launch_bounds__(kCutThreads) cut_eval_kernel(GraphDev g, const uint8_t* __restrict__ xs,
                                                                const uint32_t* __restrict__ packed,
-                                                               int64_t num_envs, int64_t* __restrict__ vs) {
+                                                               int64_t num_envs, int64_t* __restrict__ vs,
+                                                               int cut_warps) {
   extern __shared__ uint32_t sP[];
   __shared__ int sCnt[kTileEnvs];
   const int64_t tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;
@@ -25,7 +26,7 @@ __global__ void __launch_bounds__(kCutThreads) cut_eval_kernel(GraphDev g, const
       pack_tile_to_smem<VEC>(xs, num_envs, g.n, g.np, tile, sP);
     }
     __syncthreads();
-    const int cnt = tile_cut_partial(g, sP);
+    const int cnt = tile_cut_partial(g, sP, cut_warps);
     if (cnt) atomicAdd(&sCnt[threadIdx.x & 31], cnt);
     __syncthreads();
     const int64_t env = tile * kTileEnvs + threadIdx.x;
@@ -57,27 +58,26 @@ extern "C" {
 static int cut_eval_common(const rlsb_graph_t* gh, const uint8_t* xs, const uint32_t* packed, int64_t num_envs,
                            int64_t* vs, void* stream) {
   using namespace rlsb;
-  const GraphDev* g = graph_dev(gh);
-  RLSB_REQUIRE(gh != nullptr, RLSB_ERR_INVALID, "cut_eval: null graph");
-  RLSB_REQUIRE(g != nullptr, RLSB_ERR_NODEVICE, "cut_eval: graph has no device image");
+  const GraphDev* g;
+  if (int rc0 = graph_check(gh, &g, "cut_eval")) return rc0;
   RLSB_REQUIRE(num_envs >= 0, RLSB_ERR_INVALID, "cut_eval: negative num_envs");
   if (num_envs == 0) return RLSB_OK;
   RLSB_REQUIRE((xs || packed) && vs, RLSB_ERR_INVALID, "cut_eval: null pointer");
   const size_t smem = (size_t)g->np * sizeof(uint32_t);
-  RLSB_REQUIRE(smem <= 200 * 1024, RLSB_ERR_UNSUPPORTED, "cut_eval: %d nodes exceed the shared-memory tile", g->n);
-  const int64_t tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;
+    const int64_t tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;
   const unsigned grid = (unsigned)(tiles < 8 * kNumSMs ? tiles : 8 * kNumSMs);
   auto st = static_cast<cudaStream_t>(stream);
+  const int cw = cut_warps_for(g->m, kCutThreads / 32);
   int rc;
   if (packed) {
     if ((rc = set_smem(cut_eval_kernel<1, true>, smem))) return rc;
-    cut_eval_kernel<1, true><<<grid, kCutThreads, smem, st>>>(*g, nullptr, packed, num_envs, vs);
+    cut_eval_kernel<1, true><<<grid, kCutThreads, smem, st>>>(*g, nullptr, packed, num_envs, vs, cw);
   } else if (rows_vec4_ok(xs, g->n)) {
     if ((rc = set_smem(cut_eval_kernel<4, false>, smem))) return rc;
-    cut_eval_kernel<4, false><<<grid, kCutThreads, smem, st>>>(*g, xs, nullptr, num_envs, vs);
+    cut_eval_kernel<4, false><<<grid, kCutThreads, smem, st>>>(*g, xs, nullptr, num_envs, vs, cw);
   } else {
     if ((rc = set_smem(cut_eval_kernel<1, false>, smem))) return rc;
-    cut_eval_kernel<1, false><<<grid, kCutThreads, smem, st>>>(*g, xs, nullptr, num_envs, vs);
+    cut_eval_kernel<1, false><<<grid, kCutThreads, smem, st>>>(*g, xs, nullptr, num_envs, vs, cw);
   }
   RLSB_LAUNCH_OK();
   return RLSB_OK;
@@ -93,9 +93,8 @@ int rlsb_cut_eval_packed(const rlsb_graph_t* g, const uint32_t* packed, int64_t 
 
 int rlsb_cut_edges(const rlsb_graph_t* gh, const uint8_t* xs, int64_t num_envs, uint8_t* out, void* stream) {
   using namespace rlsb;
-  const GraphDev* g = graph_dev(gh);
-  RLSB_REQUIRE(gh != nullptr, RLSB_ERR_INVALID, "cut_edges: null graph");
-  RLSB_REQUIRE(g != nullptr, RLSB_ERR_NODEVICE, "cut_edges: graph has no device image");
+  const GraphDev* g;
+  if (int rc0 = graph_check(gh, &g, "cut_edges")) return rc0;
   if (num_envs <= 0 || g->md == 0) return RLSB_OK;
   RLSB_REQUIRE(xs && out, RLSB_ERR_INVALID, "cut_edges: null pointer");
   RLSB_REQUIRE(num_envs <= 65535, RLSB_ERR_UNSUPPORTED, "cut_edges: more than 65535 envs per call");

@@ -32,14 +32,39 @@ struct rlsb_graph {
   int32_t n = 0, np = 0, bidir = 0, device = -1, levels = 0, max_listed_deg = 0, max_full_deg = 0;
   int64_t m = 0;
   std::vector<int32_t> edge_u, edge_v, weight;
-  std::vector<int32_t> listed_ptr, listed_col, listed_row, full_ptr, full_col, level_ptr, level_nodes;
+  std::vector<int32_t> listed_ptr, listed_col, listed_row, listed_deg, full_ptr, full_col, level_ptr, level_nodes;
+  // tile-kernel structures (only when np <= kMaxTileNodes)
+  bool tileable = false;
+  std::vector<uint32_t> edge_pair;
+  std::vector<int32_t> level_slice;
+  struct Sell {
+    std::vector<int32_t> off;
+    std::vector<uint16_t> node, half, col;
+  } sell_listed, sell_sweep;
   void* dev_blob = nullptr;   // one allocation holding every device array
   rlsb::GraphDev dev{};
 };
 
 namespace rlsb {
-const GraphDev* graph_dev(const rlsb_graph_t* g) { return (g && g->dev_blob) ? &g->dev : nullptr; }
+const GraphDev* graph_dev(const rlsb_graph_t* g) { return (g && g->dev_blob && g->tileable) ? &g->dev : nullptr; }
 int graph_device_id(const rlsb_graph_t* g) { return g ? g->device : -1; }
+
+int graph_check(const rlsb_graph_t* g, const GraphDev** out, const char* what) {
+  *out = nullptr;
+  RLSB_REQUIRE(g != nullptr, RLSB_ERR_INVALID, "%s: null graph", what);
+  RLSB_REQUIRE(g->device >= 0, RLSB_ERR_NODEVICE, "%s: graph was built host-only (device < 0)", what);
+  RLSB_REQUIRE(g->tileable, RLSB_ERR_UNSUPPORTED,
+               "%s: graph outside the shared-memory tile kernels (padded nodes %d > %d or degree > 4095)", what, g->np,
+               kMaxTileNodes);
+  *out = &g->dev;
+  return RLSB_OK;
+}
+
+int cut_warps_for(int64_t m, int max_warps) {
+  int64_t w = (m + 2047) / 2048;          // >= 64 edges per lane before another warp joins
+  if (w < 1) w = 1;
+  return int(w < max_warps ? w : max_warps);
+}
 }  // namespace rlsb
 
 namespace {
@@ -54,6 +79,42 @@ void build_csr(int32_t n, const std::vector<int32_t>& src, const std::vector<int
   std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
   for (size_t k = 0; k < src.size(); ++k) col[fill[src[k]]++] = dst[k];
   for (int32_t i = 0; i < n; ++i) std::sort(col.begin() + ptr[i], col.begin() + ptr[i + 1]);
+}
+
+// SELL-32 over an ordered list of nodes split into groups (slices never straddle a group).
+// A slice is 32 node slots; its column ids are stored in blocks of 4 rounds, lane-major inside
+// a block (col[(block*32 + lane)*4 + r]), so a lane fetches 4 neighbour ids with one 8-byte load
+// and a warp reads 256 contiguous bytes.  Rows shorter than the slice are padded with the node's
+// own id (word ^ word == 0: padding never counts); unused slots are 0xFFFF and their columns 0.
+// `off` counts blocks.
+void build_sell(const std::vector<int32_t>& order, const std::vector<int32_t>& group_ptr,
+                const std::vector<int32_t>& ptr, const std::vector<int32_t>& col, rlsb_graph::Sell& out,
+                std::vector<int32_t>* group_slice) {
+  out.off.assign(1, 0);
+  out.node.clear(), out.half.clear(), out.col.clear();
+  if (group_slice) group_slice->assign(1, 0);
+  for (size_t gi = 0; gi + 1 < group_ptr.size(); ++gi) {
+    for (int32_t b = group_ptr[gi]; b < group_ptr[gi + 1]; b += 32) {
+      const int32_t cnt = std::min(32, group_ptr[gi + 1] - b);
+      int32_t width = 0;
+      for (int32_t l = 0; l < cnt; ++l) width = std::max(width, ptr[order[b + l] + 1] - ptr[order[b + l]]);
+      const int32_t blocks = (width + 3) / 4;
+      const size_t base = out.col.size();
+      out.col.resize(base + size_t(blocks) * 128, 0);
+      for (int32_t l = 0; l < 32; ++l) {
+        if (l >= cnt) {
+          out.node.push_back(0xFFFF), out.half.push_back(0);
+          continue;
+        }
+        const int32_t i = order[b + l], deg = ptr[i + 1] - ptr[i];
+        out.node.push_back(uint16_t(i)), out.half.push_back(uint16_t(deg / 2));
+        for (int32_t k = 0; k < blocks * 4; ++k)
+          out.col[base + (size_t(k / 4) * 32 + l) * 4 + (k % 4)] = uint16_t(k < deg ? col[ptr[i] + k] : i);
+      }
+      out.off.push_back(out.off.back() + blocks);
+    }
+    if (group_slice) group_slice->push_back(int32_t(out.off.size()) - 1);
+  }
 }
 
 }  // namespace
@@ -149,24 +210,71 @@ int rlsb_graph_create(int32_t num_nodes, int64_t num_edges, const int32_t* h_n0,
     for (int32_t i = 0; i < g->n; ++i) g->level_nodes[fill[level[i]]++] = i;
   }
 
-  if (device >= 0) {
+  g->listed_deg.assign(g->np, 0);
+  for (int32_t i = 0; i < g->n; ++i) g->listed_deg[i] = g->listed_ptr[i + 1] - g->listed_ptr[i];
+
+  g->tileable = g->np <= kMaxTileNodes && g->max_listed_deg <= 4095 && g->max_full_deg <= 4095;
+  if (g->tileable) {
+    g->edge_pair.assign((num_edges + 3) / 4 * 4, 0u);   // padded with (0,0): word ^ word == 0
+    for (int64_t k = 0; k < num_edges; ++k) g->edge_pair[k] = uint32_t(g->edge_u[k]) | (uint32_t(g->edge_v[k]) << 16);
+    // listed neighbours, natural order over the padded node range (slot == node)
+    {
+      std::vector<int32_t> order(g->np), gp{0, g->np}, ptr(g->listed_ptr);
+      std::iota(order.begin(), order.end(), 0);
+      ptr.resize(g->np + 1, g->listed_ptr.empty() ? 0 : g->listed_ptr.back());
+      build_sell(order, gp, ptr, g->listed_col, g->sell_listed, nullptr);
+    }
+    // full neighbours in sweep order: by level, degree-descending inside a level (stable)
+    {
+      std::vector<int32_t> order(g->level_nodes);
+      for (int32_t l = 0; l < g->levels; ++l)
+        std::stable_sort(order.begin() + g->level_ptr[l], order.begin() + g->level_ptr[l + 1], [&](int32_t a, int32_t b) {
+          return g->full_ptr[a + 1] - g->full_ptr[a] > g->full_ptr[b + 1] - g->full_ptr[b];
+        });
+      build_sell(order, g->level_ptr, g->full_ptr, g->full_col, g->sell_sweep, &g->level_slice);
+    }
+  }
+
+  if (device >= 0 && g->tileable) {
     int prev = 0;
     cudaError_t e = cudaGetDevice(&prev);
     if (e == cudaSuccess) e = cudaSetDevice(device);
-    constexpr int kArrays = 9;
-    const std::vector<int32_t>* arrays[kArrays] = {&g->edge_u,     &g->edge_v,   &g->listed_ptr,
-                                                   &g->listed_col, &g->listed_row, &g->full_ptr,
-                                                   &g->full_col,   &g->level_ptr,  &g->level_nodes};
-    size_t offs[kArrays], total = 0;
-    for (int a = 0; a < kArrays; ++a) {
-      offs[a] = total;
-      total += (arrays[a]->size() * sizeof(int32_t) + 255) / 256 * 256 + 256;
+    struct Blob { const void* src; size_t bytes; size_t off; };
+    std::vector<Blob> blobs;
+    size_t total = 0;
+    auto add = [&](const void* src, size_t bytes) {
+      blobs.push_back({src, bytes, total});
+      total += (bytes + 255) / 256 * 256 + 256;
+      return int(blobs.size()) - 1;
+    };
+    auto addv32 = [&](const std::vector<int32_t>& v) { return add(v.data(), v.size() * 4); };
+    auto addv16 = [&](const std::vector<uint16_t>& v) { return add(v.data(), v.size() * 2); };
+    const int b_pair = add(g->edge_pair.data(), g->edge_pair.size() * 4);
+    const int b_lptr = addv32(g->listed_ptr), b_lcol = addv32(g->listed_col), b_lrow = addv32(g->listed_row);
+    const int b_ldeg = addv32(g->listed_deg), b_fptr = addv32(g->full_ptr), b_fcol = addv32(g->full_col);
+    const int b_l_off = addv32(g->sell_listed.off), b_l_node = addv16(g->sell_listed.node);
+    const int b_l_half = addv16(g->sell_listed.half), b_l_col = addv16(g->sell_listed.col);
+    // the sweep structure is one contiguous blob so that a CTA can stage it with one bulk copy
+    std::vector<uint8_t> sblob;
+    size_t s_lvs, s_off, s_node, s_half, s_col;
+    {
+      auto put = [&](const void* src, size_t bytes) {
+        const size_t at = sblob.size();
+        sblob.resize(at + (bytes + 15) / 16 * 16, 0);
+        if (bytes) memcpy(sblob.data() + at, src, bytes);
+        return at;
+      };
+      s_lvs = put(g->level_slice.data(), g->level_slice.size() * 4);
+      s_off = put(g->sell_sweep.off.data(), g->sell_sweep.off.size() * 4);
+      s_node = put(g->sell_sweep.node.data(), g->sell_sweep.node.size() * 2);
+      s_half = put(g->sell_sweep.half.data(), g->sell_sweep.half.size() * 2);
+      s_col = put(g->sell_sweep.col.data(), g->sell_sweep.col.size() * 2);
     }
+    const int b_sweep = add(sblob.data(), sblob.size());
     if (e == cudaSuccess) e = cudaMalloc(&g->dev_blob, total);
-    for (int a = 0; a < kArrays && e == cudaSuccess; ++a)
-      if (!arrays[a]->empty())
-        e = cudaMemcpy((char*)g->dev_blob + offs[a], arrays[a]->data(), arrays[a]->size() * sizeof(int32_t),
-                       cudaMemcpyHostToDevice);
+    for (size_t a = 0; a < blobs.size() && e == cudaSuccess; ++a)
+      if (blobs[a].bytes)
+        e = cudaMemcpy((char*)g->dev_blob + blobs[a].off, blobs[a].src, blobs[a].bytes, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
       set_error("graph_create: CUDA error %s", cudaGetErrorString(e));
       if (g->dev_blob) cudaFree(g->dev_blob);
@@ -175,9 +283,21 @@ int rlsb_graph_create(int32_t num_nodes, int64_t num_edges, const int32_t* h_n0,
       return RLSB_ERR_CUDA;
     }
     cudaSetDevice(prev);
-    auto at = [&](int a) { return reinterpret_cast<const int32_t*>((char*)g->dev_blob + offs[a]); };
-    g->dev = GraphDev{g->n,  g->np, int32_t(g->m), int32_t(g->listed_col.size()), int32_t(g->full_col.size()),
-                      g->levels, g->bidir, at(0), at(1), at(2), at(3), at(4), at(5), at(6), at(7), at(8)};
+    auto i32 = [&](int b) { return reinterpret_cast<const int32_t*>((char*)g->dev_blob + blobs[b].off); };
+    auto u16 = [&](int b) { return reinterpret_cast<const uint16_t*>((char*)g->dev_blob + blobs[b].off); };
+    GraphDev& d = g->dev;
+    d.n = g->n, d.np = g->np, d.m = int32_t(g->m), d.md = int32_t(g->listed_col.size());
+    d.mf = int32_t(g->full_col.size()), d.levels = g->levels, d.bidir = g->bidir;
+    d.max_listed_deg = g->max_listed_deg, d.max_full_deg = g->max_full_deg;
+    d.edge_pair = reinterpret_cast<const uint32_t*>(i32(b_pair));
+    d.listed_ptr = i32(b_lptr), d.listed_col = i32(b_lcol), d.listed_row = i32(b_lrow), d.listed_deg = i32(b_ldeg);
+    d.full_ptr = i32(b_fptr), d.full_col = i32(b_fcol);
+    d.listed = SellDev{int32_t(g->sell_listed.off.size()) - 1, i32(b_l_off), u16(b_l_node), u16(b_l_half), u16(b_l_col)};
+    const char* sb = (const char*)g->dev_blob + blobs[b_sweep].off;
+    d.sweep_blob = sb, d.sweep_blob_bytes = int32_t(sblob.size());
+    d.sweep_lvs = int32_t(s_lvs), d.sweep_off = int32_t(s_off), d.sweep_node = int32_t(s_node);
+    d.sweep_half = int32_t(s_half), d.sweep_col = int32_t(s_col);
+    d.num_sweep_slices = int32_t(g->sell_sweep.off.size()) - 1;
   }
   *out = g;
   return RLSB_OK;
@@ -208,6 +328,27 @@ int rlsb_graph_export(const rlsb_graph_t* g, int32_t* h_listed_ptr, int32_t* h_l
   cp(h_listed_ptr, g->listed_ptr), cp(h_listed_col, g->listed_col);
   cp(h_full_ptr, g->full_ptr), cp(h_full_col, g->full_col);
   cp(h_level_ptr, g->level_ptr), cp(h_level_nodes, g->level_nodes);
+  return RLSB_OK;
+}
+
+int rlsb_graph_sell_sizes(const rlsb_graph_t* g, int32_t which, int64_t* out3) {
+  RLSB_REQUIRE(g != nullptr && out3 != nullptr && (which == 0 || which == 1), RLSB_ERR_INVALID, "graph_sell_sizes: bad argument");
+  RLSB_REQUIRE(g->tileable, RLSB_ERR_UNSUPPORTED, "graph_sell_sizes: graph has no tile structures");
+  const auto& s = which ? g->sell_sweep : g->sell_listed;
+  out3[0] = int64_t(s.off.size()) - 1, out3[1] = int64_t(s.col.size()), out3[2] = int64_t(g->level_slice.size());
+  return RLSB_OK;
+}
+
+int rlsb_graph_sell_export(const rlsb_graph_t* g, int32_t which, int32_t* h_off, uint16_t* h_node, uint16_t* h_half,
+                           uint16_t* h_col, int32_t* h_level_slice) {
+  RLSB_REQUIRE(g != nullptr && (which == 0 || which == 1), RLSB_ERR_INVALID, "graph_sell_export: bad argument");
+  RLSB_REQUIRE(g->tileable, RLSB_ERR_UNSUPPORTED, "graph_sell_export: graph has no tile structures");
+  const auto& s = which ? g->sell_sweep : g->sell_listed;
+  if (h_off) memcpy(h_off, s.off.data(), s.off.size() * 4);
+  if (h_node && !s.node.empty()) memcpy(h_node, s.node.data(), s.node.size() * 2);
+  if (h_half && !s.half.empty()) memcpy(h_half, s.half.data(), s.half.size() * 2);
+  if (h_col && !s.col.empty()) memcpy(h_col, s.col.data(), s.col.size() * 2);
+  if (h_level_slice && !g->level_slice.empty()) memcpy(h_level_slice, g->level_slice.data(), g->level_slice.size() * 4);
   return RLSB_OK;
 }
 

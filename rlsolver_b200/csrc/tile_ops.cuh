@@ -3,6 +3,7 @@
 // tile in shared memory and works on whole words, so one LOP/POPC serves 32 envs.
 #pragma once
 #include "common.cuh"
+#include "vcount.cuh"
 
 namespace rlsb {
 
@@ -98,23 +99,6 @@ __device__ __forceinline__ void unpack_tile_from_smem(const uint32_t* sP, uint8_
 // bool rows can be read/written as 4-byte words iff every row start is 4-aligned
 __host__ __device__ inline bool rows_vec4_ok(const void* p, int32_t n) {
   return (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) & 3u) == 0);
-}
-
-// ---- cut of one tile ------------------------------------------------------------
-// Lanes stream the original edge list (coalesced int32 loads, L2/L1 resident), XOR the
-// two endpoint words from shared memory (bit b set <=> edge is cut in env b), and the
-// 32 per-lane words are bit-transposed across the warp so that lane b can POPC the
-// edges cut in env b.  Returns this warp's partial count for env == lane.
-__device__ __forceinline__ int tile_cut_partial(const GraphDev& g, const uint32_t* sP) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  int cnt = 0;
-  for (int k0 = warp * 32; k0 < g.m; k0 += nwarps * 32) {
-    const int k = k0 + lane;
-    uint32_t x = 0;
-    if (k < g.m) x = sP[__ldg(g.edge_u + k)] ^ sP[__ldg(g.edge_v + k)];
-    cnt += __popc(transpose32(x, lane));
-  }
-  return cnt;
 }
 
 }  // namespace rlsb

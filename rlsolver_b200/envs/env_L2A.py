@@ -98,27 +98,27 @@ class EnvMaxcut:
         num_sims = good_xs.shape[0]
         if not good_xs.is_contiguous():
             raise RuntimeError("local_search_inplace mutates good_xs in place: it must be contiguous")
-        packed = st.pack(good_xs)
-        cross, cmin, cmax = st.cross_counts(packed, num_sims)
         if good_vs.shape == ():
-            good_vs = st.cut_eval_packed(packed, num_sims)
+            vs_in = None
         else:
-            good_vs = good_vs.long()
-            if not good_vs.is_contiguous():
-                good_vs = good_vs.contiguous()
+            vs_in = good_vs.long()
+            if not vs_in.is_contiguous():
+                vs_in = vs_in.contiguous()
+        ws = st.ls_workspace(num_sims)
+        good_vs = st.ls_begin(good_xs, vs_in, 1, noise_std, ws)
         shape = (num_sims, self.num_nodes)
         noise0 = th.randn(shape, dtype=th.float32, device=self.device)
-        thresh = st.ls_thresh(cross, cmin, cmax, 1, noise_std, noise0, num_spin)
+        st.ls_thresh(num_sims, 1, noise0, num_spin, ws)
         del noise0
         per_launch = max(1, min(16, _NOISE_BYTES_PER_LAUNCH // max(1, 4 * num_sims * self.num_nodes)))
         done = 0
         while done < num_iters:
             now = min(per_launch, num_iters - done)
             noises = [th.randn(shape, dtype=th.float32, device=self.device) for _ in range(now)]
-            st.ls_noisy_iters(packed, good_vs, cross, cmin, cmax, 1, noise_std, noises, thresh)
             done += now
-        st.flip_sweep(packed, good_vs)
-        st.unpack(packed, num_sims, out=good_xs)
+            st.ls_search(good_vs, 1, noises, done == num_iters, good_xs, ws)
+        if num_iters <= 0:
+            st.ls_search(good_vs, 1, [], True, good_xs, ws)
         return good_xs, good_vs
 
 

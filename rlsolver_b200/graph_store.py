@@ -138,6 +138,17 @@ class GraphStore:
             "listed_ptr", "listed_col", "full_ptr", "full_col", "level_ptr", "level_nodes")]), "graph_export")
         return out
 
+    def export_sell(self, which: int) -> Dict[str, np.ndarray]:
+        """Host copy of a SELL-32 structure (0 = listed neighbours, 1 = sweep order)."""
+        sizes = np.zeros(3, np.int64)
+        _lib.check(self._lib.rlsb_graph_sell_sizes(self._h, which, sizes.ctypes.data), "graph_sell_sizes")
+        out = {"off": np.zeros(sizes[0] + 1, np.int32), "node": np.zeros(sizes[0] * 32, np.uint16),
+               "half": np.zeros(sizes[0] * 32, np.uint16), "col": np.zeros(sizes[1], np.uint16),
+               "level_slice": np.zeros(sizes[2], np.int32)}
+        _lib.check(self._lib.rlsb_graph_sell_export(self._h, which, *[out[k].ctypes.data for k in (
+            "off", "node", "half", "col", "level_slice")]), "graph_sell_export")
+        return out
+
     # ------------------------------------------------------------------ layout helpers
     def tiles(self, num_envs: int) -> int:
         return (num_envs + 31) // 32
@@ -210,26 +221,59 @@ class GraphStore:
                                                         _ptr(cmax), _stream_ptr(self.device)), "node_cross_counts")
         return cross, cmin, cmax
 
-    def ls_thresh(self, cross: TEN, cmin: TEN, cmax: TEN, ws_mult: int, noise_std: float, noise: TEN,
-                  num_spin: int) -> TEN:
-        e = noise.shape[0]
-        thresh = th.empty((e,), dtype=th.float32, device=self.device)
-        with self._op("ls_thresh"):
-            _lib.check(self._lib.rlsb_ls_thresh(self._h, _ptr(cross), _ptr(cmin), _ptr(cmax), ws_mult,
-                                                float(noise_std), _ptr(noise), int(num_spin), e, _ptr(thresh),
-                                                _stream_ptr(self.device)), "ls_thresh")
-        return thresh
+    # ---- local search (env_L2A.py:87-116 / LocalSearch.py:53-86): begin -> thresh -> search
+    def ls_workspace(self, num_envs: int) -> TEN:
+        need = int(self._lib.rlsb_ls_workspace_bytes(self._h, num_envs))
+        if need < 0:
+            _lib.check(3, "ls_workspace_bytes")
+        ws = getattr(self, "_ls_ws", None)
+        if ws is None or ws.numel() < need:
+            ws = self._ls_ws = th.empty((need,), dtype=th.uint8, device=self.device)
+        return ws
 
-    def ls_noisy_iters(self, packed: TEN, vs: TEN, cross: TEN, cmin: TEN, cmax: TEN, ws_mult: int, noise_std: float,
-                       noises: Sequence[TEN], thresh: TEN) -> None:
-        if not noises:
-            return
+    def ls_section(self, workspace: TEN, num_envs: int, section: str) -> TEN:
+        """View of one workspace section (tests): 'packed', 'col_min', 'col_max', 'rd_std', 'thresh'."""
+        idx, dtype, count = {"packed": (0, th.int32, self.tiles(num_envs) * self.padded_nodes),
+                             "col_min": (2, th.int32, self.padded_nodes), "col_max": (3, th.int32, self.padded_nodes),
+                             "rd_std": (5, th.float32, self.padded_nodes), "thresh": (6, th.float32, num_envs)}[section]
+        off = int(self._lib.rlsb_ls_workspace_offset(self._h, num_envs, idx))
+        return workspace[off:off + 4 * count].view(dtype)
+
+    def ls_begin(self, xs: TEN, vs: Optional[TEN], ws_mult: int, noise_std: float, workspace: TEN) -> TEN:
+        """Packs xs, computes the cross counts / their spread over the batch (and the cut values when
+        `vs` is None).  Returns vs (int64 [E])."""
+        xs = self._check_xs(xs)
+        e = xs.shape[0]
+        compute = vs is None
+        if compute:
+            vs = th.empty((e,), dtype=th.int64, device=self.device)
+        with self._op("ls_begin", 3):
+            _lib.check(self._lib.rlsb_ls_begin(self._h, _ptr(xs), e, _ptr(vs), int(compute), int(ws_mult),
+                                               float(noise_std), _ptr(workspace), _stream_ptr(self.device)),
+                       "ls_begin")
+        return vs
+
+    def ls_thresh(self, num_envs: int, ws_mult: int, noise: TEN, num_spin: int, workspace: TEN) -> None:
+        self._check_noise(noise, num_envs)
+        with self._op("ls_thresh"):
+            _lib.check(self._lib.rlsb_ls_thresh(self._h, num_envs, int(ws_mult), _ptr(noise), int(num_spin),
+                                                _ptr(workspace), _stream_ptr(self.device)), "ls_thresh")
+
+    def ls_search(self, vs: TEN, ws_mult: int, noises: Sequence[TEN], finish: bool, xs_out: Optional[TEN],
+                  workspace: TEN) -> None:
         e = vs.shape[0]
-        ptrs = (C.c_void_p * len(noises))(*[t.data_ptr() for t in noises])
-        with self._op("ls_noisy_iters", (len(noises) + 15) // 16):
-            _lib.check(self._lib.rlsb_ls_noisy_iters(self._h, _ptr(packed), _ptr(vs), _ptr(cross), _ptr(cmin),
-                                                     _ptr(cmax), ws_mult, float(noise_std), ptrs, len(noises),
-                                                     _ptr(thresh), e, _stream_ptr(self.device)), "ls_noisy_iters")
+        for t in noises:
+            self._check_noise(t, e)
+        ptrs = (C.c_void_p * max(1, len(noises)))(*[t.data_ptr() for t in noises])
+        with self._op("ls_search", max(1, (len(noises) + 15) // 16)):
+            _lib.check(self._lib.rlsb_ls_search(self._h, e, _ptr(vs), int(ws_mult), ptrs, len(noises), int(finish),
+                                                _ptr(xs_out), _ptr(workspace), _stream_ptr(self.device)),
+                       "ls_search")
+
+    def _check_noise(self, t: TEN, num_envs: int) -> None:
+        if t.dtype != th.float32 or tuple(t.shape) != (num_envs, self.num_nodes) or not t.is_contiguous() \
+                or t.device != self.device:
+            raise TypeError(f"noise must be a contiguous float32 [{num_envs}, {self.num_nodes}] tensor on {self.device}")
 
     def flip_sweep(self, packed: TEN, vs: TEN) -> None:
         with self._op("flip_sweep"):

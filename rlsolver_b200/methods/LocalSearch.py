@@ -18,6 +18,12 @@ def update_xs_by_vs(xs0, vs0, xs1, vs1, if_maximize: bool = True):
     return _update_xs_by_vs(xs0, vs0, xs1, vs1, if_maximize)
 
 
+def update_vs_only(vs0: TEN, vs1: TEN) -> int:
+    """Value half of update_xs_by_vs when the rows were already written in place."""
+    th.maximum(vs0, vs1, out=vs0)
+    return vs0.shape[0]
+
+
 class LocalSearch:
     def __init__(self, simulator, num_nodes: int):
         self.simulator = simulator
@@ -56,22 +62,24 @@ class LocalSearch:
         st = sim.store
         num_sims = self.good_xs.shape[0]
         shape = (num_sims, sim.num_nodes)
-
-        packed = st.pack(self.good_xs)                      # prev_xs = good_xs.clone()
-        cross, cmin, cmax = st.cross_counts(packed, num_sims)
-        prev_vs = st.cut_eval_packed(packed, num_sims)      # prev_vs_raw.sum(dim=1)
-        if num_iters > 0:
-            noises = [th.randn(shape, dtype=th.float32, device=sim.device)]
-            thresh = st.ls_thresh(cross, cmin, cmax, 2, noise_std, noises[0], num_spin)
-            done = 0
-            while done < num_iters:
-                now = min(16, num_iters - done)
-                while len(noises) < now:
-                    noises.append(th.randn(shape, dtype=th.float32, device=sim.device))
-                st.ls_noisy_iters(packed, prev_vs, cross, cmin, cmax, 2, noise_std, noises, thresh)
-                done += now
-                noises = []
-        st.flip_sweep(packed, prev_vs)
-        prev_xs = st.unpack(packed, num_sims)
-        num_update = update_xs_by_vs(self.good_xs, self.good_vs, prev_xs, prev_vs)
+        if not (self.good_xs.is_contiguous() and self.good_vs.is_contiguous() and self.good_vs.dtype == th.int64):
+            raise RuntimeError("random_search updates good_xs / good_vs in place: contiguous bool / int64 needed")
+        # prev_xs = good_xs.clone(), prev_vs = cut(prev_xs).  Every accepted move has vs' >= vs, so the
+        # final update_xs_by_vs(good, prev) (LocalSearch.py:85) always takes prev: the search runs in
+        # place on good_xs / good_vs (a row of good_vs that disagrees with its good_xs row is re-evaluated).
+        ws = st.ls_workspace(num_sims)
+        prev_vs = st.ls_begin(self.good_xs, None, 2, noise_std, ws)
+        done = 0
+        first = True
+        while done < num_iters:
+            now = min(16, num_iters - done)
+            noises = [th.randn(shape, dtype=th.float32, device=sim.device) for _ in range(now)]
+            if first:        # the threshold comes from the first draw, which also drives iteration 0
+                st.ls_thresh(num_sims, 2, noises[0], num_spin, ws)
+                first = False
+            done += now
+            st.ls_search(prev_vs, 2, noises, done == num_iters, self.good_xs, ws)
+        if num_iters <= 0:
+            st.ls_search(prev_vs, 2, [], True, self.good_xs, ws)
+        num_update = update_vs_only(self.good_vs, prev_vs)
         return self.good_xs, self.good_vs, num_update

@@ -78,7 +78,7 @@ def test_device_ops_refuse_host_only_graph(lib):
     st = GraphStore([(0, 1, 1), (1, 2, 1)], False, device=None)
     out = (C.c_int64 * 4)()
     rc = lib.rlsb_cut_eval(st.handle, C.c_void_p(1), 4, out, None)
-    assert rc == 4 and b"no device image" in lib.rlsb_last_error()
+    assert rc == 4 and b"host-only" in lib.rlsb_last_error()
 
 
 def test_no_cpu_fallback():
@@ -86,3 +86,59 @@ def test_no_cpu_fallback():
     from rlsolver_b200.envs.env_L2A import EnvMaxcut
     with pytest.raises(RuntimeError, match="CUDA"):
         EnvMaxcut(mygraph=[(0, 1, 1)], device=th.device("cpu"))
+
+
+def _sell_cross(sell, words_of):
+    """NumPy model of vcount.cuh sell_cross: per slot, per env, neighbours on the other side.
+    Column ids come in blocks of 4 rounds, lane-major inside a block."""
+    out = {}
+    for s in range(len(sell["off"]) - 1):
+        rb, re_ = int(sell["off"][s]), int(sell["off"][s + 1])
+        cols = sell["col"][rb * 128:re_ * 128].reshape(re_ - rb, 32, 4)
+        for lane in range(32):
+            node = int(sell["node"][s * 32 + lane])
+            if node == 0xFFFF:
+                continue
+            nb = cols[:, lane, :].reshape(-1).astype(np.int64)
+            out[node] = (words_of[:, nb] ^ words_of[:, [node]]).sum(axis=1), int(sell["half"][s * 32 + lane]), s
+    return out
+
+
+@pytest.mark.parametrize("path", golden_files("maxcut_"), ids=os.path.basename)
+def test_sell_structures_model_the_reference(lib, path):
+    """The SELL-32 slices the tile kernels walk reproduce (a) the per-node cross counts and
+    (b), level by level, the exhaustive single-flip pass of the reference golden."""
+    z = np.load(path)
+    edges = [tuple(int(t) for t in row) for row in z["edges"]]
+    bidir = bool(z["bidirectional"])
+    st = GraphStore(edges, bidir, device=None)
+    g = om.build_graph_store(edges, bidir)
+    n, npad = st.num_nodes, st.padded_nodes
+    xs = np.zeros((z["xs"].shape[0], npad), bool)
+    xs[:, :n] = z["xs"]
+    listed = st.export_sell(0)
+    assert len(listed["off"]) - 1 == npad // 32
+    assert np.array_equal(listed["node"], np.arange(npad, dtype=np.uint16))
+    cc = _sell_cross(listed, xs)
+    got = np.stack([cc[i][0] for i in range(n)], axis=1)
+    assert np.array_equal(got, om.node_cross_counts_raw(g, z["xs"]))
+    # sweep: slices of one level in any order, levels in order
+    sweep = st.export_sell(1)
+    ls = sweep["level_slice"]
+    assert len(ls) == st.num_levels + 1 and ls[-1] == len(sweep["off"]) - 1
+    seen = []
+    cur = xs.copy()
+    for l in range(st.num_levels):
+        # evaluate every slot of the level on the state before the level, then apply
+        res = _sell_cross({"off": sweep["off"][ls[l]:ls[l + 1] + 1], "node": sweep["node"][ls[l] * 32:ls[l + 1] * 32],
+                           "half": sweep["half"][ls[l] * 32:ls[l + 1] * 32], "col": sweep["col"]}, cur)
+        nxt = cur.copy()
+        for node, (cross, half, _) in res.items():
+            flip = cross <= half
+            nxt[flip, node] = ~nxt[flip, node]
+            seen.append(node)
+        cur = nxt
+    assert sorted(seen) == list(range(n))
+    want_xs, want_vs = z["xs"].copy(), om.cut_values(g, z["xs"]).astype(np.int64)
+    om.sweep_literal(g, want_xs, want_vs)
+    assert np.array_equal(cur[:, :n], want_xs)
