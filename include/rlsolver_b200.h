@@ -133,6 +133,27 @@ int rlsb_ls_search(const rlsb_graph_t* g, int64_t num_envs, int64_t* vs, int32_t
 /* ---- the exhaustive single-flip pass alone, on packed tiles (vs is recomputed) */
 int rlsb_flip_sweep(const rlsb_graph_t* g, uint32_t* packed, int64_t* vs, int64_t num_envs, void* stream);
 
+/* ---- pattern-I step: env_PPO.EnvMaxcut.step (rlsolver/envs/env_PPO.py:92-106).
+ * xs is the reference's observation tensor, float32 [E][N] with values {0,1}; action int64 [E].
+ * Every env flips xs[e][action[e]]; reward[e] = new cut - old cut (the single-flip gain
+ * deg - 2*cross over the acted node's neighbours, O(degree) instead of a full re-evaluation;
+ * update rule of S2V_PPO/env.py:197-206); cut[e] (the env's `last_reward`) += reward[e].
+ * An action outside [0, N) (IndexError in the reference) leaves the env untouched, gives
+ * reward 0 and increments *bad_actions (device int32, caller-zeroed). */
+int rlsb_step_flip(const rlsb_graph_t* g, float* xs, const int64_t* action, int64_t num_envs, float* reward,
+                   float* cut, int32_t* bad_actions, void* stream);
+
+/* ---- greedy best-single-flip ascent, contract of greedy_maxcut (rlsolver/methods/greedy.py:33-78)
+ * batched over envs: per step all N single-flip gains, the LOWEST index among the best, accept
+ * only if the cut gets strictly better (strict != 0; strict == 0 also takes zero-gain moves, the
+ * stop rule of ECO_S2V/src/agents/solver.py:95-121), else that env stops; at most max_flips steps
+ * (greedy.py caps them at N).  max_flips = 1, strict = 1 is one call of PECO's local_search
+ * (ECO_S2V/util.py:66-75) without its spin-zeroing bug.  xs: bool [E][N] in/out, vs: int64 [E]
+ * out (final cut), flips: int32 [E] out (nullable).  The per-(node, env) gains stay resident in
+ * shared memory (int8 when every degree <= 127, else int16) and are updated in O(degree) per flip. */
+int rlsb_greedy_best_flip(const rlsb_graph_t* g, uint8_t* xs, int64_t num_envs, int64_t* vs, int32_t* flips,
+                          int32_t max_flips, int32_t strict, void* stream);
+
 /* ---- select ops on the reference's bool layout
  * select_rows: update_xs_by_vs (util_read_data.py:190-202): rows of (xs1,vs1) replace
  *   rows of (xs0,vs0) where vs1 >= vs0 (<= when maximize == 0).

@@ -314,3 +314,56 @@ def greedy_best_flip(g: GraphStore, xs: np.ndarray, strict: bool = True, max_fli
             else:
                 break
     return xs, vs, flips
+
+
+# --------------------------------------------------------------------------- pattern-I env (env_PPO)
+
+class PPOEnv:
+    """rlsolver/envs/env_PPO.py:63-126 restated on NumPy: float32 {0,1} observations, one flip
+    per env per step, reward = cut after - cut before by full re-evaluation, `done` every
+    num_steps steps."""
+
+    def __init__(self, g: GraphStore, num_steps: int):
+        self.g, self.num_steps, self.action_count = g, num_steps, 0
+        self.xs = None
+        self.last_reward = None
+
+    def reset(self, xs_bool: np.ndarray) -> np.ndarray:
+        self.xs = xs_bool.astype(np.float32)                       # env_PPO.py:85-90 (xs drawn by the caller)
+        self.last_reward = cut_values(self.g, self.xs > 0).astype(np.float32)
+        return self.xs
+
+    def step(self, action: np.ndarray):
+        self.action_count += 1
+        rows = np.arange(self.xs.shape[0])
+        self.xs[rows, action] = np.logical_not(self.xs[rows, action]).astype(np.float32)   # :94-95
+        cur = cut_values(self.g, self.xs > 0).astype(np.float32)
+        reward = cur - self.last_reward
+        self.last_reward = cur
+        done = np.full(self.xs.shape[0], float(self.action_count == self.num_steps), np.float32)
+        if self.action_count == self.num_steps:
+            self.action_count = 0
+        return self.xs, reward, done, cur
+
+
+def greedy_trace(g: GraphStore, x0: np.ndarray, num_steps=None):
+    """greedy_maxcut (rlsolver/methods/greedy.py:33-78) for ONE start state, literally: evaluate all N
+    single flips by full recompute, first index of the max, accept iff strictly better.  Returns
+    (score, solution, scores after every accepted step)."""
+    x = x0.copy()
+    n = g.num_nodes
+    steps = n if num_steps is None else min(num_steps, n)
+    cur = int(cut_values(g, x[None, :])[0])
+    scores = []
+    for _ in range(steps):
+        cand = np.repeat(x[None, :], n, axis=0)
+        cand[np.arange(n), np.arange(n)] ^= True
+        vals = cut_values(g, cand)
+        i = int(vals.argmax())
+        if vals[i] > cur:
+            cur = int(vals[i])
+            x = cand[i]
+            scores.append(cur)
+        else:
+            break
+    return cur, x, scores

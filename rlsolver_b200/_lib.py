@@ -107,6 +107,8 @@ SIGNATURES = {
     "rlsb_ls_thresh": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp]),
     "rlsb_ls_search": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
     "rlsb_flip_sweep": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "rlsb_step_flip": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "rlsb_greedy_best_flip": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp]),
     "rlsb_select_rows": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "rlsb_pick_best": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
 }

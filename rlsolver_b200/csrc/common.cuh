@@ -69,7 +69,7 @@ struct GraphDev {
   // blob {level_slice i32[levels+1], off i32[S+1], node u16[32S], half u16[32S], col u16[..]},
   // every part 16-byte aligned, so a CTA can stage it into shared memory with one bulk copy
   const char* sweep_blob;
-  int32_t sweep_blob_bytes, num_sweep_slices;
+  int32_t sweep_blob_bytes, num_sweep_slices, max_level_slices;
   int32_t sweep_lvs, sweep_off, sweep_node, sweep_half, sweep_col;   // byte offsets inside the blob
 };
 

@@ -298,6 +298,9 @@ int rlsb_graph_create(int32_t num_nodes, int64_t num_edges, const int32_t* h_n0,
     d.sweep_lvs = int32_t(s_lvs), d.sweep_off = int32_t(s_off), d.sweep_node = int32_t(s_node);
     d.sweep_half = int32_t(s_half), d.sweep_col = int32_t(s_col);
     d.num_sweep_slices = int32_t(g->sell_sweep.off.size()) - 1;
+    d.max_level_slices = 0;
+    for (size_t l = 0; l + 1 < g->level_slice.size(); ++l)
+      d.max_level_slices = std::max(d.max_level_slices, g->level_slice[l + 1] - g->level_slice[l]);
   }
   *out = g;
   return RLSB_OK;

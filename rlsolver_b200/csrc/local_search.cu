@@ -149,23 +149,28 @@ struct LsArgs {
   uint8_t* xs_out;         // [E][N] bool rows (finish)
   int cut_warps;
   int stage_sweep;         // 1: the sweep structure fits in shared memory next to the two tile copies
+  int sweep_warps;         // warps that take part in the single-flip pass
+  int negmult;             // -mult
 };
 
 // Flip-mask of one noisy iteration for the whole tile, written as candidate = accepted ^ mask.
 // Work item = (4 consecutive nodes) x (8 consecutive envs): 8 coalesced 16-byte noise loads in
 // flight per thread, one result byte per node (byte g of a word = envs 8g..8g+7).
-template <typename CrossT, int VEC>
+template <typename CrossT, int VEC, bool FULL>
 __device__ __forceinline__ void noisy_candidate(const GraphDev& g, const LsArgs& a, const float* __restrict__ noise,
                                                 int64_t env0, int valid, const float* sThresh, const uint32_t* sP,
                                                 uint32_t* sX) {
-  const CrossT* cross = static_cast<const CrossT*>(a.cross);
-  const int groups = (g.n + VEC - 1) / VEC;           // node groups
+  // tile bases once (64-bit); everything inside the tile is a 32-bit offset (32 * N < 2^31)
+  const float* __restrict__ nbase = noise + env0 * (int64_t)g.n;
+  const CrossT* __restrict__ cbase = static_cast<const CrossT*>(a.cross) + env0 * (int64_t)g.np;
+  const uint32_t n = (uint32_t)g.n, np = (uint32_t)g.np;
+  const uint32_t groups = (n + VEC - 1) / VEC;        // node groups
   const uint8_t* sPb = reinterpret_cast<const uint8_t*>(sP);
   uint8_t* sXb = reinterpret_cast<uint8_t*>(sX);
-  const int negmult = -a.mult;
-  for (int task = threadIdx.x; task < groups * 4; task += blockDim.x) {
-    const int eg = task / groups, i0 = (task - eg * groups) * VEC;
-    const int e0 = eg * 8;
+  const int negmult = a.negmult;
+  for (uint32_t task = threadIdx.x; task < groups * 4; task += blockDim.x) {
+    const uint32_t eg = task / groups, i0 = (task - eg * groups) * VEC;
+    const uint32_t e0 = eg * 8;
     float rd[VEC];
     int dm[VEC];
     if constexpr (VEC == 4) {
@@ -176,20 +181,19 @@ __device__ __forceinline__ void noisy_candidate(const GraphDev& g, const LsArgs&
     } else {
       rd[0] = __ldg(a.rd_std + i0), dm[0] = __ldg(a.degm + i0);
     }
-    const float* np_ = noise + (env0 + e0) * (int64_t)g.n + i0;
-    const CrossT* cp_ = cross + (env0 + e0) * (int64_t)g.np + i0;
     float nz[8][VEC];
     CrossVec<CrossT, VEC> cr[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (e0 + j < valid) {
+      if (FULL || (int)(e0 + j) < valid) {
+        const uint32_t no = (e0 + j) * n + i0, co = (e0 + j) * np + i0;
         if constexpr (VEC == 4) {
-          const float4 v = ldg_stream4(np_ + (int64_t)j * g.n);
+          const float4 v = ldg_stream4(nbase + no);
           nz[j][0] = v.x, nz[j][1] = v.y, nz[j][2] = v.z, nz[j][3] = v.w;
         } else {
-          nz[j][0] = ldg_stream(np_ + (int64_t)j * g.n);
+          nz[j][0] = ldg_stream(nbase + no);
         }
-        cr[j].load(cp_ + (int64_t)j * g.np);
+        cr[j].load(cbase + co);
       } else {
 #pragma unroll
         for (int b = 0; b < VEC; ++b) nz[j][b] = 0.f;
@@ -212,7 +216,7 @@ __device__ __forceinline__ void noisy_candidate(const GraphDev& g, const LsArgs&
     }
 #pragma unroll
     for (int b = 0; b < VEC; ++b) {
-      const int at = (i0 + b) * 4 + eg;
+      const uint32_t at = (i0 + b) * 4 + eg;
       sXb[at] = sPb[at] ^ (uint8_t)bits[b];
     }
   }
@@ -223,12 +227,13 @@ __device__ __forceinline__ void noisy_candidate(const GraphDev& g, const LsArgs&
 // node decides them concurrently and a barrier separates levels, which reproduces the
 // sequential order exactly.  gain = deg - 2*cross >= 0  <=>  cross <= floor(deg/2).
 template <int P, bool SMEM>
-__device__ __forceinline__ void sweep_tile(const GraphDev& g, const SweepView& sv, uint32_t* sP) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+__device__ __forceinline__ void sweep_tile(const GraphDev& g, const SweepView& sv, uint32_t* sP, int sweep_warps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp >= sweep_warps) return;      // a level never has more slices than sweep_warps (or all warps take part)
   for (int l = 0; l < g.levels; ++l) {
     const int sb = SMEM ? sv.level_slice[l] : __ldg(sv.level_slice + l);
     const int se = SMEM ? sv.level_slice[l + 1] : __ldg(sv.level_slice + l + 1);
-    for (int s = sb + warp; s < se; s += nwarps) {
+    for (int s = sb + warp; s < se; s += sweep_warps) {
       const uint32_t node = SMEM ? sv.sell.node[s * 32 + lane] : __ldg(sv.sell.node + s * 32 + lane);
       const uint32_t half = SMEM ? sv.sell.half[s * 32 + lane] : __ldg(sv.sell.half + s * 32 + lane);
       const bool active = node != 0xFFFFu;
@@ -238,7 +243,7 @@ __device__ __forceinline__ void sweep_tile(const GraphDev& g, const SweepView& s
       const uint32_t flip = vc.le(half);
       if (active) sP[node] = self ^ flip;
     }
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;" ::"r"(sweep_warps * 32) : "memory");   // only the sweeping warps
   }
 }
 
@@ -282,7 +287,10 @@ __global__ void __launch_bounds__(kLSThreads) ls_search_kernel(GraphDev g, LsArg
     __syncthreads();
     for (int it = 0; it < a.num_iters; ++it) {
       if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
-      noisy_candidate<CrossT, VEC>(g, a, a.noise.p[it], env0, valid, sThresh, sP, sX);
+      if (valid == kTileEnvs)
+        noisy_candidate<CrossT, VEC, true>(g, a, a.noise.p[it], env0, valid, sThresh, sP, sX);
+      else
+        noisy_candidate<CrossT, VEC, false>(g, a, a.noise.p[it], env0, valid, sThresh, sP, sX);
       __syncthreads();
       const int cnt = tile_cut_partial(g, sX, a.cut_warps);
       if (cnt) atomicAdd(&sCnt[lane], cnt);
@@ -303,9 +311,9 @@ __global__ void __launch_bounds__(kLSThreads) ls_search_kernel(GraphDev g, LsArg
     if (a.finish) {
       if (staged) {
         if (!sweep_landed) mbar_wait(&sBar, 0), sweep_landed = true;
-        sweep_tile<P, true>(g, sweep_view(g, sSweep), sP);
+        sweep_tile<P, true>(g, sweep_view(g, sSweep), sP, a.sweep_warps);
       } else {
-        sweep_tile<P, false>(g, sweep_view(g, g.sweep_blob), sP);
+        sweep_tile<P, false>(g, sweep_view(g, g.sweep_blob), sP, a.sweep_warps);
       }
       if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
       __syncthreads();
@@ -326,7 +334,7 @@ __global__ void __launch_bounds__(kLSThreads) ls_search_kernel(GraphDev g, LsArg
 template <int P>
 __global__ void __launch_bounds__(kLSThreads) flip_sweep_kernel(GraphDev g, uint32_t* __restrict__ packed,
                                                                 int64_t* __restrict__ vs, int64_t num_envs,
-                                                                int cut_warps) {
+                                                                int cut_warps, int sweep_warps) {
   extern __shared__ uint32_t sP[];
   __shared__ int sCnt[kTileEnvs];
   const int lane = threadIdx.x & 31;
@@ -338,7 +346,8 @@ __global__ void __launch_bounds__(kLSThreads) flip_sweep_kernel(GraphDev g, uint
     for (int i = threadIdx.x; i < g.np; i += blockDim.x) sP[i] = packed[tile * g.np + i];
     if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
     __syncthreads();
-    sweep_tile<P, false>(g, sweep_view(g, g.sweep_blob), sP);
+    sweep_tile<P, false>(g, sweep_view(g, g.sweep_blob), sP, sweep_warps);
+    __syncthreads();
     const int cnt = tile_cut_partial(g, sP, cut_warps);
     if (cnt) atomicAdd(&sCnt[lane], cnt);
     __syncthreads();
@@ -353,6 +362,11 @@ static int allow_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024)
     RLSB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return RLSB_OK;
+}
+
+static int sweep_warps_for(const GraphDev& g, int nwarps) {
+  const int w = g.max_level_slices < 1 ? 1 : g.max_level_slices;
+  return w < nwarps ? w : nwarps;
 }
 
 static int degree_class(const GraphDev& g) {
@@ -521,6 +535,7 @@ int rlsb_ls_search(const rlsb_graph_t* gh, int64_t num_envs, int64_t* vs, int32_
     a.num_iters = now, a.mult = ws_mult, a.num_envs = num_envs;
     a.finish = (finish && done + now == num_iters) ? 1 : 0;
     a.xs_out = xs_out, a.cut_warps = cut_warps_for(g->m, kLSThreads / 32);
+    a.sweep_warps = sweep_warps_for(*g, kLSThreads / 32), a.negmult = -ws_mult;
     a.stage_sweep = (a.finish && 2 * (size_t)g->np * 4 + (size_t)g->sweep_blob_bytes <= 200 * 1024) ? 1 : 0;
     int rc = dc == 0   ? launch_search<6, uint8_t>(*g, a, vec4, st)
              : dc == 1 ? launch_search<8, uint8_t>(*g, a, vec4, st)
@@ -547,7 +562,7 @@ int rlsb_flip_sweep(const rlsb_graph_t* gh, uint32_t* packed, int64_t* vs, int64
   int rc;
 #define RLSB_SWEEP(P)                                                \
   if ((rc = allow_smem(flip_sweep_kernel<P>, smem))) return rc;      \
-  flip_sweep_kernel<P><<<grid, kLSThreads, smem, st>>>(*g, packed, vs, num_envs, cw)
+  flip_sweep_kernel<P><<<grid, kLSThreads, smem, st>>>(*g, packed, vs, num_envs, cw, sweep_warps_for(*g, kLSThreads / 32))
   if (dc == 0) { RLSB_SWEEP(6); } else if (dc == 1) { RLSB_SWEEP(8); } else { RLSB_SWEEP(12); }
 #undef RLSB_SWEEP
   RLSB_LAUNCH_OK();

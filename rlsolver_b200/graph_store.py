@@ -275,6 +275,25 @@ class GraphStore:
                 or t.device != self.device:
             raise TypeError(f"noise must be a contiguous float32 [{num_envs}, {self.num_nodes}] tensor on {self.device}")
 
+    def step_flip(self, xs: TEN, action: TEN, reward: TEN, cut: TEN, bad: TEN) -> None:
+        with self._op("step_flip"):
+            _lib.check(self._lib.rlsb_step_flip(self._h, _ptr(xs), _ptr(action), xs.shape[0], _ptr(reward), _ptr(cut),
+                                                _ptr(bad), _stream_ptr(self.device)), "step_flip")
+
+    def greedy_best_flip(self, xs: TEN, max_flips: int, strict: bool = True):
+        """In place on xs (bool [E,N]).  Returns (vs int64 [E], flips int32 [E])."""
+        xs_c = self._check_xs(xs)
+        if xs_c.data_ptr() != xs.data_ptr():
+            raise RuntimeError("greedy_best_flip mutates xs in place: it must be contiguous")
+        e = xs.shape[0]
+        vs = th.empty((e,), dtype=th.int64, device=self.device)
+        flips = th.zeros((e,), dtype=th.int32, device=self.device)
+        with self._op("greedy_best_flip"):
+            _lib.check(self._lib.rlsb_greedy_best_flip(self._h, _ptr(xs), e, _ptr(vs), _ptr(flips), int(max_flips),
+                                                       int(bool(strict)), _stream_ptr(self.device)),
+                       "greedy_best_flip")
+        return vs, flips
+
     def flip_sweep(self, packed: TEN, vs: TEN) -> None:
         with self._op("flip_sweep"):
             _lib.check(self._lib.rlsb_flip_sweep(self._h, _ptr(packed), _ptr(vs), vs.shape[0],
