@@ -36,6 +36,7 @@ extern "C" {
 #define RLSB_ERR_NODEVICE 4    /* graph was built host-only (device < 0) */
 
 typedef struct rlsb_graph rlsb_graph_t;
+typedef struct rlsb_mcpg_plan rlsb_mcpg_plan_t;
 
 int rlsb_version(void);
 const char* rlsb_last_error(void);
@@ -153,6 +154,57 @@ int rlsb_step_flip(const rlsb_graph_t* g, float* xs, const int64_t* action, int6
  * shared memory (int8 when every degree <= 127, else int16) and are updated in O(degree) per flip. */
 int rlsb_greedy_best_flip(const rlsb_graph_t* g, uint8_t* xs, int64_t num_envs, int64_t* vs, int32_t* flips,
                           int32_t max_flips, int32_t strict, void* stream);
+
+/* ---- samplers.  Random numbers: every sampler either reads EXPLICIT arrays (replay of recorded
+ * draws) or, when the explicit pointers are null, computes torch's own Philox4x32-10 stream in
+ * place from (seed, offset) of the torch CUDA generator: element li of the k-th consecutive torch
+ * distribution call (torch.rand / rand_like / randint over `numel` elements) is
+ *   Philox(counter = offset/4 + k*rng_iters + (li / rng_threads)/4, subsequence = li % rng_threads)[(li / rng_threads) % 4]
+ * with rng_threads = 256 * min(#SM * (maxThreadsPerSM / 256), ceil(numel / 256)) and rng_iters =
+ * ceil(numel / (4 * rng_threads)) (ATen/native/cuda/DistributionTemplates.h).  The caller advances
+ * the generator offset by 4 * rng_iters per call the reference would have made.
+ * rlsb_torch_rand / rlsb_torch_randint regenerate `calls` consecutive torch.rand(numel) /
+ * torch.randint(0, range, [numel]) results (tests pin the stream identity with them). */
+int rlsb_torch_rand(uint64_t seed, uint64_t offset, uint32_t rng_threads, uint32_t rng_iters, int64_t calls,
+                    int64_t numel, float* out, void* stream);
+int rlsb_torch_randint(uint64_t seed, uint64_t offset, uint32_t rng_threads, uint32_t rng_iters, int64_t calls,
+                       int64_t numel, uint32_t range, int64_t* out, void* stream);
+
+/* sampler_func (rlsolver/methods/MCPG.py:120-166): num_ls Gauss-Seidel sweeps over the nodes in
+ * `order` (data.sorted_degree_nodes), x_i <- [sum_{j in N(i)} x_j + rand/4 < (deg_i + 1/4)/2] with
+ * one torch.rand(C) per node visit, then expected_cut[c] = sum_e (2x_u-1)(2x_v-1).
+ * xs: float32 [N][C] node-major {0,1}, updated in place to the swept state ({0,1} floats; call with
+ * num_ls >= 1); expected: float32 [C].  The plan holds the order-dependent structures (neighbours
+ * split into visited-before / visited-after, dependency levels of the visiting order).
+ * explicit_u: float32 [num_ls*N][C] (draw of node visit k of sweep s at row s*N + k) or null.
+ * Graphs with self loops are rejected (the reference double-lists the node as its own neighbour). */
+int rlsb_mcpg_plan_create(const rlsb_graph_t* g, const int32_t* h_order, rlsb_mcpg_plan_t** out);
+int rlsb_mcpg_plan_destroy(rlsb_mcpg_plan_t* plan);
+int32_t rlsb_mcpg_plan_num_levels(const rlsb_mcpg_plan_t* plan);
+int rlsb_mcpg_sweeps(const rlsb_graph_t* g, const rlsb_mcpg_plan_t* plan, float* xs, int64_t num_chains,
+                     int32_t num_ls, const float* explicit_u, uint64_t seed, uint64_t offset, uint32_t rng_threads,
+                     uint32_t rng_iters, float* expected, void* stream);
+
+/* metro_sampling (rlsolver/methods/MCPG.py:88-117 == MCPG/sampling.py:67-86): per iteration every
+ * chain picks a node r = randint(0, N), accepts a flip with probability (1-q)/q, q = p_r if the
+ * bit is set else 1-p_r (rand < rate).  The reference stops once the accepted moves of ALL chains
+ * reach C*max_transfer_time, checked before every iteration: call with count_only = 1 to get the
+ * accepted count of each of max_iters iterations in acc (int32 [max_iters], caller-zeroed), derive
+ * the number of iterations the reference executes, then call with count_only = 0 and that number
+ * in *num_iters_dev (device int32) to produce out.  probs: float32 [N]; start / out: float32
+ * [N][C] node-major; explicit_idx int64 / explicit_u float32: [max_iters][C] or both null. */
+int rlsb_metro_sampling(int32_t num_nodes, const float* probs, const float* start, float* out, int64_t num_chains,
+                        int32_t max_iters, const int32_t* num_iters_dev, const int64_t* explicit_idx,
+                        const float* explicit_u, uint64_t seed, uint64_t offset, uint32_t rng_threads,
+                        uint32_t rng_iters, int32_t* acc, int32_t count_only, void* stream);
+
+/* sub_set_sampling, the resampling loop (rlsolver/methods/L2A/transformer.py:346-352):
+ * xs[row][ids[row % S][k]] = rand_k[row] < vals[row % S][k] for k < top_k, one rand_like draw of
+ * `rows` floats per k.  xs: bool [rows][N] (rows = num_repeats*S) in place; ids int64 / vals
+ * float32: [S][top_k] (the topk of the determinism, smallest first); explicit_u [top_k][rows] or null. */
+int rlsb_subset_sampling(uint8_t* xs, int64_t rows, int32_t num_nodes, int64_t num_sims, int32_t top_k,
+                         const int64_t* ids, const float* vals, const float* explicit_u, uint64_t seed,
+                         uint64_t offset, uint32_t rng_threads, uint32_t rng_iters, void* stream);
 
 /* ---- select ops on the reference's bool layout
  * select_rows: update_xs_by_vs (util_read_data.py:190-202): rows of (xs1,vs1) replace

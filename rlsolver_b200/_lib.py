@@ -78,6 +78,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 # ----------------------------------------------------------------------------- signatures
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+_u32, _u64 = C.c_uint32, C.c_uint64
 
 SIGNATURES = {
     "rlsb_version": (C.c_int, []),
@@ -109,6 +110,15 @@ SIGNATURES = {
     "rlsb_flip_sweep": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "rlsb_step_flip": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "rlsb_greedy_best_flip": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp]),
+    "rlsb_torch_rand": (C.c_int, [_u64, _u64, _u32, _u32, _i64, _i64, _vp, _vp]),
+    "rlsb_torch_randint": (C.c_int, [_u64, _u64, _u32, _u32, _i64, _i64, _u32, _vp, _vp]),
+    "rlsb_mcpg_plan_create": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "rlsb_mcpg_plan_destroy": (C.c_int, [_vp]),
+    "rlsb_mcpg_plan_num_levels": (_i32, [_vp]),
+    "rlsb_mcpg_sweeps": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _u64, _u64, _u32, _u32, _vp, _vp]),
+    "rlsb_metro_sampling": (C.c_int, [_i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _u64, _u64, _u32, _u32, _vp,
+                                      _i32, _vp]),
+    "rlsb_subset_sampling": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _u64, _u64, _u32, _u32, _vp]),
     "rlsb_select_rows": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "rlsb_pick_best": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
 }

@@ -11,7 +11,7 @@
 #include <string>
 #include <vector>
 
-#include "common.cuh"
+#include "graph_host.h"
 
 namespace rlsb {
 
@@ -27,23 +27,6 @@ void set_error(const char* fmt, ...) {
 }
 
 }  // namespace rlsb
-
-struct rlsb_graph {
-  int32_t n = 0, np = 0, bidir = 0, device = -1, levels = 0, max_listed_deg = 0, max_full_deg = 0;
-  int64_t m = 0;
-  std::vector<int32_t> edge_u, edge_v, weight;
-  std::vector<int32_t> listed_ptr, listed_col, listed_row, listed_deg, full_ptr, full_col, level_ptr, level_nodes;
-  // tile-kernel structures (only when np <= kMaxTileNodes)
-  bool tileable = false;
-  std::vector<uint32_t> edge_pair;
-  std::vector<int32_t> level_slice;
-  struct Sell {
-    std::vector<int32_t> off;
-    std::vector<uint16_t> node, half, col;
-  } sell_listed, sell_sweep;
-  void* dev_blob = nullptr;   // one allocation holding every device array
-  rlsb::GraphDev dev{};
-};
 
 namespace rlsb {
 const GraphDev* graph_dev(const rlsb_graph_t* g) { return (g && g->dev_blob && g->tileable) ? &g->dev : nullptr; }
@@ -67,7 +50,7 @@ int cut_warps_for(int64_t m, int max_warps) {
 }
 }  // namespace rlsb
 
-namespace {
+namespace rlsb {
 
 // counting-sort CSR: rows = src, columns sorted ascending inside each row
 void build_csr(int32_t n, const std::vector<int32_t>& src, const std::vector<int32_t>& dst,
@@ -85,11 +68,12 @@ void build_csr(int32_t n, const std::vector<int32_t>& src, const std::vector<int
 // A slice is 32 node slots; its column ids are stored in blocks of 4 rounds, lane-major inside
 // a block (col[(block*32 + lane)*4 + r]), so a lane fetches 4 neighbour ids with one 8-byte load
 // and a warp reads 256 contiguous bytes.  Rows shorter than the slice are padded with the node's
-// own id (word ^ word == 0: padding never counts); unused slots are 0xFFFF and their columns 0.
+// own id (word ^ word == 0: padding never counts) or with pad_id when pad_id >= 0; unused slots
+// are 0xFFFF and their columns 0.
 // `off` counts blocks.
 void build_sell(const std::vector<int32_t>& order, const std::vector<int32_t>& group_ptr,
                 const std::vector<int32_t>& ptr, const std::vector<int32_t>& col, rlsb_graph::Sell& out,
-                std::vector<int32_t>* group_slice) {
+                std::vector<int32_t>* group_slice, int32_t pad_id) {
   out.off.assign(1, 0);
   out.node.clear(), out.half.clear(), out.col.clear();
   if (group_slice) group_slice->assign(1, 0);
@@ -109,7 +93,7 @@ void build_sell(const std::vector<int32_t>& order, const std::vector<int32_t>& g
         const int32_t i = order[b + l], deg = ptr[i + 1] - ptr[i];
         out.node.push_back(uint16_t(i)), out.half.push_back(uint16_t(deg / 2));
         for (int32_t k = 0; k < blocks * 4; ++k)
-          out.col[base + (size_t(k / 4) * 32 + l) * 4 + (k % 4)] = uint16_t(k < deg ? col[ptr[i] + k] : i);
+          out.col[base + (size_t(k / 4) * 32 + l) * 4 + (k % 4)] = uint16_t(k < deg ? col[ptr[i] + k] : (pad_id < 0 ? i : pad_id));
       }
       out.off.push_back(out.off.back() + blocks);
     }
@@ -117,7 +101,10 @@ void build_sell(const std::vector<int32_t>& order, const std::vector<int32_t>& g
   }
 }
 
-}  // namespace
+}  // namespace rlsb
+
+using rlsb::build_csr;
+using rlsb::build_sell;
 
 extern "C" {
 

@@ -1,0 +1,44 @@
+// torch-compatible counter-based RNG.  The reference draws its randomness with many tiny torch
+// calls (torch.rand(C) once per node per sweep, MCPG.py:140-141; randint + rand per Metropolis
+// iteration, MCPG.py:106-111; rand_like per column, L2A/transformer.py:348-352).  torch's CUDA
+// generators are Philox4x32-10 keyed by (seed, offset): element `li` of one such call gets
+//
+//     idx = li % T, k = li / T, Philox(counter = offset/4 + k/4, subsequence = idx, key = seed)[k % 4]
+//
+// with T = 256 * grid threads (ATen/native/cuda/DistributionTemplates.h: calc_execution_policy and
+// distribution_elementwise_grid_stride_kernel; curand_init(seed, idx, offset) + curand4), and
+// every call advances the generator offset by 4 * ceil(numel / (4 T)).  Because the stream is
+// counter-based, a fused kernel can compute exactly the numbers the reference's call sequence
+// would have produced -- same seed, same flip sequence -- without launching those calls.  The
+// Philox rounds and the uint32 -> float maps are curand's own inline device functions, the same
+// ones torch compiles.
+#pragma once
+#include <curand_kernel.h>
+#include <stdint.h>
+
+namespace rlsb {
+
+struct TorchRng {
+  uint64_t seed;
+  uint64_t offset4;         // generator offset / 4 at the first call
+  uint32_t threads;         // T of one call (256 * grid.x)
+  uint32_t iters_per_call;  // ceil(numel / (4 T)) = counter increments one call consumes
+};
+
+// the uint32 element `li` of consecutive call number `call` receives
+__device__ __forceinline__ uint32_t torch_philox_u32(const TorchRng& r, uint64_t call, uint32_t li) {
+  const uint32_t idx = li % r.threads, k = li / r.threads;
+  const uint64_t ctr = r.offset4 + call * r.iters_per_call + (k >> 2);
+  const uint4 o = curand_Philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), idx, 0u),
+                                       make_uint2((uint32_t)r.seed, (uint32_t)(r.seed >> 32)));
+  const uint32_t c = k & 3u;
+  return c == 0 ? o.x : c == 1 ? o.y : c == 2 ? o.z : o.w;
+}
+
+// torch.rand / rand_like (float32): curand_uniform then the (0,1] -> [0,1) bound reversal
+__device__ __forceinline__ float torch_uniform_from_u32(uint32_t x) {
+  const float u = _curand_uniform(x);
+  return u == 1.0f ? 0.0f : u;
+}
+
+}  // namespace rlsb

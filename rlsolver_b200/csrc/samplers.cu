@@ -1,0 +1,471 @@
+// The reference's samplers, each a Python loop of tiny torch kernels there, each ONE launch here:
+//
+//   mcpg_sweeps    sampler_func                rlsolver/methods/MCPG.py:120-166  (num_ls * N node updates)
+//   metro          metro_sampling              rlsolver/methods/MCPG.py:88-117   (up to 5*max_transfer iterations)
+//   subset         sub_set_sampling            rlsolver/methods/L2A/transformer.py:335-353 (top_k columns)
+//
+// Chains are bit-packed 32 per word like the environments of the other kernels (tile = 32 chains x
+// all nodes in shared memory).  Random numbers are either read from explicit arrays (replay of
+// recorded draws) or computed in place from torch's Philox stream (philox.cuh), which reproduces
+// the reference's call sequence bit for bit.
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "graph_host.h"
+#include "philox.cuh"
+#include "tile_ops.cuh"
+
+// ---------------------------------------------------------------------------- plan (host side)
+struct rlsb_mcpg_plan {
+  int32_t n = 0, np = 0, levels = 0, num_slices = 0, device = -1, max_deg = 0;
+  std::vector<int32_t> order, level_slice;
+  rlsb_graph::Sell earlier, later;
+  std::vector<uint16_t> deg, nlater, pos;
+  void* dev_blob = nullptr;
+  const rlsb_graph_t* graph = nullptr;
+  struct Dev {
+    int32_t levels, num_slices;
+    const int32_t* level_slice;
+    rlsb::SellDev earlier, later;     // node arrays shared
+    const uint16_t *deg, *nlater, *pos;
+  } dev{};
+};
+
+namespace rlsb {
+
+// ---------------------------------------------------------------------------- bit-sliced helpers
+// z += a << shift (z has Q planes, a has P planes)
+template <int Q, int P, int SHIFT>
+__device__ __forceinline__ void planes_add_shifted(uint32_t (&z)[Q], const VCount<P>& a) {
+  uint32_t carry = 0;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const uint32_t zz = z[p + SHIFT], aa = a.c[p];
+    const uint32_t u = zz ^ aa;
+    z[p + SHIFT] = u ^ carry;
+    carry = (zz & aa) | (u & carry);
+  }
+#pragma unroll
+  for (int p = 0; p < Q; ++p) {
+    if (p >= P + SHIFT) {
+      const uint32_t zz = z[p];
+      z[p] = zz ^ carry;
+      carry &= zz;
+    }
+  }
+}
+
+// masks of bit positions whose Q-plane value is < k / == k
+template <int Q>
+__device__ __forceinline__ void planes_cmp(const uint32_t (&z)[Q], uint32_t k, uint32_t& lt, uint32_t& eq) {
+  lt = 0, eq = kFull;
+#pragma unroll
+  for (int p = Q - 1; p >= 0; --p) {
+    const uint32_t km = ((k >> p) & 1u) ? kFull : 0u;
+    lt |= eq & ~z[p] & km;
+    eq &= ~(z[p] ^ km);
+  }
+}
+
+// ---------------------------------------------------------------------------- sampler_func sweeps
+constexpr int kMcpgThreads = 128;
+
+// xs: float32 [N][C] node-major (values 0/1), in place.  expected: float32 [C].
+template <int P>
+__global__ void __launch_bounds__(kMcpgThreads) mcpg_sweeps_kernel(GraphDev g, rlsb_mcpg_plan::Dev plan,
+                                                                   float* __restrict__ xs, int64_t num_chains,
+                                                                   int num_ls, const float* __restrict__ explicit_u,
+                                                                   TorchRng rng, float* __restrict__ expected,
+                                                                   int cut_warps) {
+  extern __shared__ uint32_t sP[];               // np + 32 words; [np] stays zero (padding target)
+  __shared__ int sCnt[kTileEnvs];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int64_t tiles = (num_chains + kTileEnvs - 1) / kTileEnvs;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t c0 = tile * kTileEnvs;
+    const int valid = (int)min((int64_t)kTileEnvs, num_chains - c0);
+    const uint32_t vmask = valid == 32 ? kFull : ((1u << valid) - 1u);
+    if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
+    // pack: one coalesced 128-byte row segment per node
+    for (int i = warp; i < g.np + 32; i += nwarps) {
+      float v = 0.f;
+      if (i < g.n && lane < valid) v = xs[(int64_t)i * num_chains + c0 + lane];
+      const uint32_t w = __ballot_sync(kFull, v != 0.f);
+      if (lane == 0) sP[i] = w;
+    }
+    __syncthreads();
+    for (int sweep = 0; sweep < num_ls; ++sweep) {
+      for (int l = 0; l < plan.levels; ++l) {
+        const int sb = __ldg(plan.level_slice + l), se = __ldg(plan.level_slice + l + 1);
+        for (int s = sb + warp; s < se; s += nwarps) {
+          const uint32_t node = __ldg(plan.earlier.node + s * 32 + lane);
+          const bool active = node != 0xFFFFu;
+          VCount<P> a, b;
+          sell_cross<P, false>(plan.earlier, s, lane, sP, 0u, a);     // ones among already-visited neighbours
+          sell_cross<P, false>(plan.later, s, lane, sP, 0u, b);       // ones among not-yet-visited neighbours
+          const uint32_t deg = __ldg(plan.deg + s * 32 + lane);
+          // 2*S = 2a + 4b - later  (first sweep: unvisited entries still hold {-0.5, 1.5}, MCPG.py:132-133)
+          //     = 2a + 2b          (afterwards);   set iff S + rand/4 < (deg + 1/4) / 2
+          uint32_t z[P + 3];
+#pragma unroll
+          for (int p = 0; p < P + 3; ++p) z[p] = 0;
+          planes_add_shifted<P + 3, P, 1>(z, a);
+          if (sweep == 0) planes_add_shifted<P + 3, P, 2>(z, b);
+          else planes_add_shifted<P + 3, P, 1>(z, b);
+          const uint32_t k = deg + (sweep == 0 ? (uint32_t)__ldg(plan.nlater + s * 32 + lane) : 0u);
+          uint32_t lt, eq;
+          planes_cmp<P + 3>(z, k, lt, eq);
+          uint32_t word = lt;
+          uint32_t ties = active ? (eq & vmask) : 0u;
+          if (ties) {       // S == deg/2: the coin decides, in float32 exactly as the reference adds it
+            const float sf = 0.5f * (float)deg, tf = sf + 0.125f;
+            const uint64_t call = (uint64_t)sweep * g.n + __ldg(plan.pos + s * 32 + lane);
+            while (ties) {
+              const int bpos = __ffs(ties) - 1;
+              ties &= ties - 1;
+              const uint32_t chain = (uint32_t)(c0 + bpos);
+              const float u = explicit_u ? __ldg(explicit_u + call * num_chains + chain)
+                                         : torch_uniform_from_u32(torch_philox_u32(rng, call, chain));
+              if (__fadd_rn(sf, __fmul_rn(u, 0.25f)) < tf) word |= 1u << bpos;
+            }
+          }
+          if (active) sP[node] = word & vmask;
+        }
+        __syncthreads();
+      }
+    }
+    // expected_cut = sum_e (2x_u - 1)(2x_v - 1) = M - 2 * cut   (MCPG.py:148-154)
+    const int cnt = tile_cut_partial(g, sP, cut_warps);
+    if (cnt) atomicAdd(&sCnt[lane], cnt);
+    __syncthreads();
+    if (threadIdx.x < valid) expected[c0 + threadIdx.x] = (float)(g.m - 2 * sCnt[threadIdx.x]);
+    for (int i = warp; i < g.n; i += nwarps) {
+      const uint32_t w = sP[i];
+      if (lane < valid) xs[(int64_t)i * num_chains + c0 + lane] = (float)((w >> lane) & 1u);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------- metro_sampling
+// One warp per tile of 32 chains, lane = chain.  count_only: accumulate the number of accepted
+// moves of every iteration into acc[t] (the reference's global stop rule needs them);
+// otherwise run *num_iters_dev iterations and write the final state.
+constexpr int kMetroWarps = 4;
+
+__global__ void __launch_bounds__(kMetroWarps * 32) metro_kernel(int n, int np, const float* __restrict__ probs,
+                                                                  const float* __restrict__ start, float* __restrict__ out,
+                                                                  int64_t num_chains, int max_iters,
+                                                                  const int32_t* __restrict__ num_iters_dev,
+                                                                  const int64_t* __restrict__ explicit_idx,
+                                                                  const float* __restrict__ explicit_u, TorchRng rng,
+                                                                  int32_t* __restrict__ acc, int count_only) {
+  extern __shared__ uint32_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* sP = smem + (size_t)warp * np;
+  const int64_t tiles = (num_chains + kTileEnvs - 1) / kTileEnvs;
+  const int iters = count_only ? max_iters : min(max_iters, *num_iters_dev);
+  for (int64_t tile = (int64_t)blockIdx.x * kMetroWarps + warp; tile < tiles; tile += (int64_t)gridDim.x * kMetroWarps) {
+    const int64_t c0 = tile * kTileEnvs;
+    const bool live = c0 + lane < num_chains;
+    const uint32_t chain = (uint32_t)(c0 + lane);
+    for (int i = 0; i < n; ++i) {
+      const float v = live ? start[(int64_t)i * num_chains + chain] : 0.f;
+      const uint32_t w = __ballot_sync(kFull, v != 0.f);       // start_status.bool()
+      if (lane == 0) sP[i] = w;
+    }
+    __syncwarp();
+    for (int t = 0; t < iters; ++t) {
+      uint32_t r;
+      float u;
+      if (explicit_idx) {
+        r = live ? (uint32_t)explicit_idx[(int64_t)t * num_chains + chain] : 0u;
+        u = live ? explicit_u[(int64_t)t * num_chains + chain] : 2.f;
+      } else {
+        r = torch_philox_u32(rng, 2 * (uint64_t)t, chain) % (uint32_t)n;           // torch.randint(0, N, [C])
+        u = torch_uniform_from_u32(torch_philox_u32(rng, 2 * (uint64_t)t + 1, chain));   // torch.rand(C)
+      }
+      const bool bit = (sP[r] >> lane) & 1u;
+      const float p = __ldg(probs + r);
+      const float q = bit ? p : __fsub_rn(1.f, p);
+      const float rate = __fdiv_rn(__fsub_rn(1.f, q), q);       // (1 - q) / q, IEEE division like torch
+      const bool accept = live && (u < rate);
+      __syncwarp();
+      if (accept) atomicXor(&sP[r], 1u << lane);
+      __syncwarp();
+      if (count_only) {
+        const int k = __popc(__ballot_sync(kFull, accept));
+        if (lane == 0 && k) atomicAdd(acc + t, k);
+      }
+    }
+    if (!count_only) {
+      for (int i = 0; i < n; ++i)
+        if (live) out[(int64_t)i * num_chains + chain] = (float)((sP[i] >> lane) & 1u);
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------- sub_set_sampling
+// xs[row][ids[row % S][k]] = rand_k[row] < vals[row % S][k]   for every (row, k); ids of one row are distinct
+__global__ void subset_kernel(uint8_t* __restrict__ xs, int64_t rows, int n, int64_t num_sims, int top_k,
+                              const int64_t* __restrict__ ids, const float* __restrict__ vals,
+                              const float* __restrict__ explicit_u, TorchRng rng) {
+  const int64_t task = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (task >= rows * top_k) return;
+  const int64_t k = task / rows, row = task - k * rows;          // consecutive threads -> consecutive rows
+  const int64_t sim = row % num_sims;
+  const float u = explicit_u ? explicit_u[k * rows + row]
+                             : torch_uniform_from_u32(torch_philox_u32(rng, (uint64_t)k, (uint32_t)row));
+  xs[row * n + ids[sim * top_k + k]] = (uint8_t)(u < vals[sim * top_k + k]);
+}
+
+// ---------------------------------------------------------------------------- RNG test hooks
+__global__ void torch_rand_kernel(TorchRng rng, int64_t calls, int64_t numel, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= calls * numel) return;
+  out[i] = torch_uniform_from_u32(torch_philox_u32(rng, (uint64_t)(i / numel), (uint32_t)(i % numel)));
+}
+__global__ void torch_randint_kernel(TorchRng rng, int64_t calls, int64_t numel, uint32_t range,
+                                     int64_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= calls * numel) return;
+  out[i] = (int64_t)(torch_philox_u32(rng, (uint64_t)(i / numel), (uint32_t)(i % numel)) % range);
+}
+
+static TorchRng make_rng(uint64_t seed, uint64_t offset, uint32_t threads, uint32_t iters) {
+  TorchRng r;
+  r.seed = seed, r.offset4 = offset / 4, r.threads = threads ? threads : 1, r.iters_per_call = iters ? iters : 1;
+  return r;
+}
+
+}  // namespace rlsb
+
+extern "C" {
+
+int rlsb_mcpg_plan_create(const rlsb_graph_t* g, const int32_t* h_order, rlsb_mcpg_plan_t** out) {
+  using namespace rlsb;
+  RLSB_REQUIRE(out != nullptr, RLSB_ERR_INVALID, "mcpg_plan_create: out is null");
+  *out = nullptr;
+  const GraphDev* gd;
+  if (int rc = graph_check(g, &gd, "mcpg_plan_create")) return rc;
+  RLSB_REQUIRE(h_order != nullptr || g->n == 0, RLSB_ERR_INVALID, "mcpg_plan_create: null order");
+  const int32_t n = g->n;
+  std::vector<int32_t> pos(n, -1);
+  for (int32_t k = 0; k < n; ++k) {
+    RLSB_REQUIRE(h_order[k] >= 0 && h_order[k] < n && pos[h_order[k]] < 0, RLSB_ERR_INVALID,
+                 "mcpg_plan_create: order is not a permutation of 0..N-1 (entry %d)", k);
+    pos[h_order[k]] = k;
+  }
+  for (int64_t k = 0; k < g->m; ++k)
+    RLSB_REQUIRE(g->edge_u[k] != g->edge_v[k], RLSB_ERR_UNSUPPORTED,
+                 "mcpg_plan_create: self loop at edge %lld (the reference adds a node to its own neighbour list twice)",
+                 (long long)k);
+  auto* p = new rlsb_mcpg_plan();
+  p->n = n, p->np = g->np, p->device = g->device, p->graph = g, p->max_deg = g->max_full_deg;
+  p->order.assign(h_order, h_order + n);
+  // neighbours split by visiting order
+  std::vector<int32_t> es, ed, ls, ld;
+  for (int32_t i = 0; i < n; ++i)
+    for (int32_t k = g->full_ptr[i]; k < g->full_ptr[i + 1]; ++k) {
+      const int32_t j = g->full_col[k];
+      if (pos[j] < pos[i]) es.push_back(i), ed.push_back(j);
+      else ls.push_back(i), ld.push_back(j);
+    }
+  std::vector<int32_t> eptr, ecol, lptr, lcol;
+  build_csr(n, es, ed, eptr, ecol);
+  build_csr(n, ls, ld, lptr, lcol);
+  // dependency levels in visiting order
+  std::vector<int32_t> level(n, 0);
+  int32_t nlev = n ? 1 : 0;
+  for (int32_t k = 0; k < n; ++k) {
+    const int32_t i = h_order[k];
+    int32_t lv = 0;
+    for (int32_t e = eptr[i]; e < eptr[i + 1]; ++e) lv = std::max(lv, level[ecol[e]] + 1);
+    level[i] = lv;
+    nlev = std::max(nlev, lv + 1);
+  }
+  p->levels = nlev;
+  std::vector<int32_t> level_ptr(nlev + 1, 0), nodes(n);
+  for (int32_t i = 0; i < n; ++i) level_ptr[level[i] + 1]++;
+  for (int32_t l = 0; l < nlev; ++l) level_ptr[l + 1] += level_ptr[l];
+  {
+    std::vector<int32_t> fill(level_ptr.begin(), level_ptr.end() - 1);
+    for (int32_t k = 0; k < n; ++k) nodes[fill[level[h_order[k]]]++] = h_order[k];
+  }
+  for (int32_t l = 0; l < nlev; ++l)
+    std::stable_sort(nodes.begin() + level_ptr[l], nodes.begin() + level_ptr[l + 1], [&](int32_t a, int32_t b) {
+      return g->full_ptr[a + 1] - g->full_ptr[a] > g->full_ptr[b + 1] - g->full_ptr[b];
+    });
+  std::vector<int32_t> ls_e, ls_l;
+  build_sell(nodes, level_ptr, eptr, ecol, p->earlier, &ls_e, g->np);   // padding -> the zero word sP[np]
+  build_sell(nodes, level_ptr, lptr, lcol, p->later, &ls_l, g->np);
+  p->level_slice = ls_e;
+  p->num_slices = int32_t(p->earlier.off.size()) - 1;
+  p->deg.assign(size_t(p->num_slices) * 32, 0), p->nlater = p->deg, p->pos = p->deg;
+  for (size_t slot = 0; slot < p->earlier.node.size(); ++slot) {
+    const uint16_t i = p->earlier.node[slot];
+    if (i == 0xFFFF) continue;
+    p->deg[slot] = uint16_t(g->full_ptr[i + 1] - g->full_ptr[i]);
+    p->nlater[slot] = uint16_t(lptr[i + 1] - lptr[i]);
+    p->pos[slot] = uint16_t(pos[i]);
+  }
+  // device image
+  int prev = 0;
+  cudaError_t e = cudaGetDevice(&prev);
+  if (e == cudaSuccess) e = cudaSetDevice(g->device);
+  struct Part { const void* src; size_t bytes, off; };
+  std::vector<Part> parts;
+  size_t total = 0;
+  auto add = [&](const void* src, size_t bytes) {
+    parts.push_back({src, bytes, total});
+    total += (bytes + 255) / 256 * 256 + 256;
+    return int(parts.size()) - 1;
+  };
+  const int b_ls = add(p->level_slice.data(), p->level_slice.size() * 4);
+  const int b_eoff = add(p->earlier.off.data(), p->earlier.off.size() * 4);
+  const int b_loff = add(p->later.off.data(), p->later.off.size() * 4);
+  const int b_node = add(p->earlier.node.data(), p->earlier.node.size() * 2);
+  const int b_deg = add(p->deg.data(), p->deg.size() * 2), b_nl = add(p->nlater.data(), p->nlater.size() * 2);
+  const int b_pos = add(p->pos.data(), p->pos.size() * 2);
+  const int b_ecol = add(p->earlier.col.data(), p->earlier.col.size() * 2);
+  const int b_lcol = add(p->later.col.data(), p->later.col.size() * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&p->dev_blob, total);
+  for (size_t a = 0; a < parts.size() && e == cudaSuccess; ++a)
+    if (parts[a].bytes)
+      e = cudaMemcpy((char*)p->dev_blob + parts[a].off, parts[a].src, parts[a].bytes, cudaMemcpyHostToDevice);
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    set_error("mcpg_plan_create: CUDA error %s", cudaGetErrorString(e));
+    if (p->dev_blob) cudaFree(p->dev_blob);
+    delete p;
+    return RLSB_ERR_CUDA;
+  }
+  auto i32 = [&](int b) { return reinterpret_cast<const int32_t*>((char*)p->dev_blob + parts[b].off); };
+  auto u16 = [&](int b) { return reinterpret_cast<const uint16_t*>((char*)p->dev_blob + parts[b].off); };
+  p->dev.levels = p->levels, p->dev.num_slices = p->num_slices, p->dev.level_slice = i32(b_ls);
+  p->dev.earlier = SellDev{p->num_slices, i32(b_eoff), u16(b_node), u16(b_deg), u16(b_ecol)};
+  p->dev.later = SellDev{p->num_slices, i32(b_loff), u16(b_node), u16(b_deg), u16(b_lcol)};
+  p->dev.deg = u16(b_deg), p->dev.nlater = u16(b_nl), p->dev.pos = u16(b_pos);
+  *out = p;
+  return RLSB_OK;
+}
+
+int rlsb_mcpg_plan_destroy(rlsb_mcpg_plan_t* p) {
+  if (!p) return RLSB_OK;
+  if (p->dev_blob) cudaFree(p->dev_blob);
+  delete p;
+  return RLSB_OK;
+}
+
+int32_t rlsb_mcpg_plan_num_levels(const rlsb_mcpg_plan_t* p) { return p ? p->levels : 0; }
+
+int rlsb_mcpg_sweeps(const rlsb_graph_t* gh, const rlsb_mcpg_plan_t* plan, float* xs, int64_t num_chains,
+                     int32_t num_ls, const float* explicit_u, uint64_t seed, uint64_t offset, uint32_t rng_threads,
+                     uint32_t rng_iters, float* expected, void* stream) {
+  using namespace rlsb;
+  const GraphDev* g;
+  if (int rc = graph_check(gh, &g, "mcpg_sweeps")) return rc;
+  RLSB_REQUIRE(plan != nullptr && plan->graph == gh, RLSB_ERR_INVALID, "mcpg_sweeps: plan does not belong to this graph");
+  RLSB_REQUIRE(num_chains >= 0 && num_ls >= 0, RLSB_ERR_INVALID, "mcpg_sweeps: negative size");
+  RLSB_REQUIRE(num_chains < (int64_t(1) << 31), RLSB_ERR_UNSUPPORTED, "mcpg_sweeps: more than 2^31 chains");
+  if (num_chains == 0 || g->n == 0) return RLSB_OK;
+  RLSB_REQUIRE(xs && expected, RLSB_ERR_INVALID, "mcpg_sweeps: null pointer");
+  RLSB_REQUIRE(explicit_u || (rng_threads > 0 && rng_iters > 0), RLSB_ERR_INVALID, "mcpg_sweeps: no random source");
+  const size_t smem = ((size_t)g->np + 32) * 4;
+  const int64_t tiles = (num_chains + kTileEnvs - 1) / kTileEnvs;
+  const unsigned grid = (unsigned)(tiles < 16 * kNumSMs ? tiles : 16 * kNumSMs);
+  auto st = static_cast<cudaStream_t>(stream);
+  const TorchRng rng = make_rng(seed, offset, rng_threads, rng_iters);
+  const int cw = cut_warps_for(g->m, kMcpgThreads / 32);
+#define RLSB_MCPG(P)                                                                                        \
+  do {                                                                                                      \
+    if (smem > 48 * 1024)                                                                                   \
+      RLSB_CUDA_OK(cudaFuncSetAttribute(mcpg_sweeps_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        (int)smem));                                                        \
+    mcpg_sweeps_kernel<P><<<grid, kMcpgThreads, smem, st>>>(*g, plan->dev, xs, num_chains, num_ls, explicit_u, \
+                                                            rng, expected, cw);                             \
+  } while (0)
+  if (plan->max_deg <= 63) RLSB_MCPG(6);
+  else if (plan->max_deg <= 255) RLSB_MCPG(8);
+  else RLSB_MCPG(12);
+#undef RLSB_MCPG
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+int rlsb_metro_sampling(int32_t num_nodes, const float* probs, const float* start, float* out, int64_t num_chains,
+                        int32_t max_iters, const int32_t* num_iters_dev, const int64_t* explicit_idx,
+                        const float* explicit_u, uint64_t seed, uint64_t offset, uint32_t rng_threads,
+                        uint32_t rng_iters, int32_t* acc, int32_t count_only, void* stream) {
+  using namespace rlsb;
+  RLSB_REQUIRE(num_nodes > 0 && num_chains >= 0 && max_iters >= 0, RLSB_ERR_INVALID, "metro_sampling: bad size");
+  RLSB_REQUIRE(num_chains < (int64_t(1) << 31), RLSB_ERR_UNSUPPORTED, "metro_sampling: more than 2^31 chains");
+  if (num_chains == 0) return RLSB_OK;
+  RLSB_REQUIRE(probs && start && (count_only ? acc != nullptr : (out != nullptr && num_iters_dev != nullptr)),
+               RLSB_ERR_INVALID, "metro_sampling: null pointer");
+  RLSB_REQUIRE((explicit_idx == nullptr) == (explicit_u == nullptr), RLSB_ERR_INVALID,
+               "metro_sampling: explicit_idx and explicit_u go together");
+  RLSB_REQUIRE(explicit_u || (rng_threads > 0 && rng_iters > 0), RLSB_ERR_INVALID, "metro_sampling: no random source");
+  const int np = (num_nodes + 31) / 32 * 32;
+  const size_t smem = (size_t)kMetroWarps * np * 4;
+  RLSB_REQUIRE(smem <= 220 * 1024, RLSB_ERR_UNSUPPORTED, "metro_sampling: %d nodes exceed the shared-memory tiles",
+               num_nodes);
+  if (smem > 48 * 1024)
+    RLSB_CUDA_OK(cudaFuncSetAttribute(metro_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t tiles = (num_chains + kTileEnvs - 1) / kTileEnvs;
+  const int64_t ctas = (tiles + kMetroWarps - 1) / kMetroWarps;
+  const unsigned grid = (unsigned)(ctas < 32 * kNumSMs ? ctas : 32 * kNumSMs);
+  metro_kernel<<<grid, kMetroWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+      num_nodes, np, probs, start, out, num_chains, max_iters, num_iters_dev, explicit_idx, explicit_u,
+      make_rng(seed, offset, rng_threads, rng_iters), acc, count_only);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+int rlsb_subset_sampling(uint8_t* xs, int64_t rows, int32_t num_nodes, int64_t num_sims, int32_t top_k,
+                         const int64_t* ids, const float* vals, const float* explicit_u, uint64_t seed,
+                         uint64_t offset, uint32_t rng_threads, uint32_t rng_iters, void* stream) {
+  using namespace rlsb;
+  RLSB_REQUIRE(rows >= 0 && num_nodes > 0 && num_sims > 0 && top_k >= 0 && rows % num_sims == 0, RLSB_ERR_INVALID,
+               "subset_sampling: bad shape (rows must be num_repeats * num_sims)");
+  RLSB_REQUIRE(rows < (int64_t(1) << 31), RLSB_ERR_UNSUPPORTED, "subset_sampling: more than 2^31 rows");
+  if (rows == 0 || top_k == 0) return RLSB_OK;
+  RLSB_REQUIRE(xs && ids && vals, RLSB_ERR_INVALID, "subset_sampling: null pointer");
+  RLSB_REQUIRE(explicit_u || (rng_threads > 0 && rng_iters > 0), RLSB_ERR_INVALID, "subset_sampling: no random source");
+  const int64_t tasks = rows * top_k;
+  subset_kernel<<<(unsigned)((tasks + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      xs, rows, num_nodes, num_sims, top_k, ids, vals, explicit_u, make_rng(seed, offset, rng_threads, rng_iters));
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+int rlsb_torch_rand(uint64_t seed, uint64_t offset, uint32_t rng_threads, uint32_t rng_iters, int64_t calls,
+                    int64_t numel, float* out, void* stream) {
+  using namespace rlsb;
+  RLSB_REQUIRE(calls >= 0 && numel >= 0 && rng_threads > 0 && rng_iters > 0 && numel < (int64_t(1) << 31),
+               RLSB_ERR_INVALID, "torch_rand: bad argument");
+  if (calls * numel == 0) return RLSB_OK;
+  RLSB_REQUIRE(out != nullptr, RLSB_ERR_INVALID, "torch_rand: null pointer");
+  torch_rand_kernel<<<(unsigned)((calls * numel + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      make_rng(seed, offset, rng_threads, rng_iters), calls, numel, out);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+int rlsb_torch_randint(uint64_t seed, uint64_t offset, uint32_t rng_threads, uint32_t rng_iters, int64_t calls,
+                       int64_t numel, uint32_t range, int64_t* out, void* stream) {
+  using namespace rlsb;
+  RLSB_REQUIRE(calls >= 0 && numel >= 0 && rng_threads > 0 && rng_iters > 0 && range > 0 && range < (1u << 28) &&
+                   numel < (int64_t(1) << 31),
+               RLSB_ERR_INVALID, "torch_randint: bad argument (range must be below 2^28: torch's 32-bit path)");
+  if (calls * numel == 0) return RLSB_OK;
+  RLSB_REQUIRE(out != nullptr, RLSB_ERR_INVALID, "torch_randint: null pointer");
+  torch_randint_kernel<<<(unsigned)((calls * numel + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      make_rng(seed, offset, rng_threads, rng_iters), calls, numel, range, out);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+}  // extern "C"
