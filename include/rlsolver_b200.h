@@ -37,6 +37,7 @@ extern "C" {
 
 typedef struct rlsb_graph rlsb_graph_t;
 typedef struct rlsb_mcpg_plan rlsb_mcpg_plan_t;
+typedef struct rlsb_qubo rlsb_qubo_t;
 
 int rlsb_version(void);
 const char* rlsb_last_error(void);
@@ -205,6 +206,23 @@ int rlsb_metro_sampling(int32_t num_nodes, const float* probs, const float* star
 int rlsb_subset_sampling(uint8_t* xs, int64_t rows, int32_t num_nodes, int64_t num_sims, int32_t top_k,
                          const int64_t* ids, const float* vals, const float* explicit_u, uint64_t seed,
                          uint64_t offset, uint32_t rng_threads, uint32_t rng_iters, void* stream);
+
+/* ---- dense QUBO Hamiltonian on the tensor cores: E[c] = x_c^T Q x_c, the "compute value" step of
+ * mcpg_sampling_qubo / _qubo_bin (rlsolver/methods/MCPG/sampling.py:339-340, 364-365) and the
+ * dense energy of PISCO (rlsolver/envs/env_ISCO.py:436-444).
+ * qubo_create: q = float32 [N][N] DEVICE pointer; splits Q once into three bf16 limbs (exact) and
+ *   builds the TMA descriptor.  N is padded to a multiple of 128 internally.
+ * qubo_energy: x = float32 [N][C] node-major DEVICE pointer whose entries are exactly representable
+ *   in bf16 (the reference's {-1,+1}, {0,1}, or 0 for a masked variable); energy = float32 [C].
+ *   tcgen05.mma (bf16 x bf16 -> fp32 in tensor memory) with the x^T (Q x) reduction fused into the
+ *   epilogue; deterministic.  Accuracy: fp32 accumulation like the reference's SGEMM; the tests hold
+ *   it to 1e-5 relative against float64.  workspace: 256-byte aligned, rlsb_qubo_workspace_bytes(). */
+int rlsb_qubo_create(const float* q, int32_t num_vars, int32_t device, rlsb_qubo_t** out, void* stream);
+int rlsb_qubo_destroy(rlsb_qubo_t* h);
+int32_t rlsb_qubo_padded_vars(const rlsb_qubo_t* h);
+int64_t rlsb_qubo_workspace_bytes(const rlsb_qubo_t* h, int64_t num_chains);
+int rlsb_qubo_energy(const rlsb_qubo_t* h, const float* x, int64_t num_chains, float* energy, void* workspace,
+                     void* stream);
 
 /* ---- select ops on the reference's bool layout
  * select_rows: update_xs_by_vs (util_read_data.py:190-202): rows of (xs1,vs1) replace

@@ -119,6 +119,11 @@ SIGNATURES = {
     "rlsb_metro_sampling": (C.c_int, [_i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _u64, _u64, _u32, _u32, _vp,
                                       _i32, _vp]),
     "rlsb_subset_sampling": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _u64, _u64, _u32, _u32, _vp]),
+    "rlsb_qubo_create": (C.c_int, [_vp, _i32, _i32, C.POINTER(_vp), _vp]),
+    "rlsb_qubo_destroy": (C.c_int, [_vp]),
+    "rlsb_qubo_padded_vars": (_i32, [_vp]),
+    "rlsb_qubo_workspace_bytes": (_i64, [_vp, _i64]),
+    "rlsb_qubo_energy": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "rlsb_select_rows": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "rlsb_pick_best": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
 }

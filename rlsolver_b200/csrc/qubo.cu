@@ -1,0 +1,376 @@
+// Dense QUBO Hamiltonian  E[c] = x_c^T Q x_c  for a batch of chains -- the "compute value" step of
+// mcpg_sampling_qubo / mcpg_sampling_qubo_bin (rlsolver/methods/MCPG/sampling.py:339-340, 364-365:
+// res = matmul(Q, X); sum(X * res, dim=0)) and the energy of PISCO's dense model
+// (rlsolver/envs/env_ISCO.py:436-444).  This is the one place on the path where the work really is
+// a batched contraction, so it runs on the 5th-generation tensor cores:
+//
+//   * Q (float32) is split once into three bf16 limbs hi + mid + lo (3 x 8 = 24 significand bits:
+//     the split is exact), X in {-1, 0, +1} is exact in bf16, products are exact and the
+//     accumulation is fp32 in tensor memory -- the same arithmetic class as the reference's SGEMM.
+//   * One CTA computes a 128 (rows of Q) x 256 (chains) tile of Y = Q X over the whole K = N range:
+//     TMA (cp.async.bulk.tensor, 128B swizzle) feeds a 2-stage shared-memory ring, one elected
+//     thread issues tcgen05.mma (M128 N256 K16, kind::f16, bf16 in / f32 out) for the three limbs
+//     into one TMEM accumulator, completion is signalled through tcgen05.commit -> mbarrier.
+//   * The epilogue never writes Y: four warps read the accumulator with tcgen05.ld, multiply by
+//     x[row][chain] (kept as two bit masks per thread), reduce over the 128 rows (transposing
+//     butterfly, 31 shuffles per 32 columns) and store one partial energy per (row block, chain); a
+//     tiny kernel adds the row blocks in a fixed order (deterministic, no atomics).
+//   * K is accumulated in tensor memory in chunks of 512 and the two 256-column accumulators
+//     alternate (MMA fills one while the epilogue drains the other): the tensor core's truncating
+//     fp32 adds would otherwise drift past the 1e-5 tolerance at N = 4096.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace rlsb {
+
+constexpr int kQM = 128, kQN = 256, kQK = 64, kQStages = 2, kQLimbs = 3;
+constexpr int kQThreads = 192;                       // warp 0 TMA, warp 1 MMA + TMEM, warps 2-5 epilogue
+constexpr uint32_t kTileA = kQM * kQK * 2;           // 16 KB
+constexpr uint32_t kTileB = kQN * kQK * 2;           // 32 KB
+constexpr uint32_t kStageBytes = kQLimbs * kTileA + kTileB;   // 80 KB
+
+constexpr int kQChunk = 8;                           // k-blocks (512 of K) accumulated in tensor memory before a drain
+
+struct QuboSmem {
+  uint8_t tiles[kQStages][kStageBytes];              // [A_hi | A_mid | A_lo | B], each 1024-byte aligned
+  float part[4][kQN];
+  uint32_t negm[kQN / 32][128], zerom[kQN / 32][128];   // x[row][chain] of this tile as sign / zero bit masks
+  uint64_t full_bar[kQStages], empty_bar[kQStages], tmem_full_bar[2], tmem_empty_bar[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t umma_desc(const void* tile) {
+  const uint32_t addr = smem_u32(tile);
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// The tensor core adds every K=16 step into the fp32 accumulator with truncation, so a long K
+// loop drifts (measured 2.7e-5 relative at K = 4096 x 3 limbs).  K is therefore cut into chunks of
+// kQChunk k-blocks that accumulate in tensor memory; the two 256-column accumulators alternate, and
+// while one fills the epilogue warps drain the other into round-to-nearest fp32 running sums.
+__global__ void __launch_bounds__(kQThreads, 1)
+qubo_energy_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __nv_bfloat16* __restrict__ xt, int np, int cp, float* __restrict__ partial) {
+  extern __shared__ uint8_t smem_raw[];
+  QuboSmem& S = *reinterpret_cast<QuboSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kQM, n0 = blockIdx.y * kQN;
+  const int kblocks = np / kQK;
+  const int chunks = (kblocks + kQChunk - 1) / kQChunk;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kQStages; ++s) mbar_init(&S.full_bar[s], 1), mbar_init(&S.empty_bar[s], 1);
+    for (int b = 0; b < 2; ++b) mbar_init(&S.tmem_full_bar[b], 1), mbar_init(&S.tmem_empty_bar[b], 4);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {   // tensor memory: two accumulators of 256 fp32 columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
+                 "r"((uint32_t)(2 * kQN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp == 0) {
+    if (elect_one()) {                                   // ===== TMA producer
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int s = kb % kQStages, ph = (kb / kQStages) & 1;
+        mbar_wait(&S.empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&S.full_bar[s], kStageBytes);
+        for (int l = 0; l < kQLimbs; ++l)
+          tma_load_2d(S.tiles[s] + l * kTileA, &tmA, &S.full_bar[s], kb * kQK, l * np + m0);
+        tma_load_2d(S.tiles[s] + kQLimbs * kTileA, &tmB, &S.full_bar[s], kb * kQK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {                                   // ===== MMA issuer
+      // instruction descriptor: D = f32, A = B = bf16, both K-major, N = 256, M = 128
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kQN >> 3) << 17) | ((uint32_t)(kQM >> 4) << 24);
+      for (int ch = 0; ch < chunks; ++ch) {
+        const int buf = ch & 1;
+        mbar_wait(&S.tmem_empty_bar[buf], ((ch >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int kb_end = min(kblocks, (ch + 1) * kQChunk);
+        for (int kb = ch * kQChunk; kb < kb_end; ++kb) {
+          const int s = kb % kQStages, ph = (kb / kQStages) & 1;
+          mbar_wait(&S.full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t db = umma_desc(S.tiles[s] + kQLimbs * kTileA);
+#pragma unroll
+          for (int l = 0; l < kQLimbs; ++l) {
+            const uint64_t da = umma_desc(S.tiles[s] + l * kTileA);
+#pragma unroll
+            for (int k = 0; k < kQK / 16; ++k)             // 32 bytes = 2 x 16-byte units along K per step
+              umma_bf16(tmem + buf * kQN, da + 2 * k, db + 2 * k, idesc,
+                        (kb != ch * kQChunk || l != 0 || k != 0) ? 1u : 0u);
+          }
+          umma_commit(&S.empty_bar[s]);                    // frees the stage when these MMAs retire
+        }
+        umma_commit(&S.tmem_full_bar[buf]);
+      }
+    }
+  } else {                                               // ===== epilogue: warps 2..5
+    const int q = warp & 3;                                // TMEM lane quarter this warp may read
+    const int row = m0 + 32 * q + lane;
+    // x[row][n0 .. n0+255] as two bit masks (negative / zero); 32 consecutive rows of one chain are 64 contiguous bytes
+    const int et = threadIdx.x - 64;                       // 0..127 within the epilogue group
+#pragma unroll 1
+    for (int g = 0; g < kQN / 32; ++g) {
+      uint32_t nm = 0, zm = 0;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const float xv = __bfloat162float(xt[(size_t)(n0 + g * 32 + j) * np + row]);
+        nm |= (uint32_t)(xv < 0.f) << j;
+        zm |= (uint32_t)(xv == 0.f) << j;
+      }
+      S.negm[g][et] = nm, S.zerom[g][et] = zm;
+      S.part[q][g * 32 + lane] = 0.f;                      // running sum of column g*32 + lane over this warp's rows
+    }
+    for (int ch = 0; ch < chunks; ++ch) {
+      const int buf = ch & 1;
+      mbar_wait(&S.tmem_full_bar[buf], (ch >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int g = 0; g < kQN / 32; ++g) {
+        const uint32_t neg = S.negm[g][et], zero = S.zerom[g][et];
+        uint32_t r[32];
+        const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * kQN + g * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {       // y * x with x in {-1, 0, +1}: flip the sign bit / clear
+          const uint32_t sgn = ((neg >> j) & 1u) << 31;
+          const uint32_t keep = ((zero >> j) & 1u) ? 0u : kFull;
+          v[j] = __uint_as_float((r[j] ^ sgn) & keep);
+        }
+        // sum over the 32 lanes (rows) of every column; lane j ends up with column g*32 + j
+#pragma unroll
+        for (int h = 16; h >= 1; h >>= 1) {
+#pragma unroll
+          for (int j = 0; j < h; ++j) {
+            const bool upper = (lane & h) != 0;
+            const float send = upper ? v[j] : v[j + h];
+            const float kept = upper ? v[j + h] : v[j];
+            v[j] = kept + __shfl_xor_sync(kFull, send, h);
+          }
+        }
+        S.part[q][g * 32 + lane] += v[0];
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.tmem_empty_bar[buf]);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");        // the four epilogue warps
+    for (int c = et; c < kQN; c += 128)
+      partial[(size_t)blockIdx.x * cp + n0 + c] = (S.part[0][c] + S.part[1][c]) + (S.part[2][c] + S.part[3][c]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(2 * kQN)) : "memory");
+}
+
+// Q fp32 [n][n] -> three bf16 limbs [3][np][np], zero padded; hi + mid + lo == q exactly
+__global__ void qubo_split_kernel(const float* __restrict__ q, int n, int np, __nv_bfloat16* __restrict__ limbs) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)np * np) return;
+  const int i = (int)(idx / np), j = (int)(idx % np);
+  const float v = (i < n && j < n) ? q[(int64_t)i * n + j] : 0.f;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(hi);
+  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(mid);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
+  const int64_t plane = (int64_t)np * np;
+  limbs[idx] = hi, limbs[plane + idx] = mid, limbs[2 * plane + idx] = lo;
+}
+
+// X float32 [n][c] (node-major) -> Xt bf16 [cp][np] (chain-major, zero padded), 32x32 tiles through smem
+__global__ void qubo_xt_kernel(const float* __restrict__ x, int n, int64_t c, int np, int64_t cp,
+                               __nv_bfloat16* __restrict__ xt) {
+  __shared__ float tile[32][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 32;
+  const int i0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = i0 + r;
+    const int64_t cc = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (i < n && cc < c) ? x[(int64_t)i * c + cc] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t cc = c0 + r;
+    const int i = i0 + threadIdx.x;
+    if (cc < cp && i < np) xt[cc * np + i] = __float2bfloat16_rn(tile[threadIdx.x][r]);
+  }
+}
+
+__global__ void qubo_reduce_kernel(const float* __restrict__ partial, int mblocks, int64_t cp, int64_t c,
+                                   float* __restrict__ energy) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  float acc = 0.f;
+  for (int mb = 0; mb < mblocks; ++mb) acc += partial[(size_t)mb * cp + i];
+  energy[i] = acc;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 row-major [rows][cols] -> tensor map with a [box_rows][64] box, 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  RLSB_REQUIRE(fn != nullptr, RLSB_ERR_CUDA, "qubo: cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kQK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RLSB_REQUIRE(r == CUDA_SUCCESS, RLSB_ERR_CUDA, "qubo: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return RLSB_OK;
+}
+
+}  // namespace rlsb
+
+struct rlsb_qubo {
+  int32_t n = 0, np = 0, device = -1;
+  __nv_bfloat16* limbs = nullptr;      // [3][np][np]
+  CUtensorMap map_a;
+};
+
+extern "C" {
+
+int rlsb_qubo_create(const float* q, int32_t num_vars, int32_t device, rlsb_qubo_t** out, void* stream) {
+  using namespace rlsb;
+  RLSB_REQUIRE(out != nullptr, RLSB_ERR_INVALID, "qubo_create: out is null");
+  *out = nullptr;
+  RLSB_REQUIRE(q != nullptr && num_vars > 0 && device >= 0, RLSB_ERR_INVALID, "qubo_create: bad argument");
+  auto* h = new rlsb_qubo();
+  h->n = num_vars, h->np = (num_vars + kQM - 1) / kQM * kQM, h->device = device;
+  const size_t bytes = (size_t)3 * h->np * h->np * sizeof(__nv_bfloat16);
+  cudaError_t e = cudaMalloc(&h->limbs, bytes);
+  if (e != cudaSuccess) {
+    set_error("qubo_create: cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
+    delete h;
+    return RLSB_ERR_CUDA;
+  }
+  const int64_t total = (int64_t)h->np * h->np;
+  qubo_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(q, num_vars, h->np,
+                                                                                                   h->limbs);
+  int rc = RLSB_OK;
+  if (cudaGetLastError() != cudaSuccess) rc = RLSB_ERR_CUDA, set_error("qubo_create: split kernel launch failed");
+  if (rc == RLSB_OK) rc = make_map(&h->map_a, h->limbs, (uint64_t)3 * h->np, (uint64_t)h->np, kQM);
+  if (rc != RLSB_OK) {
+    cudaFree(h->limbs);
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return RLSB_OK;
+}
+
+int rlsb_qubo_destroy(rlsb_qubo_t* h) {
+  if (!h) return RLSB_OK;
+  if (h->limbs) cudaFree(h->limbs);
+  delete h;
+  return RLSB_OK;
+}
+
+int32_t rlsb_qubo_padded_vars(const rlsb_qubo_t* h) { return h ? h->np : 0; }
+
+int64_t rlsb_qubo_workspace_bytes(const rlsb_qubo_t* h, int64_t num_chains) {
+  using namespace rlsb;
+  if (!h || num_chains < 0) return -1;
+  const int64_t cp = (num_chains + kQN - 1) / kQN * kQN;
+  return cp * h->np * 2 + (int64_t)(h->np / kQM) * cp * 4 + 512;
+}
+
+int rlsb_qubo_energy(const rlsb_qubo_t* h, const float* x, int64_t num_chains, float* energy, void* workspace,
+                     void* stream) {
+  using namespace rlsb;
+  RLSB_REQUIRE(h != nullptr, RLSB_ERR_INVALID, "qubo_energy: null handle");
+  RLSB_REQUIRE(num_chains >= 0, RLSB_ERR_INVALID, "qubo_energy: negative num_chains");
+  if (num_chains == 0) return RLSB_OK;
+  RLSB_REQUIRE(x && energy && workspace, RLSB_ERR_INVALID, "qubo_energy: null pointer");
+  RLSB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, RLSB_ERR_INVALID,
+               "qubo_energy: workspace must be 256-byte aligned");
+  auto st = static_cast<cudaStream_t>(stream);
+  const int64_t cp = (num_chains + kQN - 1) / kQN * kQN;
+  auto* xt = static_cast<__nv_bfloat16*>(workspace);
+  auto* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + ((cp * h->np * 2 + 255) / 256 * 256));
+  dim3 tb(32, 8), tg((unsigned)(cp / 32), (unsigned)(h->np / 32));
+  qubo_xt_kernel<<<tg, tb, 0, st>>>(x, h->n, num_chains, h->np, cp, xt);
+  RLSB_LAUNCH_OK();
+  CUtensorMap map_b;
+  if (int rc = make_map(&map_b, xt, (uint64_t)cp, (uint64_t)h->np, kQN)) return rc;
+  const size_t smem = sizeof(QuboSmem) + 1024;
+  RLSB_CUDA_OK(cudaFuncSetAttribute(qubo_energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)(h->np / kQM), (unsigned)(cp / kQN));
+  qubo_energy_kernel<<<grid, kQThreads, smem, st>>>(h->map_a, map_b, xt, h->np, (int)cp, partial);
+  RLSB_LAUNCH_OK();
+  qubo_reduce_kernel<<<(unsigned)((num_chains + 255) / 256), 256, 0, st>>>(partial, h->np / kQM, cp, num_chains, energy);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+}  // extern "C"
