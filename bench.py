@@ -30,6 +30,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "maxcut_env_steps_per_sec"
 UNIT = "env-steps/s"
 GRAPH, NUM_ENVS, NUM_ITERS, NUM_SPIN, NOISE_STD = "G22", 4096, 8, 8, 0.3
+SETTLE_STEPS = 1000     # untimed, identical on every rank
 
 
 def workload_name(envs):
@@ -158,6 +159,7 @@ def run_b200(args):
     th.cuda.set_device(local)
     dev = th.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     rlsolver_b200.build()
 
@@ -196,12 +198,11 @@ def run_b200(args):
         return [a.elapsed_time(b) for a, b in evs]
 
     clocks = ClockSampler(local) if rank == 0 else None
-    # warm-up: at least W steps and at least ~1.5 s of load so the clocks settle
+    # warm-up: W steps plus a fixed number of settle steps (~0.5 s of load so the clocks settle).  The
+    # count must not depend on wall time: every rank has to issue the same sequence of collectives.
     t_w = time.time()
-    done = 0
-    while done < max(3, args.warmup) or time.time() - t_w < 1.5:
+    for _ in range(max(3, args.warmup) + SETTLE_STEPS):
         timed_steps(1)
-        done += 1
     barrier()
     launches0 = sim.store.launch_count
     t0 = time.time()
@@ -300,7 +301,7 @@ def run_b200(args):
                 "config": {"workload": workload_name(envs), "envs_per_gpu": envs, "nodes": n, "edges": sim.num_edges,
                            "env_steps_per_step_per_gpu": per_call, "l2": "flushed between steps (256 MiB write)",
                            "rng": "torch CUDA Philox randn, 1+8 draws of [E,N] f32 per step inside the timed region",
-                           "multi_gpu": "env batch sharded, graph replicated, best-cut allreduce per step"},
+                           "multi_gpu": "env batch sharded, graph replicated, one best-cut exchange per step (all-gather of 8+N byte records, no host sync)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": envs * n,
                         "d2h_bytes_per_step": envs * n + 8 * envs, "ms_per_step": float(e2e_total.item()) / args.steps},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info}
