@@ -178,11 +178,21 @@ def run_b200(args):
             dist.barrier()
         th.cuda.synchronize()
 
+    def local_part():
+        return sim.local_search_inplace(xs, sentinel, NUM_ITERS, NUM_SPIN, NOISE_STD)
+
+    state = {"graph": None, "out": None}
+
     def one_step():
-        gx, gv = sim.local_search_inplace(xs, sentinel, NUM_ITERS, NUM_SPIN, NOISE_STD)
-        if world > 1:     # the path's only exchange: best cut + its argmax + the winner's spins
-            best_allreduce(gv, gx, rank, world, envs)
-        return gx, gv
+        if state["graph"] is not None:
+            state["graph"].replay()
+            gx, gv = state["out"]
+        else:
+            gx, gv = local_part()
+        best = None
+        if world > 1:     # the path's only exchange: best cut + its argmax + the winner's spins (eager: 1 kernel + 1 all-gather)
+            best = best_allreduce(gv, gx, rank, world, envs)
+        return gx, gv, best
 
     def timed_steps(k):
         evs = []
@@ -197,10 +207,44 @@ def run_b200(args):
         th.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in evs]
 
+    def try_capture():
+        """The local part of the step is a fixed sequence of 14 launches (torch's RNG kernels and this
+        library's kernels): capture it once into a CUDA graph so its host cost is one replay.  torch's
+        graph-safe Philox state keeps the random stream identical to eager execution."""
+        if args.no_graph:
+            return "disabled (--no-graph)"
+        try:
+            side = th.cuda.Stream(device=dev)
+            side.wait_stream(th.cuda.current_stream(dev))
+            with th.cuda.stream(side):
+                for _ in range(3):
+                    local_part()
+            th.cuda.current_stream(dev).wait_stream(side)
+            th.cuda.synchronize()
+            g = th.cuda.CUDAGraph()
+            with th.cuda.graph(g):
+                out = local_part()
+            th.cuda.synchronize()
+            state["graph"], state["out"] = g, out
+            return "captured"
+        except Exception as exc:                                   # noqa: BLE001 - eager remains correct
+            state["graph"] = None
+            th.cuda.synchronize()
+            return f"eager ({type(exc).__name__}: {str(exc)[:80]})"
+
     clocks = ClockSampler(local) if rank == 0 else None
     # warm-up: W steps plus a fixed number of settle steps (~0.5 s of load so the clocks settle).  The
     # count must not depend on wall time: every rank has to issue the same sequence of collectives.
     t_w = time.time()
+    launches_before = sim.store.launch_count
+    timed_steps(1)
+    launches_per_step = sim.store.launch_count - launches_before
+    graph_status = try_capture()
+    if world > 1:       # all ranks must agree on the mode (the collective sequence is part of it)
+        flag = th.tensor([1 if state["graph"] is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and state["graph"] is not None:
+            state["graph"], graph_status = None, "eager (another rank could not capture)"
     for _ in range(max(3, args.warmup) + SETTLE_STEPS):
         timed_steps(1)
     barrier()
@@ -209,7 +253,7 @@ def run_b200(args):
     ms = timed_steps(args.steps)
     barrier()
     t1 = time.time()
-    launches = sim.store.launch_count - launches0
+    launches = launches_per_step * args.steps          # kernels of this library per step (counted on an eager step)
     total_ms = th.tensor([sum(ms)], dtype=th.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -223,10 +267,8 @@ def run_b200(args):
     h_out_vs = th.empty((envs,), dtype=th.int64).pin_memory()
 
     def e2e_step():
-        d_xs = h_xs.to(dev, non_blocking=True)
-        gx, gv = sim.local_search_inplace(d_xs, sentinel, NUM_ITERS, NUM_SPIN, NOISE_STD)
-        if world > 1:
-            best_allreduce(gv, gx, rank, world, envs)
+        xs.copy_(h_xs, non_blocking=True)                          # H2D into the step's input buffer
+        gx, gv, _ = one_step()
         h_out_xs.copy_(gx, non_blocking=True)
         h_out_vs.copy_(gv, non_blocking=True)
 
@@ -250,8 +292,10 @@ def run_b200(args):
     clock_info = clocks.stop(t_w, time.time()) if clocks else None
 
     # ---- per-kernel pass (CUDA events around every launch of this library) for the roofline
+    saved_graph, state["graph"] = state["graph"], None          # per-kernel events need eager launches
     sim.store.timer = OpTimer()
     timed_steps(args.steps)
+    state["graph"] = saved_graph
     spans = sim.store.timer.summary()
     sim.store.timer = None
     step_ms_prof = sum(v[1] for v in spans.values()) / args.steps
@@ -299,7 +343,7 @@ def run_b200(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-packed spins / int64 values / f32 noise",
                 "data": "synthetic",
                 "config": {"workload": workload_name(envs), "envs_per_gpu": envs, "nodes": n, "edges": sim.num_edges,
-                           "env_steps_per_step_per_gpu": per_call, "l2": "flushed between steps (256 MiB write)",
+                           "env_steps_per_step_per_gpu": per_call, "l2": "flushed between steps (256 MiB write)", "cuda_graph": graph_status,
                            "rng": "torch CUDA Philox randn, 1+8 draws of [E,N] f32 per step inside the timed region",
                            "multi_gpu": "env batch sharded, graph replicated, one best-cut exchange per step (all-gather of 8+N byte records, no host sync)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": envs * n,
@@ -318,6 +362,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=NUM_ENVS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -234,6 +234,16 @@ int rlsb_select_rows(uint8_t* xs0, int64_t* vs0, const uint8_t* xs1, const int64
 int rlsb_pick_best(const uint8_t* xs, const int64_t* vs, int32_t num_repeats, int64_t num_sims, int32_t num_nodes,
                    int32_t maximize, uint8_t* out_xs, int64_t* out_vs, void* stream);
 
+/* ---- multi-GPU best-cut exchange (new; the reference is single-process): the record a rank
+ * contributes to the all-gather -- int64 key (cut << 32) | (0xFFFFFFFF - global_env_id) of its best
+ * row (cut values must be >= 0; ties go to the lowest global env id), then the row's N bytes.
+ * vs int64 [E], xs bool [E][N], record uint8 [8 + N] (8-byte aligned); env_offset = rank * E. */
+int rlsb_best_record(const int64_t* vs, const uint8_t* xs, int64_t num_envs, int32_t num_nodes, int64_t env_offset,
+                     uint8_t* record, void* stream);
+/* winner of `world` gathered records (uint8 [world][8 + N]): out2[0] = best cut, out2[1] = its global
+ * env id, row = its N spin bytes. */
+int rlsb_best_pick(const uint8_t* gathered, int32_t world, int32_t num_nodes, int64_t* out2, uint8_t* row, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

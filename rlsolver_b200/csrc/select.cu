@@ -66,9 +66,75 @@ __global__ void __launch_bounds__(128) pick_best_kernel(const uint8_t* __restric
   copy_row(out_xs + sim * (int64_t)n, xs + ((int64_t)r * num_sims + sim) * (int64_t)n, n, threadIdx.x, blockDim.x);
 }
 
+// The per-rank record of the multi-GPU best-cut exchange: int64 key (cut << 32 | 0xFFFFFFFF - global
+// env id) of the best local row, followed by that row.  One CTA: block-wide max, then the row copy.
+__global__ void __launch_bounds__(1024) best_record_kernel(const int64_t* __restrict__ vs, const uint8_t* __restrict__ xs,
+                                                           int64_t num_envs, int n, int64_t env_offset,
+                                                           uint8_t* __restrict__ record) {
+  __shared__ unsigned long long sBest[32];
+  unsigned long long best = 0;
+  for (int64_t e = threadIdx.x; e < num_envs; e += blockDim.x) {
+    const unsigned long long key =
+        ((unsigned long long)vs[e] << 32) | (unsigned long long)(0xFFFFFFFFull - (unsigned long long)(env_offset + e));
+    best = key > best ? key : best;
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(kFull, best, off);
+    best = o > best ? o : best;
+  }
+  if ((threadIdx.x & 31) == 0) sBest[threadIdx.x >> 5] = best;
+  __syncthreads();
+  best = sBest[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = sBest[w] > best ? sBest[w] : best;
+  const int64_t local = (int64_t)(0xFFFFFFFFull - (best & 0xFFFFFFFFull)) - env_offset;
+  if (threadIdx.x == 0) *reinterpret_cast<unsigned long long*>(record) = best;
+  const uint8_t* row = xs + local * (int64_t)n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) record[8 + i] = row[i];
+}
+
+// winner of the gathered records: out[0] = cut, out[1] = global env id, row = its spins
+__global__ void __launch_bounds__(256) best_pick_kernel(const uint8_t* __restrict__ gathered, int world, int n,
+                                                        int64_t* __restrict__ out, uint8_t* __restrict__ row) {
+  const int64_t stride = 8 + (int64_t)n;
+  unsigned long long best = 0;
+  int win = 0;
+  for (int r = 0; r < world; ++r) {
+    unsigned long long key = 0;
+    for (int b = 7; b >= 0; --b) key = (key << 8) | gathered[r * stride + b];     // records are only byte aligned
+    if (r == 0 || key > best) best = key, win = r;
+  }
+  if (threadIdx.x == 0) {
+    out[0] = (int64_t)(best >> 32);
+    out[1] = (int64_t)(0xFFFFFFFFull - (best & 0xFFFFFFFFull));
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) row[i] = gathered[win * stride + 8 + i];
+}
+
 }  // namespace rlsb
 
 extern "C" {
+
+int rlsb_best_pick(const uint8_t* gathered, int32_t world, int32_t num_nodes, int64_t* out2, uint8_t* row, void* stream) {
+  using namespace rlsb;
+  RLSB_REQUIRE(world > 0 && num_nodes >= 0, RLSB_ERR_INVALID, "best_pick: bad shape");
+  RLSB_REQUIRE(gathered && out2 && row, RLSB_ERR_INVALID, "best_pick: null pointer");
+  best_pick_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(gathered, world, num_nodes, out2, row);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+int rlsb_best_record(const int64_t* vs, const uint8_t* xs, int64_t num_envs, int32_t num_nodes, int64_t env_offset,
+                     uint8_t* record, void* stream) {
+  using namespace rlsb;
+  RLSB_REQUIRE(num_envs > 0 && num_nodes >= 0 && env_offset >= 0 && env_offset + num_envs <= 0xFFFFFFFFll,
+               RLSB_ERR_INVALID, "best_record: bad shape (global env ids must fit 32 bits, at least one env)");
+  RLSB_REQUIRE(vs && xs && record, RLSB_ERR_INVALID, "best_record: null pointer");
+  RLSB_REQUIRE((reinterpret_cast<uintptr_t>(record) & 7u) == 0, RLSB_ERR_INVALID, "best_record: record must be 8-byte aligned");
+  best_record_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(vs, xs, num_envs, num_nodes, env_offset, record);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
 
 int rlsb_select_rows(uint8_t* xs0, int64_t* vs0, const uint8_t* xs1, const int64_t* vs1, int64_t num_envs,
                      int32_t num_nodes, int32_t maximize, void* stream) {

@@ -28,18 +28,38 @@ def decode_key(key: int) -> Tuple[int, int]:
     return key >> 32, _LOW - (key & _LOW)
 
 
-def best_allreduce(vs: TEN, xs: TEN, rank: int, world: int, envs_per_rank: int, group=None):
-    """Returns (best_cut int64 [], global_env_id int64 [], best_x bool [N]) as tensors on the
-    input's device -- identical on every rank.  No `.item()`: nothing here blocks the host."""
+def _local_record(vs: TEN, xs: TEN, rank: int, envs_per_rank: int) -> TEN:
+    """uint8 [8 + N]: key of the best local row, then the row."""
+    n = xs.shape[1]
+    if vs.is_cuda and vs.dtype == th.int64 and xs.dtype == th.bool and vs.is_contiguous() and xs.is_contiguous():
+        from . import _lib                      # one kernel instead of a dozen tiny torch ops
+        record = th.empty((8 + n,), dtype=th.uint8, device=vs.device)
+        _lib.check(_lib.lib().rlsb_best_record(vs.data_ptr(), xs.data_ptr(), vs.shape[0], n, rank * envs_per_rank,
+                                               record.data_ptr(), th.cuda.current_stream(vs.device).cuda_stream),
+                   "best_record")
+        return record
     gid = th.arange(vs.shape[0], device=vs.device, dtype=th.int64) + rank * envs_per_rank
     keys = (vs.to(th.int64) << 32) | (_LOW - gid)
     local = keys.argmax()                         # keys are distinct (they embed the env id)
-    record = th.cat([keys[local].reshape(1).view(th.uint8), xs[local].view(th.uint8)])
+    return th.cat([keys[local].reshape(1).view(th.uint8), xs[local].view(th.uint8)])
+
+
+def best_allreduce(vs: TEN, xs: TEN, rank: int, world: int, envs_per_rank: int, group=None):
+    """Returns (best_cut int64 [], global_env_id int64 [], best_x bool [N]) as tensors on the
+    input's device -- identical on every rank.  No `.item()`: nothing here blocks the host."""
+    record = _local_record(vs, xs, rank, envs_per_rank)
     if world > 1:
         gathered = th.empty((world, record.numel()), dtype=th.uint8, device=vs.device)
         dist.all_gather_into_tensor(gathered, record.unsqueeze(0), group=group)
     else:
         gathered = record.unsqueeze(0)
+    if gathered.is_cuda:
+        from . import _lib
+        out2 = th.empty((2,), dtype=th.int64, device=vs.device)
+        row = th.empty((xs.shape[1],), dtype=th.bool, device=vs.device)
+        _lib.check(_lib.lib().rlsb_best_pick(gathered.data_ptr(), gathered.shape[0], xs.shape[1], out2.data_ptr(),
+                                             row.data_ptr(), th.cuda.current_stream(vs.device).cuda_stream), "best_pick")
+        return out2[0], out2[1], row
     all_keys = gathered[:, :8].contiguous().view(th.int64).reshape(-1)
     win = all_keys.argmax()
     key = all_keys[win]
