@@ -224,6 +224,35 @@ int64_t rlsb_qubo_workspace_bytes(const rlsb_qubo_t* h, int64_t num_chains);
 int rlsb_qubo_energy(const rlsb_qubo_t* h, const float* x, int64_t num_chains, float* energy, void* workspace,
                      void* stream);
 
+/* ---- pattern-I environment with one graph per environment: SpinSystemUnbiased of
+ * rlsolver/methods/ECO_S2V/src/envs/spinsystem_PECO.py (reset 151-193, step 306-486).
+ * matrix: float32 [E][N][N], symmetric (the reference's generators produce symmetric matrices);
+ * spins are +-1 floats; state is the reference's observation block float32 [E][num_obs][N] whose
+ * row 0 is the spin state.
+ * peco_fields: as[e][j] = (A s)_j, fields[e][j] = s_j (A s)_j (_get_immeditate_cuts_avaialable,
+ *   660-662), cut[e] = calculate_cut (601-607); each output nullable.
+ * peco_step: flips state[e][0][action[e]], updates the resident (A s) by one matrix row, score +=
+ *   -fields_new[action], reward (reward_signal 1 DENSE, 2 BLS, 4 CUSTOM_BLS; / N if norm_rewards;
+ *   stag punishment / basin reward against the visited-state history), best_score / best_spins, and
+ *   rewrites the observables in place.  h_obs_rows: HOST int32[7] = state row of
+ *   {IMMEDIATE_REWARD_AVAILABLE, TIME_SINCE_FLIP, EPISODE_TIME, TERMINATION_IMMANENCY,
+ *   NUMBER_OF_GREEDY_ACTIONS_AVAILABLE, DISTANCE_FROM_BEST_SCORE, DISTANCE_FROM_BEST_STATE}, -1 =
+ *   absent.  inv_steps = float32(1/max_steps); termination = the TERMINATION_IMMANENCY value of
+ *   this step (a host scalar).  history: uint32 [capacity][E][ceil(N/32)] (nullable), hist_len =
+ *   states recorded since reset; the kernel appends the new state at index hist_len.
+ *   scalar_div_as_cuda: the reference divides by the Python scalar n_spins in two places; torch's CUDA
+ *   kernel multiplies by the float32 reciprocal there, torch's CPU kernel divides (1 ulp apart): 1
+ *   reproduces the reference running on a GPU, 0 the reference running on the CPU (the goldens).
+ *   Infinite memory (memory_length None), reversible spins, ExtraAction.NONE only. */
+int rlsb_peco_fields(const float* matrix, const float* spins, int64_t num_envs, int32_t num_spins, float* as,
+                     float* fields, float* cut, void* stream);
+int rlsb_peco_step(const float* matrix, float* state, float* as, const int64_t* action, float* score,
+                   float* best_score, float* best_spins, const float* max_local, float* reward, uint32_t* history,
+                   int32_t hist_len, int32_t* bad_actions, int64_t num_envs, int32_t num_spins, int32_t num_obs,
+                   const int32_t* h_obs_rows, int32_t reward_signal, int32_t norm_rewards, float inv_steps,
+                   float termination, int32_t use_stag, float stag, int32_t use_basin, float basin,
+                   int32_t scalar_div_as_cuda, void* stream);
+
 /* ---- select ops on the reference's bool layout
  * select_rows: update_xs_by_vs (util_read_data.py:190-202): rows of (xs1,vs1) replace
  *   rows of (xs0,vs0) where vs1 >= vs0 (<= when maximize == 0).

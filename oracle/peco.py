@@ -1,0 +1,113 @@
+"""NumPy (float32) restatement of the reference's PECO pattern-I environment.  TEST INFRASTRUCTURE ONLY.
+SpinSystemUnbiased of rlsolver/methods/ECO_S2V/src/envs/spinsystem_PECO.py: _reset_state (212-236),
+step (306-486), calculate_cut (601-607), _get_immeditate_cuts_avaialable (660-662); HistoryBuffer.update of
+util_envs_PECO.py:262-288.  Configuration subset: unbiased, ExtraAction.NONE, reversible spins, infinite
+memory, reward signals DENSE / BLS / CUSTOM_BLS.  Observables are named as in util_envs.py:40-51."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+
+f32 = np.float32
+SPIN, IMM, TSF, EPT, TERM, GREEDY, DSCORE, DSTATE = range(1, 9)       # Observable enum values
+DENSE, BLS, CUSTOM_BLS = 1, 2, 4
+
+
+def fields(matrix: np.ndarray, spins: np.ndarray) -> np.ndarray:
+    """matmul(matrix, spins) * spins per env (660-662)."""
+    return (np.einsum("ejk,ek->ej", matrix.astype(f32), spins.astype(f32)).astype(f32) * spins).astype(f32)
+
+
+def cut(matrix: np.ndarray, spins: np.ndarray) -> np.ndarray:
+    """(1/4) * sum(matmul(A, s) * -s) + (1/4) * sum(A) (601-607)."""
+    t = (np.einsum("ejk,ek->ej", matrix.astype(f32), spins.astype(f32)).astype(f32) * -spins).sum(axis=-1, dtype=f32)
+    return (f32(0.25) * t + f32(0.25) * matrix.sum(axis=(-1, -2), dtype=f32)).astype(f32)
+
+
+class SpinSystem:
+    def __init__(self, matrix, spins, observables: List[int], max_steps: int, reward_signal: int, norm_rewards: bool,
+                 horizon_length: Optional[int] = None, stag_punishment=None, basin_reward=None,
+                 scalar_div_as_cuda: bool = False):
+        self.m = matrix.astype(f32)
+        self.e, self.n = spins.shape
+        self.obs = list(enumerate(observables))
+        self.max_steps, self.reward_signal, self.norm = max_steps, reward_signal, norm_rewards
+        self.horizon = horizon_length if horizon_length is not None else max_steps
+        self.stag, self.basin = stag_punishment, basin_reward
+        # x / n_spins: torch CPU divides; torch CUDA multiplies by float32(1/n) (div_true_kernel_cuda)
+        self.div_n = (lambda x: (x * (f32(1) / f32(self.n))).astype(f32)) if scalar_div_as_cuda else \
+            (lambda x: (x / f32(self.n)).astype(f32))
+        self.current_step = 0
+        ones = np.ones((self.e, self.n), f32)
+        self.max_local = fields(self.m, ones).max(axis=-1)
+        self.state = np.zeros((self.e, len(observables), self.n), f32)
+        self.state[:, 0, :] = spins
+        imm = fields(self.m, spins)
+        for idx, o in self.obs:
+            if o == IMM:
+                self.state[:, idx, :] = imm / self.max_local[:, None]
+            elif o == GREEDY:
+                self.state[:, idx, :] = (f32(1) - self.div_n((imm <= 0).sum(axis=-1).astype(f32)))[:, None]
+        self.score = cut(self.m, spins)
+        self.best_score = self.score.copy()
+        self.best_spins = spins.astype(f32).copy()
+        self.history: List[np.ndarray] = []
+
+    def step(self, action: np.ndarray):
+        self.current_step += 1
+        rows = np.arange(self.e)
+        st = self.state
+        st[rows, 0, action] = -st[rows, 0, action]
+        spins = st[:, 0, :]
+        imm = fields(self.m, spins)
+        delta = -imm[rows, action]
+        self.score = (self.score + delta).astype(f32)
+        improvement = (self.score - self.best_score).astype(f32)          # best_obs_score == best_score (infinite memory)
+        if self.reward_signal == BLS:
+            rew = np.where(improvement > 0, improvement, f32(0)).astype(f32)
+        elif self.reward_signal == CUSTOM_BLS:
+            rew = np.where(improvement > 0, improvement / (improvement + f32(0.1)), f32(0)).astype(f32)
+        else:
+            rew = delta.astype(f32)
+        if self.norm:
+            rew = self.div_n(rew)
+        if self.stag is not None or self.basin is not None:
+            key = [tuple(r) for r in (spins > 0)]
+            if not self.history:
+                fresh = np.ones(self.e, bool)
+            else:
+                fresh = np.asarray([all(key[e] != h[e] for h in self.history) for e in range(self.e)])
+            self.history.append(key)
+            if self.stag is not None:
+                rew[~fresh] = (rew[~fresh] - f32(self.stag)).astype(f32)
+            if self.basin is not None:
+                mask = (imm <= 0).all(axis=-1) & fresh
+                rew[mask] = (rew[mask] + f32(self.basin)).astype(f32)
+        better = self.score > self.best_score
+        self.best_score = np.where(better, self.score, self.best_score).astype(f32)
+        self.best_spins = np.where(better[:, None], spins, self.best_spins).astype(f32)
+        for idx, o in self.obs:
+            if o == IMM:
+                st[:, idx, :] = imm / self.max_local[:, None]
+            elif o == TSF:
+                st[:, idx, :] = (st[:, idx, :] + f32(1. / self.max_steps)).astype(f32)
+                st[rows, idx, action] = 0
+            elif o == EPT:
+                st[:, idx, :] = (st[:, idx, :] + f32(1. / self.max_steps)).astype(f32)
+            elif o == TERM:
+                st[:, idx, :] = max(f32(0), f32((self.current_step - self.max_steps) / self.horizon) + f32(1))
+            elif o == GREEDY:
+                st[:, idx, :] = (f32(1) - self.div_n((imm <= 0).sum(axis=-1).astype(f32)))[:, None]
+            elif o == DSCORE:
+                st[:, idx, :] = (np.abs(self.score - self.best_score) / self.max_local)[:, None]
+            elif o == DSTATE:
+                st[:, idx, :] = np.count_nonzero(self.best_spins - spins, axis=-1).astype(f32)[:, None]
+        done = np.full(self.e, self.current_step == self.max_steps)
+        return rew, done
+
+    def observation(self, binary: bool) -> np.ndarray:
+        state = self.state.copy()
+        if binary:
+            state[:, 0, :] = (1 - state[:, 0, :]) / 2
+        return np.concatenate([state, self.m], axis=-2)
