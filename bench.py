@@ -306,9 +306,10 @@ def run_b200(args):
     cb = 1 if max(sim.store.max_listed_degree, sim.store.max_full_degree) <= 255 else 2   # cross-count bytes
     graph_b = 4 * sim.num_edges + 2 * sim.store.num_full + 12 * np_
     alg_bytes = {   # algorithmic bytes per launch group, DESIGN.md "Kernels"
-        # noise + cross counts per iteration; packed tile in/out, bool rows + values out, graph once
-        "ls_search": NUM_ITERS * (4 * envs * n + cb * envs * np_) + 2 * envs * np_ // 8 + envs * n + 16 * envs
-                     + graph_b,
+        # ls_run: noise + cross counts per pass (threshold pass + NUM_ITERS iterations); packed tile in/out,
+        # thresholds, bool rows + values out, graph once
+        "ls_search": (1 + NUM_ITERS) * (4 * envs * n + cb * envs * np_) + 2 * envs * np_ // 8 + envs * n + 20 * envs
+                     + 8 * np_ + graph_b,
         "ls_thresh": 4 * envs * n + cb * envs * np_ + 4 * envs + 8 * np_,
         "ls_begin": envs * n + envs * np_ // 8 + cb * envs * np_ + 8 * envs + graph_b,
         "pack_spins": envs * n + envs * np_ // 8,

@@ -98,7 +98,8 @@ int rlsb_node_cross_counts(const rlsb_graph_t* g, const uint32_t* packed, int64_
                            int32_t* col_min, int32_t* col_max, void* stream);
 
 /* ---- local search: EnvMaxcut.local_search_inplace (env_L2A.py:87-116) and
- * LocalSearch.random_search (LocalSearch.py:53-86) in four calls on one stream.  State between
+ * LocalSearch.random_search (LocalSearch.py:53-86) in two calls on one stream (ls_begin, ls_run;
+ * ls_thresh / ls_search are the two halves of ls_run for callers that want them apart).  State between
  * the calls lives in a caller-provided, 256-byte aligned device workspace of
  * rlsb_ls_workspace_bytes(g, E) bytes (returns -1 on a bad handle).
  *
@@ -118,10 +119,14 @@ int rlsb_node_cross_counts(const rlsb_graph_t* g, const uint32_t* packed, int64_
  *            Gauss-Seidel; O(2M) word operations per 32 envs instead of N full evaluations; the
  *            gain rule is the batched form of S2V_PPO/env.py:197-206), writes the bool rows to
  *            xs_out [E][N] and the final cut values to vs.  vs must be consistent with the state
- *            (vs[e] == cut of row e) when ls_begin was called with compute_vs == 0. */
+ *            (vs[e] == cut of row e) when ls_begin was called with compute_vs == 0.
+ * ls_run   : ls_thresh on thresh_noise (skipped when NULL; num_spin is then ignored) followed by
+ *            ls_search, fused into one launch per 16 noise tensors: a TMA-fed shared-memory ring
+ *            streams noise and cross counts, the next iteration's noise lands while the current
+ *            candidate is evaluated.  thresh_noise may alias h_noise_ptrs[0] (LocalSearch.py:68). */
 int64_t rlsb_ls_workspace_bytes(const rlsb_graph_t* g, int64_t num_envs);
 /* byte offset of a workspace section (tests / debugging): 0 packed u32 [W][Np], 1 cross counts
- * (uint8, or uint16 when a degree exceeds 255) [E][Np], 2 col_min i32 [Np], 3 col_max i32 [Np],
+ * (uint8, or uint16 when a degree exceeds 255) tiled [W][Np/4][32 envs][4 nodes], 2 col_min i32 [Np], 3 col_max i32 [Np],
  * 4 listed degree + 0x4B400000 i32 [Np], 5 rd_std f32 [Np], 6 thresh f32 [E]; -1 on error. */
 int64_t rlsb_ls_workspace_offset(const rlsb_graph_t* g, int64_t num_envs, int32_t section);
 int rlsb_ls_begin(const rlsb_graph_t* g, const uint8_t* xs, int64_t num_envs, int64_t* vs, int32_t compute_vs,
@@ -131,6 +136,14 @@ int rlsb_ls_thresh(const rlsb_graph_t* g, int64_t num_envs, int32_t ws_mult, con
 int rlsb_ls_search(const rlsb_graph_t* g, int64_t num_envs, int64_t* vs, int32_t ws_mult,
                    const float* const* h_noise_ptrs, int32_t num_iters, int32_t finish, uint8_t* xs_out,
                    void* workspace, void* stream);
+int rlsb_ls_run(const rlsb_graph_t* g, int64_t num_envs, int64_t* vs, int32_t ws_mult, const float* thresh_noise,
+                int32_t num_spin, const float* const* h_noise_ptrs, int32_t num_iters, int32_t finish,
+                uint8_t* xs_out, void* workspace, void* stream);
+
+/* profiling aid: with RLSB_LS_TIMES=1 in the environment CTA 0 of every pipelined ls_run launch
+ * records clock64 stamps (start, then per pass: candidate done / accepted, then finish done);
+ * this copies the 64 slots out (host pointer).  RLSB_ERR_INVALID when the variable is unset. */
+int rlsb_ls_debug_times(int64_t* out64);
 
 /* ---- the exhaustive single-flip pass alone, on packed tiles (vs is recomputed) */
 int rlsb_flip_sweep(const rlsb_graph_t* g, uint32_t* packed, int64_t* vs, int64_t num_envs, void* stream);

@@ -107,6 +107,8 @@ SIGNATURES = {
     "rlsb_ls_begin": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _f32, _vp, _vp]),
     "rlsb_ls_thresh": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp]),
     "rlsb_ls_search": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "rlsb_ls_debug_times": (C.c_int, [_vp]),
+    "rlsb_ls_run": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
     "rlsb_flip_sweep": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "rlsb_step_flip": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "rlsb_greedy_best_flip": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp]),

@@ -16,6 +16,7 @@ namespace rlsb {
 
 constexpr int kPrepThreads = 512;
 
+// Row-major layout [E][Np] (the public rlsb_node_cross_counts result).
 template <int P, typename CrossT>
 __device__ __forceinline__ void store_cross(const VCount<P>& vc, CrossT* __restrict__ cross, int64_t env0, int valid,
                                             int np, int i) {
@@ -39,14 +40,46 @@ __device__ __forceinline__ void store_cross(const VCount<P>& vc, CrossT* __restr
   }
 }
 
+// Tiled layout of the local-search workspace: per tile [node/4][env][node%4], so that the search
+// kernel's lane (= env) finds the 4 counts of a node group in one word and a warp reads 128
+// contiguous bytes.  Lane = node holds, per q, the counts of envs 4q..4q+3 as 4 bytes; a 4x4 byte
+// transpose among the 4 lanes of a node group (2 shuffles) turns that into "4 nodes of one env",
+// which is one aligned 4-byte store.  All 32 env slots are written (idle envs count 0).
+template <int P, typename CrossT>
+__device__ __forceinline__ void store_cross_tiled(const VCount<P>& vc, CrossT* __restrict__ cross, int64_t tile,
+                                                  int np, int i, int lane) {
+  CrossT* tbase = cross + tile * (int64_t)np * kTileEnvs;
+  if (sizeof(CrossT) == 1) {
+    const int j = lane & 3;
+    uint32_t* gbase = reinterpret_cast<uint32_t*>(tbase) + (i >> 2) * kTileEnvs;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint32_t x = vc.bytes4(q);
+      uint32_t y = __shfl_xor_sync(kFull, x, 2);
+      x = (j & 2) ? __byte_perm(x, y, 0x3276) : __byte_perm(x, y, 0x5410);
+      y = __shfl_xor_sync(kFull, x, 1);
+      x = (j & 1) ? __byte_perm(x, y, 0x3715) : __byte_perm(x, y, 0x6240);
+      gbase[4 * q + j] = x;      // env 4q+j, nodes 4*(i/4) .. +3
+    }
+  } else {
+    CrossT* gbase = tbase + ((int64_t)(i >> 2) * kTileEnvs << 2) + (i & 3);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const uint32_t h = vc.halves2(q);
+      gbase[(2 * q) << 2] = (CrossT)(h & 0xffffu);
+      gbase[(2 * q + 1) << 2] = (CrossT)(h >> 16);
+    }
+  }
+}
+
 // VEC: 0 = packed input, 1 / 4 = bool rows read bytewise / as 4-byte words
 template <int P, typename CrossT, int VEC>
 __global__ void __launch_bounds__(kPrepThreads) prepare_kernel(GraphDev g, const uint8_t* __restrict__ xs,
                                                                const uint32_t* __restrict__ packed_in,
                                                                int64_t num_envs, uint32_t* __restrict__ packed_out,
-                                                               CrossT* __restrict__ cross, int32_t* col_min,
-                                                               int32_t* col_max, int64_t* __restrict__ vs,
-                                                               int cut_warps) {
+                                                               CrossT* __restrict__ cross, int tiled,
+                                                               int32_t* col_min, int32_t* col_max,
+                                                               int64_t* __restrict__ vs, int cut_warps) {
   extern __shared__ uint32_t sP[];
   __shared__ int sCnt[kTileEnvs];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -73,7 +106,10 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_kernel(GraphDev g, const
         const int i = slice * 32 + lane;
         VCount<P> vc;
         sell_cross<P, false>(g.listed, slice, lane, sP, sP[i], vc);
-        if (cross) store_cross<P, CrossT>(vc, cross, env0, valid, g.np, i);
+        if (cross) {
+          if (tiled) store_cross_tiled<P, CrossT>(vc, cross, tile, g.np, i, lane);
+          else store_cross<P, CrossT>(vc, cross, env0, valid, g.np, i);
+        }
         if (col_min && i < g.n) {
           atomicMin(col_min + i, (int)vc.min_over(vmask));
           atomicMax(col_max + i, (int)vc.max_over(vmask));
@@ -93,15 +129,15 @@ __global__ void fill_minmax_kernel(int32_t* mn, int32_t* mx, int n) {
 
 template <int P, typename CrossT, int VEC>
 static int launch_prepare(const GraphDev& g, const uint8_t* xs, const uint32_t* packed_in, int64_t num_envs,
-                          uint32_t* packed_out, CrossT* cross, int32_t* col_min, int32_t* col_max, int64_t* vs,
-                          cudaStream_t st) {
+                          uint32_t* packed_out, CrossT* cross, int tiled, int32_t* col_min, int32_t* col_max,
+                          int64_t* vs, cudaStream_t st) {
   const size_t smem = (size_t)g.np * sizeof(uint32_t);
   auto kernel = prepare_kernel<P, CrossT, VEC>;
   if (smem > 48 * 1024)
     RLSB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;
   const unsigned grid = (unsigned)(tiles < 8 * kNumSMs ? tiles : 8 * kNumSMs);
-  kernel<<<grid, kPrepThreads, smem, st>>>(g, xs, packed_in, num_envs, packed_out, cross, col_min, col_max, vs,
+  kernel<<<grid, kPrepThreads, smem, st>>>(g, xs, packed_in, num_envs, packed_out, cross, tiled, col_min, col_max, vs,
                                            cut_warps_for(g.m, kPrepThreads / 32));
   RLSB_LAUNCH_OK();
   return RLSB_OK;
@@ -109,29 +145,32 @@ static int launch_prepare(const GraphDev& g, const uint8_t* xs, const uint32_t* 
 
 template <typename CrossT, int VEC>
 static int dispatch_planes(const GraphDev& g, const uint8_t* xs, const uint32_t* packed_in, int64_t num_envs,
-                           uint32_t* packed_out, CrossT* cross, int32_t* col_min, int32_t* col_max, int64_t* vs,
-                           cudaStream_t st) {
+                           uint32_t* packed_out, CrossT* cross, int tiled, int32_t* col_min, int32_t* col_max,
+                           int64_t* vs, cudaStream_t st) {
   if (g.max_listed_deg <= 63)
-    return launch_prepare<6, CrossT, VEC>(g, xs, packed_in, num_envs, packed_out, cross, col_min, col_max, vs, st);
+    return launch_prepare<6, CrossT, VEC>(g, xs, packed_in, num_envs, packed_out, cross, tiled, col_min, col_max, vs, st);
   if (g.max_listed_deg <= 255)
-    return launch_prepare<8, CrossT, VEC>(g, xs, packed_in, num_envs, packed_out, cross, col_min, col_max, vs, st);
+    return launch_prepare<8, CrossT, VEC>(g, xs, packed_in, num_envs, packed_out, cross, tiled, col_min, col_max, vs, st);
   if (sizeof(CrossT) == 1) {
     set_error("prepare: listed degree %d needs uint16 counts", g.max_listed_deg);
     return RLSB_ERR_INVALID;
   }
-  return launch_prepare<12, CrossT, VEC>(g, xs, packed_in, num_envs, packed_out, cross, col_min, col_max, vs, st);
+  return launch_prepare<12, CrossT, VEC>(g, xs, packed_in, num_envs, packed_out, cross, tiled, col_min, col_max, vs, st);
 }
 
-// Used by rlsb_ls_begin (local_search.cu).  cross_is_u8 selects the element type of `cross`.
+// Used by rlsb_ls_begin (local_search.cu).  cross_layout: 0 = uint16 [E][Np] row-major,
+// 1 = uint8 tiled, 2 = uint16 tiled (store_cross_tiled).
 int prepare_tiles(const GraphDev& g, const uint8_t* xs, const uint32_t* packed_in, int64_t num_envs,
-                  uint32_t* packed_out, void* cross, bool cross_is_u8, int32_t* col_min, int32_t* col_max, int64_t* vs,
+                  uint32_t* packed_out, void* cross, int cross_layout, int32_t* col_min, int32_t* col_max, int64_t* vs,
                   cudaStream_t st) {
+  const bool cross_is_u8 = cross_layout == 1;
+  const int tiled = cross_layout != 0;
   if (col_min && g.n > 0) {
     fill_minmax_kernel<<<(g.n + 255) / 256, 256, 0, st>>>(col_min, col_max, g.n);
     RLSB_LAUNCH_OK();
   }
   if (num_envs == 0 || g.n == 0) return RLSB_OK;
-#define RLSB_PREP(T, V) dispatch_planes<T, V>(g, xs, packed_in, num_envs, packed_out, (T*)cross, col_min, col_max, vs, st)
+#define RLSB_PREP(T, V) dispatch_planes<T, V>(g, xs, packed_in, num_envs, packed_out, (T*)cross, tiled, col_min, col_max, vs, st)
   if (packed_in) return cross_is_u8 ? RLSB_PREP(uint8_t, 0) : RLSB_PREP(uint16_t, 0);
   if (rows_vec4_ok(xs, g.n)) return cross_is_u8 ? RLSB_PREP(uint8_t, 4) : RLSB_PREP(uint16_t, 4);
   return cross_is_u8 ? RLSB_PREP(uint8_t, 1) : RLSB_PREP(uint16_t, 1);
@@ -149,6 +188,6 @@ extern "C" int rlsb_node_cross_counts(const rlsb_graph_t* gh, const uint32_t* pa
   RLSB_REQUIRE((col_min == nullptr) == (col_max == nullptr), RLSB_ERR_INVALID,
                "node_cross_counts: col_min and col_max must both be given or both be null");
   RLSB_REQUIRE(num_envs == 0 || g->n == 0 || (packed && cross), RLSB_ERR_INVALID, "node_cross_counts: null pointer");
-  return prepare_tiles(*g, nullptr, packed, num_envs, nullptr, cross, false, col_min, col_max, nullptr,
+  return prepare_tiles(*g, nullptr, packed, num_envs, nullptr, cross, 0, col_min, col_max, nullptr,
                        static_cast<cudaStream_t>(stream));
 }

@@ -44,7 +44,7 @@ int graph_check(const rlsb_graph_t* g, const GraphDev** out, const char* what) {
 }
 
 int cut_warps_for(int64_t m, int max_warps) {
-  int64_t w = (m + 2047) / 2048;          // >= 64 edges per lane before another warp joins
+  int64_t w = (m + 1023) / 1024;          // >= 32 edges per lane before another warp joins
   if (w < 1) w = 1;
   return int(w < max_warps ? w : max_warps);
 }

@@ -1,34 +1,48 @@
 // Local search: the three phases of EnvMaxcut.local_search_inplace
 // (rlsolver/envs/env_L2A.py:87-116) and LocalSearch.random_search
-// (rlsolver/methods/LocalSearch.py:53-86) as four launches:
+// (rlsolver/methods/LocalSearch.py:53-86) as three launches:
 //
 //   ls_begin   (cross_counts.cu prepare_kernel) pack + objective + per-node cross counts + their
 //              max/min over the env batch (the `ws_std` coupling, env_L2A.py:92-93)
 //   ls_rdstd   rd_std[i] = float(mult * (max_i - min_i)) * noise_std                  (N floats)
-//   ls_thresh  kth-value threshold of the noise-perturbed weights (env_L2A.py:94-96)
-//   ls_search  ALL noisy multi-flip iterations (97-107) + the exhaustive single-flip pass
-//              (110-115) + unpack, one CTA per tile of 32 envs, state in shared memory.  Only the
-//              float32 noise (4 B per env-node-iteration) and the 1-byte cross counts stream in.
+//   ls_run     kth-value threshold of the noise-perturbed weights (env_L2A.py:94-96), ALL noisy
+//              multi-flip iterations (97-107), the exhaustive single-flip pass (110-115) and the
+//              unpack -- one CTA per tile of 32 envs, state in shared memory.
+//
+// ls_run is a producer/consumer pipeline.  Everything that streams -- the float32 noise (4 B per
+// env-node-pass, the HBM traffic of this path) and the 1-byte cross counts -- is moved by the TMA
+// engine: one producer thread issues, per 128-node chunk, ONE tensor copy of the 32-env x 128-node
+// noise box (3-D tensor map {16 floats, env rows, N/16 column groups}, 64-byte swizzle) plus one
+// bulk copy of the chunk's cross counts into a shared-memory ring and runs ahead across passes,
+// so the next iteration's noise lands while the 16 consumer warps evaluate the cut of the current
+// candidate.  (Per-row 512-byte bulk copies were tried first: the copy engine retires only about
+// one small copy per ~85 cycles per SM and the consumers starved.)  Consumers work lane = env:
+// one conflict-free LDS.128 gives a lane 4 nodes of its env, the compare result of the 32 lanes
+// is one BALLOT = the 32-env flip word of a node.
 //
 // Floating point: spin_rand = ws + noise * rd_std is evaluated exactly as the reference's torch
 // kernels do -- one IEEE round-to-nearest multiply, one add, no FMA contraction; float(ws) is
 // exact (small integer).
+#include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "tile_ops.cuh"
 
 namespace rlsb {
 
 int prepare_tiles(const GraphDev& g, const uint8_t* xs, const uint32_t* packed_in, int64_t num_envs,
-                  uint32_t* packed_out, void* cross, bool cross_is_u8, int32_t* col_min, int32_t* col_max, int64_t* vs,
+                  uint32_t* packed_out, void* cross, int cross_layout, int32_t* col_min, int32_t* col_max, int64_t* vs,
                   cudaStream_t st);
 
 // float(k) for |k| < 2^22 without the conversion pipe: 0x4B400000 is 12582912.0f (1.5 * 2^23)
 constexpr int kMagicI = 0x4B400000;
 constexpr float kMagicF = 12582912.0f;
 
-__device__ __forceinline__ float spin_rand(int degm, int mult, int cross, float noise, float rd_std) {
-  const float wsf = __fadd_rn(__int_as_float(degm - mult * cross), -kMagicF);   // exact float(deg - mult*cross)
+// degm = listed degree + kMagicI, negmult = -mult
+__device__ __forceinline__ float spin_rand(int degm, int negmult, int cross, float noise, float rd_std) {
+  const float wsf = __fadd_rn(__int_as_float(cross * negmult + degm), -kMagicF);   // exact float(deg - mult*cross)
   return __fadd_rn(wsf, __fmul_rn(noise, rd_std));
 }
 
@@ -41,18 +55,23 @@ __device__ __forceinline__ float key_float(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// cross counts of VEC consecutive nodes, kept packed until they are used
-template <typename CrossT, int VEC>
-struct CrossVec {
+// Cross counts of the local-search workspace are stored per tile as [node/4][env][node%4]
+// (kCrossTiled, cross_counts.cu): the 4 counts a lane (= env) needs for one node group are one
+// word (uint8) / two words (uint16), and a warp reads 128 / 256 contiguous bytes.
+template <typename CrossT>
+__device__ __forceinline__ int cross_at(const CrossT* __restrict__ cross_tile, int i, int e) {
+  return (int)__ldg(cross_tile + (((i >> 2) * kTileEnvs + e) << 2) + (i & 3));
+}
+
+template <typename CrossT>
+struct Cross4 {
   uint32_t lo, hi;
-  __device__ __forceinline__ void load(const CrossT* p) {
-    if constexpr (VEC == 4 && sizeof(CrossT) == 1) {
-      lo = __ldg(reinterpret_cast<const uint32_t*>(p)), hi = 0;
-    } else if constexpr (VEC == 4) {
-      const uint2 c = __ldg(reinterpret_cast<const uint2*>(p));
-      lo = c.x, hi = c.y;
+  __device__ __forceinline__ void load_shared(const char* p) {   // p -> the lane's 4 counts
+    if constexpr (sizeof(CrossT) == 1) {
+      lo = *reinterpret_cast<const uint32_t*>(p), hi = 0;
     } else {
-      lo = (uint32_t)__ldg(p), hi = 0;
+      const uint2 c = *reinterpret_cast<const uint2*>(p);
+      lo = c.x, hi = c.y;
     }
   }
   __device__ __forceinline__ int get(int b) const {
@@ -70,24 +89,15 @@ __global__ void ls_rdstd_kernel(GraphDev g, const int32_t* __restrict__ col_min,
   degm[i] = (real ? g.listed_deg[i] : 0) + kMagicI;
 }
 
-// ---------------------------------------------------------------- thresh (kthvalue)
-// One warp per environment.  Each lane keeps the KMAX largest values of its share in a sorted
-// register list; the lists are then merged by K rounds of warp-max.
-template <int KMAX, typename CrossT, int VEC>
-__global__ void __launch_bounds__(256) ls_thresh_kernel(GraphDev g, const CrossT* __restrict__ cross,
-                                                        const float* __restrict__ rd_std,
-                                                        const int32_t* __restrict__ degm, int mult,
-                                                        const float* __restrict__ noise, int kth_big,
-                                                        int64_t num_envs, float* __restrict__ thresh) {
-  const int lane = threadIdx.x & 31;
-  const int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (env >= num_envs) return;
-  float top[KMAX];
+// sorted (descending) list of the KMAX largest values seen
+template <int KMAX>
+struct TopList {
+  float top[KMAX > 0 ? KMAX : 1];
+  __device__ __forceinline__ void clear() {
 #pragma unroll
-  for (int t = 0; t < KMAX; ++t) top[t] = -INFINITY;
-  const CrossT* crow = cross + env * (int64_t)g.np;
-  const float* nrow = noise + env * (int64_t)g.n;
-  auto push = [&](float s) {
+    for (int t = 0; t < KMAX; ++t) top[t] = -INFINITY;
+  }
+  __device__ __forceinline__ void push(float s) {
     if (s > top[KMAX - 1]) {
 #pragma unroll
       for (int t = 0; t < KMAX; ++t) {
@@ -96,41 +106,67 @@ __global__ void __launch_bounds__(256) ls_thresh_kernel(GraphDev g, const CrossT
         top[t] = hi;
       }
     }
-  };
-  if (VEC == 4) {
-    for (int i = lane * 4; i < g.n; i += 128) {
-      const float4 nz = ldg_stream4(nrow + i);
-      const float4 rd = __ldg(reinterpret_cast<const float4*>(rd_std + i));
-      const int4 dm = __ldg(reinterpret_cast<const int4*>(degm + i));
-      CrossVec<CrossT, 4> cv;
-      cv.load(crow + i);
-      const int c0 = cv.get(0), c1 = cv.get(1), c2 = cv.get(2), c3 = cv.get(3);
-      push(spin_rand(dm.x, mult, c0, nz.x, rd.x));
-      push(spin_rand(dm.y, mult, c1, nz.y, rd.y));
-      push(spin_rand(dm.z, mult, c2, nz.z, rd.z));
-      push(spin_rand(dm.w, mult, c3, nz.w, rd.w));
-    }
-  } else {
-    for (int i = lane; i < g.n; i += 32)
-      push(spin_rand(__ldg(degm + i), mult, (int)__ldg(crow + i), ldg_stream(nrow + i), __ldg(rd_std + i)));
   }
+  __device__ __forceinline__ void pop() {
+#pragma unroll
+    for (int t = 0; t + 1 < KMAX; ++t) top[t] = top[t + 1];
+    top[KMAX - 1] = -INFINITY;
+  }
+};
+
+// ---------------------------------------------------------------- generic thresh (kthvalue)
+// Fallback for rows that are not 16-byte aligned (N % 4 != 0).  One warp per environment; each
+// lane keeps the KMAX largest values of its share; the lists are merged by K rounds of warp-max.
+template <int KMAX, typename CrossT>
+__global__ void __launch_bounds__(256) ls_thresh_kernel(GraphDev g, const CrossT* __restrict__ cross,
+                                                        const float* __restrict__ rd_std,
+                                                        const int32_t* __restrict__ degm, int mult,
+                                                        const float* __restrict__ noise, int kth_big,
+                                                        int64_t num_envs, float* __restrict__ thresh) {
+  const int lane = threadIdx.x & 31;
+  const int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (env >= num_envs) return;
+  TopList<KMAX> tl;
+  tl.clear();
+  const CrossT* ctile = cross + (env / kTileEnvs) * (int64_t)g.np * kTileEnvs;
+  const int e = (int)(env % kTileEnvs);
+  const float* nrow = noise + env * (int64_t)g.n;
+  for (int i = lane; i < g.n; i += 32)
+    tl.push(spin_rand(__ldg(degm + i), -mult, cross_at(ctile, i, e), ldg_stream(nrow + i), __ldg(rd_std + i)));
   uint32_t best = 0;
   for (int r = 0; r < kth_big; ++r) {
-    const uint32_t head = float_key(top[0]);
+    const uint32_t head = float_key(tl.top[0]);
     best = __reduce_max_sync(kFull, head);
     const unsigned who = __ballot_sync(kFull, head == best);
-    if (lane == __ffs(who) - 1) {
-#pragma unroll
-      for (int t = 0; t + 1 < KMAX; ++t) top[t] = top[t + 1];
-      top[KMAX - 1] = -INFINITY;
-    }
+    if (lane == __ffs(who) - 1) tl.pop();
   }
   if (lane == 0) thresh[env] = key_float(best);
 }
 
 // ---------------------------------------------------------------- fused search kernel
-constexpr int kLSThreads = 512;
-constexpr int kLSMaxIters = 16;   // noise tensors per launch (pointers travel by value)
+constexpr int kLSThreads = 512;                 // consumer threads
+constexpr int kLSWarps = kLSThreads / 32;
+constexpr int kPipeThreads = kLSThreads + 32;   // + the producer warp
+constexpr int kLSMaxIters = 16;                 // noise tensors per launch (pointers travel by value)
+constexpr int kChunkGroups = 32;                // node groups (of 4 nodes) per pipeline chunk
+constexpr int kChunkG16 = kChunkGroups / 4;     // the same in 16-float column groups (tensor-map dim 2)
+// noise box in shared memory: [column group of 16 floats][env row][64 B], 16-byte pieces swizzled
+// by the TMA engine (SWIZZLE_64B: piece ^= (address >> 7) & 3) -- lane = env reads are conflict free
+constexpr int kNoiseStageBytes = kChunkG16 * kTileEnvs * 64;  // 16384
+constexpr int kMaxStages = 8;
+
+struct TmapPack {
+  CUtensorMap m[kLSMaxIters + 1];   // [0]: thresh noise, [1 + k]: noise of iteration k
+};
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 struct NoisePtrs {
   const float* p[kLSMaxIters];
 };
@@ -138,88 +174,37 @@ struct NoisePtrs {
 struct LsArgs {
   uint32_t* packed;        // [W][Np] in/out (workspace)
   int64_t* vs;             // [E] in/out
-  const void* cross;       // [E][Np] uint8 / uint16
+  const void* cross;       // [W][Np/4][32][4] uint8 / uint16
   const float* rd_std;     // [Np]
   const int32_t* degm;     // [Np] listed degree + kMagicI
-  const float* thresh;     // [E]
+  float* thresh;           // [E]
+  const float* thresh_noise;   // non-null: first compute thresh from this tensor
   NoisePtrs noise;
-  int num_iters, mult;
+  int num_iters, mult, kth_big;
   int64_t num_envs;
   int finish;              // 1: run the single-flip pass and write the bool rows
   uint8_t* xs_out;         // [E][N] bool rows (finish)
+  int unpack_vec4;
   int cut_warps;
-  int stage_sweep;         // 1: the sweep structure fits in shared memory next to the two tile copies
+  int stage_sweep;         // 1: the sweep structure is staged into shared memory
   int sweep_warps;         // warps that take part in the single-flip pass
   int negmult;             // -mult
+  int stages, stage_bytes; // ring geometry (pipe kernel)
+  long long* times;        // debug: phase timestamps of CTA 0 (RLSB_LS_TIMES), else null
 };
 
-// Flip-mask of one noisy iteration for the whole tile, written as candidate = accepted ^ mask.
-// Work item = (4 consecutive nodes) x (8 consecutive envs): 8 coalesced 16-byte noise loads in
-// flight per thread, one result byte per node (byte g of a word = envs 8g..8g+7).
-template <typename CrossT, int VEC, bool FULL>
-__device__ __forceinline__ void noisy_candidate(const GraphDev& g, const LsArgs& a, const float* __restrict__ noise,
-                                                int64_t env0, int valid, const float* sThresh, const uint32_t* sP,
-                                                uint32_t* sX) {
-  // tile bases once (64-bit); everything inside the tile is a 32-bit offset (32 * N < 2^31)
-  const float* __restrict__ nbase = noise + env0 * (int64_t)g.n;
-  const CrossT* __restrict__ cbase = static_cast<const CrossT*>(a.cross) + env0 * (int64_t)g.np;
-  const uint32_t n = (uint32_t)g.n, np = (uint32_t)g.np;
-  const uint32_t groups = (n + VEC - 1) / VEC;        // node groups
-  const uint8_t* sPb = reinterpret_cast<const uint8_t*>(sP);
-  uint8_t* sXb = reinterpret_cast<uint8_t*>(sX);
-  const int negmult = a.negmult;
-  for (uint32_t task = threadIdx.x; task < groups * 4; task += blockDim.x) {
-    const uint32_t eg = task / groups, i0 = (task - eg * groups) * VEC;
-    const uint32_t e0 = eg * 8;
-    float rd[VEC];
-    int dm[VEC];
-    if constexpr (VEC == 4) {
-      const float4 r = __ldg(reinterpret_cast<const float4*>(a.rd_std + i0));
-      const int4 d = __ldg(reinterpret_cast<const int4*>(a.degm + i0));
-      rd[0] = r.x, rd[1] = r.y, rd[2] = r.z, rd[3] = r.w;
-      dm[0] = d.x, dm[1] = d.y, dm[2] = d.z, dm[3] = d.w;
-    } else {
-      rd[0] = __ldg(a.rd_std + i0), dm[0] = __ldg(a.degm + i0);
-    }
-    float nz[8][VEC];
-    CrossVec<CrossT, VEC> cr[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (FULL || (int)(e0 + j) < valid) {
-        const uint32_t no = (e0 + j) * n + i0, co = (e0 + j) * np + i0;
-        if constexpr (VEC == 4) {
-          const float4 v = ldg_stream4(nbase + no);
-          nz[j][0] = v.x, nz[j][1] = v.y, nz[j][2] = v.z, nz[j][3] = v.w;
-        } else {
-          nz[j][0] = ldg_stream(nbase + no);
-        }
-        cr[j].load(cbase + co);
-      } else {
-#pragma unroll
-        for (int b = 0; b < VEC; ++b) nz[j][b] = 0.f;
-        cr[j].lo = cr[j].hi = 0;
-      }
-    }
-    uint32_t bits[VEC];
-#pragma unroll
-    for (int b = 0; b < VEC; ++b) bits[b] = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float th = sThresh[e0 + j];      // +inf for envs past the batch: never flips
-#pragma unroll
-      for (int b = 0; b < VEC; ++b) {
-        // exact float(deg - mult*cross) via the magic-number add, then one multiply and one add
-        const float wsf = __fadd_rn(__int_as_float(cr[j].get(b) * negmult + dm[b]), -kMagicF);
-        const float sr = __fadd_rn(wsf, __fmul_rn(nz[j][b], rd[b]));
-        if (sr > th) bits[b] |= (1u << j);
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < VEC; ++b) {
-      const uint32_t at = (i0 + b) * 4 + eg;
-      sXb[at] = sPb[at] ^ (uint8_t)bits[b];
-    }
-  }
+__device__ __forceinline__ void stamp(const LsArgs& a, int& k) {
+  if (a.times && blockIdx.x == 0 && threadIdx.x == 0) a.times[k] = clock64();
+  ++k;
+}
+
+// barrier over the consumer threads only (the producer warp never joins it)
+__device__ __forceinline__ void ls_sync() {
+  asm volatile("bar.sync 2, %0;" ::"n"(kLSThreads) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // Exhaustive single-flip pass, Gauss-Seidel over nodes 0..N-1 with acceptance gain >= 0.
@@ -247,87 +232,400 @@ __device__ __forceinline__ void sweep_tile(const GraphDev& g, const SweepView& s
   }
 }
 
-template <int P, typename CrossT, int VEC>
-__global__ void __launch_bounds__(kLSThreads) ls_search_kernel(GraphDev g, LsArgs a) {
-  extern __shared__ __align__(16) uint32_t smem[];
+// Shared tail of both search kernels (consumer threads only): evaluate the candidate in sX and
+// keep rows that are not worse (vs1 >= vs0, util_read_data.py:199).  my_vs: warp 0, lane = env.
+__device__ __forceinline__ void evaluate_and_accept(const GraphDev& g, const LsArgs& a, uint32_t* sP,
+                                                    const uint32_t* sX, int* sCnt, uint32_t* sAccept, int valid,
+                                                    int64_t& my_vs) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cnt = tile_cut_partial(g, sX, a.cut_warps);
+  if (cnt) atomicAdd(&sCnt[lane], cnt);
+  ls_sync();
+  if (warp == 0) {
+    const int64_t cand = sCnt[lane];
+    const bool keep = lane < valid && cand >= my_vs;
+    if (keep) my_vs = cand;
+    const unsigned acc = __ballot_sync(kFull, keep);
+    if (lane == 0) *sAccept = acc;
+    sCnt[lane] = 0;
+  }
+  ls_sync();
+  const uint32_t acc = *sAccept;
+  for (int i = threadIdx.x; i < g.n; i += kLSThreads) sP[i] = (sX[i] & acc) | (sP[i] & ~acc);
+  ls_sync();
+}
+
+// single-flip pass + final values + bool rows (consumer threads only; sCnt is zero on entry)
+template <int P>
+__device__ __forceinline__ void finish_tile(const GraphDev& g, const LsArgs& a, uint32_t* sP, const char* sSweep,
+                                            uint64_t* sBar, int* sCnt, int64_t tile, int valid) {
+  const int lane = threadIdx.x & 31;
+  if (a.stage_sweep) {
+    mbar_wait(sBar, 0);
+    sweep_tile<P, true>(g, sweep_view(g, sSweep), sP, a.sweep_warps);
+  } else {
+    sweep_tile<P, false>(g, sweep_view(g, g.sweep_blob), sP, a.sweep_warps);
+  }
+  ls_sync();
+  const int cnt = tile_cut_partial(g, sP, a.cut_warps);
+  if (cnt) atomicAdd(&sCnt[lane], cnt);
+  ls_sync();
+  if (threadIdx.x < valid) a.vs[tile * kTileEnvs + threadIdx.x] = sCnt[threadIdx.x];
+  if (a.unpack_vec4)
+    unpack_tile_from_smem<4>(sP, a.xs_out, a.num_envs, g.n, g.np, tile, kLSWarps);
+  else
+    unpack_tile_from_smem<1>(sP, a.xs_out, a.num_envs, g.n, g.np, tile, kLSWarps);
+}
+
+// one thread: TMA the sweep structure into shared memory (it lands while other work runs)
+__device__ __forceinline__ void stage_sweep_blob(const GraphDev& g, char* dst, uint64_t* sBar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of dst are done
+  mbar_expect_tx(sBar, (uint32_t)g.sweep_blob_bytes);
+  for (int off = 0; off < g.sweep_blob_bytes; off += 32768) {
+    const int len = g.sweep_blob_bytes - off < 32768 ? g.sweep_blob_bytes - off : 32768;
+    bulk_g2s(dst + off, g.sweep_blob + off, (uint32_t)len, sBar);
+  }
+}
+
+// Threshold pass of the pipelined kernel.  With lane = env a per-lane sorted top-K list diverges on
+// almost every value (some lane of the 32 always inserts; measured 26 us for G22 x 4096).  Instead
+// every env has an append buffer in shared memory ([slot][env], conflict free): a value is
+// appended iff it exceeds the env's current bound (predicated, no divergence), and when a buffer
+// could overflow during the next chunk the CTA compacts all buffers to their kth_big largest
+// values (two envs per warp, rounds of warp-max) and raises the bounds to the kth_big-th largest
+// seen so far.  After the first chunk the bound is already tight: ~kth*ln(N/128) later appends.
+constexpr int kSelCap = 192;                           // slots per env
+constexpr int kSelBytes = kSelCap * kTileEnvs * 4;     // 24 KB of dynamic shared memory
+
+// kth_big largest values of env e's buffer -> slots 0..kth_big-1 (descending); returns the last
+__device__ __forceinline__ float select_env(float* sSel, int* sSelCnt, int e, int kth_big, int lane) {
+  const int cnt = sSelCnt[e];
+  float v[kSelCap / 32];
+#pragma unroll
+  for (int j = 0; j < kSelCap / 32; ++j) v[j] = (lane + 32 * j < cnt) ? sSel[(lane + 32 * j) * kTileEnvs + e] : -INFINITY;
+  __syncwarp();
+  float kth = -INFINITY;
+  for (int r = 0; r < kth_big; ++r) {
+    float m = v[0];
+#pragma unroll
+    for (int j = 1; j < kSelCap / 32; ++j) m = fmaxf(m, v[j]);
+    const uint32_t key = float_key(m);
+    const uint32_t best = __reduce_max_sync(kFull, key);
+    const unsigned who = __ballot_sync(kFull, key == best);
+    if (lane == __ffs(who) - 1) {          // drop ONE instance (ties are separate elements)
+      bool done = false;
+#pragma unroll
+      for (int j = 0; j < kSelCap / 32; ++j)
+        if (!done && v[j] == m) v[j] = -INFINITY, done = true;
+    }
+    kth = key_float(best);
+    if (lane == 0) sSel[r * kTileEnvs + e] = kth;
+  }
+  __syncwarp();
+  if (lane == 0) sSelCnt[e] = kth_big < cnt ? kth_big : cnt;
+  return kth;
+}
+
+// ---- consumer side of the ring.  Per chunk a warp owns node groups `warp` and `warp + 16`; the
+// lane's offsets inside a stage are the same for every chunk (noise: [group of 16 floats][env][64 B]
+// with swizzled 16-byte pieces; cross: [node group][env][4]; then rd_std and degm of the chunk).
+template <typename CrossT>
+struct PipeCtx {
+  const char* ring;
+  int stage_bytes, stages;
+  uint64_t *sFull, *sEmpty;
+  int groups, nchunks, negmult;
+  int s;            // ring cursor
+  uint32_t phase;
+  static constexpr int kCrossBytes = kChunkGroups * kTileEnvs * 4 * (int)sizeof(CrossT);
+  static constexpr int kNodeOff = kNoiseStageBytes + kCrossBytes;
+
+  // spin_rand of the lane's env for the 4 nodes of group (warp + half * 16) of the stage
+  __device__ __forceinline__ void group_values(const char* st, int half, float (&sr)[4]) const {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = warp + half * kLSWarps;
+    const float4 nz = *reinterpret_cast<const float4*>(st + (q >> 2) * (kTileEnvs * 64) + lane * 64 +
+                                                       (((q & 3) ^ ((lane >> 1) & 3)) << 4));
+    Cross4<CrossT> cr;
+    cr.load_shared(st + kNoiseStageBytes + (q * kTileEnvs + lane) * (4 * (int)sizeof(CrossT)));
+    const float4 rd = *reinterpret_cast<const float4*>(st + kNodeOff + q * 16);                      // broadcast
+    const int4 dm = *reinterpret_cast<const int4*>(st + kNodeOff + kChunkGroups * 16 + q * 16);
+    sr[0] = spin_rand(dm.x, negmult, cr.get(0), nz.x, rd.x);
+    sr[1] = spin_rand(dm.y, negmult, cr.get(1), nz.y, rd.y);
+    sr[2] = spin_rand(dm.z, negmult, cr.get(2), nz.z, rd.z);
+    sr[3] = spin_rand(dm.w, negmult, cr.get(3), nz.w, rd.w);
+  }
+  __device__ __forceinline__ const char* acquire() const {
+    mbar_wait(&sFull[s], phase);
+    return ring + s * stage_bytes;
+  }
+  __device__ __forceinline__ void release() {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&sEmpty[s]);
+    if (++s == stages) s = 0, phase ^= 1;
+  }
+};
+
+// One noisy iteration's candidate: sX = sP ^ (spin_rand > thresh).  The ballot of the 32 lanes
+// (= envs) is the 32-env flip word of a node.
+template <typename CrossT>
+__device__ __forceinline__ void mask_pass(PipeCtx<CrossT>& cx, float th, const uint32_t* sP, uint32_t* sX) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto emit = [&](const float(&sr)[4], int i0) {
+    const uint32_t b0 = __ballot_sync(kFull, sr[0] > th), b1 = __ballot_sync(kFull, sr[1] > th);
+    const uint32_t b2 = __ballot_sync(kFull, sr[2] > th), b3 = __ballot_sync(kFull, sr[3] > th);
+    const uint4 pw = *reinterpret_cast<const uint4*>(sP + i0);
+    if (lane == 0) *reinterpret_cast<uint4*>(sX + i0) = make_uint4(pw.x ^ b0, pw.y ^ b1, pw.z ^ b2, pw.w ^ b3);
+  };
+  for (int c = 0; c < cx.nchunks; ++c) {
+    const char* st = cx.acquire();
+    const int gc = cx.groups - c * kChunkGroups;           // node groups left (>= 32: a full chunk)
+    const int i0 = (c * kChunkGroups + warp) * 4;
+    float sa[4], sb[4];
+    if (gc >= kChunkGroups) {
+      cx.group_values(st, 0, sa);
+      cx.group_values(st, 1, sb);
+      emit(sa, i0);
+      emit(sb, i0 + 4 * kLSWarps);
+    } else {
+      if (warp < gc) cx.group_values(st, 0, sa), emit(sa, i0);
+      if (warp + kLSWarps < gc) cx.group_values(st, 1, sb), emit(sb, i0 + 4 * kLSWarps);
+    }
+    cx.release();
+  }
+}
+
+// Threshold pass: returns the kth_big-th largest spin_rand of the lane's env.
+template <typename CrossT>
+__device__ __forceinline__ float thresh_pass(PipeCtx<CrossT>& cx, float* sSel, int* sSelCnt, int* sSelFull,
+                                             float* sBound, int kth_big) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < kTileEnvs) sSelCnt[threadIdx.x] = 0;
+  if (threadIdx.x < 3) sSelFull[threadIdx.x] = 0;
+  ls_sync();
+  float bound = -INFINITY;
+  int flag_slot = 0;
+  // append the values above the env's bound to its buffer (lane = env; predicated, no divergence)
+  auto append = [&](const float(&sr)[4]) {
+    const bool q0 = sr[0] > bound, q1 = sr[1] > bound, q2 = sr[2] > bound, q3 = sr[3] > bound;
+    const int cnt = (int)q0 + (int)q1 + (int)q2 + (int)q3;
+    if (cnt) {
+      int at = atomicAdd(&sSelCnt[lane], cnt);
+      // a buffer must be able to take a whole further chunk (128 values): ask for a compaction
+      // (the env's last appender of the chunk sees the full count)
+      if (at + cnt + 4 * kChunkGroups > kSelCap) sSelFull[flag_slot] = 1;
+      if (q0) sSel[(at++) * kTileEnvs + lane] = sr[0];
+      if (q1) sSel[(at++) * kTileEnvs + lane] = sr[1];
+      if (q2) sSel[(at++) * kTileEnvs + lane] = sr[2];
+      if (q3) sSel[at * kTileEnvs + lane] = sr[3];
+    }
+  };
+  for (int c = 0; c < cx.nchunks; ++c) {
+    const char* st = cx.acquire();
+    const int gc = cx.groups - c * kChunkGroups;
+    float sa[4], sb[4];
+    if (warp < gc) cx.group_values(st, 0, sa), append(sa);
+    if (warp + kLSWarps < gc) cx.group_values(st, 1, sb), append(sb);
+    cx.release();
+    // Flag slots rotate over 3 chunks: slot (c+2)%3 was last read before this barrier and is next
+    // written after the following one, so thread 0 can clear it in between.
+    ls_sync();
+    const bool compact = sSelFull[flag_slot] != 0 || c + 1 == cx.nchunks;
+    flag_slot = flag_slot == 2 ? 0 : flag_slot + 1;
+    if (threadIdx.x == 0) sSelFull[flag_slot == 2 ? 0 : flag_slot + 1] = 0;
+    if (compact) {
+      const float b0 = select_env(sSel, sSelCnt, 2 * warp, kth_big, lane);
+      const float b1 = select_env(sSel, sSelCnt, 2 * warp + 1, kth_big, lane);
+      if (lane == 0) {      // fewer than kth_big values so far: no bound yet
+        sBound[2 * warp] = sSelCnt[2 * warp] >= kth_big ? b0 : -INFINITY;
+        sBound[2 * warp + 1] = sSelCnt[2 * warp + 1] >= kth_big ? b1 : -INFINITY;
+      }
+      ls_sync();
+      bound = sBound[lane];
+    }
+  }
+  return bound;
+}
+
+// ---- pipelined kernel (rows made of whole 64-byte column groups).  THRESH: the threshold pass is
+// compiled in.
+template <int P, typename CrossT, bool THRESH>
+__global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(GraphDev g, LsArgs a,
+                                                                  const __grid_constant__ TmapPack maps) {
+  extern __shared__ __align__(1024) uint32_t smem[];
   uint32_t* sP = smem;           // accepted state of the tile
   uint32_t* sX = smem + g.np;    // candidate state
-  char* sSweep = reinterpret_cast<char*>(smem + 2 * g.np);   // staged sweep structure (a.stage_sweep)
+  // noise/cross stages (1024-byte aligned for the swizzle); later the sweep structure
+  char* ring = reinterpret_cast<char*>(smem) + ((2 * (size_t)g.np * 4 + 1023) & ~(size_t)1023);
+  __shared__ int sCnt[kTileEnvs];
+  __shared__ uint32_t sAccept;
+  __shared__ __align__(8) uint64_t sFull[kMaxStages], sEmpty[kMaxStages], sBar;
+  __shared__ int sSelCnt[kTileEnvs];
+  __shared__ int sSelFull[3];        // "some buffer is past half" flag of chunk c lives in slot c % 3
+  __shared__ float sBound[kTileEnvs];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t tile = blockIdx.x;
+  const int64_t env0 = tile * kTileEnvs;
+  const int valid = (int)min((int64_t)kTileEnvs, a.num_envs - env0);
+  const bool has_thresh = THRESH && a.thresh_noise != nullptr;
+  const int passes = (has_thresh ? 1 : 0) + a.num_iters;
+  const int groups = g.n >> 2;                                   // N % 4 == 0 on this path
+  const int nchunks = (groups + kChunkGroups - 1) / kChunkGroups;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) mbar_init(&sFull[s], 1), mbar_init(&sEmpty[s], kLSWarps);
+    mbar_init(&sBar, 1);
+    if (a.finish && a.stage_sweep && passes == 0) stage_sweep_blob(g, ring, &sBar);
+  }
+  __syncthreads();
+
+  if (warp == kLSWarps) {
+    // ---------------- producer: one thread feeds the ring
+    if (lane == 0) {
+      const char* cross_tile = static_cast<const char*>(a.cross) + tile * (int64_t)g.np * kTileEnvs * sizeof(CrossT);
+      int s = 0, round = 0;
+      for (int p = 0; p < passes; ++p) {
+        const CUtensorMap* map = &maps.m[has_thresh ? p : p + 1];
+        for (int c = 0; c < nchunks; ++c) {
+          if (round > 0) mbar_wait(&sEmpty[s], (round - 1) & 1);
+          char* st = ring + s * a.stage_bytes;
+          const int gc = min(kChunkGroups, groups - c * kChunkGroups);
+          const uint32_t cross_bytes = gc * (kTileEnvs * 4 * (int)sizeof(CrossT));
+          mbar_expect_tx(&sFull[s], kNoiseStageBytes + cross_bytes + 2 * gc * 16);   // the box is always written whole
+          tma_load_3d(st, map, &sFull[s], 0, (int)env0, c * kChunkG16);  // (rows / groups past the tensor: zeros)
+          bulk_g2s(st + kNoiseStageBytes, cross_tile + (int64_t)c * kChunkGroups * (kTileEnvs * 4 * sizeof(CrossT)),
+                   cross_bytes, &sFull[s]);
+          // the chunk's rd_std / degree words ride along, so the consumers' loop has no global load at all
+          char* nd = st + kNoiseStageBytes + kChunkGroups * kTileEnvs * 4 * (int)sizeof(CrossT);
+          bulk_g2s(nd, a.rd_std + c * (kChunkGroups * 4), gc * 16, &sFull[s]);
+          bulk_g2s(nd + kChunkGroups * 16, a.degm + c * (kChunkGroups * 4), gc * 16, &sFull[s]);
+          if (++s == a.stages) s = 0, ++round;
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumer warps
+  for (int i = threadIdx.x; i < g.np; i += kLSThreads) {
+    const uint32_t w = a.packed[tile * g.np + i];
+    sP[i] = w, sX[i] = w;        // padding nodes stay equal in both copies
+  }
+  if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
+  int64_t my_vs = 0;   // warp 0: lane e owns env e's value
+  if (warp == 0 && lane < valid) my_vs = a.vs[env0 + lane];
+  float th = INFINITY;   // +inf for envs past the batch: never flips
+  if (!has_thresh && a.num_iters > 0 && lane < valid) th = a.thresh[env0 + lane];
+  ls_sync();
+
+  PipeCtx<CrossT> cx;
+  cx.ring = ring, cx.stage_bytes = a.stage_bytes, cx.stages = a.stages, cx.sFull = sFull, cx.sEmpty = sEmpty;
+  cx.groups = groups, cx.nchunks = nchunks, cx.negmult = a.negmult, cx.s = 0, cx.phase = 0;
+  float* sSel = reinterpret_cast<float*>(ring + (size_t)a.stages * a.stage_bytes);   // [kSelCap][32] (THRESH)
+  int tk = 0;
+  stamp(a, tk);
+  for (int p = 0; p < passes; ++p) {
+    if (THRESH && has_thresh && p == 0) {
+      const float kth = thresh_pass<CrossT>(cx, sSel, sSelCnt, sSelFull, sBound, a.kth_big);
+      if (lane < valid) {
+        th = kth;            // == the kth_big-th largest of the row (N > num_spin)
+        if (warp == 0) a.thresh[env0 + lane] = kth;
+      }
+      stamp(a, tk);
+      stamp(a, tk);
+      continue;
+    }
+    mask_pass<CrossT>(cx, th, sP, sX);
+    ls_sync();     // candidate complete
+    stamp(a, tk);
+    if (p == passes - 1 && a.finish && a.stage_sweep && threadIdx.x == 0) stage_sweep_blob(g, ring, &sBar);
+    evaluate_and_accept(g, a, sP, sX, sCnt, &sAccept, valid, my_vs);
+    stamp(a, tk);
+  }
+  if (has_thresh && passes == 1) {
+    ls_sync();     // all reads of the ring are done
+    if (a.finish && a.stage_sweep && threadIdx.x == 0) stage_sweep_blob(g, ring, &sBar);
+  }
+  const uint32_t vmask = valid == 32 ? kFull : ((1u << valid) - 1u);
+  if (a.finish) {
+    finish_tile<P>(g, a, sP, ring, &sBar, sCnt, tile, valid);
+  } else {
+    if (warp == 0 && lane < valid) a.vs[env0 + lane] = my_vs;
+  }
+  stamp(a, tk);
+  for (int i = threadIdx.x; i < g.np; i += kLSThreads) a.packed[tile * g.np + i] = sP[i] & vmask;
+}
+
+// ---- generic kernel (any N / alignment): direct global loads, thresh precomputed by
+// ls_thresh_kernel.  Work item = one node x 8 consecutive envs (byte g of a word = envs 8g..8g+7).
+template <typename CrossT>
+__device__ __forceinline__ void noisy_candidate(const GraphDev& g, const LsArgs& a, const float* __restrict__ noise,
+                                                int64_t tile, int valid, const float* sThresh, const uint32_t* sP,
+                                                uint32_t* sX) {
+  const float* __restrict__ nbase = noise + tile * kTileEnvs * (int64_t)g.n;
+  const CrossT* __restrict__ ctile = static_cast<const CrossT*>(a.cross) + tile * (int64_t)g.np * kTileEnvs;
+  const uint32_t n = (uint32_t)g.n;
+  const uint8_t* sPb = reinterpret_cast<const uint8_t*>(sP);
+  uint8_t* sXb = reinterpret_cast<uint8_t*>(sX);
+  for (uint32_t task = threadIdx.x; task < n * 4; task += kLSThreads) {
+    const uint32_t eg = task / n, i = task - eg * n;
+    const uint32_t e0 = eg * 8;
+    const float rd = __ldg(a.rd_std + i);
+    const int dm = __ldg(a.degm + i);
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if ((int)(e0 + j) < valid) {
+        const float sr = spin_rand(dm, a.negmult, cross_at(ctile, (int)i, (int)(e0 + j)),
+                                   ldg_stream(nbase + (e0 + j) * n + i), rd);
+        if (sr > sThresh[e0 + j]) bits |= 1u << j;
+      }
+    }
+    const uint32_t at = i * 4 + eg;
+    sXb[at] = sPb[at] ^ (uint8_t)bits;
+  }
+}
+
+template <int P, typename CrossT>
+__global__ void __launch_bounds__(kLSThreads) ls_generic_kernel(GraphDev g, LsArgs a) {
+  extern __shared__ __align__(1024) uint32_t smem[];
+  uint32_t* sP = smem;
+  uint32_t* sX = smem + g.np;
+  char* sSweep = reinterpret_cast<char*>(smem + 2 * g.np);
   __shared__ float sThresh[kTileEnvs];
   __shared__ int sCnt[kTileEnvs];
   __shared__ uint32_t sAccept;
   __shared__ __align__(8) uint64_t sBar;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t tiles = (a.num_envs + kTileEnvs - 1) / kTileEnvs;
-  // The single-flip pass walks the graph level by level, one dependent load after another: have
-  // the TMA engine copy the whole sweep structure into shared memory now; it lands while the
-  // noisy iterations run.
-  const bool staged = a.finish && a.stage_sweep;
-  if (staged && threadIdx.x == 0) {
+  const int64_t tile = blockIdx.x;
+  const int64_t env0 = tile * kTileEnvs;
+  const int valid = (int)min((int64_t)kTileEnvs, a.num_envs - env0);
+  if (threadIdx.x == 0) {
     mbar_init(&sBar, 1);
-    mbar_expect_tx(&sBar, (uint32_t)g.sweep_blob_bytes);
-    for (int off = 0; off < g.sweep_blob_bytes; off += 32768) {
-      const int len = g.sweep_blob_bytes - off < 32768 ? g.sweep_blob_bytes - off : 32768;
-      bulk_g2s(sSweep + off, g.sweep_blob + off, (uint32_t)len, &sBar);
-    }
+    if (a.finish && a.stage_sweep) stage_sweep_blob(g, sSweep, &sBar);
   }
-  bool sweep_landed = false;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t env0 = tile * kTileEnvs;
-    const int valid = (int)min((int64_t)kTileEnvs, a.num_envs - env0);
-    const uint32_t vmask = valid == 32 ? kFull : ((1u << valid) - 1u);
-    for (int i = threadIdx.x; i < g.np; i += blockDim.x) {
-      const uint32_t w = a.packed[tile * g.np + i];
-      sP[i] = w, sX[i] = w;        // padding nodes stay equal in both copies
-    }
-    if (threadIdx.x < kTileEnvs)
-      sThresh[threadIdx.x] = (a.num_iters > 0 && threadIdx.x < valid) ? a.thresh[env0 + threadIdx.x] : INFINITY;
-    int64_t my_vs = 0;   // warp 0: lane e owns env e's value
-    if (warp == 0 && lane < valid) my_vs = a.vs[env0 + lane];
-    __syncthreads();
-    for (int it = 0; it < a.num_iters; ++it) {
-      if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
-      if (valid == kTileEnvs)
-        noisy_candidate<CrossT, VEC, true>(g, a, a.noise.p[it], env0, valid, sThresh, sP, sX);
-      else
-        noisy_candidate<CrossT, VEC, false>(g, a, a.noise.p[it], env0, valid, sThresh, sP, sX);
-      __syncthreads();
-      const int cnt = tile_cut_partial(g, sX, a.cut_warps);
-      if (cnt) atomicAdd(&sCnt[lane], cnt);
-      __syncthreads();
-      // keep rows that are not worse (vs1 >= vs0, util_read_data.py:199)
-      if (warp == 0) {
-        const int64_t cand = sCnt[lane];
-        const bool keep = lane < valid && cand >= my_vs;
-        if (keep) my_vs = cand;
-        const unsigned acc = __ballot_sync(kFull, keep);
-        if (lane == 0) sAccept = acc;
-      }
-      __syncthreads();
-      const uint32_t acc = sAccept;
-      for (int i = threadIdx.x; i < g.n; i += blockDim.x) sP[i] = (sX[i] & acc) | (sP[i] & ~acc);
-      __syncthreads();
-    }
-    if (a.finish) {
-      if (staged) {
-        if (!sweep_landed) mbar_wait(&sBar, 0), sweep_landed = true;
-        sweep_tile<P, true>(g, sweep_view(g, sSweep), sP, a.sweep_warps);
-      } else {
-        sweep_tile<P, false>(g, sweep_view(g, g.sweep_blob), sP, a.sweep_warps);
-      }
-      if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
-      __syncthreads();
-      const int cnt = tile_cut_partial(g, sP, a.cut_warps);
-      if (cnt) atomicAdd(&sCnt[lane], cnt);
-      __syncthreads();
-      if (threadIdx.x < valid) a.vs[env0 + threadIdx.x] = sCnt[threadIdx.x];
-      unpack_tile_from_smem<VEC>(sP, a.xs_out, a.num_envs, g.n, g.np, tile);
-    } else {
-      if (warp == 0 && lane < valid) a.vs[env0 + lane] = my_vs;
-    }
-    for (int i = threadIdx.x; i < g.np; i += blockDim.x) a.packed[tile * g.np + i] = sP[i] & vmask;
-    __syncthreads();
+  for (int i = threadIdx.x; i < g.np; i += kLSThreads) {
+    const uint32_t w = a.packed[tile * g.np + i];
+    sP[i] = w, sX[i] = w;
   }
+  if (threadIdx.x < kTileEnvs) {
+    sThresh[threadIdx.x] = (a.num_iters > 0 && threadIdx.x < valid) ? a.thresh[env0 + threadIdx.x] : INFINITY;
+    sCnt[threadIdx.x] = 0;
+  }
+  int64_t my_vs = 0;
+  if (warp == 0 && lane < valid) my_vs = a.vs[env0 + lane];
+  ls_sync();
+  for (int it = 0; it < a.num_iters; ++it) {
+    noisy_candidate<CrossT>(g, a, a.noise.p[it], tile, valid, sThresh, sP, sX);
+    ls_sync();
+    evaluate_and_accept(g, a, sP, sX, sCnt, &sAccept, valid, my_vs);
+  }
+  const uint32_t vmask = valid == 32 ? kFull : ((1u << valid) - 1u);
+  if (a.finish) {
+    finish_tile<P>(g, a, sP, sSweep, &sBar, sCnt, tile, valid);
+  } else {
+    if (warp == 0 && lane < valid) a.vs[env0 + lane] = my_vs;
+  }
+  for (int i = threadIdx.x; i < g.np; i += kLSThreads) a.packed[tile * g.np + i] = sP[i] & vmask;
 }
 
 // single-flip pass on packed tiles only (rlsb_flip_sweep)
@@ -394,7 +692,7 @@ static LsWorkspace carve(const GraphDev& g, int64_t num_envs, void* base) {
   };
   LsWorkspace w;
   w.packed = reinterpret_cast<uint32_t*>(take((size_t)tiles * g.np * 4));
-  w.cross = take((size_t)num_envs * g.np * cross_elt);
+  w.cross = take((size_t)tiles * kTileEnvs * g.np * cross_elt);
   w.col_min = reinterpret_cast<int32_t*>(take((size_t)g.np * 4));
   w.col_max = reinterpret_cast<int32_t*>(take((size_t)g.np * 4));
   w.degm = reinterpret_cast<int32_t*>(take((size_t)g.np * 4));
@@ -404,37 +702,166 @@ static LsWorkspace carve(const GraphDev& g, int64_t num_envs, void* base) {
   return w;
 }
 
-template <int P, typename CrossT>
-static int launch_search(const GraphDev& g, const LsArgs& a, bool vec4, cudaStream_t st) {
-  const size_t smem = 2 * (size_t)g.np * sizeof(uint32_t) + (a.stage_sweep ? (size_t)g.sweep_blob_bytes : 0);
-  const int64_t tiles = (a.num_envs + kTileEnvs - 1) / kTileEnvs;
-  const unsigned grid = (unsigned)(tiles < 4 * kNumSMs ? tiles : 4 * kNumSMs);
-  int rc;
-  if (vec4) {
-    if ((rc = allow_smem(ls_search_kernel<P, CrossT, 4>, smem))) return rc;
-    ls_search_kernel<P, CrossT, 4><<<grid, kLSThreads, smem, st>>>(g, a);
-  } else {
-    if ((rc = allow_smem(ls_search_kernel<P, CrossT, 1>, smem))) return rc;
-    ls_search_kernel<P, CrossT, 1><<<grid, kLSThreads, smem, st>>>(g, a);
+constexpr size_t kSmemBudget = 220 * 1024;   // dynamic shared memory a search CTA may use
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
   }
+  return fn;
+}
+
+// float32 [E][N] row-major seen as {16 floats, E rows, N/16 column groups}; box = 16 x 32 x kChunkG16
+static int make_noise_map(CUtensorMap* map, const float* base, int64_t num_envs, int n) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  RLSB_REQUIRE(fn != nullptr, RLSB_ERR_CUDA, "ls_run: cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {16, (cuuint64_t)num_envs, (cuuint64_t)(n / 16)};
+  const cuuint64_t strides[2] = {(cuuint64_t)n * 4, 64};
+  const cuuint32_t box[3] = {16, (cuuint32_t)kTileEnvs, (cuuint32_t)kChunkG16};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RLSB_REQUIRE(r == CUDA_SUCCESS, RLSB_ERR_CUDA, "ls_run: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return RLSB_OK;
+}
+
+template <int P, typename CrossT, bool THRESH>
+static int launch_pipe(const GraphDev& g, LsArgs a, const TmapPack& maps, cudaStream_t st) {
+  const size_t tiles_bytes = (2 * (size_t)g.np * sizeof(uint32_t) + 1023) / 1024 * 1024 + (THRESH ? kSelBytes : 0);
+  a.stage_bytes = kNoiseStageBytes + kChunkGroups * kTileEnvs * 4 * (int)sizeof(CrossT) + 1024;   // + rd_std, degm
+  const int passes = (a.thresh_noise ? 1 : 0) + a.num_iters;
+  const int chunks = passes * ((g.n / 4 + kChunkGroups - 1) / kChunkGroups);
+  int stages = (int)((kSmemBudget - tiles_bytes) / a.stage_bytes);
+  stages = stages > kMaxStages ? kMaxStages : stages;
+  stages = stages > chunks ? (chunks > 0 ? chunks : 1) : stages;
+  a.stages = stages;
+  size_t ring = (size_t)stages * a.stage_bytes;
+  a.stage_sweep = (a.finish && tiles_bytes + (size_t)g.sweep_blob_bytes <= kSmemBudget) ? 1 : 0;
+  if (a.stage_sweep && (size_t)g.sweep_blob_bytes > ring) ring = (size_t)g.sweep_blob_bytes;
+  const size_t smem = tiles_bytes + ring;      // the selection buffers sit behind the ring stages
+  const int64_t tiles = (a.num_envs + kTileEnvs - 1) / kTileEnvs;
+  if (int rc = allow_smem(ls_pipe_kernel<P, CrossT, THRESH>, smem)) return rc;
+  ls_pipe_kernel<P, CrossT, THRESH><<<(unsigned)tiles, kPipeThreads, smem, st>>>(g, a, maps);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+template <int P, typename CrossT>
+static int launch_pipe_k(const GraphDev& g, const LsArgs& a, const TmapPack& maps, cudaStream_t st) {
+  if (!a.thresh_noise) return launch_pipe<P, CrossT, false>(g, a, maps, st);
+  return launch_pipe<P, CrossT, true>(g, a, maps, st);
+}
+
+template <int P, typename CrossT>
+static int launch_generic(const GraphDev& g, LsArgs a, cudaStream_t st) {
+  const size_t tiles_bytes = 2 * (size_t)g.np * sizeof(uint32_t);
+  a.stage_sweep = (a.finish && tiles_bytes + (size_t)g.sweep_blob_bytes <= kSmemBudget) ? 1 : 0;
+  const size_t smem = tiles_bytes + (a.stage_sweep ? (size_t)g.sweep_blob_bytes : 0);
+  const int64_t tiles = (a.num_envs + kTileEnvs - 1) / kTileEnvs;
+  if (int rc = allow_smem(ls_generic_kernel<P, CrossT>, smem)) return rc;
+  ls_generic_kernel<P, CrossT><<<(unsigned)tiles, kLSThreads, smem, st>>>(g, a);
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }
 
 template <typename CrossT>
 static int launch_thresh(const GraphDev& g, const LsWorkspace& w, int mult, const float* noise, int kth_big,
-                         int64_t num_envs, bool vec4, cudaStream_t st) {
+                         int64_t num_envs, cudaStream_t st) {
   const unsigned grid = (unsigned)((num_envs + 7) / 8);
   const CrossT* cross = static_cast<const CrossT*>(w.cross);
-#define RLSB_THRESH(KMAX, V) \
-  ls_thresh_kernel<KMAX, CrossT, V><<<grid, 256, 0, st>>>(g, cross, w.rd_std, w.degm, mult, noise, kth_big, num_envs, w.thresh)
-  if (kth_big <= 10) {
-    if (vec4) RLSB_THRESH(10, 4); else RLSB_THRESH(10, 1);
-  } else {
-    if (vec4) RLSB_THRESH(32, 4); else RLSB_THRESH(32, 1);
-  }
-#undef RLSB_THRESH
+  if (kth_big <= 10)
+    ls_thresh_kernel<10, CrossT><<<grid, 256, 0, st>>>(g, cross, w.rd_std, w.degm, mult, noise, kth_big, num_envs,
+                                                       w.thresh);
+  else
+    ls_thresh_kernel<32, CrossT><<<grid, 256, 0, st>>>(g, cross, w.rd_std, w.degm, mult, noise, kth_big, num_envs,
+                                                       w.thresh);
   RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+// RLSB_LS_TIMES=1: CTA 0 of every pipe launch writes clock64 phase stamps into a device buffer
+// that rlsb_ls_debug_times() copies out (profiling aid, tools/ls_phase_times.py)
+static long long* ls_debug_times() {
+  static long long* buf = nullptr;
+  static int init = 0;
+  if (!init) {
+    init = 1;
+    const char* e = getenv("RLSB_LS_TIMES");
+    if (e && e[0] == '1' && cudaMalloc(&buf, 64 * sizeof(long long)) == cudaSuccess)
+      cudaMemset(buf, 0, 64 * sizeof(long long));
+    else
+      buf = nullptr;
+  }
+  return buf;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// thresh (optional) + iterations + finish (optional), in launches of at most kLSMaxIters tensors
+static int run_search(const GraphDev& g, int64_t num_envs, int64_t* vs, int ws_mult, const float* thresh_noise,
+                      int num_spin, const float* const* h_noise_ptrs, int num_iters, int finish, uint8_t* xs_out,
+                      void* workspace, cudaStream_t st) {
+  const LsWorkspace w = carve(g, num_envs, workspace);
+  const int dc = degree_class(g);
+  const int kth_big = num_spin + 1;   // kth smallest with k = N - num_spin  ==  (num_spin+1)-th largest
+  // the pipelined kernel needs rows made of whole 64-byte column groups (tensor-map dim 0) and room for
+  // two ring stages next to the tile copies
+  bool pipe = g.n % 16 == 0 &&
+              2 * (size_t)g.np * 4 + 1024 + kSelBytes + 2 * (size_t)(kNoiseStageBytes + 8192 + 1024) <= kSmemBudget;
+  if (thresh_noise) pipe = pipe && aligned16(thresh_noise);
+  for (int k = 0; k < num_iters; ++k) {
+    RLSB_REQUIRE(h_noise_ptrs[k] != nullptr, RLSB_ERR_INVALID, "ls_search: null noise tensor %d", k);
+    pipe = pipe && aligned16(h_noise_ptrs[k]);
+  }
+  if (thresh_noise && !pipe) {
+    if (int rc = dc == 2 ? launch_thresh<uint16_t>(g, w, ws_mult, thresh_noise, kth_big, num_envs, st)
+                         : launch_thresh<uint8_t>(g, w, ws_mult, thresh_noise, kth_big, num_envs, st))
+      return rc;
+    thresh_noise = nullptr;
+    if (num_iters == 0 && !finish) return RLSB_OK;
+  }
+  int done = 0;
+  do {
+    const int now = num_iters - done < kLSMaxIters ? num_iters - done : kLSMaxIters;
+    LsArgs a{};
+    a.packed = w.packed, a.vs = vs, a.cross = w.cross, a.rd_std = w.rd_std, a.degm = w.degm, a.thresh = w.thresh;
+    a.thresh_noise = done == 0 ? thresh_noise : nullptr;
+    a.kth_big = kth_big;
+    for (int k = 0; k < now; ++k) a.noise.p[k] = h_noise_ptrs[done + k];
+    a.num_iters = now, a.mult = ws_mult, a.num_envs = num_envs;
+    a.finish = (finish && done + now == num_iters) ? 1 : 0;
+    a.xs_out = xs_out, a.unpack_vec4 = (xs_out && rows_vec4_ok(xs_out, g.n)) ? 1 : 0;
+    a.cut_warps = cut_warps_for(g.m, kLSWarps);
+    a.sweep_warps = sweep_warps_for(g, kLSWarps), a.negmult = -ws_mult;
+    a.times = ls_debug_times();
+    int rc;
+    if (pipe) {
+      TmapPack maps;
+      memset(&maps, 0, sizeof(maps));
+      if (a.thresh_noise)
+        if ((rc = make_noise_map(&maps.m[0], a.thresh_noise, num_envs, g.n))) return rc;
+      for (int k = 0; k < now; ++k)
+        if ((rc = make_noise_map(&maps.m[1 + k], a.noise.p[k], num_envs, g.n))) return rc;
+      rc = dc == 0   ? launch_pipe_k<6, uint8_t>(g, a, maps, st)
+           : dc == 1 ? launch_pipe_k<8, uint8_t>(g, a, maps, st)
+                     : launch_pipe_k<12, uint16_t>(g, a, maps, st);
+    } else
+      rc = dc == 0   ? launch_generic<6, uint8_t>(g, a, st)
+           : dc == 1 ? launch_generic<8, uint8_t>(g, a, st)
+                     : launch_generic<12, uint16_t>(g, a, st);
+    if (rc) return rc;
+    done += now;
+  } while (done < num_iters);
   return RLSB_OK;
 }
 
@@ -467,7 +894,7 @@ int rlsb_ls_begin(const rlsb_graph_t* gh, const uint8_t* xs, int64_t num_envs, i
   if (int rc = graph_check(gh, &g, "ls_begin")) return rc;
   RLSB_REQUIRE(num_envs >= 0, RLSB_ERR_INVALID, "ls_begin: negative num_envs");
   RLSB_REQUIRE(ws_mult == 1 || ws_mult == 2, RLSB_ERR_INVALID, "ls_begin: ws_mult must be 1 or 2");
-  RLSB_REQUIRE(2 * (size_t)g->np * 4 <= 220 * 1024, RLSB_ERR_UNSUPPORTED,
+  RLSB_REQUIRE(2 * (size_t)g->np * 4 <= kSmemBudget, RLSB_ERR_UNSUPPORTED,
                "ls_begin: %d nodes exceed the two-copy shared-memory tile of the search kernel", g->n);
   if (num_envs == 0 || g->n == 0) return RLSB_OK;
   RLSB_REQUIRE(xs && workspace && (vs || !compute_vs), RLSB_ERR_INVALID, "ls_begin: null pointer");
@@ -475,11 +902,32 @@ int rlsb_ls_begin(const rlsb_graph_t* gh, const uint8_t* xs, int64_t num_envs, i
                "ls_begin: workspace must be 256-byte aligned");
   auto st = static_cast<cudaStream_t>(stream);
   const LsWorkspace w = carve(*g, num_envs, workspace);
-  if (int rc = prepare_tiles(*g, xs, nullptr, num_envs, w.packed, w.cross, degree_class(*g) != 2, w.col_min, w.col_max,
-                             compute_vs ? vs : nullptr, st))
+  if (int rc = prepare_tiles(*g, xs, nullptr, num_envs, w.packed, w.cross, degree_class(*g) != 2 ? 1 : 2, w.col_min,
+                             w.col_max, compute_vs ? vs : nullptr, st))
     return rc;
   ls_rdstd_kernel<<<(g->np + 255) / 256, 256, 0, st>>>(*g, w.col_min, w.col_max, ws_mult, noise_std, w.rd_std, w.degm);
   RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+static int ls_check(const rlsb_graph_t* gh, const rlsb::GraphDev** g, const char* what, int64_t num_envs,
+                    int32_t ws_mult) {
+  using namespace rlsb;
+  if (int rc = graph_check(gh, g, what)) return rc;
+  RLSB_REQUIRE(num_envs >= 0, RLSB_ERR_INVALID, "%s: negative num_envs", what);
+  RLSB_REQUIRE(ws_mult == 1 || ws_mult == 2, RLSB_ERR_INVALID, "%s: ws_mult must be 1 or 2", what);
+  RLSB_REQUIRE(2 * (size_t)(*g)->np * 4 <= kSmemBudget, RLSB_ERR_UNSUPPORTED,
+               "%s: %d nodes exceed the two-copy shared-memory tile", what, (*g)->n);
+  return RLSB_OK;
+}
+
+static int spin_check(const rlsb::GraphDev& g, int32_t num_spin, const char* what) {
+  using namespace rlsb;
+  // torch.kthvalue(k = N - num_spin) needs 1 <= k <= N
+  RLSB_REQUIRE(num_spin >= 0 && num_spin < g.n, RLSB_ERR_INVALID,
+               "%s: k = N - num_spin = %d out of range for N = %d (torch.kthvalue raises)", what, g.n - num_spin, g.n);
+  RLSB_REQUIRE(num_spin + 1 <= 32, RLSB_ERR_UNSUPPORTED, "%s: num_spin %d above the in-register limit 31", what,
+               num_spin);
   return RLSB_OK;
 }
 
@@ -487,63 +935,43 @@ int rlsb_ls_thresh(const rlsb_graph_t* gh, int64_t num_envs, int32_t ws_mult, co
                    void* workspace, void* stream) {
   using namespace rlsb;
   const GraphDev* g;
-  if (int rc = graph_check(gh, &g, "ls_thresh")) return rc;
-  RLSB_REQUIRE(num_envs >= 0, RLSB_ERR_INVALID, "ls_thresh: negative num_envs");
-  // torch.kthvalue(k = N - num_spin) needs 1 <= k <= N
-  RLSB_REQUIRE(num_spin >= 0 && num_spin < g->n, RLSB_ERR_INVALID,
-               "ls_thresh: k = N - num_spin = %d out of range for N = %d (torch.kthvalue raises)", g->n - num_spin,
-               g->n);
-  RLSB_REQUIRE(ws_mult == 1 || ws_mult == 2, RLSB_ERR_INVALID, "ls_thresh: ws_mult must be 1 or 2");
+  if (int rc = ls_check(gh, &g, "ls_thresh", num_envs, ws_mult)) return rc;
+  if (int rc = spin_check(*g, num_spin, "ls_thresh")) return rc;
   if (num_envs == 0) return RLSB_OK;
   RLSB_REQUIRE(noise && workspace, RLSB_ERR_INVALID, "ls_thresh: null pointer");
-  const int kth_big = num_spin + 1;   // kth smallest with k = N - num_spin  ==  (num_spin+1)-th largest
-  RLSB_REQUIRE(kth_big <= 32, RLSB_ERR_UNSUPPORTED, "ls_thresh: num_spin %d above the in-register limit 31", num_spin);
-  auto st = static_cast<cudaStream_t>(stream);
   const LsWorkspace w = carve(*g, num_envs, workspace);
-  const bool vec4 = rows_vec4_ok(noise, g->n) && (reinterpret_cast<uintptr_t>(noise) & 15u) == 0;
-  return degree_class(*g) == 2 ? launch_thresh<uint16_t>(*g, w, ws_mult, noise, kth_big, num_envs, vec4, st)
-                               : launch_thresh<uint8_t>(*g, w, ws_mult, noise, kth_big, num_envs, vec4, st);
+  auto st = static_cast<cudaStream_t>(stream);
+  return degree_class(*g) == 2 ? launch_thresh<uint16_t>(*g, w, ws_mult, noise, num_spin + 1, num_envs, st)
+                               : launch_thresh<uint8_t>(*g, w, ws_mult, noise, num_spin + 1, num_envs, st);
+}
+
+int rlsb_ls_run(const rlsb_graph_t* gh, int64_t num_envs, int64_t* vs, int32_t ws_mult, const float* thresh_noise,
+                int32_t num_spin, const float* const* h_noise_ptrs, int32_t num_iters, int32_t finish,
+                uint8_t* xs_out, void* workspace, void* stream) {
+  using namespace rlsb;
+  const GraphDev* g;
+  if (int rc = ls_check(gh, &g, "ls_run", num_envs, ws_mult)) return rc;
+  RLSB_REQUIRE(num_iters >= 0, RLSB_ERR_INVALID, "ls_run: negative num_iters");
+  if (thresh_noise)
+    if (int rc = spin_check(*g, num_spin, "ls_run")) return rc;
+  if (num_envs == 0 || g->n == 0) return RLSB_OK;
+  RLSB_REQUIRE(vs && workspace && (num_iters == 0 || h_noise_ptrs) && (!finish || xs_out), RLSB_ERR_INVALID,
+               "ls_run: null pointer");
+  return run_search(*g, num_envs, vs, ws_mult, thresh_noise, thresh_noise ? num_spin : 0, h_noise_ptrs, num_iters,
+                    finish, xs_out, workspace, static_cast<cudaStream_t>(stream));
+}
+
+int rlsb_ls_debug_times(int64_t* out64) {
+  long long* buf = rlsb::ls_debug_times();
+  if (!buf) return RLSB_ERR_INVALID;
+  RLSB_CUDA_OK(cudaMemcpy(out64, buf, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return RLSB_OK;
 }
 
 int rlsb_ls_search(const rlsb_graph_t* gh, int64_t num_envs, int64_t* vs, int32_t ws_mult,
                    const float* const* h_noise_ptrs, int32_t num_iters, int32_t finish, uint8_t* xs_out,
                    void* workspace, void* stream) {
-  using namespace rlsb;
-  const GraphDev* g;
-  if (int rc = graph_check(gh, &g, "ls_search")) return rc;
-  RLSB_REQUIRE(num_envs >= 0 && num_iters >= 0, RLSB_ERR_INVALID, "ls_search: negative size");
-  RLSB_REQUIRE(ws_mult == 1 || ws_mult == 2, RLSB_ERR_INVALID, "ls_search: ws_mult must be 1 or 2");
-  if (num_envs == 0 || g->n == 0) return RLSB_OK;
-  RLSB_REQUIRE(vs && workspace && (num_iters == 0 || h_noise_ptrs) && (!finish || xs_out), RLSB_ERR_INVALID,
-               "ls_search: null pointer");
-  RLSB_REQUIRE(2 * (size_t)g->np * 4 <= 220 * 1024, RLSB_ERR_UNSUPPORTED,
-               "ls_search: %d nodes exceed the two-copy shared-memory tile", g->n);
-  auto st = static_cast<cudaStream_t>(stream);
-  const LsWorkspace w = carve(*g, num_envs, workspace);
-  const int dc = degree_class(*g);
-  int done = 0;
-  do {
-    const int now = num_iters - done < kLSMaxIters ? num_iters - done : kLSMaxIters;
-    LsArgs a{};
-    a.packed = w.packed, a.vs = vs, a.cross = w.cross, a.rd_std = w.rd_std, a.degm = w.degm, a.thresh = w.thresh;
-    bool vec4 = g->n % 4 == 0 && (!xs_out || rows_vec4_ok(xs_out, g->n));
-    for (int k = 0; k < now; ++k) {
-      RLSB_REQUIRE(h_noise_ptrs[done + k] != nullptr, RLSB_ERR_INVALID, "ls_search: null noise tensor %d", done + k);
-      a.noise.p[k] = h_noise_ptrs[done + k];
-      vec4 = vec4 && (reinterpret_cast<uintptr_t>(a.noise.p[k]) & 15u) == 0;
-    }
-    a.num_iters = now, a.mult = ws_mult, a.num_envs = num_envs;
-    a.finish = (finish && done + now == num_iters) ? 1 : 0;
-    a.xs_out = xs_out, a.cut_warps = cut_warps_for(g->m, kLSThreads / 32);
-    a.sweep_warps = sweep_warps_for(*g, kLSThreads / 32), a.negmult = -ws_mult;
-    a.stage_sweep = (a.finish && 2 * (size_t)g->np * 4 + (size_t)g->sweep_blob_bytes <= 200 * 1024) ? 1 : 0;
-    int rc = dc == 0   ? launch_search<6, uint8_t>(*g, a, vec4, st)
-             : dc == 1 ? launch_search<8, uint8_t>(*g, a, vec4, st)
-                       : launch_search<12, uint16_t>(*g, a, vec4, st);
-    if (rc) return rc;
-    done += now;
-  } while (done < num_iters);
-  return RLSB_OK;
+  return rlsb_ls_run(gh, num_envs, vs, ws_mult, nullptr, 0, h_noise_ptrs, num_iters, finish, xs_out, workspace, stream);
 }
 
 int rlsb_flip_sweep(const rlsb_graph_t* gh, uint32_t* packed, int64_t* vs, int64_t num_envs, void* stream) {

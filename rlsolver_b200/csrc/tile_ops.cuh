@@ -84,8 +84,10 @@ __device__ __forceinline__ void unpack_strip(const uint32_t (&w)[VEC], uint8_t* 
 
 template <int VEC>
 __device__ __forceinline__ void unpack_tile_from_smem(const uint32_t* sP, uint8_t* __restrict__ xs,
-                                                      int64_t num_envs, int32_t n, int32_t np, int64_t tile) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+                                                      int64_t num_envs, int32_t n, int32_t np, int64_t tile,
+                                                      int nwarps = 0) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (nwarps == 0) nwarps = blockDim.x >> 5;   // nwarps: the warps that call this (all of the CTA by default)
   const int strips = (np + 32 * VEC - 1) / (32 * VEC);
   for (int s = warp; s < strips; s += nwarps) {
     const int node0 = s * 32 * VEC + lane * VEC;

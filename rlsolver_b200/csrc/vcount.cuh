@@ -152,13 +152,20 @@ __device__ __forceinline__ int tile_cut_partial(const GraphDev& g, const uint32_
   VCount<8> vc;
   vc.clear();
   int blocks = 0;
-  for (int q0 = warp * 32; q0 < quads; q0 += 4 * T) {   // warp-uniform trip count; 16 edges per lane per trip
-    uint4 e[4];
+  // software pipeline: the four 16-byte edge loads of the next trip are in flight while this trip's
+  // 32 shared-memory gathers and adds run (the list comes from L2: ~1000 cycles under load)
+  auto load_trip = [&](int q0, uint4(&e)[4]) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int q = q0 + lane + j * T;
       e[j] = q < quads ? __ldg(pairs + q) : make_uint4(0, 0, 0, 0);
     }
+  };
+  uint4 e[4], en[4];
+  if (warp * 32 < quads) load_trip(warp * 32, e);
+  for (int q0 = warp * 32; q0 < quads; q0 += 4 * T) {   // warp-uniform trip count; 16 edges per lane per trip
+    const bool more = q0 + 4 * T < quads;
+    if (more) load_trip(q0 + 4 * T, en);
     vc.add8(pair_xor(sP, e[0].x), pair_xor(sP, e[0].y), pair_xor(sP, e[0].z), pair_xor(sP, e[0].w),
             pair_xor(sP, e[1].x), pair_xor(sP, e[1].y), pair_xor(sP, e[1].z), pair_xor(sP, e[1].w));
     vc.add8(pair_xor(sP, e[2].x), pair_xor(sP, e[2].y), pair_xor(sP, e[2].z), pair_xor(sP, e[2].w),
@@ -168,6 +175,10 @@ __device__ __forceinline__ int tile_cut_partial(const GraphDev& g, const uint32_
       total += vc.flush_warp(lane);
       vc.clear();
       blocks = 0;
+    }
+    if (more) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) e[j] = en[j];
     }
   }
   total += vc.flush_warp(lane);

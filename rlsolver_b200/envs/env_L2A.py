@@ -108,17 +108,15 @@ class EnvMaxcut:
         good_vs = st.ls_begin(good_xs, vs_in, 1, noise_std, ws)
         shape = (num_sims, self.num_nodes)
         noise0 = th.randn(shape, dtype=th.float32, device=self.device)
-        st.ls_thresh(num_sims, 1, noise0, num_spin, ws)
-        del noise0
         per_launch = max(1, min(16, _NOISE_BYTES_PER_LAUNCH // max(1, 4 * num_sims * self.num_nodes)))
         done = 0
-        while done < num_iters:
+        while done < num_iters or noise0 is not None:
             now = min(per_launch, num_iters - done)
             noises = [th.randn(shape, dtype=th.float32, device=self.device) for _ in range(now)]
             done += now
-            st.ls_search(good_vs, 1, noises, done == num_iters, good_xs, ws)
-        if num_iters <= 0:
-            st.ls_search(good_vs, 1, [], True, good_xs, ws)
+            # the first launch also derives the threshold from noise0 (env_L2A.py:94-96)
+            st.ls_run(good_vs, 1, noise0, num_spin, noises, done == num_iters, good_xs, ws)
+            noise0 = None
         return good_xs, good_vs
 
 

@@ -270,6 +270,21 @@ class GraphStore:
                                                 _ptr(xs_out), _ptr(workspace), _stream_ptr(self.device)),
                        "ls_search")
 
+    def ls_run(self, vs: TEN, ws_mult: int, thresh_noise: Optional[TEN], num_spin: int, noises: Sequence[TEN],
+               finish: bool, xs_out: Optional[TEN], workspace: TEN) -> None:
+        """Threshold from `thresh_noise` (if given) + one noisy iteration per tensor of `noises` + (finish)
+        the single-flip pass, one launch per 16 tensors."""
+        e = vs.shape[0]
+        for t in noises:
+            self._check_noise(t, e)
+        if thresh_noise is not None:
+            self._check_noise(thresh_noise, e)
+        ptrs = (C.c_void_p * max(1, len(noises)))(*[t.data_ptr() for t in noises])
+        with self._op("ls_search", max(1, (len(noises) + 15) // 16)):
+            _lib.check(self._lib.rlsb_ls_run(self._h, e, _ptr(vs), int(ws_mult), _ptr(thresh_noise), int(num_spin),
+                                             ptrs, len(noises), int(finish), _ptr(xs_out), _ptr(workspace),
+                                             _stream_ptr(self.device)), "ls_run")
+
     def _check_noise(self, t: TEN, num_envs: int) -> None:
         if t.dtype != th.float32 or tuple(t.shape) != (num_envs, self.num_nodes) or not t.is_contiguous() \
                 or t.device != self.device:

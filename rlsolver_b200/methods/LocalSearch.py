@@ -74,11 +74,10 @@ class LocalSearch:
         while done < num_iters:
             now = min(16, num_iters - done)
             noises = [th.randn(shape, dtype=th.float32, device=sim.device) for _ in range(now)]
-            if first:        # the threshold comes from the first draw, which also drives iteration 0
-                st.ls_thresh(num_sims, 2, noises[0], num_spin, ws)
-                first = False
             done += now
-            st.ls_search(prev_vs, 2, noises, done == num_iters, self.good_xs, ws)
+            # the threshold comes from the first draw, which also drives iteration 0
+            st.ls_run(prev_vs, 2, noises[0] if first else None, num_spin, noises, done == num_iters, self.good_xs, ws)
+            first = False
         if num_iters <= 0:
             st.ls_search(prev_vs, 2, [], True, self.good_xs, ws)
         num_update = update_vs_only(self.good_vs, prev_vs)
