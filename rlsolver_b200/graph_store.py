@@ -138,6 +138,10 @@ class GraphStore:
             "listed_ptr", "listed_col", "full_ptr", "full_col", "level_ptr", "level_nodes")]), "graph_export")
         return out
 
+    def listed_degree_numpy(self) -> np.ndarray:
+        """Listed degree per node (== n0_num_n1 of the reference), int64 [N]."""
+        return np.diff(self.export()["listed_ptr"].astype(np.int64))
+
     def export_sell(self, which: int) -> Dict[str, np.ndarray]:
         """Host copy of a SELL-32 structure (0 = listed neighbours, 1 = sweep order)."""
         sizes = np.zeros(3, np.int64)
