@@ -236,6 +236,15 @@ int32_t rlsb_qubo_padded_vars(const rlsb_qubo_t* h);
 int64_t rlsb_qubo_workspace_bytes(const rlsb_qubo_t* h, int64_t num_chains);
 int rlsb_qubo_energy(const rlsb_qubo_t* h, const float* x, int64_t num_chains, float* energy, void* workspace,
                      void* stream);
+/* qubo_sweeps: the local-search sweeps of mcpg_sampling_qubo (binary == 0: x in {-1,+1},
+ *   x_i <- sign(Q_i . x with x_i zeroed), ties -> -1; sampling.py:331-337) and mcpg_sampling_qubo_bin
+ *   (binary != 0: x in {0,1}, x_i <- [Q_i . x > -Q_ii / 2]; sampling.py:356-362), num_sweeps passes
+ *   over index 0..N-1 in order, in place on x = float32 [N][C].  q = the float32 [N][N] matrix the
+ *   handle was created from (diagonal blocks are read in full precision).  Blocked Gauss-Seidel:
+ *   per 128 rows one tensor-core GEMM tile + the in-order corrections; decisions are exact for
+ *   integer-valued Q, and differ from an fp32 GEMV only where |Q_i . x| is below its rounding error. */
+int rlsb_qubo_sweeps(const rlsb_qubo_t* h, const float* q, float* x, int64_t num_chains, int32_t num_sweeps,
+                     int32_t binary, void* workspace, void* stream);
 
 /* ---- pattern-I environment with one graph per environment: SpinSystemUnbiased of
  * rlsolver/methods/ECO_S2V/src/envs/spinsystem_PECO.py (reset 151-193, step 306-486).

@@ -126,6 +126,7 @@ SIGNATURES = {
     "rlsb_qubo_padded_vars": (_i32, [_vp]),
     "rlsb_qubo_workspace_bytes": (_i64, [_vp, _i64]),
     "rlsb_qubo_energy": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "rlsb_qubo_sweeps": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "rlsb_peco_fields": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "rlsb_peco_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _i32, _vp,
                                  _i32, _i32, _f32, _f32, _i32, _f32, _i32, _f32, _i32, _vp]),

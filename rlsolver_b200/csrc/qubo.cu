@@ -216,6 +216,182 @@ qubo_energy_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(2 * kQN)) : "memory");
 }
 
+// ---------------------------------------------------------------- coordinate-ascent sweeps
+// Local-search sweeps of mcpg_sampling_qubo / mcpg_sampling_qubo_bin
+// (rlsolver/methods/MCPG/sampling.py:331-337, 356-362): for index in 0..N-1 (Gauss-Seidel):
+//     x[index] = 0; res = Q[index] . x; x[index] = (res > 0) ? +1 : -1        (+-1 form)
+//     x[index] = 0; res = Q[index] . x; x[index] = (res > -Q[index][index]/2)  (0/1 form)
+// for every chain -- N dependent GEMVs in the reference.  Blocked form: for a block of 64 rows
+//     F^T = X^T Q[block, :]^T     (128 chains x 64 rows x N: one tensor-core GEMM tile as above, with
+//                                  the chains on the M side so that a TMEM lane = a chain)
+// and then the 64 decisions of the block in order, each one correcting the rows after it,
+//     res_i = F_i - Q_ii x_i ;  x_i' = rule(res_i) ;  F_j += Q_ji (x_i' - x_i)  for j > i in the block,
+// which is algebraically the reference's sequence.  Chains are independent and a thread of the four
+// epilogue warps owns one chain: F[64] and x[64] live in its registers, so the in-block
+// corrections (64*63/2 FMAs against the broadcast diagonal block of Q in shared memory) need no
+// barrier and no shuffles.  One launch per row block (the next block's GEMM reads the X this one wrote).
+constexpr int kSM = 128;                              // chains per CTA (MMA M)
+constexpr int kSB = 64;                               // rows of Q per block (MMA N)
+constexpr int kSStages = 3;
+constexpr uint32_t kSTileX = kSM * kQK * 2;           // 16 KB
+constexpr uint32_t kSTileQ = kSB * kQK * 2;           // 8 KB
+constexpr uint32_t kSStageBytes = kSTileX + kQLimbs * kSTileQ;   // 40 KB
+
+struct SweepSmem {
+  uint8_t tiles[kSStages][kSStageBytes];              // [X | Q_hi | Q_mid | Q_lo]
+  float qd[kSB][kSB];                                 // qd[j][i] = Q[m0 + j][m0 + i]
+  uint64_t full_bar[kSStages], empty_bar[kSStages], tmem_full_bar[2], tmem_empty_bar[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kQThreads, 1)
+qubo_sweep_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQ,
+                  const float* __restrict__ q, int n, int np, int m0, int64_t num_chains, int binary,
+                  __nv_bfloat16* __restrict__ xt, float* __restrict__ x) {
+  extern __shared__ uint8_t smem_raw[];
+  SweepSmem& S = *reinterpret_cast<SweepSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * kSM;                        // first chain of this CTA
+  const int kblocks = np / kQK;
+  const int chunks = (kblocks + kQChunk - 1) / kQChunk;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSStages; ++s) mbar_init(&S.full_bar[s], 1), mbar_init(&S.empty_bar[s], 1);
+    for (int b = 0; b < 2; ++b) mbar_init(&S.tmem_full_bar[b], 1), mbar_init(&S.tmem_empty_bar[b], 4);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
+                 "r"((uint32_t)(2 * kSB))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp == 0) {
+    if (elect_one()) {                                   // ===== TMA producer
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int s = kb % kSStages, ph = (kb / kSStages) & 1;
+        mbar_wait(&S.empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&S.full_bar[s], kSStageBytes);
+        tma_load_2d(S.tiles[s], &tmX, &S.full_bar[s], kb * kQK, n0);
+        for (int l = 0; l < kQLimbs; ++l)
+          tma_load_2d(S.tiles[s] + kSTileX + l * kSTileQ, &tmQ, &S.full_bar[s], kb * kQK, l * np + m0);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {                                   // ===== MMA issuer (M128 chains, N64 rows, K16)
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kSB >> 3) << 17) | ((uint32_t)(kSM >> 4) << 24);
+      for (int ch = 0; ch < chunks; ++ch) {
+        const int buf = ch & 1;
+        mbar_wait(&S.tmem_empty_bar[buf], ((ch >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int kb_end = min(kblocks, (ch + 1) * kQChunk);
+        for (int kb = ch * kQChunk; kb < kb_end; ++kb) {
+          const int s = kb % kSStages, ph = (kb / kSStages) & 1;
+          mbar_wait(&S.full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = umma_desc(S.tiles[s]);
+#pragma unroll
+          for (int l = 0; l < kQLimbs; ++l) {
+            const uint64_t db = umma_desc(S.tiles[s] + kSTileX + l * kSTileQ);
+#pragma unroll
+            for (int k = 0; k < kQK / 16; ++k)
+              umma_bf16(tmem + buf * kSB, da + 2 * k, db + 2 * k, idesc,
+                        (kb != ch * kQChunk || l != 0 || k != 0) ? 1u : 0u);
+          }
+          umma_commit(&S.empty_bar[s]);
+        }
+        umma_commit(&S.tmem_full_bar[buf]);
+      }
+    }
+  } else {                                               // ===== warps 2..5: one thread per chain
+    const int qw = warp & 3;                               // TMEM lane quarter this warp may read
+    const int64_t chain = n0 + 32 * qw + lane;             // < cp (padded chains carry zeros)
+    const int et = threadIdx.x - 64;
+    for (int idx = et; idx < kSB * kSB; idx += 128) {      // diagonal block of Q in full precision
+      const int j = idx / kSB, i = idx % kSB;
+      S.qd[j][i] = (m0 + j < n && m0 + i < n) ? __ldg(q + (int64_t)(m0 + j) * n + m0 + i) : 0.f;
+    }
+    float xv[kSB], f[kSB];
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(xt + (size_t)chain * np + m0);     // 128 contiguous bytes
+#pragma unroll
+      for (int v8 = 0; v8 < kSB / 8; ++v8) {
+        const uint4 w = src[v8];
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          xv[v8 * 8 + 2 * k] = __uint_as_float(ws[k] << 16);              // bf16 -> f32
+          xv[v8 * 8 + 2 * k + 1] = __uint_as_float(ws[k] & 0xffff0000u);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kSB; ++c) f[c] = 0.f;
+    for (int ch = 0; ch < chunks; ++ch) {
+      const int buf = ch & 1;
+      mbar_wait(&S.tmem_full_bar[buf], (ch >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int g = 0; g < kSB / 32; ++g) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem + ((uint32_t)(32 * qw) << 16) + (uint32_t)(buf * kSB + g * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[g * 32 + j] += __uint_as_float(v[j]);     // round-to-nearest running sums
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.tmem_empty_bar[buf]);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");        // qd complete
+    const float lo = binary ? 0.f : -1.f;
+#pragma unroll
+    for (int i = 0; i < kSB; ++i) {
+      const float qii = S.qd[i][i];
+      const float res = f[i] - qii * xv[i];                // Q[i] . x with x_i zeroed
+      const float xn = res > (binary ? -qii * 0.5f : 0.f) ? 1.f : lo;
+      const float d = (m0 + i < n) ? xn - xv[i] : 0.f;     // padding rows never move
+      xv[i] += d;
+#pragma unroll
+      for (int j = i + 1; j < kSB; ++j) f[j] = fmaf(S.qd[j][i], d, f[j]);
+    }
+    // new x of the block: the bf16 chain-major copy the next block's GEMM reads, and float32 [N][C]
+    {
+      uint4* dst = reinterpret_cast<uint4*>(xt + (size_t)chain * np + m0);
+#pragma unroll
+      for (int v8 = 0; v8 < kSB / 8; ++v8) {
+        uint32_t ws[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)       // values are -1, 0, +1: exact in bf16 (upper half of the f32 pattern)
+          ws[k] = (__float_as_uint(xv[v8 * 8 + 2 * k]) >> 16) | (__float_as_uint(xv[v8 * 8 + 2 * k + 1]) & 0xffff0000u);
+        dst[v8] = make_uint4(ws[0], ws[1], ws[2], ws[3]);
+      }
+    }
+    if (chain < num_chains) {
+#pragma unroll
+      for (int i = 0; i < kSB; ++i)
+        if (m0 + i < n) x[(int64_t)(m0 + i) * num_chains + chain] = xv[i];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(2 * kSB)) : "memory");
+}
+
 // Q fp32 [n][n] -> three bf16 limbs [3][np][np], zero padded; hi + mid + lo == q exactly
 __global__ void qubo_split_kernel(const float* __restrict__ q, int n, int np, __nv_bfloat16* __restrict__ limbs) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -370,6 +546,36 @@ int rlsb_qubo_energy(const rlsb_qubo_t* h, const float* x, int64_t num_chains, f
   RLSB_LAUNCH_OK();
   qubo_reduce_kernel<<<(unsigned)((num_chains + 255) / 256), 256, 0, st>>>(partial, h->np / kQM, cp, num_chains, energy);
   RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+int rlsb_qubo_sweeps(const rlsb_qubo_t* h, const float* q, float* x, int64_t num_chains, int32_t num_sweeps,
+                     int32_t binary, void* workspace, void* stream) {
+  using namespace rlsb;
+  RLSB_REQUIRE(h != nullptr, RLSB_ERR_INVALID, "qubo_sweeps: null handle");
+  RLSB_REQUIRE(num_chains >= 0 && num_sweeps >= 0, RLSB_ERR_INVALID, "qubo_sweeps: negative size");
+  if (num_chains == 0 || num_sweeps == 0) return RLSB_OK;
+  RLSB_REQUIRE(q && x && workspace, RLSB_ERR_INVALID, "qubo_sweeps: null pointer");
+  RLSB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, RLSB_ERR_INVALID,
+               "qubo_sweeps: workspace must be 256-byte aligned");
+  auto st = static_cast<cudaStream_t>(stream);
+  const int64_t cp = (num_chains + kQN - 1) / kQN * kQN;
+  auto* xt = static_cast<__nv_bfloat16*>(workspace);
+  dim3 tb(32, 8), tg((unsigned)(cp / 32), (unsigned)(h->np / 32));
+  qubo_xt_kernel<<<tg, tb, 0, st>>>(x, h->n, num_chains, h->np, cp, xt);
+  RLSB_LAUNCH_OK();
+  CUtensorMap map_x, map_q;
+  if (int rc = make_map(&map_x, xt, (uint64_t)cp, (uint64_t)h->np, kSM)) return rc;
+  if (int rc = make_map(&map_q, h->limbs, (uint64_t)3 * h->np, (uint64_t)h->np, kSB)) return rc;
+  const size_t smem = sizeof(SweepSmem) + 1024;
+  RLSB_CUDA_OK(cudaFuncSetAttribute(qubo_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)((num_chains + kSM - 1) / kSM);
+  for (int sweep = 0; sweep < num_sweeps; ++sweep)
+    for (int m0 = 0; m0 < h->n; m0 += kSB) {
+      qubo_sweep_kernel<<<grid, kQThreads, smem, st>>>(map_x, map_q, q, h->n, h->np, m0, num_chains, binary ? 1 : 0,
+                                                       xt, x);
+      RLSB_LAUNCH_OK();
+    }
   return RLSB_OK;
 }
 

@@ -24,10 +24,17 @@ def case(samp, name, fn, n, total_mcmc, repeat, seed, integer):
     c = total_mcmc * repeat
     probs = th.rand(n) * 0.6 + 0.2
     start = th.randint(0, 2, (n, c)).float()
+    rng_state = th.get_rng_state()
     max_res, best, raw, value = fn(data, start, probs, 2, 3, total_mcmc, device=th.device("cpu"))
+    # the same call with every chain as its own group hands back ALL chains after the sweeps
+    # (samples[:, index] with index = arange(C)): the input / output pair of the local-search sweeps
+    th.set_rng_state(rng_state)
+    all_res, all_samples, raw2, _ = fn(data, start, probs, 2, 3, c, device=th.device("cpu"))
+    assert th.equal(raw, raw2)
     np.savez_compressed(os.path.join(OUT, f"qubo_{name}.npz"), Q=q.numpy(), total_mcmc=np.asarray(total_mcmc),
                         max_res=max_res.numpy(), best=best.numpy(), value=value.numpy(),
-                        binary=np.asarray(fn.__name__.endswith("_bin")))
+                        binary=np.asarray(fn.__name__.endswith("_bin")), raw=raw.numpy(), num_ls=np.asarray(2),
+                        all_res=all_res.numpy(), all_samples=all_samples.numpy())
     print("wrote qubo_" + name, "max_res[:3]", max_res[:3].tolist())
 
 
