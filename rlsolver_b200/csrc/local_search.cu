@@ -81,12 +81,16 @@ struct Cross4 {
 };
 
 __global__ void ls_rdstd_kernel(GraphDev g, const int32_t* __restrict__ col_min, const int32_t* __restrict__ col_max,
-                                int mult, float noise_std, float* __restrict__ rd_std, int32_t* __restrict__ degm) {
+                                int mult, float noise_std, float* __restrict__ rd_std, int32_t* __restrict__ degm,
+                                uint32_t* __restrict__ nd) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.np) return;
   const bool real = i < g.n;
-  rd_std[i] = real ? __fmul_rn((float)(mult * (col_max[i] - col_min[i])), noise_std) : 0.f;
-  degm[i] = (real ? g.listed_deg[i] : 0) + kMagicI;
+  const float rd = real ? __fmul_rn((float)(mult * (col_max[i] - col_min[i])), noise_std) : 0.f;
+  const int dm = (real ? g.listed_deg[i] : 0) + kMagicI;
+  rd_std[i] = rd, degm[i] = dm;
+  nd[(i >> 2) * 8 + (i & 3)] = __float_as_uint(rd);
+  nd[(i >> 2) * 8 + 4 + (i & 3)] = (uint32_t)dm;
 }
 
 // sorted (descending) list of the KMAX largest values seen
@@ -157,13 +161,28 @@ constexpr int kMaxStages = 8;
 
 struct TmapPack {
   CUtensorMap m[kLSMaxIters + 1];   // [0]: thresh noise, [1 + k]: noise of iteration k
+  CUtensorMap cross, nd;            // cross counts (tiled); rd_std + degree words interleaved per node group
 };
+
+__device__ __forceinline__ void tma_load_1d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0) {
+  asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0)
+               : "memory");
+}
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
           smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
 
@@ -177,6 +196,7 @@ struct LsArgs {
   const void* cross;       // [W][Np/4][32][4] uint8 / uint16
   const float* rd_std;     // [Np]
   const int32_t* degm;     // [Np] listed degree + kMagicI
+  const uint32_t* nd;      // [Np/4][rd_std x4 | degm x4]: the two arrays interleaved per node group (pipe kernel)
   float* thresh;           // [E]
   const float* thresh_noise;   // non-null: first compute thresh from this tensor
   NoisePtrs noise;
@@ -190,6 +210,8 @@ struct LsArgs {
   int sweep_warps;         // warps that take part in the single-flip pass
   int negmult;             // -mult
   int stages, stage_bytes; // ring geometry (pipe kernel)
+  int skip;                // diagnostic: see PipeCtx::skip
+  int ring_off;            // byte offset of the ring in dynamic shared memory
   long long* times;        // debug: phase timestamps of CTA 0 (RLSB_LS_TIMES), else null
 };
 
@@ -337,6 +359,7 @@ struct PipeCtx {
   int groups, nchunks, negmult;
   int s;            // ring cursor
   uint32_t phase;
+  int skip;         // diagnostic (RLSB_LS_SKIP=1): consume the ring without evaluating anything
   static constexpr int kCrossBytes = kChunkGroups * kTileEnvs * 4 * (int)sizeof(CrossT);
   static constexpr int kNodeOff = kNoiseStageBytes + kCrossBytes;
 
@@ -348,8 +371,8 @@ struct PipeCtx {
                                                        (((q & 3) ^ ((lane >> 1) & 3)) << 4));
     Cross4<CrossT> cr;
     cr.load_shared(st + kNoiseStageBytes + (q * kTileEnvs + lane) * (4 * (int)sizeof(CrossT)));
-    const float4 rd = *reinterpret_cast<const float4*>(st + kNodeOff + q * 16);                      // broadcast
-    const int4 dm = *reinterpret_cast<const int4*>(st + kNodeOff + kChunkGroups * 16 + q * 16);
+    const float4 rd = *reinterpret_cast<const float4*>(st + kNodeOff + q * 32);                      // broadcast
+    const int4 dm = *reinterpret_cast<const int4*>(st + kNodeOff + q * 32 + 16);
     sr[0] = spin_rand(dm.x, negmult, cr.get(0), nz.x, rd.x);
     sr[1] = spin_rand(dm.y, negmult, cr.get(1), nz.y, rd.y);
     sr[2] = spin_rand(dm.z, negmult, cr.get(2), nz.z, rd.z);
@@ -382,7 +405,9 @@ __device__ __forceinline__ void mask_pass(PipeCtx<CrossT>& cx, float th, const u
     const int gc = cx.groups - c * kChunkGroups;           // node groups left (>= 32: a full chunk)
     const int i0 = (c * kChunkGroups + warp) * 4;
     float sa[4], sb[4];
-    if (gc >= kChunkGroups) {
+    if (cx.skip) {
+      // nothing: measures the pure streaming rate of the ring
+    } else if (gc >= kChunkGroups) {
       cx.group_values(st, 0, sa);
       cx.group_values(st, 1, sb);
       emit(sa, i0);
@@ -453,10 +478,10 @@ template <int P, typename CrossT, bool THRESH>
 __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(GraphDev g, LsArgs a,
                                                                   const __grid_constant__ TmapPack maps) {
   extern __shared__ __align__(1024) uint32_t smem[];
-  uint32_t* sP = smem;           // accepted state of the tile
-  uint32_t* sX = smem + g.np;    // candidate state
+  uint32_t* sP = smem;               // accepted state of the tile
+  uint32_t* sX = smem + g.np;        // candidate state
   // noise/cross stages (1024-byte aligned for the swizzle); later the sweep structure
-  char* ring = reinterpret_cast<char*>(smem) + ((2 * (size_t)g.np * 4 + 1023) & ~(size_t)1023);
+  char* ring = reinterpret_cast<char*>(smem) + a.ring_off;
   __shared__ int sCnt[kTileEnvs];
   __shared__ uint32_t sAccept;
   __shared__ __align__(8) uint64_t sFull[kMaxStages], sEmpty[kMaxStages], sBar;
@@ -481,23 +506,22 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(GraphDev g, Ls
   if (warp == kLSWarps) {
     // ---------------- producer: one thread feeds the ring
     if (lane == 0) {
-      const char* cross_tile = static_cast<const char*>(a.cross) + tile * (int64_t)g.np * kTileEnvs * sizeof(CrossT);
       int s = 0, round = 0;
       for (int p = 0; p < passes; ++p) {
         const CUtensorMap* map = &maps.m[has_thresh ? p : p + 1];
         for (int c = 0; c < nchunks; ++c) {
           if (round > 0) mbar_wait(&sEmpty[s], (round - 1) & 1);
           char* st = ring + s * a.stage_bytes;
-          const int gc = min(kChunkGroups, groups - c * kChunkGroups);
-          const uint32_t cross_bytes = gc * (kTileEnvs * 4 * (int)sizeof(CrossT));
-          mbar_expect_tx(&sFull[s], kNoiseStageBytes + cross_bytes + 2 * gc * 16);   // the box is always written whole
-          tma_load_3d(st, map, &sFull[s], 0, (int)env0, c * kChunkG16);  // (rows / groups past the tensor: zeros)
-          bulk_g2s(st + kNoiseStageBytes, cross_tile + (int64_t)c * kChunkGroups * (kTileEnvs * 4 * sizeof(CrossT)),
-                   cross_bytes, &sFull[s]);
-          // the chunk's rd_std / degree words ride along, so the consumers' loop has no global load at all
-          char* nd = st + kNoiseStageBytes + kChunkGroups * kTileEnvs * 4 * (int)sizeof(CrossT);
-          bulk_g2s(nd, a.rd_std + c * (kChunkGroups * 4), gc * 16, &sFull[s]);
-          bulk_g2s(nd + kChunkGroups * 16, a.degm + c * (kChunkGroups * 4), gc * 16, &sFull[s]);
+          // Everything goes through TENSOR copies: plain cp.async.bulk copies stream at only ~6 B/clk per SM
+          // (measured: the 4 KB cross-count copy per chunk capped the ring at 36 GB/s per SM).  Boxes are
+          // always written whole (elements past the tensor read as zeros).
+          mbar_expect_tx(&sFull[s], (uint32_t)a.stage_bytes);
+          tma_load_3d(st, map, &sFull[s], 0, (int)env0, c * kChunkG16);
+          tma_load_2d(st + kNoiseStageBytes, &maps.cross, &sFull[s], 0, (int)(tile * (g.np / 4)) + c * kChunkGroups);
+          // the chunk's rd_std / degree words ride along (interleaved per node group: one copy), so the
+          // consumers' loop has no global load at all
+          tma_load_1d(st + kNoiseStageBytes + kChunkGroups * kTileEnvs * 4 * (int)sizeof(CrossT), &maps.nd, &sFull[s],
+                      c * (kChunkGroups * 8));
           if (++s == a.stages) s = 0, ++round;
         }
       }
@@ -519,7 +543,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(GraphDev g, Ls
 
   PipeCtx<CrossT> cx;
   cx.ring = ring, cx.stage_bytes = a.stage_bytes, cx.stages = a.stages, cx.sFull = sFull, cx.sEmpty = sEmpty;
-  cx.groups = groups, cx.nchunks = nchunks, cx.negmult = a.negmult, cx.s = 0, cx.phase = 0;
+  cx.groups = groups, cx.nchunks = nchunks, cx.negmult = a.negmult, cx.s = 0, cx.phase = 0, cx.skip = a.skip;
   float* sSel = reinterpret_cast<float*>(ring + (size_t)a.stages * a.stage_bytes);   // [kSelCap][32] (THRESH)
   int tk = 0;
   stamp(a, tk);
@@ -678,6 +702,7 @@ struct LsWorkspace {
   void* cross;
   int32_t *col_min, *col_max, *degm;
   float *rd_std, *thresh;
+  uint32_t* nd;
   size_t bytes;
 };
 
@@ -698,6 +723,7 @@ static LsWorkspace carve(const GraphDev& g, int64_t num_envs, void* base) {
   w.degm = reinterpret_cast<int32_t*>(take((size_t)g.np * 4));
   w.rd_std = reinterpret_cast<float*>(take((size_t)g.np * 4));
   w.thresh = reinterpret_cast<float*>(take((size_t)num_envs * 4));
+  w.nd = reinterpret_cast<uint32_t*>(take((size_t)g.np * 8));
   w.bytes = off + 256;
   return w;
 }
@@ -720,7 +746,9 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// float32 [E][N] row-major seen as {16 floats, E rows, N/16 column groups}; box = 16 x 32 x kChunkG16
+// float32 [E][N] row-major seen as {16 floats, E rows, N/16 column groups}; box = 16 x 32 x kChunkG16: ONE copy
+// per 128-node chunk (the producer thread retires a TMA instruction only every ~100 cycles, so the number of
+// copies per chunk, not their size, bounds the ring's fill rate).  Rows / groups past the tensor read as zeros.
 static int make_noise_map(CUtensorMap* map, const float* base, int64_t num_envs, int n) {
   EncodeTiledFn fn = encode_tiled_fn();
   RLSB_REQUIRE(fn != nullptr, RLSB_ERR_CUDA, "ls_run: cuTensorMapEncodeTiled is not available from this driver");
@@ -735,12 +763,37 @@ static int make_noise_map(CUtensorMap* map, const float* base, int64_t num_envs,
   return RLSB_OK;
 }
 
+// cross counts [tiles * Np/4 groups][32 envs x 4 counts] -> rows of 128 (uint8) / 256 (uint16) bytes, box = 32 groups;
+// rd_std / degree words [Np] -> 1-D, box = 128 elements
+static int make_side_maps(TmapPack* maps, const GraphDev& g, const LsArgs& a, size_t cross_elt) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  RLSB_REQUIRE(fn != nullptr, RLSB_ERR_CUDA, "ls_run: cuTensorMapEncodeTiled is not available from this driver");
+  const int64_t tiles = (a.num_envs + kTileEnvs - 1) / kTileEnvs;
+  const cuuint32_t row = (cuuint32_t)(kTileEnvs * 4 * cross_elt);
+  const cuuint64_t cdims[2] = {row, (cuuint64_t)(tiles * (g.np / 4))};
+  const cuuint64_t cstr[1] = {row};
+  const cuuint32_t cbox[2] = {row, (cuuint32_t)kChunkGroups};
+  const cuuint32_t one[2] = {1, 1};
+  CUresult r = fn(&maps->cross, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(a.cross), cdims, cstr, cbox, one,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RLSB_REQUIRE(r == CUDA_SUCCESS, RLSB_ERR_CUDA, "ls_run: tensor map for the cross counts failed (CUresult %d)", (int)r);
+  const cuuint64_t ndims[1] = {(cuuint64_t)2 * g.np};
+  const cuuint32_t nbox[1] = {(cuuint32_t)(kChunkGroups * 8)};
+  r = fn(&maps->nd, CU_TENSOR_MAP_DATA_TYPE_UINT32, 1, const_cast<uint32_t*>(a.nd), ndims, cstr, nbox, one,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RLSB_REQUIRE(r == CUDA_SUCCESS, RLSB_ERR_CUDA, "ls_run: tensor map for the node words failed (CUresult %d)", (int)r);
+  return RLSB_OK;
+}
+
 template <int P, typename CrossT, bool THRESH>
 static int launch_pipe(const GraphDev& g, LsArgs a, const TmapPack& maps, cudaStream_t st) {
-  const size_t tiles_bytes = (2 * (size_t)g.np * sizeof(uint32_t) + 1023) / 1024 * 1024 + (THRESH ? kSelBytes : 0);
   a.stage_bytes = kNoiseStageBytes + kChunkGroups * kTileEnvs * 4 * (int)sizeof(CrossT) + 1024;   // + rd_std, degm
   const int passes = (a.thresh_noise ? 1 : 0) + a.num_iters;
   const int chunks = passes * ((g.n / 4 + kChunkGroups - 1) / kChunkGroups);
+  a.ring_off = (int)((2 * (size_t)g.np * sizeof(uint32_t) + 1023) / 1024 * 1024);
+  const size_t tiles_bytes = a.ring_off + (THRESH ? kSelBytes : 0);
   int stages = (int)((kSmemBudget - tiles_bytes) / a.stage_bytes);
   stages = stages > kMaxStages ? kMaxStages : stages;
   stages = stages > chunks ? (chunks > 0 ? chunks : 1) : stages;
@@ -835,6 +888,7 @@ static int run_search(const GraphDev& g, int64_t num_envs, int64_t* vs, int ws_m
     const int now = num_iters - done < kLSMaxIters ? num_iters - done : kLSMaxIters;
     LsArgs a{};
     a.packed = w.packed, a.vs = vs, a.cross = w.cross, a.rd_std = w.rd_std, a.degm = w.degm, a.thresh = w.thresh;
+    a.nd = w.nd;
     a.thresh_noise = done == 0 ? thresh_noise : nullptr;
     a.kth_big = kth_big;
     for (int k = 0; k < now; ++k) a.noise.p[k] = h_noise_ptrs[done + k];
@@ -844,6 +898,14 @@ static int run_search(const GraphDev& g, int64_t num_envs, int64_t* vs, int ws_m
     a.cut_warps = cut_warps_for(g.m, kLSWarps);
     a.sweep_warps = sweep_warps_for(g, kLSWarps), a.negmult = -ws_mult;
     a.times = ls_debug_times();
+    {
+      static int skip = -1;
+      if (skip < 0) {
+        const char* e = getenv("RLSB_LS_SKIP");
+        skip = (e && e[0] == '1') ? 1 : 0;
+      }
+      a.skip = skip;
+    }
     int rc;
     if (pipe) {
       TmapPack maps;
@@ -852,6 +914,7 @@ static int run_search(const GraphDev& g, int64_t num_envs, int64_t* vs, int ws_m
         if ((rc = make_noise_map(&maps.m[0], a.thresh_noise, num_envs, g.n))) return rc;
       for (int k = 0; k < now; ++k)
         if ((rc = make_noise_map(&maps.m[1 + k], a.noise.p[k], num_envs, g.n))) return rc;
+      if ((rc = make_side_maps(&maps, g, a, dc == 2 ? 2 : 1))) return rc;
       rc = dc == 0   ? launch_pipe_k<6, uint8_t>(g, a, maps, st)
            : dc == 1 ? launch_pipe_k<8, uint8_t>(g, a, maps, st)
                      : launch_pipe_k<12, uint16_t>(g, a, maps, st);
@@ -905,7 +968,8 @@ int rlsb_ls_begin(const rlsb_graph_t* gh, const uint8_t* xs, int64_t num_envs, i
   if (int rc = prepare_tiles(*g, xs, nullptr, num_envs, w.packed, w.cross, degree_class(*g) != 2 ? 1 : 2, w.col_min,
                              w.col_max, compute_vs ? vs : nullptr, st))
     return rc;
-  ls_rdstd_kernel<<<(g->np + 255) / 256, 256, 0, st>>>(*g, w.col_min, w.col_max, ws_mult, noise_std, w.rd_std, w.degm);
+  ls_rdstd_kernel<<<(g->np + 255) / 256, 256, 0, st>>>(*g, w.col_min, w.col_max, ws_mult, noise_std, w.rd_std, w.degm,
+                                                       w.nd);
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }

@@ -142,8 +142,10 @@ __device__ __forceinline__ uint32_t pair_xor(const uint32_t* sP, uint32_t pr) {
   return sP[pr & 0xffffu] ^ sP[pr >> 16];
 }
 
-__device__ __forceinline__ int tile_cut_partial(const GraphDev& g, const uint32_t* sP, int warps) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// `warp` = this warp's index among the `warps` that take edges (default: its index in the CTA).
+__device__ __forceinline__ int tile_cut_partial(const GraphDev& g, const uint32_t* sP, int warps, int warp = -1) {
+  const int lane = threadIdx.x & 31;
+  if (warp < 0) warp = threadIdx.x >> 5;
   if (warp >= warps) return 0;
   const int T = warps * 32;
   const int quads = (g.m + 3) >> 2;                     // the list is zero-padded to whole quads
