@@ -47,7 +47,6 @@ class EnvMaxcut:
         self.n1_ids = th.from_numpy(col.copy()).to(self.device)[None, :]
         self.sim_ids = th.zeros((1, self.store.num_listed), dtype=th.long, device=self.device)
         self.n0_num_n1 = th.from_numpy(np.diff(ptr)).to(self.device)[None, :]
-        self._side_stream = None
         self._adjacency_bool: Optional[TEN] = None
         self._adjacency_indies: Optional[List[TEN]] = None
 
@@ -106,11 +105,8 @@ class EnvMaxcut:
             if not vs_in.is_contiguous():
                 vs_in = vs_in.contiguous()
         ws = st.ls_workspace(num_sims)
-        shape = (num_sims, self.num_nodes)
-        num_iters = max(int(num_iters), 0)
-        if (1 + num_iters) * 4 * num_sims * self.num_nodes <= _NOISE_BYTES_PER_LAUNCH and num_iters <= 16:
-            return self._local_search_two_streams(good_xs, vs_in, num_iters, num_spin, noise_std, ws, shape)
         good_vs = st.ls_begin(good_xs, vs_in, 1, noise_std, ws)
+        shape = (num_sims, self.num_nodes)
         noise0 = th.randn(shape, dtype=th.float32, device=self.device)
         per_launch = max(1, min(16, _NOISE_BYTES_PER_LAUNCH // max(1, 4 * num_sims * self.num_nodes)))
         done = 0
@@ -121,36 +117,6 @@ class EnvMaxcut:
             # the first launch also derives the threshold from noise0 (env_L2A.py:94-96)
             st.ls_run(good_vs, 1, noise0, num_spin, noises, done == num_iters, good_xs, ws)
             noise0 = None
-        return good_xs, good_vs
-
-    def _local_search_two_streams(self, good_xs, vs_in, num_iters, num_spin, noise_std, ws, shape):
-        """Same torch RNG calls in the same order (the generator hands out Philox offsets at call time, so
-        the draws are those of the sequential code), but issued on a side stream: torch's randn kernels are
-        ALU bound and fit next to the search kernel's one CTA per SM, so generating the later noise tensors
-        overlaps `ls_begin` and the first half of the search instead of preceding it."""
-        st = self.store
-        main = th.cuda.current_stream(self.device)
-        side = self._side_stream
-        if side is None:
-            side = self._side_stream = th.cuda.Stream(device=self.device)
-        side.wait_stream(main)
-        noises, ready = [], []
-        with th.cuda.stream(side):
-            for _ in range(1 + num_iters):
-                noises.append(th.randn(shape, dtype=th.float32, device=self.device))
-                ev = th.cuda.Event()
-                ev.record(side)
-                ready.append(ev)
-        good_vs = st.ls_begin(good_xs, vs_in, 1, noise_std, ws)
-        split = (num_iters + 1) // 2 if num_iters >= 4 else num_iters        # iterations of the first launch
-        main.wait_event(ready[split])
-        st.ls_run(good_vs, 1, noises[0], num_spin, noises[1:1 + split], split == num_iters, good_xs, ws)
-        if split < num_iters:
-            main.wait_event(ready[num_iters])
-            st.ls_run(good_vs, 1, None, num_spin, noises[1 + split:], True, good_xs, ws)
-        if not th.cuda.is_current_stream_capturing():      # (a captured graph owns its memory pool)
-            for t in noises:
-                t.record_stream(main)
         return good_xs, good_vs
 
 
