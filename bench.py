@@ -221,6 +221,7 @@ def run_b200(args):
                     local_part()
             th.cuda.current_stream(dev).wait_stream(side)
             th.cuda.synchronize()
+            sim.store.rng_cursor_sync()        # the captured kernels read the generator state from device memory
             g = th.cuda.CUDAGraph()
             with th.cuda.graph(g):
                 out = local_part()
@@ -308,9 +309,15 @@ def run_b200(args):
     alg_bytes = {   # algorithmic bytes per launch group, DESIGN.md "Kernels"
         # ls_run: noise + cross counts per pass (threshold pass + NUM_ITERS iterations); packed tile in/out,
         # thresholds, bool rows + values out, graph once
-        "ls_search": (1 + NUM_ITERS) * (4 * envs * n + cb * envs * np_) + 2 * envs * np_ // 8 + envs * n + 20 * envs
-                     + 8 * np_ + graph_b,
+        # ls_run here = the threshold pass only (noise of draw 0 + cross counts in, thresholds out)
+        "ls_search": 4 * envs * n + cb * envs * np_ + 2 * envs * np_ // 8 + 20 * envs + 8 * np_,
         "ls_thresh": 4 * envs * n + cb * envs * np_ + 4 * envs + 8 * np_,
+        # bound pass (cross counts in, one byte per element out) + per draw one byte per element in, one bit out
+        "ls_noise_masks": envs * np_ + envs * n + NUM_ITERS * (envs * n + envs * n // 8) + 4 * envs + 8 * np_,
+        # packed tile in/out, one mask bit per element and iteration, bool rows + values out, graph once
+        "ls_run_masks": 2 * envs * np_ // 8 + NUM_ITERS * envs * n // 8 + envs * n + 16 * envs + graph_b,
+        "torch_randn": 4 * envs * n,
+        "rng_cursor_advance": 16,
         "ls_begin": envs * n + envs * np_ // 8 + cb * envs * np_ + 8 * envs + graph_b,
         "pack_spins": envs * n + envs * np_ // 8,
         "unpack_spins": envs * n + envs * np_ // 8,
@@ -345,7 +352,8 @@ def run_b200(args):
                 "data": "synthetic",
                 "config": {"workload": workload_name(envs), "envs_per_gpu": envs, "nodes": n, "edges": sim.num_edges,
                            "env_steps_per_step_per_gpu": per_call, "l2": "flushed between steps (256 MiB write)", "cuda_graph": graph_status,
-                           "rng": "torch CUDA Philox randn, 1+8 draws of [E,N] f32 per step inside the timed region",
+                           "rng": "torch's CUDA Philox stream, 1+8 draws of randn [E,N] f32 per step inside the timed region: draw 0 "
+                                  "(threshold) as a tensor, draws 1-8 recomputed in place by ls_noise_masks (flip bits only)",
                            "multi_gpu": "env batch sharded, graph replicated, one best-cut exchange per step (all-gather of 8+N byte records, no host sync)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": envs * n,
                         "d2h_bytes_per_step": envs * n + 8 * envs, "ms_per_step": float(e2e_total.item()) / args.steps},

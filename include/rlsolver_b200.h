@@ -127,7 +127,8 @@ int rlsb_node_cross_counts(const rlsb_graph_t* g, const uint32_t* packed, int64_
 int64_t rlsb_ls_workspace_bytes(const rlsb_graph_t* g, int64_t num_envs);
 /* byte offset of a workspace section (tests / debugging): 0 packed u32 [W][Np], 1 cross counts
  * (uint8, or uint16 when a degree exceeds 255) tiled [W][Np/4][32 envs][4 nodes], 2 col_min i32 [Np], 3 col_max i32 [Np],
- * 4 listed degree + 0x4B400000 i32 [Np], 5 rd_std f32 [Np], 6 thresh f32 [E]; -1 on error. */
+ * 4 listed degree + 0x4B400000 i32 [Np], 5 rd_std f32 [Np], 6 thresh f32 [E], 7 cross counts uint8 row-major
+ * [32W][Np] (absent when a degree exceeds 255); -1 on error. */
 int64_t rlsb_ls_workspace_offset(const rlsb_graph_t* g, int64_t num_envs, int32_t section);
 int rlsb_ls_begin(const rlsb_graph_t* g, const uint8_t* xs, int64_t num_envs, int64_t* vs, int32_t compute_vs,
                   int32_t ws_mult, float noise_std, void* workspace, void* stream);
@@ -139,6 +140,34 @@ int rlsb_ls_search(const rlsb_graph_t* g, int64_t num_envs, int64_t* vs, int32_t
 int rlsb_ls_run(const rlsb_graph_t* g, int64_t num_envs, int64_t* vs, int32_t ws_mult, const float* thresh_noise,
                 int32_t num_spin, const float* const* h_noise_ptrs, int32_t num_iters, int32_t finish,
                 uint8_t* xs_out, void* workspace, void* stream);
+
+/* ---- the noisy iterations without noise tensors.  The reference draws `randn [E,N] float32` once per
+ * iteration (env_L2A.py:99, LocalSearch.py:66) and uses one bit of each number (`spin_rand > thresh`,
+ * env_L2A.py:100-101).  torch's CUDA generator is counter based (Philox4x32-10 keyed by seed and offset), so
+ * ls_noise_masks recomputes exactly the numbers `num_draws` consecutive torch.randn([E,N]) calls starting
+ * at generator state (seed, offset) would have produced (curand_normal4, as ATen's normal_ kernel), evaluates
+ * spin_rand on them in registers against the thresholds in the workspace (ls_run / ls_thresh put them there)
+ * and writes, per draw, the flip mask as a flat bit array: bit (e*N + n) of masks[k*mask_words ...], where
+ * mask_words = rlsb_ls_mask_words(g, E) uint32 words per draw (-1: not available -- counts wider than
+ * 8 bits or 2^31 and more elements per draw -- use rlsb_ls_run with explicit noise).  rng_threads /
+ * rng_iters are the call geometry of ONE such torch call (ATen calc_execution_policy: T = 256 * min(SMs *
+ * blocks per SM, ceil(numel / 256)), iters = ceil(numel / 4T)); the caller advances the generator offset by
+ * 4 * rng_iters per draw.  ls_run_masks then runs the iterations (one per mask array) and, if finish != 0,
+ * the single-flip pass, as rlsb_ls_search does.  rlsb_torch_randn writes the same draws as float32
+ * [num_draws][numel] (equal to torch.randn bit for bit; tests pin it). */
+int64_t rlsb_ls_mask_words(const rlsb_graph_t* g, int64_t num_envs);
+int rlsb_ls_noise_masks(const rlsb_graph_t* g, int64_t num_envs, int32_t ws_mult, uint64_t seed, uint64_t offset,
+                        const uint64_t* rng_dev, int32_t rng_threads, int32_t rng_iters, int32_t num_draws,
+                        uint32_t* masks, void* workspace, void* stream);
+int rlsb_ls_run_masks(const rlsb_graph_t* g, int64_t num_envs, int64_t* vs, const uint32_t* masks, int32_t num_iters,
+                      int32_t finish, uint8_t* xs_out, void* workspace, void* stream);
+int rlsb_torch_randn(float* out, int64_t numel, uint64_t seed, uint64_t offset, const uint64_t* rng_dev,
+                     int32_t rng_threads, int32_t rng_iters, int32_t num_draws, void* stream);
+/* Device-resident generator state for CUDA-graph replays: rng_dev -> {seed, offset} (2 x uint64 in device
+ * memory).  When rng_dev is non-NULL the two calls above take the seed from it and count `offset` from its
+ * offset (pass the offset of the draw relative to the cursor); rlsb_rng_cursor_advance moves the cursor on
+ * the device, so every replay of a captured sequence continues the stream where the last one stopped. */
+int rlsb_rng_cursor_advance(uint64_t* rng_dev, uint64_t delta, void* stream);
 
 /* profiling aid: with RLSB_LS_TIMES=1 in the environment CTA 0 of every pipelined ls_run launch
  * records clock64 stamps (start, then per pass: candidate done / accepted, then finish done);

@@ -45,9 +45,12 @@ __device__ __forceinline__ void store_cross(const VCount<P>& vc, CrossT* __restr
 // contiguous bytes.  Lane = node holds, per q, the counts of envs 4q..4q+3 as 4 bytes; a 4x4 byte
 // transpose among the 4 lanes of a node group (2 shuffles) turns that into "4 nodes of one env",
 // which is one aligned 4-byte store.  All 32 env slots are written (idle envs count 0).
+// `rows` (uint8 only, optional): the same words also go to a row-major [E][Np] copy -- "4 nodes of one
+// env" is an aligned 4-byte store there too -- which the mask generator (noise_masks.cu) reads with
+// lane = node.
 template <int P, typename CrossT>
 __device__ __forceinline__ void store_cross_tiled(const VCount<P>& vc, CrossT* __restrict__ cross, int64_t tile,
-                                                  int np, int i, int lane) {
+                                                  int np, int i, int lane, uint8_t* __restrict__ rows) {
   CrossT* tbase = cross + tile * (int64_t)np * kTileEnvs;
   if (sizeof(CrossT) == 1) {
     const int j = lane & 3;
@@ -60,6 +63,8 @@ __device__ __forceinline__ void store_cross_tiled(const VCount<P>& vc, CrossT* _
       y = __shfl_xor_sync(kFull, x, 1);
       x = (j & 1) ? __byte_perm(x, y, 0x3715) : __byte_perm(x, y, 0x6240);
       gbase[4 * q + j] = x;      // env 4q+j, nodes 4*(i/4) .. +3
+      if (rows)
+        *reinterpret_cast<uint32_t*>(rows + (tile * kTileEnvs + 4 * q + j) * (int64_t)np + (i & ~3)) = x;
     }
   } else {
     CrossT* gbase = tbase + ((int64_t)(i >> 2) * kTileEnvs << 2) + (i & 3);
@@ -78,6 +83,7 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_kernel(GraphDev g, const
                                                                const uint32_t* __restrict__ packed_in,
                                                                int64_t num_envs, uint32_t* __restrict__ packed_out,
                                                                CrossT* __restrict__ cross, int tiled,
+                                                               uint8_t* __restrict__ cross_rows,
                                                                int32_t* col_min, int32_t* col_max,
                                                                int64_t* __restrict__ vs, int cut_warps) {
   extern __shared__ uint32_t sP[];
@@ -107,7 +113,7 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_kernel(GraphDev g, const
         VCount<P> vc;
         sell_cross<P, false>(g.listed, slice, lane, sP, sP[i], vc);
         if (cross) {
-          if (tiled) store_cross_tiled<P, CrossT>(vc, cross, tile, g.np, i, lane);
+          if (tiled) store_cross_tiled<P, CrossT>(vc, cross, tile, g.np, i, lane, cross_rows);
           else store_cross<P, CrossT>(vc, cross, env0, valid, g.np, i);
         }
         if (col_min && i < g.n) {
@@ -129,15 +135,15 @@ __global__ void fill_minmax_kernel(int32_t* mn, int32_t* mx, int n) {
 
 template <int P, typename CrossT, int VEC>
 static int launch_prepare(const GraphDev& g, const uint8_t* xs, const uint32_t* packed_in, int64_t num_envs,
-                          uint32_t* packed_out, CrossT* cross, int tiled, int32_t* col_min, int32_t* col_max,
-                          int64_t* vs, cudaStream_t st) {
+                          uint32_t* packed_out, CrossT* cross, int tiled, uint8_t* cross_rows, int32_t* col_min,
+                          int32_t* col_max, int64_t* vs, cudaStream_t st) {
   const size_t smem = (size_t)g.np * sizeof(uint32_t);
   auto kernel = prepare_kernel<P, CrossT, VEC>;
   if (smem > 48 * 1024)
     RLSB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;
   const unsigned grid = (unsigned)(tiles < 8 * kNumSMs ? tiles : 8 * kNumSMs);
-  kernel<<<grid, kPrepThreads, smem, st>>>(g, xs, packed_in, num_envs, packed_out, cross, tiled, col_min, col_max, vs,
+  kernel<<<grid, kPrepThreads, smem, st>>>(g, xs, packed_in, num_envs, packed_out, cross, tiled, cross_rows, col_min, col_max, vs,
                                            cut_warps_for(g.m, kPrepThreads / 32));
   RLSB_LAUNCH_OK();
   return RLSB_OK;
@@ -145,24 +151,25 @@ static int launch_prepare(const GraphDev& g, const uint8_t* xs, const uint32_t* 
 
 template <typename CrossT, int VEC>
 static int dispatch_planes(const GraphDev& g, const uint8_t* xs, const uint32_t* packed_in, int64_t num_envs,
-                           uint32_t* packed_out, CrossT* cross, int tiled, int32_t* col_min, int32_t* col_max,
-                           int64_t* vs, cudaStream_t st) {
+                           uint32_t* packed_out, CrossT* cross, int tiled, uint8_t* cross_rows, int32_t* col_min,
+                           int32_t* col_max, int64_t* vs, cudaStream_t st) {
   if (g.max_listed_deg <= 63)
-    return launch_prepare<6, CrossT, VEC>(g, xs, packed_in, num_envs, packed_out, cross, tiled, col_min, col_max, vs, st);
+    return launch_prepare<6, CrossT, VEC>(g, xs, packed_in, num_envs, packed_out, cross, tiled, cross_rows, col_min, col_max, vs, st);
   if (g.max_listed_deg <= 255)
-    return launch_prepare<8, CrossT, VEC>(g, xs, packed_in, num_envs, packed_out, cross, tiled, col_min, col_max, vs, st);
+    return launch_prepare<8, CrossT, VEC>(g, xs, packed_in, num_envs, packed_out, cross, tiled, cross_rows, col_min, col_max, vs, st);
   if (sizeof(CrossT) == 1) {
     set_error("prepare: listed degree %d needs uint16 counts", g.max_listed_deg);
     return RLSB_ERR_INVALID;
   }
-  return launch_prepare<12, CrossT, VEC>(g, xs, packed_in, num_envs, packed_out, cross, tiled, col_min, col_max, vs, st);
+  return launch_prepare<12, CrossT, VEC>(g, xs, packed_in, num_envs, packed_out, cross, tiled, cross_rows, col_min, col_max, vs, st);
 }
 
 // Used by rlsb_ls_begin (local_search.cu).  cross_layout: 0 = uint16 [E][Np] row-major,
-// 1 = uint8 tiled, 2 = uint16 tiled (store_cross_tiled).
+// 1 = uint8 tiled, 2 = uint16 tiled (store_cross_tiled).  cross_rows: optional row-major uint8 copy (layout 1).
 int prepare_tiles(const GraphDev& g, const uint8_t* xs, const uint32_t* packed_in, int64_t num_envs,
-                  uint32_t* packed_out, void* cross, int cross_layout, int32_t* col_min, int32_t* col_max, int64_t* vs,
-                  cudaStream_t st) {
+                  uint32_t* packed_out, void* cross, int cross_layout, uint8_t* cross_rows, int32_t* col_min,
+                  int32_t* col_max, int64_t* vs, cudaStream_t st) {
+  if (cross_layout != 1) cross_rows = nullptr;
   const bool cross_is_u8 = cross_layout == 1;
   const int tiled = cross_layout != 0;
   if (col_min && g.n > 0) {
@@ -170,7 +177,7 @@ int prepare_tiles(const GraphDev& g, const uint8_t* xs, const uint32_t* packed_i
     RLSB_LAUNCH_OK();
   }
   if (num_envs == 0 || g.n == 0) return RLSB_OK;
-#define RLSB_PREP(T, V) dispatch_planes<T, V>(g, xs, packed_in, num_envs, packed_out, (T*)cross, tiled, col_min, col_max, vs, st)
+#define RLSB_PREP(T, V) dispatch_planes<T, V>(g, xs, packed_in, num_envs, packed_out, (T*)cross, tiled, cross_rows, col_min, col_max, vs, st)
   if (packed_in) return cross_is_u8 ? RLSB_PREP(uint8_t, 0) : RLSB_PREP(uint16_t, 0);
   if (rows_vec4_ok(xs, g.n)) return cross_is_u8 ? RLSB_PREP(uint8_t, 4) : RLSB_PREP(uint16_t, 4);
   return cross_is_u8 ? RLSB_PREP(uint8_t, 1) : RLSB_PREP(uint16_t, 1);
@@ -188,6 +195,6 @@ extern "C" int rlsb_node_cross_counts(const rlsb_graph_t* gh, const uint32_t* pa
   RLSB_REQUIRE((col_min == nullptr) == (col_max == nullptr), RLSB_ERR_INVALID,
                "node_cross_counts: col_min and col_max must both be given or both be null");
   RLSB_REQUIRE(num_envs == 0 || g->n == 0 || (packed && cross), RLSB_ERR_INVALID, "node_cross_counts: null pointer");
-  return prepare_tiles(*g, nullptr, packed, num_envs, nullptr, cross, 0, col_min, col_max, nullptr,
+  return prepare_tiles(*g, nullptr, packed, num_envs, nullptr, cross, 0, nullptr, col_min, col_max, nullptr,
                        static_cast<cudaStream_t>(stream));
 }

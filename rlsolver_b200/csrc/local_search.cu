@@ -28,23 +28,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "ls_workspace.cuh"
 #include "tile_ops.cuh"
 
 namespace rlsb {
 
 int prepare_tiles(const GraphDev& g, const uint8_t* xs, const uint32_t* packed_in, int64_t num_envs,
-                  uint32_t* packed_out, void* cross, int cross_layout, int32_t* col_min, int32_t* col_max, int64_t* vs,
-                  cudaStream_t st);
-
-// float(k) for |k| < 2^22 without the conversion pipe: 0x4B400000 is 12582912.0f (1.5 * 2^23)
-constexpr int kMagicI = 0x4B400000;
-constexpr float kMagicF = 12582912.0f;
-
-// degm = listed degree + kMagicI, negmult = -mult
-__device__ __forceinline__ float spin_rand(int degm, int negmult, int cross, float noise, float rd_std) {
-  const float wsf = __fadd_rn(__int_as_float(cross * negmult + degm), -kMagicF);   // exact float(deg - mult*cross)
-  return __fadd_rn(wsf, __fmul_rn(noise, rd_std));
-}
+                  uint32_t* packed_out, void* cross, int cross_layout, uint8_t* cross_rows, int32_t* col_min,
+                  int32_t* col_max, int64_t* vs, cudaStream_t st);
 
 // order-preserving float -> uint32 key (so REDUX max works on floats)
 __device__ __forceinline__ uint32_t float_key(float f) {
@@ -652,6 +643,95 @@ __global__ void __launch_bounds__(kLSThreads) ls_generic_kernel(GraphDev g, LsAr
   for (int i = threadIdx.x; i < g.np; i += kLSThreads) a.packed[tile * g.np + i] = sP[i] & vmask;
 }
 
+// ---- bit-mask kernel (rlsb_ls_run_masks): the flip masks of every iteration were produced by
+// noise_masks.cu as flat bit arrays (bit e*N + n).  Lane = env fetches the 32 node bits of its row
+// for one block of 32 nodes (two words + funnel shift: rows start at any bit), a 32x32 bit
+// transpose turns them into the 32-env flip words of those nodes.
+//
+// A warp handles node blocks warp, warp + 16, ...; the words of four blocks are fetched together (8 loads in
+// flight per lane) and the first four of the NEXT iteration are fetched before the current candidate is
+// evaluated, so the L2 latency of the mask words stays off the critical path.
+struct MaskChunk {
+  uint32_t lo[4], hi[4];
+};
+
+__device__ __forceinline__ MaskChunk mask_chunk_load(const uint32_t* __restrict__ mask, uint64_t row, int b0, int blocks,
+                                                     bool live) {
+  MaskChunk c;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int b = b0 + u * kLSWarps;
+    c.lo[u] = c.hi[u] = 0;
+    if (live && b < blocks) {
+      const uint64_t o = row + 32u * (uint32_t)b;
+      c.lo[u] = __ldg(mask + (o >> 5)), c.hi[u] = __ldg(mask + (o >> 5) + 1);
+    }
+  }
+  return c;
+}
+
+__device__ __forceinline__ void mask_chunk_apply(const MaskChunk& c, uint64_t row, int b0, int n, const uint32_t* sP,
+                                                 uint32_t* sX) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int b = b0 + u * kLSWarps;
+    if (32 * b >= n) break;                                         // warp-uniform
+    const uint32_t word = __funnelshift_r(c.lo[u], c.hi[u], (uint32_t)(row + 32u * (uint32_t)b) & 31u);
+    const uint32_t t = transpose32(word, lane);                     // lane = node 32b + lane, bit = env
+    const int i = 32 * b + lane;
+    if (i < n) sX[i] = sP[i] ^ t;
+  }
+}
+
+template <int P>
+__global__ void __launch_bounds__(kLSThreads) ls_bits_kernel(GraphDev g, LsArgs a, const uint32_t* __restrict__ masks,
+                                                             int64_t mask_words) {
+  extern __shared__ __align__(1024) uint32_t smem[];
+  uint32_t* sP = smem;
+  uint32_t* sX = smem + g.np;
+  char* sSweep = reinterpret_cast<char*>(smem + 2 * g.np);
+  __shared__ int sCnt[kTileEnvs];
+  __shared__ uint32_t sAccept;
+  __shared__ __align__(8) uint64_t sBar;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t tile = blockIdx.x;
+  const int64_t env0 = tile * kTileEnvs;
+  const int valid = (int)min((int64_t)kTileEnvs, a.num_envs - env0);
+  if (threadIdx.x == 0) {
+    mbar_init(&sBar, 1);
+    if (a.finish && a.stage_sweep) stage_sweep_blob(g, sSweep, &sBar);
+  }
+  for (int i = threadIdx.x; i < g.np; i += kLSThreads) {
+    const uint32_t w = a.packed[tile * g.np + i];
+    sP[i] = w, sX[i] = w;
+  }
+  if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
+  int64_t my_vs = 0;
+  if (warp == 0 && lane < valid) my_vs = a.vs[env0 + lane];
+  ls_sync();
+  const int blocks = (g.n + 31) >> 5;
+  const uint64_t row = (uint64_t)(env0 + lane) * (uint64_t)g.n;     // first bit of the lane's env row
+  const bool live = lane < valid;
+  MaskChunk pre = mask_chunk_load(masks, row, warp, a.num_iters > 0 ? blocks : 0, live);
+  for (int it = 0; it < a.num_iters; ++it) {
+    const uint32_t* mask = masks + it * mask_words;
+    mask_chunk_apply(pre, row, warp, g.n, sP, sX);
+    for (int b0 = warp + 4 * kLSWarps; b0 < blocks; b0 += 4 * kLSWarps)
+      mask_chunk_apply(mask_chunk_load(mask, row, b0, blocks, live), row, b0, g.n, sP, sX);
+    ls_sync();
+    pre = mask_chunk_load(mask + mask_words, row, warp, it + 1 < a.num_iters ? blocks : 0, live);
+    evaluate_and_accept(g, a, sP, sX, sCnt, &sAccept, valid, my_vs);
+  }
+  const uint32_t vmask = valid == 32 ? kFull : ((1u << valid) - 1u);
+  if (a.finish) {
+    finish_tile<P>(g, a, sP, sSweep, &sBar, sCnt, tile, valid);
+  } else {
+    if (warp == 0 && lane < valid) a.vs[env0 + lane] = my_vs;
+  }
+  for (int i = threadIdx.x; i < g.np; i += kLSThreads) a.packed[tile * g.np + i] = sP[i] & vmask;
+}
+
 // single-flip pass on packed tiles only (rlsb_flip_sweep)
 template <int P>
 __global__ void __launch_bounds__(kLSThreads) flip_sweep_kernel(GraphDev g, uint32_t* __restrict__ packed,
@@ -689,43 +769,6 @@ static int allow_smem(K kernel, size_t bytes) {
 static int sweep_warps_for(const GraphDev& g, int nwarps) {
   const int w = g.max_level_slices < 1 ? 1 : g.max_level_slices;
   return w < nwarps ? w : nwarps;
-}
-
-static int degree_class(const GraphDev& g) {
-  const int d = g.max_listed_deg > g.max_full_deg ? g.max_listed_deg : g.max_full_deg;
-  return d <= 63 ? 0 : d <= 255 ? 1 : 2;
-}
-
-// workspace carving (all sections 256-byte aligned)
-struct LsWorkspace {
-  uint32_t* packed;
-  void* cross;
-  int32_t *col_min, *col_max, *degm;
-  float *rd_std, *thresh;
-  uint32_t* nd;
-  size_t bytes;
-};
-
-static LsWorkspace carve(const GraphDev& g, int64_t num_envs, void* base) {
-  const int64_t tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;
-  const size_t cross_elt = degree_class(g) == 2 ? 2 : 1;
-  size_t off = 0;
-  auto take = [&](size_t bytes) {
-    char* p = base ? static_cast<char*>(base) + off : nullptr;
-    off += (bytes + 255) / 256 * 256;
-    return p;
-  };
-  LsWorkspace w;
-  w.packed = reinterpret_cast<uint32_t*>(take((size_t)tiles * g.np * 4));
-  w.cross = take((size_t)tiles * kTileEnvs * g.np * cross_elt);
-  w.col_min = reinterpret_cast<int32_t*>(take((size_t)g.np * 4));
-  w.col_max = reinterpret_cast<int32_t*>(take((size_t)g.np * 4));
-  w.degm = reinterpret_cast<int32_t*>(take((size_t)g.np * 4));
-  w.rd_std = reinterpret_cast<float*>(take((size_t)g.np * 4));
-  w.thresh = reinterpret_cast<float*>(take((size_t)num_envs * 4));
-  w.nd = reinterpret_cast<uint32_t*>(take((size_t)g.np * 8));
-  w.bytes = off + 256;
-  return w;
 }
 
 constexpr size_t kSmemBudget = 220 * 1024;   // dynamic shared memory a search CTA may use
@@ -823,6 +866,18 @@ static int launch_generic(const GraphDev& g, LsArgs a, cudaStream_t st) {
   const int64_t tiles = (a.num_envs + kTileEnvs - 1) / kTileEnvs;
   if (int rc = allow_smem(ls_generic_kernel<P, CrossT>, smem)) return rc;
   ls_generic_kernel<P, CrossT><<<(unsigned)tiles, kLSThreads, smem, st>>>(g, a);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+template <int P>
+static int launch_bits(const GraphDev& g, LsArgs a, const uint32_t* masks, cudaStream_t st) {
+  const size_t tiles_bytes = 2 * (size_t)g.np * sizeof(uint32_t);
+  a.stage_sweep = (a.finish && tiles_bytes + (size_t)g.sweep_blob_bytes <= kSmemBudget) ? 1 : 0;
+  const size_t smem = tiles_bytes + (a.stage_sweep ? (size_t)g.sweep_blob_bytes : 0);
+  const int64_t tiles = (a.num_envs + kTileEnvs - 1) / kTileEnvs;
+  if (int rc = allow_smem(ls_bits_kernel<P>, smem)) return rc;
+  ls_bits_kernel<P><<<(unsigned)tiles, kLSThreads, smem, st>>>(g, a, masks, ls_mask_words(a.num_envs, g.n));
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }
@@ -945,8 +1000,8 @@ int64_t rlsb_ls_workspace_offset(const rlsb_graph_t* gh, int64_t num_envs, int32
   if (graph_check(gh, &g, "ls_workspace_offset") || num_envs < 0) return -1;
   char* base = reinterpret_cast<char*>(uintptr_t(4096));
   const LsWorkspace w = carve(*g, num_envs, base);
-  const void* at[7] = {w.packed, w.cross, w.col_min, w.col_max, w.degm, w.rd_std, w.thresh};
-  if (section < 0 || section > 6) return -1;
+  const void* at[8] = {w.packed, w.cross, w.col_min, w.col_max, w.degm, w.rd_std, w.thresh, w.cross_rows};
+  if (section < 0 || section > 7 || !at[section]) return -1;
   return static_cast<const char*>(at[section]) - base;
 }
 
@@ -965,8 +1020,8 @@ int rlsb_ls_begin(const rlsb_graph_t* gh, const uint8_t* xs, int64_t num_envs, i
                "ls_begin: workspace must be 256-byte aligned");
   auto st = static_cast<cudaStream_t>(stream);
   const LsWorkspace w = carve(*g, num_envs, workspace);
-  if (int rc = prepare_tiles(*g, xs, nullptr, num_envs, w.packed, w.cross, degree_class(*g) != 2 ? 1 : 2, w.col_min,
-                             w.col_max, compute_vs ? vs : nullptr, st))
+  if (int rc = prepare_tiles(*g, xs, nullptr, num_envs, w.packed, w.cross, degree_class(*g) != 2 ? 1 : 2, w.cross_rows,
+                             w.col_min, w.col_max, compute_vs ? vs : nullptr, st))
     return rc;
   ls_rdstd_kernel<<<(g->np + 255) / 256, 256, 0, st>>>(*g, w.col_min, w.col_max, ws_mult, noise_std, w.rd_std, w.degm,
                                                        w.nd);
@@ -1023,6 +1078,26 @@ int rlsb_ls_run(const rlsb_graph_t* gh, int64_t num_envs, int64_t* vs, int32_t w
                "ls_run: null pointer");
   return run_search(*g, num_envs, vs, ws_mult, thresh_noise, thresh_noise ? num_spin : 0, h_noise_ptrs, num_iters,
                     finish, xs_out, workspace, static_cast<cudaStream_t>(stream));
+}
+
+int rlsb_ls_run_masks(const rlsb_graph_t* gh, int64_t num_envs, int64_t* vs, const uint32_t* masks, int32_t num_iters,
+                      int32_t finish, uint8_t* xs_out, void* workspace, void* stream) {
+  using namespace rlsb;
+  const GraphDev* g;
+  if (int rc = ls_check(gh, &g, "ls_run_masks", num_envs, 1)) return rc;
+  RLSB_REQUIRE(num_iters >= 0, RLSB_ERR_INVALID, "ls_run_masks: negative num_iters");
+  if (num_envs == 0 || g->n == 0) return RLSB_OK;
+  RLSB_REQUIRE(vs && workspace && (num_iters == 0 || masks) && (!finish || xs_out), RLSB_ERR_INVALID,
+               "ls_run_masks: null pointer");
+  const LsWorkspace w = carve(*g, num_envs, workspace);
+  LsArgs a{};
+  a.packed = w.packed, a.vs = vs, a.num_iters = num_iters, a.num_envs = num_envs;
+  a.finish = finish ? 1 : 0, a.xs_out = xs_out, a.unpack_vec4 = (xs_out && rows_vec4_ok(xs_out, g->n)) ? 1 : 0;
+  a.cut_warps = cut_warps_for(g->m, kLSWarps), a.sweep_warps = sweep_warps_for(*g, kLSWarps);
+  auto st = static_cast<cudaStream_t>(stream);
+  const int dc = degree_class(*g);
+  return dc == 0 ? launch_bits<6>(*g, a, masks, st) : dc == 1 ? launch_bits<8>(*g, a, masks, st)
+                                                              : launch_bits<12>(*g, a, masks, st);
 }
 
 int rlsb_ls_debug_times(int64_t* out64) {

@@ -1,0 +1,303 @@
+// Flip masks of the noisy multi-flip iterations without the noise tensors.
+//
+// The reference draws `randn [E, N] float32` once per iteration (env_L2A.py:99, LocalSearch.py:66)
+// and only ever looks at one bit of each number: `spin_rand > thresh` (env_L2A.py:100-101).  With
+// explicit noise tensors (rlsb_ls_run) every draw costs torch's generator kernel, a 4-byte write
+// and a 4-byte read per (env, node).  torch's CUDA generator is counter based (philox.cuh), so
+// this kernel recomputes exactly the numbers those calls would have produced -- same Philox
+// counters, curand's own Box-Muller (`curand_normal4`, the function torch's normal_ kernel calls,
+// ATen/native/cuda/DistributionTemplates.h normal_and_transform) -- evaluates the reference's
+// expression on them in registers and emits the flip bit.  Per draw the output is a flat bit
+// array (bit e*N + n), E*N/8 bytes instead of 4*E*N; rlsb_ls_run_masks consumes it.
+//
+// Work decomposition = torch's own: thread `idx` of call `k`, round `j` owns the Philox block
+// (counter offset/4 + k*iters + j, subsequence idx) whose four normals belong to the elements
+// idx + T*(4j + {0,1,2,3}); consecutive lanes hold consecutive elements, so one BALLOT is one
+// 32-bit word of the bit array (noise_mask_kernel, the plain form: every normal is evaluated).
+//
+// Early-out form (the default).  Only ~num_spin of N numbers per row pass the threshold, and
+// whether one CAN pass is decided by the first uint32 of its Box-Muller pair alone: the two
+// normals of a pair are s*sin(v), s*cos(v) with s = sqrt(-2 ln u), u = x * 2^-32 + 2^-33, so
+// |normal| <= s and s is decreasing in x.  mask_bound_kernel turns the per-element requirement
+// "noise > (thresh - ws) / rd_std" into one byte c per element, once per call (ws, rd_std and
+// thresh are the same for all draws): the element can flip only if (x >> 24) <= c.  The
+// generator then costs one Philox block + four byte compares per four elements; the few pairs
+// that pass go to a shared-memory queue and are evaluated exactly -- curand's Box-Muller, the
+// reference's expression, the exact compare -- by the first threads of the block, which OR the
+// flip bits into the (zeroed) arrays.  The bound is conservative (margins below), the decision
+// is always made by the exact expression, so the masks are identical to the plain form's.
+#include <stdlib.h>
+
+#include "ls_workspace.cuh"
+#include "philox.cuh"
+
+namespace rlsb {
+
+struct MaskArgs {
+  const uint8_t* cross_rows;   // [E][Np] cross counts, row-major (ls_begin)
+  const float* rd_std;         // [Np]
+  const int32_t* degm;         // [Np] listed degree + kMagicI
+  const float* thresh;         // [E]
+  uint32_t* masks;             // [draws][mask_words]
+  int64_t mask_words;
+  uint32_t numel, n, np;
+  uint32_t step_e, step_n;     // T / N, T % N
+  int negmult;
+};
+
+__global__ void __launch_bounds__(256) noise_mask_kernel(MaskArgs a, TorchRng r) {
+  const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
+  const uint32_t j = blockIdx.y, k = blockIdx.z;
+  const PhiloxKey key = philox_key(r);
+  const uint64_t ctr = key.offset4 + (uint64_t)k * r.iters_per_call + j;
+  const uint4 o = curand_Philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), idx, 0u),
+                                       make_uint2((uint32_t)key.seed, (uint32_t)(key.seed >> 32)));
+  // curand_normal4: (x, y) -> the first two normals, (z, w) -> the other two.  torch's transform
+  // `rand * std + mean` with std = 1, mean = 0 leaves the value as it is.
+  const float2 n01 = _curand_box_muller(o.x, o.y), n23 = _curand_box_muller(o.z, o.w);
+  const float z[4] = {n01.x, n01.y, n23.x, n23.y};
+  uint32_t li = idx + r.threads * 4u * j;
+  uint32_t e = li / a.n, nn = li - e * a.n;
+  uint32_t* out = a.masks + (int64_t)k * a.mask_words;
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii) {
+    bool bit = false;
+    if (li < a.numel) {
+      const int cross = (int)__ldg(a.cross_rows + (uint64_t)e * a.np + nn);
+      const float sr = spin_rand(__ldg(a.degm + nn), a.negmult, cross, z[ii], __ldg(a.rd_std + nn));
+      bit = sr > __ldg(a.thresh + e);
+    }
+    const uint32_t word = __ballot_sync(kFull, bit);
+    if ((threadIdx.x & 31) == 0 && li < a.numel) out[li >> 5] = word;
+    li += r.threads, e += a.step_e, nn += a.step_n;
+    if (nn >= a.n) nn -= a.n, ++e;
+  }
+}
+
+
+// ---- early-out bound.  flip  <=>  fl(ws + fl(z * rd)) > th.  Rounding is monotone and th is a float, so a
+// flip implies ws + fl(z*rd) > th in real arithmetic, hence z * rd > t' for any float t' <= th - ws, hence
+// (t' > 0) z > t' / rd.  With |z| <= s = sqrt(-2 ln u): a flip needs s > zmin = t' / rd, i.e.
+// u < exp(-zmin^2 / 2).  (x >> 24) > c gives u >= (c + 1) / 256, so c + 1 >= 256 * exp(-zmin^2 / 2) makes
+// "(x >> 24) > c  =>  no flip" true.  Margins: t' = fl(th - ws) * (1 - 2^-20) absorbs the rounding of the
+// difference, zmin * 0.999 the division, logf / sqrtf (<= 2 ulp) and the intrinsic's error, * 1.001 __expf.
+// t' <= 0 (or rd = 0 with ws > th, or NaN): c = 255 = always evaluated exactly.
+__device__ __forceinline__ uint32_t bound_byte(const MaskArgs& a, float th, int cross, int degm, float rd) {
+  const float wsf = __fadd_rn(__int_as_float(cross * a.negmult + degm), -kMagicF);
+  const float t = __fadd_rn(th, -wsf);
+  if (!(t > 0.f)) return 255u;
+  const float zmin = __fdiv_rn(t * 0.999999f, rd) * 0.999f;   // rd = 0 -> +inf -> c = 0
+  const float p = 256.f * 1.001f * __expf(-0.5f * zmin * zmin);
+  return p >= 255.f ? 255u : (uint32_t)p;
+}
+
+// Indexed like the generator: thread (idx, round j) owns the elements idx + T*(4j + {0,1,2,3}) = two
+// Box-Muller pairs, and stores one byte per PAIR (the larger of its two elements' bytes; 0 for slots past
+// the tensor -- the exact path re-checks the range).  One uint16 per generator thread and round.
+__global__ void __launch_bounds__(256) mask_bound_kernel(MaskArgs a, uint16_t* __restrict__ bound2, uint32_t T) {
+  const uint32_t idx = blockIdx.x * 256 + threadIdx.x, j = blockIdx.y;
+  uint32_t li = idx + 4u * T * j;
+  uint32_t e = li / a.n, nn = li - e * a.n;
+  uint32_t c[4];
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii) {
+    c[ii] = 0;
+    if (li < a.numel)
+      c[ii] = bound_byte(a, __ldg(a.thresh + e), (int)__ldg(a.cross_rows + (uint64_t)e * a.np + nn), __ldg(a.degm + nn),
+                         __ldg(a.rd_std + nn));
+    li += T, e += a.step_e, nn += a.step_n;
+    if (nn >= a.n) nn -= a.n, ++e;
+  }
+  bound2[(uint64_t)j * T + idx] = (uint16_t)(max(c[0], c[1]) | (max(c[2], c[3]) << 8));
+}
+
+// Generator, early-out form.  grid = (T / 256, rounds split, draws); a thread walks the rounds j = blockIdx.y,
+// blockIdx.y + gridDim.y, ... of its Philox subsequence: one 2-byte load, one Philox block, two byte
+// compares.  A thread-round with a passing pair is queued PER WARP as one word (round, lane, which pairs)
+// -- ballot-compacted, no atomics, no block barrier -- and whenever a warp has 32 of them all its lanes take
+// one each: recompute that Philox block, curand's Box-Muller, the reference's expression, the exact
+// compare.  The exact path so runs with full warps although only a few percent of the pairs need it.
+constexpr int kWarpQueue = 64;   // < 32 left over + at most 32 new per round
+
+__device__ __forceinline__ void mask_exact_pair(const MaskArgs& a, uint32_t* __restrict__ out, uint32_t x, uint32_t y,
+                                                uint32_t l0, uint32_t T) {
+  const float2 z = _curand_box_muller(x, y);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t l = l0 + h * T;
+    if (l < a.numel) {
+      const uint32_t e = l / a.n, nn = l - e * a.n;
+      const int cross = (int)__ldg(a.cross_rows + (uint64_t)e * a.np + nn);
+      const float sr = spin_rand(__ldg(a.degm + nn), a.negmult, cross, h ? z.y : z.x, __ldg(a.rd_std + nn));
+      if (sr > __ldg(a.thresh + e)) atomicOr(out + (l >> 5), 1u << (l & 31u));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) noise_mask_fast_kernel(MaskArgs a, const uint16_t* __restrict__ bound2,
+                                                              TorchRng r) {
+  __shared__ uint32_t queue[8][kWarpQueue];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
+  const uint32_t k = blockIdx.z;
+  const PhiloxKey key = philox_key(r);
+  const uint64_t ctr0 = key.offset4 + (uint64_t)k * r.iters_per_call;
+  const uint2 pkey = make_uint2((uint32_t)key.seed, (uint32_t)(key.seed >> 32));
+  const uint32_t T = r.threads;
+  uint32_t* out = a.masks + (int64_t)k * a.mask_words;
+  uint32_t* q = queue[warp];
+  const uint32_t jstep = gridDim.y;
+  const uint16_t* bp = bound2 + (uint64_t)blockIdx.y * T + idx;
+  const uint64_t bstride = (uint64_t)jstep * T;
+
+  auto exact = [&](uint32_t ent) {
+    const uint32_t jj = ent >> 8, src = idx - lane + ((ent >> 2) & 31u);
+    const uint64_t ctr = ctr0 + jj;
+    const uint4 o = curand_Philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), src, 0u), pkey);
+    const uint32_t l0 = src + 4u * T * jj;
+    if (ent & 1u) mask_exact_pair(a, out, o.x, o.y, l0, T);
+    if (ent & 2u) mask_exact_pair(a, out, o.z, o.w, l0 + 2u * T, T);
+  };
+
+  uint32_t cw = __ldg(bp);
+  int cnt = 0;
+  for (uint32_t j = blockIdx.y; j < r.iters_per_call; j += jstep) {
+    bp += bstride;
+    uint32_t cwn = 0;
+    if (j + jstep < r.iters_per_call) cwn = __ldg(bp);      // next round's bytes travel during this round's Philox block
+    const uint64_t ctr = ctr0 + j;
+    const uint4 o = curand_Philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), idx, 0u), pkey);
+    const uint32_t fa = (o.x >> 24) <= (cw & 0xffu) ? 1u : 0u, fb = (o.z >> 24) <= (cw >> 8) ? 2u : 0u;
+    const uint32_t ball = __ballot_sync(kFull, (fa | fb) != 0u);
+    if (fa | fb) q[cnt + __popc(ball & lt)] = (j << 8) | ((uint32_t)lane << 2) | fa | fb;
+    cnt += __popc(ball);
+    __syncwarp();
+    if (cnt >= 32) {
+      cnt -= 32;
+      const uint32_t ent = q[cnt + lane];
+      __syncwarp();
+      exact(ent);
+    }
+    cw = cwn;
+  }
+  if (lane < cnt) exact(q[lane]);
+}
+
+// the same draws as explicit float32 tensors (tests: must equal torch.randn bit for bit)
+__global__ void __launch_bounds__(256) noise_values_kernel(float* __restrict__ out, uint32_t numel, TorchRng r) {
+  const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
+  const uint32_t j = blockIdx.y, k = blockIdx.z;
+  const PhiloxKey key = philox_key(r);
+  const uint64_t ctr = key.offset4 + (uint64_t)k * r.iters_per_call + j;
+  const uint4 o = curand_Philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), idx, 0u),
+                                       make_uint2((uint32_t)key.seed, (uint32_t)(key.seed >> 32)));
+  const float2 n01 = _curand_box_muller(o.x, o.y), n23 = _curand_box_muller(o.z, o.w);
+  const float z[4] = {n01.x, n01.y, n23.x, n23.y};
+  uint32_t li = idx + r.threads * 4u * j;
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii) {
+    if (li < numel) out[(uint64_t)k * numel + li] = z[ii];
+    li += r.threads;
+  }
+}
+
+__global__ void cursor_advance_kernel(uint64_t* cur, uint64_t delta) { cur[1] += delta; }
+
+static int rng_check(const char* what, int64_t numel, uint64_t offset, int32_t rng_threads, int32_t rng_iters,
+                     int32_t num_draws) {
+  RLSB_REQUIRE(numel > 0 && numel < (int64_t(1) << 31), RLSB_ERR_UNSUPPORTED,
+               "%s: %lld elements per draw (torch splits calls of 2^31 elements and more)", what, (long long)numel);
+  RLSB_REQUIRE(rng_threads > 0 && rng_threads % 256 == 0 && rng_iters > 0 && rng_iters <= 65535, RLSB_ERR_INVALID,
+               "%s: bad call geometry (threads %d, iters %d)", what, rng_threads, rng_iters);
+  RLSB_REQUIRE((int64_t)rng_threads * 4 * rng_iters >= numel, RLSB_ERR_INVALID,
+               "%s: call geometry (threads %d, iters %d) does not cover %lld elements", what, rng_threads, rng_iters,
+               (long long)numel);
+  RLSB_REQUIRE(offset % 4 == 0, RLSB_ERR_INVALID, "%s: generator offset must be a multiple of 4", what);
+  RLSB_REQUIRE(num_draws >= 0 && num_draws <= 65535, RLSB_ERR_INVALID, "%s: num_draws out of range", what);
+  return RLSB_OK;
+}
+
+}  // namespace rlsb
+
+extern "C" {
+
+int64_t rlsb_ls_mask_words(const rlsb_graph_t* gh, int64_t num_envs) {
+  using namespace rlsb;
+  const GraphDev* g;
+  if (graph_check(gh, &g, "ls_mask_words") || num_envs < 0) return -1;
+  if (degree_class(*g) == 2 || num_envs * (int64_t)g->n >= (int64_t(1) << 31)) return -1;
+  return ls_mask_words(num_envs, g->n);
+}
+
+int rlsb_ls_noise_masks(const rlsb_graph_t* gh, int64_t num_envs, int32_t ws_mult, uint64_t seed, uint64_t offset,
+                        const uint64_t* rng_dev, int32_t rng_threads, int32_t rng_iters, int32_t num_draws,
+                        uint32_t* masks, void* workspace, void* stream) {
+  using namespace rlsb;
+  const GraphDev* g;
+  if (int rc = graph_check(gh, &g, "ls_noise_masks")) return rc;
+  RLSB_REQUIRE(num_envs >= 0, RLSB_ERR_INVALID, "ls_noise_masks: negative num_envs");
+  RLSB_REQUIRE(ws_mult == 1 || ws_mult == 2, RLSB_ERR_INVALID, "ls_noise_masks: ws_mult must be 1 or 2");
+  if (num_envs == 0 || g->n == 0 || num_draws == 0) return RLSB_OK;
+  RLSB_REQUIRE(degree_class(*g) != 2, RLSB_ERR_UNSUPPORTED,
+               "ls_noise_masks: degrees above 255 keep uint16 counts (use rlsb_ls_run with noise tensors)");
+  const int64_t numel = num_envs * (int64_t)g->n;
+  if (int rc = rng_check("ls_noise_masks", numel, offset, rng_threads, rng_iters, num_draws)) return rc;
+  RLSB_REQUIRE(masks && workspace, RLSB_ERR_INVALID, "ls_noise_masks: null pointer");
+  const LsWorkspace w = carve(*g, num_envs, workspace);
+  MaskArgs a;
+  a.cross_rows = w.cross_rows, a.rd_std = w.rd_std, a.degm = w.degm, a.thresh = w.thresh;
+  a.masks = masks, a.mask_words = ls_mask_words(num_envs, g->n);
+  a.numel = (uint32_t)numel, a.n = (uint32_t)g->n, a.np = (uint32_t)g->np;
+  a.step_e = (uint32_t)rng_threads / a.n, a.step_n = (uint32_t)rng_threads % a.n;
+  a.negmult = -ws_mult;
+  TorchRng r{seed, offset / 4, (uint32_t)rng_threads, (uint32_t)rng_iters, rng_dev};
+  dim3 grid((unsigned)(rng_threads / 256), (unsigned)rng_iters, 1);
+  auto st = static_cast<cudaStream_t>(stream);
+  // RLSB_LS_PLAIN_MASKS=1: evaluate every normal (cross-check of the early-out form; read per call)
+  const char* env = getenv("RLSB_LS_PLAIN_MASKS");
+  if (env && env[0] == '1') {
+    grid.z = (unsigned)num_draws;
+    noise_mask_kernel<<<grid, 256, 0, st>>>(a, r);
+    RLSB_LAUNCH_OK();
+    return RLSB_OK;
+  }
+  RLSB_REQUIRE(w.bound != nullptr, RLSB_ERR_INVALID, "ls_noise_masks: workspace without the bound section");
+  RLSB_REQUIRE((int64_t)rng_threads * rng_iters * 2 <= ls_bound_bytes(numel), RLSB_ERR_INVALID,
+               "ls_noise_masks: call geometry (threads %d, iters %d) larger than a B200's", rng_threads, rng_iters);
+  uint16_t* bound2 = reinterpret_cast<uint16_t*>(w.bound);
+  mask_bound_kernel<<<grid, 256, 0, st>>>(a, bound2, (uint32_t)rng_threads);
+  RLSB_LAUNCH_OK();
+  RLSB_CUDA_OK(cudaMemsetAsync(masks, 0, (size_t)num_draws * a.mask_words * sizeof(uint32_t), st));
+  // rounds are split over blockIdx.y only when there would be too few blocks to fill the GPU otherwise
+  int jsplit = 1;
+  while ((int64_t)grid.x * jsplit * num_draws < 4 * 8 * kNumSMs && jsplit < rng_iters) jsplit *= 2;
+  if (jsplit > rng_iters) jsplit = rng_iters;
+  grid.y = (unsigned)jsplit, grid.z = (unsigned)num_draws;
+  noise_mask_fast_kernel<<<grid, 256, 0, st>>>(a, bound2, r);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+int rlsb_torch_randn(float* out, int64_t numel, uint64_t seed, uint64_t offset, const uint64_t* rng_dev,
+                     int32_t rng_threads, int32_t rng_iters, int32_t num_draws, void* stream) {
+  using namespace rlsb;
+  if (numel == 0 || num_draws == 0) return RLSB_OK;
+  if (int rc = rng_check("torch_randn", numel, offset, rng_threads, rng_iters, num_draws)) return rc;
+  RLSB_REQUIRE(out, RLSB_ERR_INVALID, "torch_randn: null pointer");
+  TorchRng r{seed, offset / 4, (uint32_t)rng_threads, (uint32_t)rng_iters, rng_dev};
+  const dim3 grid((unsigned)(rng_threads / 256), (unsigned)rng_iters, (unsigned)num_draws);
+  noise_values_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, (uint32_t)numel, r);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+int rlsb_rng_cursor_advance(uint64_t* rng_dev, uint64_t delta, void* stream) {
+  using namespace rlsb;
+  RLSB_REQUIRE(rng_dev != nullptr && delta % 4 == 0, RLSB_ERR_INVALID, "rng_cursor_advance: bad argument");
+  cursor_advance_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(rng_dev, delta);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+}  // extern "C"

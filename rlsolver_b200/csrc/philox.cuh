@@ -23,7 +23,19 @@ struct TorchRng {
   uint64_t offset4;         // generator offset / 4 at the first call
   uint32_t threads;         // T of one call (256 * grid.x)
   uint32_t iters_per_call;  // ceil(numel / (4 T)) = counter increments one call consumes
+  // Optional device-resident generator state {seed, offset} (CUDA-graph replays: the state advances on
+  // the device, rlsb_rng_cursor_advance).  When set it replaces `seed`, and `offset4` counts from it.
+  const uint64_t* dev;
 };
+
+struct PhiloxKey {
+  uint64_t seed, offset4;
+};
+__device__ __forceinline__ PhiloxKey philox_key(const TorchRng& r) {
+  PhiloxKey k{r.seed, r.offset4};
+  if (r.dev) k.seed = __ldg(r.dev), k.offset4 += __ldg(r.dev + 1) >> 2;
+  return k;
+}
 
 // the uint32 element `li` of consecutive call number `call` receives
 __device__ __forceinline__ uint32_t torch_philox_u32(const TorchRng& r, uint64_t call, uint32_t li) {

@@ -25,6 +25,13 @@ _NOISE_BYTES_PER_LAUNCH = 4 << 30
 
 
 class EnvMaxcut:
+    # True: the noisy iterations consume torch's CUDA generator in place (csrc/noise_masks.cu: the numbers
+    # the reference's randn calls would return are recomputed in registers, only flip bits leave the
+    # kernel; the generator ends where the reference's calls would leave it).  False: every draw is a
+    # torch.randn tensor streamed through rlsb_ls_run -- the form to use when the noise itself must be
+    # supplied (tests replaying recorded draws) and the one taken when the mask path does not apply.
+    fused_rng = True
+
     def __init__(self, sim_name: str = 'max_cut', mygraph: MyGraph = (),
                  device=th.device('cpu'), if_bidirectional: bool = False):
         self.device = require_cuda(device)
@@ -106,6 +113,9 @@ class EnvMaxcut:
                 vs_in = vs_in.contiguous()
         ws = st.ls_workspace(num_sims)
         good_vs = st.ls_begin(good_xs, vs_in, 1, noise_std, ws)
+        if self.fused_rng and num_sims > 0 and st.ls_mask_words(num_sims) >= 0:
+            st.ls_fused(good_vs, 1, num_spin, num_iters, False, good_xs, ws)
+            return good_xs, good_vs
         shape = (num_sims, self.num_nodes)
         noise0 = th.randn(shape, dtype=th.float32, device=self.device)
         per_launch = max(1, min(16, _NOISE_BYTES_PER_LAUNCH // max(1, 4 * num_sims * self.num_nodes)))

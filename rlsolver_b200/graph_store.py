@@ -11,7 +11,7 @@ from typing import Dict, Optional, Sequence, Tuple
 import numpy as np
 import torch as th
 
-from . import _lib
+from . import _lib, rng
 
 TEN = th.Tensor
 
@@ -288,6 +288,104 @@ class GraphStore:
             _lib.check(self._lib.rlsb_ls_run(self._h, e, _ptr(vs), int(ws_mult), _ptr(thresh_noise), int(num_spin),
                                              ptrs, len(noises), int(finish), _ptr(xs_out), _ptr(workspace),
                                              _stream_ptr(self.device)), "ls_run")
+
+    # ---- noisy iterations without noise tensors (csrc/noise_masks.cu): the draws of torch's CUDA generator
+    # are recomputed in place and only the flip bits leave the kernel
+    def ls_mask_words(self, num_envs: int) -> int:
+        """uint32 words per draw of the flip-mask arrays; -1 when this path is not available for the
+        graph / batch (counts wider than 8 bits, 2^31 and more elements per draw)."""
+        return int(self._lib.rlsb_ls_mask_words(self._h, num_envs))
+
+    def rng_cursor(self) -> TEN:
+        """Device-resident generator state {seed, offset} used while a CUDA graph is being captured /
+        replayed (the kernels read it, rng_cursor_advance moves it on the device)."""
+        cur = getattr(self, "_rng_cursor", None)
+        if cur is None:
+            cur = self._rng_cursor = th.zeros((2,), dtype=th.int64, device=self.device)
+        return cur
+
+    def rng_cursor_sync(self) -> None:
+        """cursor <- torch's CUDA generator (seed, offset).  Call before capturing / replaying a graph
+        that contains local-search calls."""
+        gen = rng.generator(self.device)
+        seed = int(gen.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        seed = seed - (1 << 64) if seed >= (1 << 63) else seed
+        self.rng_cursor().copy_(th.tensor([seed, int(gen.get_offset())], dtype=th.int64))
+
+    def rng_cursor_commit(self) -> None:
+        """torch's CUDA generator offset <- cursor (after the replays; synchronises)."""
+        rng.generator(self.device).set_offset(int(self.rng_cursor()[1].item()))
+
+    def rng_cursor_advance(self, delta: int) -> None:
+        with self._op("rng_cursor_advance"):
+            _lib.check(self._lib.rlsb_rng_cursor_advance(_ptr(self.rng_cursor()), int(delta),
+                                                         _stream_ptr(self.device)), "rng_cursor_advance")
+
+    def torch_randn(self, numel: int, num_draws: int, seed: int, offset: int, threads: int, iters: int,
+                    cursor: Optional[TEN] = None) -> TEN:
+        """float32 [num_draws, numel]: the values `num_draws` consecutive torch.randn(numel) calls would
+        return from generator state (seed, offset) -- or from the device cursor + offset."""
+        out = th.empty((num_draws, numel), dtype=th.float32, device=self.device)
+        with self._op("torch_randn"):
+            _lib.check(self._lib.rlsb_torch_randn(_ptr(out), int(numel), int(seed), int(offset), _ptr(cursor),
+                                                  int(threads), int(iters), int(num_draws),
+                                                  _stream_ptr(self.device)), "torch_randn")
+        return out
+
+    def ls_noise_masks(self, num_envs: int, ws_mult: int, num_draws: int, seed: int, offset: int, threads: int,
+                       iters: int, workspace: TEN, cursor: Optional[TEN] = None) -> TEN:
+        """Flip masks (bit e*N + n of row k) of `num_draws` consecutive randn [E, N] draws starting at
+        generator state (seed, offset), against the thresholds in the workspace."""
+        words = self.ls_mask_words(num_envs)
+        if words < 0:
+            _lib.check(3, "ls_mask_words")
+        masks = th.empty((max(num_draws, 1), words), dtype=th.int32, device=self.device)
+        with self._op("ls_noise_masks", 3):
+            _lib.check(self._lib.rlsb_ls_noise_masks(self._h, num_envs, int(ws_mult), int(seed), int(offset),
+                                                     _ptr(cursor), int(threads), int(iters), int(num_draws),
+                                                     _ptr(masks), _ptr(workspace), _stream_ptr(self.device)),
+                       "ls_noise_masks")
+        return masks
+
+    def ls_run_masks(self, vs: TEN, masks: Optional[TEN], num_iters: int, finish: bool, xs_out: Optional[TEN],
+                     workspace: TEN) -> None:
+        with self._op("ls_run_masks"):
+            _lib.check(self._lib.rlsb_ls_run_masks(self._h, vs.shape[0], _ptr(vs), _ptr(masks), int(num_iters),
+                                                   int(finish), _ptr(xs_out), _ptr(workspace),
+                                                   _stream_ptr(self.device)), "ls_run_masks")
+
+    def ls_fused(self, vs: TEN, ws_mult: int, num_spin: int, num_iters: int, first_draw_is_iter: bool,
+                 xs_out: TEN, workspace: TEN) -> None:
+        """Threshold + noisy iterations + single-flip pass with the generator consumed in place.
+        RNG use == the reference's: one randn [E, N] for the threshold -- which is also the first
+        iteration's noise when `first_draw_is_iter` (LocalSearch.py:66-68) -- then one per iteration.
+        Eager: torch draws the threshold noise, the rest is recomputed from (seed, offset) and torch's
+        generator is advanced past it.  While a CUDA graph is captured every draw comes from the device
+        cursor (rng_cursor_sync before, rng_cursor_commit after the replays)."""
+        e, n = vs.shape[0], self.num_nodes
+        numel = e * n
+        threads, iters = rng.torch_call_geometry(self.device, numel)
+        draws = num_iters + (0 if first_draw_is_iter else 1)      # randn calls of the reference
+        if draws <= 0:
+            self.ls_run_masks(vs, None, 0, True, xs_out, workspace)
+            return
+        if th.cuda.is_current_stream_capturing():
+            cur = self.rng_cursor()
+            noise0 = self.torch_randn(numel, 1, 0, 0, threads, iters, cursor=cur).view(e, n)
+            self.ls_run(vs, ws_mult, noise0, num_spin, [], False, None, workspace)
+            first = 0 if first_draw_is_iter else 1
+            masks = self.ls_noise_masks(e, ws_mult, num_iters, 0, 4 * iters * first, threads, iters, workspace,
+                                        cursor=cur)
+            self.rng_cursor_advance(4 * iters * draws)
+        else:
+            seed, offset, _, _ = rng.peek(self.device, numel)
+            noise0 = th.randn((e, n), dtype=th.float32, device=self.device)
+            self.ls_run(vs, ws_mult, noise0, num_spin, [], False, None, workspace)
+            first = 0 if first_draw_is_iter else 1
+            masks = self.ls_noise_masks(e, ws_mult, num_iters, seed, offset + 4 * iters * first, threads, iters,
+                                        workspace)
+            rng.advance(self.device, numel, draws - 1)
+        self.ls_run_masks(vs, masks, num_iters, True, xs_out, workspace)
 
     def _check_noise(self, t: TEN, num_envs: int) -> None:
         if t.dtype != th.float32 or tuple(t.shape) != (num_envs, self.num_nodes) or not t.is_contiguous() \

@@ -69,6 +69,11 @@ class LocalSearch:
         # place on good_xs / good_vs (a row of good_vs that disagrees with its good_xs row is re-evaluated).
         ws = st.ls_workspace(num_sims)
         prev_vs = st.ls_begin(self.good_xs, None, 2, noise_std, ws)
+        if getattr(sim, "fused_rng", False) and num_sims > 0 and num_iters > 0 and st.ls_mask_words(num_sims) >= 0:
+            # the threshold comes from the first draw, which also drives iteration 0 (LocalSearch.py:66-68)
+            st.ls_fused(prev_vs, 2, num_spin, num_iters, True, self.good_xs, ws)
+            num_update = update_vs_only(self.good_vs, prev_vs)
+            return self.good_xs, self.good_vs, num_update
         done = 0
         first = True
         while done < num_iters:
