@@ -262,7 +262,11 @@ def run_b200(args):
     per_call = env_steps_per_call(envs, n, NUM_ITERS, n)
     value = per_call * world * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end from pinned host buffers through the public API
+    # ---- end to end from pinned host buffers through the public API.  Every step copies its spins from pinned host
+    # memory to the device, runs the step, and copies spins + values back.  Two measurements: `serial` (copy in,
+    # compute, copy out, one after the other, one event pair per step) and `pipelined` (three streams, double
+    # buffered: the H2D of step i+1 and the D2H of step i-1 run under the compute of step i; one event pair around
+    # all K steps, fill and drain included) -- the headline, since that is how a host-fed loop runs the device.
     h_xs = xs0.cpu().pin_memory()
     h_out_xs = th.empty_like(h_xs).pin_memory()
     h_out_vs = th.empty((envs,), dtype=th.int64).pin_memory()
@@ -286,7 +290,60 @@ def run_b200(args):
         th.cuda.synchronize()
         e2e_ms.append(a.elapsed_time(b))
     barrier()
-    e2e_total = th.tensor([sum(e2e_ms)], dtype=th.float64, device=dev)
+    serial_total = th.tensor([sum(e2e_ms)], dtype=th.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(serial_total, op=dist.ReduceOp.MAX)
+    serial_ms = float(serial_total.item()) / args.steps
+
+    cur = th.cuda.current_stream(dev)
+    s_in, s_out = th.cuda.Stream(device=dev), th.cuda.Stream(device=dev)
+    st_in = [th.empty_like(xs) for _ in range(2)]
+    st_xs = [th.empty_like(xs) for _ in range(2)]
+    st_vs = [th.empty((envs,), dtype=th.int64, device=dev) for _ in range(2)]
+    small_flush = flush[:160 << 20]                                # > 126 MB L2, inside the timed region
+
+    def e2e_pipelined(k):
+        in_ready = [th.cuda.Event() for _ in range(2)]
+        in_free = [th.cuda.Event() for _ in range(2)]
+        out_ready = [th.cuda.Event() for _ in range(2)]
+        out_free = [th.cuda.Event() for _ in range(2)]
+        for e in in_free + out_free:
+            e.record(cur)
+        s_in.wait_stream(cur)
+        s_out.wait_stream(cur)
+        t0, t1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        t0.record(cur)
+        s_in.wait_event(t0)
+        for i in range(k):
+            b = i & 1
+            with th.cuda.stream(s_in):
+                s_in.wait_event(in_free[b])
+                st_in[b].copy_(h_xs, non_blocking=True)            # H2D of step i
+                in_ready[b].record(s_in)
+            cur.wait_event(in_ready[b])
+            xs.copy_(st_in[b])
+            in_free[b].record(cur)
+            small_flush.zero_()                                    # evict L2 between steps (timed)
+            gx, gv, _ = one_step()
+            cur.wait_event(out_free[b])
+            st_xs[b].copy_(gx)
+            st_vs[b].copy_(gv)
+            out_ready[b].record(cur)
+            with th.cuda.stream(s_out):
+                s_out.wait_event(out_ready[b])
+                h_out_xs.copy_(st_xs[b], non_blocking=True)        # D2H of step i
+                h_out_vs.copy_(st_vs[b], non_blocking=True)
+                out_free[b].record(s_out)
+        cur.wait_stream(s_out)
+        cur.wait_stream(s_in)
+        t1.record(cur)
+        th.cuda.synchronize()
+        return t0.elapsed_time(t1)
+
+    e2e_pipelined(4)
+    barrier()
+    e2e_total = th.tensor([e2e_pipelined(args.steps)], dtype=th.float64, device=dev)
+    barrier()
     if world > 1:
         dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
     e2e_value = per_call * world * args.steps / (float(e2e_total.item()) * 1e-3)
@@ -312,8 +369,10 @@ def run_b200(args):
         # ls_run here = the threshold pass only (noise of draw 0 + cross counts in, thresholds out)
         "ls_search": 4 * envs * n + cb * envs * np_ + 2 * envs * np_ // 8 + 20 * envs + 8 * np_,
         "ls_thresh": 4 * envs * n + cb * envs * np_ + 4 * envs + 8 * np_,
-        # bound pass (cross counts in, one byte per element out) + per draw one byte per element in, one bit out
-        "ls_noise_masks": envs * np_ + envs * n + NUM_ITERS * (envs * n + envs * n // 8) + 4 * envs + 8 * np_,
+        # early-out pass (cross counts in, one byte per Box-Muller pair out) + per draw those bytes in, one bit per
+        # element out (zeroed, then OR-ed).  The float32 noise itself (4 B per element and draw) never exists.
+        "ls_noise_masks": envs * np_ + envs * n // 2 + NUM_ITERS * (envs * n // 2 + 2 * envs * n // 8) + 4 * envs
+                          + 8 * np_,
         # packed tile in/out, one mask bit per element and iteration, bool rows + values out, graph once
         "ls_run_masks": 2 * envs * np_ // 8 + NUM_ITERS * envs * n // 8 + envs * n + 16 * envs + graph_b,
         "torch_randn": 4 * envs * n,
@@ -335,7 +394,13 @@ def run_b200(args):
                 "ms_per_launch": kernel_ms[dom], "algorithmic_bytes_per_launch": alg_bytes[dom],
                 "share_of_step": share,
                 "all_kernels_gbs": {k: alg_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9 for k in kernel_ms if k in alg_bytes},
-                "pass": "separate K-step pass with CUDA events around each launch of this library"}
+                "pass": "separate K-step pass with CUDA events around each call of this library, single stream",
+                "note": ("the step no longer streams noise: ls_noise_masks recomputes torch's Philox/Box-Muller stream in "
+                         "registers (issue-bound, see profiles/), its algorithmic HBM bytes are the early-out bytes and "
+                         "the mask bits; noise_equivalent_gbs = the 4 B per element and draw a streaming implementation "
+                         "reads, over the same time"),
+                "noise_equivalent_gbs": (NUM_ITERS * 4 * envs * n / (kernel_ms["ls_noise_masks"] * 1e-3) / 1e9
+                                         if "ls_noise_masks" in kernel_ms else None)}
     traffic_path = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(traffic_path):
         roofline["traffic"] = json.load(open(traffic_path)).get(dom)
@@ -356,7 +421,11 @@ def run_b200(args):
                                   "(threshold) as a tensor, draws 1-8 recomputed in place by ls_noise_masks (flip bits only)",
                            "multi_gpu": "env batch sharded, graph replicated, one best-cut exchange per step (all-gather of 8+N byte records, no host sync)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": envs * n,
-                        "d2h_bytes_per_step": envs * n + 8 * envs, "ms_per_step": float(e2e_total.item()) / args.steps},
+                        "d2h_bytes_per_step": envs * n + 8 * envs, "ms_per_step": float(e2e_total.item()) / args.steps,
+                        "mode": ("pipelined: H2D(i+1) | step(i) | D2H(i-1) on three streams, double buffered, one event "
+                                 "pair around all K steps (fill + drain and a 160 MiB L2-evicting write per step included)"),
+                        "serial_ms_per_step": serial_ms,
+                        "serial_value": per_call * world / (serial_ms * 1e-3)},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info}
         print(json.dumps(line))
     if world > 1:

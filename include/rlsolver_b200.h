@@ -152,13 +152,14 @@ int rlsb_ls_run(const rlsb_graph_t* g, int64_t num_envs, int64_t* vs, int32_t ws
  * 8 bits or 2^31 and more elements per draw -- use rlsb_ls_run with explicit noise).  rng_threads /
  * rng_iters are the call geometry of ONE such torch call (ATen calc_execution_policy: T = 256 * min(SMs *
  * blocks per SM, ceil(numel / 256)), iters = ceil(numel / 4T)); the caller advances the generator offset by
- * 4 * rng_iters per draw.  ls_run_masks then runs the iterations (one per mask array) and, if finish != 0,
+ * 4 * rng_iters per draw.  reuse_bound != 0: the early-out bytes written by the previous call on this workspace
+ * are still valid (same state, same thresholds: a later group of draws of the same search).  ls_run_masks then runs the iterations (one per mask array) and, if finish != 0,
  * the single-flip pass, as rlsb_ls_search does.  rlsb_torch_randn writes the same draws as float32
  * [num_draws][numel] (equal to torch.randn bit for bit; tests pin it). */
 int64_t rlsb_ls_mask_words(const rlsb_graph_t* g, int64_t num_envs);
 int rlsb_ls_noise_masks(const rlsb_graph_t* g, int64_t num_envs, int32_t ws_mult, uint64_t seed, uint64_t offset,
                         const uint64_t* rng_dev, int32_t rng_threads, int32_t rng_iters, int32_t num_draws,
-                        uint32_t* masks, void* workspace, void* stream);
+                        int32_t reuse_bound, uint32_t* masks, void* workspace, void* stream);
 int rlsb_ls_run_masks(const rlsb_graph_t* g, int64_t num_envs, int64_t* vs, const uint32_t* masks, int32_t num_iters,
                       int32_t finish, uint8_t* xs_out, void* workspace, void* stream);
 int rlsb_torch_randn(float* out, int64_t numel, uint64_t seed, uint64_t offset, const uint64_t* rng_dev,

@@ -110,7 +110,7 @@ SIGNATURES = {
     "rlsb_ls_debug_times": (C.c_int, [_vp]),
     "rlsb_ls_run": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
     "rlsb_ls_mask_words": (_i64, [_vp, _i64]),
-    "rlsb_ls_noise_masks": (C.c_int, [_vp, _i64, _i32, _u64, _u64, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "rlsb_ls_noise_masks": (C.c_int, [_vp, _i64, _i32, _u64, _u64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "rlsb_rng_cursor_advance": (C.c_int, [_vp, _u64, _vp]),
     "rlsb_ls_run_masks": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "rlsb_torch_randn": (C.c_int, [_vp, _i64, _u64, _u64, _vp, _i32, _i32, _i32, _vp]),

@@ -25,7 +25,7 @@ inline int degree_class(const GraphDev& g) {
   return d <= 63 ? 0 : d <= 255 ? 1 : 2;
 }
 
-// Early-out section: 2 bytes per generator thread and round.  T * 4 * iters < numel + 4 T and T <= 2048 threads
+// Early-out section: 2 bytes (one per Box-Muller pair) per generator thread and round.  T * 4 * iters < numel + 4 T and T <= 2048 threads
 // on each of the 148 SMs (ATen calc_execution_policy on a B200).
 inline int64_t ls_bound_bytes(int64_t numel) { return (numel + 4 * (int64_t)kNumSMs * 2048) / 2 + 256; }
 
@@ -37,7 +37,7 @@ struct LsWorkspace {
   float *rd_std, *thresh;
   uint32_t* nd;
   uint8_t* cross_rows;   // [E][Np] uint8 row-major copy of the cross counts (mask generator); null for uint16 counts
-  uint8_t* bound;        // early-out bytes of the mask generator (noise_masks.cu: one uint16 per thread-round)
+  uint8_t* bound;        // early-out bytes of the mask generator (noise_masks.cu: two planes of one byte per thread-round)
   size_t bytes;
 };
 

@@ -42,8 +42,14 @@ struct MaskArgs {
   int64_t mask_words;
   uint32_t numel, n, np;
   uint32_t step_e, step_n;     // T / N, T % N
+  uint32_t div_m, div_s;       // floor(l / N) = (l * div_m) >> (31 + div_s) for every l < 2^31
   int negmult;
 };
+
+// exact floor(l / n) for l < 2^31 (Granlund-Montgomery, 31-bit dividends: the magic number fits 32 bits)
+__device__ __forceinline__ uint32_t div_n(const MaskArgs& a, uint32_t l) {
+  return (uint32_t)(((uint64_t)l * a.div_m) >> (31u + a.div_s));
+}
 
 __global__ void __launch_bounds__(256) noise_mask_kernel(MaskArgs a, TorchRng r) {
   const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
@@ -57,7 +63,7 @@ __global__ void __launch_bounds__(256) noise_mask_kernel(MaskArgs a, TorchRng r)
   const float2 n01 = _curand_box_muller(o.x, o.y), n23 = _curand_box_muller(o.z, o.w);
   const float z[4] = {n01.x, n01.y, n23.x, n23.y};
   uint32_t li = idx + r.threads * 4u * j;
-  uint32_t e = li / a.n, nn = li - e * a.n;
+  uint32_t e = div_n(a, li), nn = li - e * a.n;
   uint32_t* out = a.masks + (int64_t)k * a.mask_words;
 #pragma unroll
   for (int ii = 0; ii < 4; ++ii) {
@@ -86,38 +92,55 @@ __device__ __forceinline__ uint32_t bound_byte(const MaskArgs& a, float th, int 
   const float wsf = __fadd_rn(__int_as_float(cross * a.negmult + degm), -kMagicF);
   const float t = __fadd_rn(th, -wsf);
   if (!(t > 0.f)) return 255u;
-  const float zmin = __fdiv_rn(t * 0.999999f, rd) * 0.999f;   // rd = 0 -> +inf -> c = 0
+  const float zmin = __fdividef(t * 0.999999f, rd) * 0.999f;   // rd = 0 -> +inf -> c = 0; the approximate division's 2 ulp sit inside the 0.999
   const float p = 256.f * 1.001f * __expf(-0.5f * zmin * zmin);
   return p >= 255.f ? 255u : (uint32_t)p;
 }
 
-// Indexed like the generator: thread (idx, round j) owns the elements idx + T*(4j + {0,1,2,3}) = two
-// Box-Muller pairs, and stores one byte per PAIR (the larger of its two elements' bytes; 0 for slots past
-// the tensor -- the exact path re-checks the range).  One uint16 per generator thread and round.
-__global__ void __launch_bounds__(256) mask_bound_kernel(MaskArgs a, uint16_t* __restrict__ bound2, uint32_t T) {
-  const uint32_t idx = blockIdx.x * 256 + threadIdx.x, j = blockIdx.y;
-  uint32_t li = idx + 4u * T * j;
-  uint32_t e = li / a.n, nn = li - e * a.n;
-  uint32_t c[4];
-#pragma unroll
-  for (int ii = 0; ii < 4; ++ii) {
-    c[ii] = 0;
-    if (li < a.numel)
-      c[ii] = bound_byte(a, __ldg(a.thresh + e), (int)__ldg(a.cross_rows + (uint64_t)e * a.np + nn), __ldg(a.degm + nn),
-                         __ldg(a.rd_std + nn));
-    li += T, e += a.step_e, nn += a.step_n;
-    if (nn >= a.n) nn -= a.n, ++e;
-  }
-  bound2[(uint64_t)j * T + idx] = (uint16_t)(max(c[0], c[1]) | (max(c[2], c[3]) << 8));
+// One byte per Box-Muller PAIR (the larger of its two elements' bytes; 0 for slots past the tensor -- the
+// exact path re-checks the range), in two planes [pair of the block][round j][thread idx] so that the
+// generator's thread (idx, j) finds them with two coalesced byte loads.  blockIdx = (idx group, j, pair).
+// VEC4 (N % 4 == 0): a thread covers four consecutive idx = four consecutive nodes of one env row for each
+// of the pair's two elements (they are T apart), all loads and the store are words.
+__device__ __forceinline__ uint32_t bound_of(const MaskArgs& a, uint32_t l) {
+  if (l >= a.numel) return 0u;
+  const uint32_t e = div_n(a, l), nn = l - e * a.n;
+  return bound_byte(a, __ldg(a.thresh + e), (int)__ldg(a.cross_rows + (uint64_t)e * a.np + nn), __ldg(a.degm + nn),
+                    __ldg(a.rd_std + nn));
+}
+
+__device__ __forceinline__ uint32_t bound_of4(const MaskArgs& a, uint32_t l) {
+  if (l >= a.numel) return 0u;                              // numel % 4 == 0: a group is inside or outside
+  const uint32_t e = div_n(a, l), nn = l - e * a.n;         // nn % 4 == 0
+  const float th = __ldg(a.thresh + e);
+  const uint32_t cr = __ldg(reinterpret_cast<const uint32_t*>(a.cross_rows + (uint64_t)e * a.np + nn));
+  const int4 dm = __ldg(reinterpret_cast<const int4*>(a.degm + nn));
+  const float4 rd = __ldg(reinterpret_cast<const float4*>(a.rd_std + nn));
+  return bound_byte(a, th, (int)(cr & 0xffu), dm.x, rd.x) | (bound_byte(a, th, (int)((cr >> 8) & 0xffu), dm.y, rd.y) << 8) |
+         (bound_byte(a, th, (int)((cr >> 16) & 0xffu), dm.z, rd.z) << 16) |
+         (bound_byte(a, th, (int)(cr >> 24), dm.w, rd.w) << 24);
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(256) mask_bound_kernel(MaskArgs a, uint8_t* __restrict__ planes, uint32_t T,
+                                                         uint32_t iters) {
+  const uint32_t idx = (blockIdx.x * 256 + threadIdx.x) * (VEC4 ? 4u : 1u), j = blockIdx.y, pair = blockIdx.z;
+  if (idx >= T) return;
+  const uint32_t l = idx + T * (4u * j + 2u * pair);
+  uint8_t* dst = planes + ((uint64_t)pair * iters + j) * T + idx;
+  if (VEC4)
+    *reinterpret_cast<uint32_t*>(dst) = __vmaxu4(bound_of4(a, l), bound_of4(a, l + T));
+  else
+    *dst = (uint8_t)max(bound_of(a, l), bound_of(a, l + T));
 }
 
 // Generator, early-out form.  grid = (T / 256, rounds split, draws); a thread walks the rounds j = blockIdx.y,
 // blockIdx.y + gridDim.y, ... of its Philox subsequence: one 2-byte load, one Philox block, two byte
-// compares.  A thread-round with a passing pair is queued PER WARP as one word (round, lane, which pairs)
+// compares.  A passing pair is queued PER WARP as one word (round, lane, which pair of the block)
 // -- ballot-compacted, no atomics, no block barrier -- and whenever a warp has 32 of them all its lanes take
 // one each: recompute that Philox block, curand's Box-Muller, the reference's expression, the exact
 // compare.  The exact path so runs with full warps although only a few percent of the pairs need it.
-constexpr int kWarpQueue = 64;   // < 32 left over + at most 32 new per round
+constexpr int kWarpQueue = 96;   // < 32 left over + at most 64 new per round
 
 __device__ __forceinline__ void mask_exact_pair(const MaskArgs& a, uint32_t* __restrict__ out, uint32_t x, uint32_t y,
                                                 uint32_t l0, uint32_t T) {
@@ -126,7 +149,7 @@ __device__ __forceinline__ void mask_exact_pair(const MaskArgs& a, uint32_t* __r
   for (int h = 0; h < 2; ++h) {
     const uint32_t l = l0 + h * T;
     if (l < a.numel) {
-      const uint32_t e = l / a.n, nn = l - e * a.n;
+      const uint32_t e = div_n(a, l), nn = l - e * a.n;
       const int cross = (int)__ldg(a.cross_rows + (uint64_t)e * a.np + nn);
       const float sr = spin_rand(__ldg(a.degm + nn), a.negmult, cross, h ? z.y : z.x, __ldg(a.rd_std + nn));
       if (sr > __ldg(a.thresh + e)) atomicOr(out + (l >> 5), 1u << (l & 31u));
@@ -134,7 +157,7 @@ __device__ __forceinline__ void mask_exact_pair(const MaskArgs& a, uint32_t* __r
   }
 }
 
-__global__ void __launch_bounds__(256) noise_mask_fast_kernel(MaskArgs a, const uint16_t* __restrict__ bound2,
+__global__ void __launch_bounds__(256) noise_mask_fast_kernel(MaskArgs a, const uint8_t* __restrict__ planes,
                                                               TorchRng r) {
   __shared__ uint32_t queue[8][kWarpQueue];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -148,38 +171,39 @@ __global__ void __launch_bounds__(256) noise_mask_fast_kernel(MaskArgs a, const 
   uint32_t* out = a.masks + (int64_t)k * a.mask_words;
   uint32_t* q = queue[warp];
   const uint32_t jstep = gridDim.y;
-  const uint16_t* bp = bound2 + (uint64_t)blockIdx.y * T + idx;
-  const uint64_t bstride = (uint64_t)jstep * T;
+  const uint8_t* bp = planes + (uint64_t)blockIdx.y * T + idx;           // pair A plane; pair B one plane further
+  const uint64_t bstride = (uint64_t)jstep * T, plane = (uint64_t)r.iters_per_call * T;
 
-  auto exact = [&](uint32_t ent) {
+  auto exact = [&](uint32_t ent) {      // one queued pair: bit 0 = second pair of the block
     const uint32_t jj = ent >> 8, src = idx - lane + ((ent >> 2) & 31u);
     const uint64_t ctr = ctr0 + jj;
     const uint4 o = curand_Philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), src, 0u), pkey);
-    const uint32_t l0 = src + 4u * T * jj;
-    if (ent & 1u) mask_exact_pair(a, out, o.x, o.y, l0, T);
-    if (ent & 2u) mask_exact_pair(a, out, o.z, o.w, l0 + 2u * T, T);
+    const bool second = (ent & 1u) != 0u;
+    mask_exact_pair(a, out, second ? o.z : o.x, second ? o.w : o.y, src + T * (4u * jj + (second ? 2u : 0u)), T);
   };
 
-  uint32_t cw = __ldg(bp);
+  uint32_t ca = __ldg(bp), cb = __ldg(bp + plane);
   int cnt = 0;
   for (uint32_t j = blockIdx.y; j < r.iters_per_call; j += jstep) {
     bp += bstride;
-    uint32_t cwn = 0;
-    if (j + jstep < r.iters_per_call) cwn = __ldg(bp);      // next round's bytes travel during this round's Philox block
+    uint32_t can = 0, cbn = 0;
+    if (j + jstep < r.iters_per_call) can = __ldg(bp), cbn = __ldg(bp + plane);   // next round's bytes travel during this Philox block
     const uint64_t ctr = ctr0 + j;
     const uint4 o = curand_Philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), idx, 0u), pkey);
-    const uint32_t fa = (o.x >> 24) <= (cw & 0xffu) ? 1u : 0u, fb = (o.z >> 24) <= (cw >> 8) ? 2u : 0u;
-    const uint32_t ball = __ballot_sync(kFull, (fa | fb) != 0u);
-    if (fa | fb) q[cnt + __popc(ball & lt)] = (j << 8) | ((uint32_t)lane << 2) | fa | fb;
-    cnt += __popc(ball);
+    const bool pa = (o.x >> 24) <= ca, pb = (o.z >> 24) <= cb;
+    const uint32_t ba = __ballot_sync(kFull, pa), bb = __ballot_sync(kFull, pb);
+    const uint32_t ent = (j << 8) | ((uint32_t)lane << 2);
+    if (pa) q[cnt + __popc(ba & lt)] = ent;
+    if (pb) q[cnt + __popc(ba) + __popc(bb & lt)] = ent | 1u;
+    cnt += __popc(ba) + __popc(bb);
     __syncwarp();
-    if (cnt >= 32) {
+    while (cnt >= 32) {
       cnt -= 32;
-      const uint32_t ent = q[cnt + lane];
+      const uint32_t mine = q[cnt + lane];
       __syncwarp();
-      exact(ent);
+      exact(mine);
     }
-    cw = cwn;
+    ca = can, cb = cbn;
   }
   if (lane < cnt) exact(q[lane]);
 }
@@ -232,7 +256,7 @@ int64_t rlsb_ls_mask_words(const rlsb_graph_t* gh, int64_t num_envs) {
 
 int rlsb_ls_noise_masks(const rlsb_graph_t* gh, int64_t num_envs, int32_t ws_mult, uint64_t seed, uint64_t offset,
                         const uint64_t* rng_dev, int32_t rng_threads, int32_t rng_iters, int32_t num_draws,
-                        uint32_t* masks, void* workspace, void* stream) {
+                        int32_t reuse_bound, uint32_t* masks, void* workspace, void* stream) {
   using namespace rlsb;
   const GraphDev* g;
   if (int rc = graph_check(gh, &g, "ls_noise_masks")) return rc;
@@ -251,6 +275,9 @@ int rlsb_ls_noise_masks(const rlsb_graph_t* gh, int64_t num_envs, int32_t ws_mul
   a.numel = (uint32_t)numel, a.n = (uint32_t)g->n, a.np = (uint32_t)g->np;
   a.step_e = (uint32_t)rng_threads / a.n, a.step_n = (uint32_t)rng_threads % a.n;
   a.negmult = -ws_mult;
+  a.div_s = 0;
+  while ((1u << a.div_s) < a.n) ++a.div_s;
+  a.div_m = (uint32_t)(((uint64_t(1) << (31 + a.div_s)) + a.n - 1) / a.n);
   TorchRng r{seed, offset / 4, (uint32_t)rng_threads, (uint32_t)rng_iters, rng_dev};
   dim3 grid((unsigned)(rng_threads / 256), (unsigned)rng_iters, 1);
   auto st = static_cast<cudaStream_t>(stream);
@@ -265,16 +292,22 @@ int rlsb_ls_noise_masks(const rlsb_graph_t* gh, int64_t num_envs, int32_t ws_mul
   RLSB_REQUIRE(w.bound != nullptr, RLSB_ERR_INVALID, "ls_noise_masks: workspace without the bound section");
   RLSB_REQUIRE((int64_t)rng_threads * rng_iters * 2 <= ls_bound_bytes(numel), RLSB_ERR_INVALID,
                "ls_noise_masks: call geometry (threads %d, iters %d) larger than a B200's", rng_threads, rng_iters);
-  uint16_t* bound2 = reinterpret_cast<uint16_t*>(w.bound);
-  mask_bound_kernel<<<grid, 256, 0, st>>>(a, bound2, (uint32_t)rng_threads);
-  RLSB_LAUNCH_OK();
+  if (!reuse_bound) {
+    if (g->n % 4 == 0)
+      mask_bound_kernel<true><<<dim3((unsigned)((rng_threads + 1023) / 1024), (unsigned)rng_iters, 2), 256, 0, st>>>(
+          a, w.bound, (uint32_t)rng_threads, (uint32_t)rng_iters);
+    else
+      mask_bound_kernel<false><<<dim3((unsigned)(rng_threads / 256), (unsigned)rng_iters, 2), 256, 0, st>>>(
+          a, w.bound, (uint32_t)rng_threads, (uint32_t)rng_iters);
+    RLSB_LAUNCH_OK();
+  }
   RLSB_CUDA_OK(cudaMemsetAsync(masks, 0, (size_t)num_draws * a.mask_words * sizeof(uint32_t), st));
   // rounds are split over blockIdx.y only when there would be too few blocks to fill the GPU otherwise
   int jsplit = 1;
   while ((int64_t)grid.x * jsplit * num_draws < 4 * 8 * kNumSMs && jsplit < rng_iters) jsplit *= 2;
   if (jsplit > rng_iters) jsplit = rng_iters;
   grid.y = (unsigned)jsplit, grid.z = (unsigned)num_draws;
-  noise_mask_fast_kernel<<<grid, 256, 0, st>>>(a, bound2, r);
+  noise_mask_fast_kernel<<<grid, 256, 0, st>>>(a, w.bound, r);
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }

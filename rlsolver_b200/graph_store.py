@@ -333,18 +333,19 @@ class GraphStore:
         return out
 
     def ls_noise_masks(self, num_envs: int, ws_mult: int, num_draws: int, seed: int, offset: int, threads: int,
-                       iters: int, workspace: TEN, cursor: Optional[TEN] = None) -> TEN:
+                       iters: int, workspace: TEN, cursor: Optional[TEN] = None, out: Optional[TEN] = None,
+                       reuse_bound: bool = False) -> TEN:
         """Flip masks (bit e*N + n of row k) of `num_draws` consecutive randn [E, N] draws starting at
         generator state (seed, offset), against the thresholds in the workspace."""
         words = self.ls_mask_words(num_envs)
         if words < 0:
             _lib.check(3, "ls_mask_words")
-        masks = th.empty((max(num_draws, 1), words), dtype=th.int32, device=self.device)
-        with self._op("ls_noise_masks", 3):
+        masks = out if out is not None else th.empty((max(num_draws, 1), words), dtype=th.int32, device=self.device)
+        with self._op("ls_noise_masks", 2 if reuse_bound else 3):
             _lib.check(self._lib.rlsb_ls_noise_masks(self._h, num_envs, int(ws_mult), int(seed), int(offset),
                                                      _ptr(cursor), int(threads), int(iters), int(num_draws),
-                                                     _ptr(masks), _ptr(workspace), _stream_ptr(self.device)),
-                       "ls_noise_masks")
+                                                     int(reuse_bound), _ptr(masks), _ptr(workspace),
+                                                     _stream_ptr(self.device)), "ls_noise_masks")
         return masks
 
     def ls_run_masks(self, vs: TEN, masks: Optional[TEN], num_iters: int, finish: bool, xs_out: Optional[TEN],
@@ -369,23 +370,23 @@ class GraphStore:
         if draws <= 0:
             self.ls_run_masks(vs, None, 0, True, xs_out, workspace)
             return
-        if th.cuda.is_current_stream_capturing():
-            cur = self.rng_cursor()
+        first = 0 if first_draw_is_iter else 1
+        capturing = th.cuda.is_current_stream_capturing()
+        if capturing:
+            cur, seed, base = self.rng_cursor(), 0, 0
             noise0 = self.torch_randn(numel, 1, 0, 0, threads, iters, cursor=cur).view(e, n)
-            self.ls_run(vs, ws_mult, noise0, num_spin, [], False, None, workspace)
-            first = 0 if first_draw_is_iter else 1
-            masks = self.ls_noise_masks(e, ws_mult, num_iters, 0, 4 * iters * first, threads, iters, workspace,
-                                        cursor=cur)
+        else:
+            cur = None
+            seed, base, _, _ = rng.peek(self.device, numel)
+            noise0 = th.randn((e, n), dtype=th.float32, device=self.device)
+        self.ls_run(vs, ws_mult, noise0, num_spin, [], False, None, workspace)
+        masks = self.ls_noise_masks(e, ws_mult, num_iters, seed, base + 4 * iters * first, threads, iters, workspace,
+                                    cursor=cur)
+        self.ls_run_masks(vs, masks, num_iters, True, xs_out, workspace)
+        if capturing:
             self.rng_cursor_advance(4 * iters * draws)
         else:
-            seed, offset, _, _ = rng.peek(self.device, numel)
-            noise0 = th.randn((e, n), dtype=th.float32, device=self.device)
-            self.ls_run(vs, ws_mult, noise0, num_spin, [], False, None, workspace)
-            first = 0 if first_draw_is_iter else 1
-            masks = self.ls_noise_masks(e, ws_mult, num_iters, seed, offset + 4 * iters * first, threads, iters,
-                                        workspace)
             rng.advance(self.device, numel, draws - 1)
-        self.ls_run_masks(vs, masks, num_iters, True, xs_out, workspace)
 
     def _check_noise(self, t: TEN, num_envs: int) -> None:
         if t.dtype != th.float32 or tuple(t.shape) != (num_envs, self.num_nodes) or not t.is_contiguous() \

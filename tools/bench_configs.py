@@ -116,10 +116,29 @@ def maxcut_config(tag, name, envs, dev, flush, with_samplers=False):
     report(cfg, "K3+K2 local_search_inplace kernel", "ls_run: threshold + 8 iterations + sweep + unpack", ms_full,
            envs * (9 + n), 9 * it_bytes + 2 * envs * np_ // 8 + envs * n + 20 * envs)
     del nz
-    # whole reference call incl. torch's randn draws
+    # K3 without noise tensors: the generator recomputed in place (noise_masks.cu) + the bit-mask tile kernel
+    from rlsolver_b200 import rng as _rng
+    if st.ls_mask_words(envs) >= 0:
+        seed, offset, threads, iters = _rng.peek(dev, envs * n)
+        ms_gen = timeit(lambda: st.ls_noise_masks(envs, 1, 8, seed, offset, threads, iters, ws), flush)
+        gen_bytes = envs * np_ + envs * n // 2 + 8 * (envs * n // 2 + 2 * envs * n // 8)
+        report(cfg, "K3 mask generator (8 draws, early-out)", "ls_noise_masks", ms_gen, 8 * envs, gen_bytes,
+               note=f"issue bound (Philox); stands in for {8 * 4 * envs * n / 1e6:.0f} MB of float32 noise = "
+                    f"{8 * 4 * envs * n / (ms_gen * 1e-3) / 1e9:.0f} GB/s noise-equivalent")
+        masks = st.ls_noise_masks(envs, 1, 8, seed, offset, threads, iters, ws)
+        ms_bits = timeit(lambda: st.ls_run_masks(vs2, masks, 8, True, x2, ws), flush)
+        report(cfg, "K3+K2 bit-mask tile kernel", "ls_run_masks: 8 iterations + sweep + unpack", ms_bits, envs * (8 + n),
+               2 * envs * np_ // 8 + 8 * envs * n // 8 + envs * n + 16 * envs,
+               note="working set is SM resident: latency / issue bound, not HBM")
+    # whole reference call: RNG consumed in place (default) and as explicit torch.randn tensors
     ms = timeit(lambda: sim.local_search_inplace(xs.clone(), th.empty(())), flush)
-    report(cfg, "local_search_inplace (public API, with torch randn)", "EnvMaxcut.local_search_inplace", ms,
+    report(cfg, "local_search_inplace (public API, generator consumed in place)", "EnvMaxcut.local_search_inplace", ms,
            envs * (9 + n))
+    sim.fused_rng = False
+    ms = timeit(lambda: sim.local_search_inplace(xs.clone(), th.empty(())), flush)
+    report(cfg, "local_search_inplace (public API, explicit torch.randn tensors)", "EnvMaxcut.local_search_inplace "
+           "(fused_rng=False)", ms, envs * (9 + n))
+    sim.fused_rng = True
     if not with_samplers:
         uni = EnvMaxcut(mygraph=edges, device=dev, if_bidirectional=False)   # as env_MCPG.py:416 builds it
         ls = LocalSearch(uni, n)
