@@ -137,7 +137,7 @@ def run_reference(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- B200 arm
@@ -159,7 +159,6 @@ def run_b200(args):
     th.cuda.set_device(local)
     dev = th.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     rlsolver_b200.build()
 
@@ -427,9 +426,33 @@ def run_b200(args):
                         "serial_ms_per_step": serial_ms,
                         "serial_value": per_call * world / (serial_ms * 1e-3)},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+class _QuietStdout:
+    """Everything libraries write to fd 1 while the bench runs (NCCL's version banner, ...) goes to stderr;
+    stdout carries exactly the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+def emit(line):
+    _RESULT.append(json.dumps(line))
+
+
+_RESULT = []
 
 
 def main():
@@ -442,10 +465,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    with _QuietStdout():
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+    for text in _RESULT:
+        print(text, flush=True)
 
 
 if __name__ == "__main__":

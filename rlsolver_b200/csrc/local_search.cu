@@ -271,7 +271,7 @@ __device__ __forceinline__ void evaluate_and_accept(const GraphDev& g, const LsA
 // single-flip pass + final values + bool rows (consumer threads only; sCnt is zero on entry)
 template <int P>
 __device__ __forceinline__ void finish_tile(const GraphDev& g, const LsArgs& a, uint32_t* sP, const char* sSweep,
-                                            uint64_t* sBar, int* sCnt, int64_t tile, int valid) {
+                                            uint64_t* sBar, int* sCnt, int64_t tile, int valid, int* tk = nullptr) {
   const int lane = threadIdx.x & 31;
   if (a.stage_sweep) {
     mbar_wait(sBar, 0);
@@ -280,9 +280,11 @@ __device__ __forceinline__ void finish_tile(const GraphDev& g, const LsArgs& a, 
     sweep_tile<P, false>(g, sweep_view(g, g.sweep_blob), sP, a.sweep_warps);
   }
   ls_sync();
+  if (tk) stamp(a, *tk);
   const int cnt = tile_cut_partial(g, sP, a.cut_warps);
   if (cnt) atomicAdd(&sCnt[lane], cnt);
   ls_sync();
+  if (tk) stamp(a, *tk);
   if (threadIdx.x < valid) a.vs[tile * kTileEnvs + threadIdx.x] = sCnt[threadIdx.x];
   if (a.unpack_vec4)
     unpack_tile_from_smem<4>(sP, a.xs_out, a.num_envs, g.n, g.np, tile, kLSWarps);
@@ -670,8 +672,10 @@ __device__ __forceinline__ MaskChunk mask_chunk_load(const uint32_t* __restrict_
   return c;
 }
 
+// sF / sNF (optional): the nodes whose flip word is not zero are appended to a list (ballot-compacted, one
+// shared-memory atomic per block of 32 nodes) for the delta evaluation below.
 __device__ __forceinline__ void mask_chunk_apply(const MaskChunk& c, uint64_t row, int b0, int n, const uint32_t* sP,
-                                                 uint32_t* sX) {
+                                                 uint32_t* sX, uint16_t* sF, int* sNF) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
@@ -680,19 +684,105 @@ __device__ __forceinline__ void mask_chunk_apply(const MaskChunk& c, uint64_t ro
     const uint32_t word = __funnelshift_r(c.lo[u], c.hi[u], (uint32_t)(row + 32u * (uint32_t)b) & 31u);
     const uint32_t t = transpose32(word, lane);                     // lane = node 32b + lane, bit = env
     const int i = 32 * b + lane;
+    const bool flips = i < n && t != 0u;
     if (i < n) sX[i] = sP[i] ^ t;
+    if (sF) {
+      const uint32_t ball = __ballot_sync(kFull, flips);
+      if (ball) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(sNF, __popc(ball));
+        base = __shfl_sync(kFull, base, 0);
+        if (flips) sF[base + __popc(ball & ((1u << lane) - 1u))] = (uint16_t)i;
+      }
+    }
+  }
+}
+
+// Delta evaluation of a candidate.  Only ~num_spin nodes per env flip in an iteration, so instead of
+// re-counting all M edges (env_L2A.py:102 does a full calculate_obj_values) the value moves by the edges that
+// toggle: for a flipped node i and a neighbour j that does NOT flip in the same env, edge (i, j) goes from
+// cut to uncut (-1) or back (+1); edges whose two ends flip keep their state.  One lane per flipped node walks
+// its row of the full-neighbour SELL structure (the sweep's, found through the node -> slot map sInv) and adds
+// the words t = m_i & ~m_j split by the edge's current state into two vertical counters; cand = vs + U - C.
+// Short rows are padded with the node's own id (t == 0).  Integer-exact, same decisions as the full count.
+template <int P, bool SMEM>
+__device__ __forceinline__ void delta_partial(const SweepView& sv, const uint16_t* sInv, const uint16_t* sF, int nf,
+                                              const uint32_t* sP, const uint32_t* sX, int* sCnt) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k0 = warp * 32; k0 < nf; k0 += kLSThreads) {            // warp-uniform
+    const int k = k0 + lane;
+    VCount<P> up, down;
+    up.clear(), down.clear();
+    if (k < nf) {
+      const uint32_t i = sF[k];
+      const uint32_t xi = sP[i], mi = xi ^ sX[i];
+      const int slot = sInv[i], slice = slot >> 5;
+      const int gb = SMEM ? sv.sell.off[slice] : __ldg(sv.sell.off + slice);
+      const int nb = (SMEM ? sv.sell.off[slice + 1] : __ldg(sv.sell.off + slice + 1)) - gb;
+      const uint2* col = reinterpret_cast<const uint2*>(sv.sell.col) + (int64_t)gb * 32 + (slot & 31);
+      const uint32_t own = i | (i << 16);
+      for (int b = 0; b < nb; b += 2) {
+        const uint2 i0 = SMEM ? col[b * 32] : __ldg(col + b * 32);
+        uint2 i1 = make_uint2(own, own);
+        if (b + 1 < nb) i1 = SMEM ? col[(b + 1) * 32] : __ldg(col + (b + 1) * 32);
+        uint32_t u[8], d[8];
+        const uint32_t ids[8] = {i0.x & 0xffffu, i0.x >> 16, i0.y & 0xffffu, i0.y >> 16,
+                                 i1.x & 0xffffu, i1.x >> 16, i1.y & 0xffffu, i1.y >> 16};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t xj = sP[ids[q]], t = mi & ~(xj ^ sX[ids[q]]), cut = xi ^ xj;
+          u[q] = t & ~cut, d[q] = t & cut;
+        }
+        up.add8(u[0], u[1], u[2], u[3], u[4], u[5], u[6], u[7]);
+        down.add8(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
+      }
+    }
+    const int delta = up.flush_warp(lane) - down.flush_warp(lane);
+    if (delta) atomicAdd(&sCnt[lane], delta);
   }
 }
 
 template <int P>
+__device__ __forceinline__ void evaluate_delta_and_accept(const GraphDev& g, const LsArgs& a, const char* sSweep,
+                                                          const uint16_t* sInv, const uint16_t* sF, int* sNF,
+                                                          uint32_t* sP, const uint32_t* sX, int* sCnt,
+                                                          uint32_t* sAccept, int valid, int64_t& my_vs) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nf = *sNF;
+  if (a.stage_sweep)
+    delta_partial<P, true>(sweep_view(g, sSweep), sInv, sF, nf, sP, sX, sCnt);
+  else
+    delta_partial<P, false>(sweep_view(g, g.sweep_blob), sInv, sF, nf, sP, sX, sCnt);
+  ls_sync();
+  if (warp == 0) {
+    const int delta = sCnt[lane];
+    const bool keep = lane < valid && delta >= 0;                  // vs' >= vs (util_read_data.py:199)
+    if (keep) my_vs += delta;
+    const unsigned acc = __ballot_sync(kFull, keep);
+    if (lane == 0) *sAccept = acc, *sNF = 0;
+    sCnt[lane] = 0;
+  }
+  ls_sync();
+  const uint32_t acc = *sAccept;
+  for (int k = threadIdx.x; k < nf; k += kLSThreads) {
+    const uint32_t i = sF[k];
+    sP[i] = (sX[i] & acc) | (sP[i] & ~acc);
+  }
+  ls_sync();
+}
+
+template <int P>
 __global__ void __launch_bounds__(kLSThreads) ls_bits_kernel(GraphDev g, LsArgs a, const uint32_t* __restrict__ masks,
-                                                             int64_t mask_words) {
+                                                             int64_t mask_words, int use_delta) {
   extern __shared__ __align__(1024) uint32_t smem[];
   uint32_t* sP = smem;
   uint32_t* sX = smem + g.np;
-  char* sSweep = reinterpret_cast<char*>(smem + 2 * g.np);
+  uint16_t* sInv = reinterpret_cast<uint16_t*>(smem + 2 * g.np);     // node -> slot of the sweep structure
+  uint16_t* sF = sInv + g.np;                                        // nodes flipped by the current candidate
+  char* sSweep = reinterpret_cast<char*>(smem + 3 * g.np);
   __shared__ int sCnt[kTileEnvs];
   __shared__ uint32_t sAccept;
+  __shared__ int sNF;
   __shared__ __align__(8) uint64_t sBar;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t tile = blockIdx.x;
@@ -700,11 +790,19 @@ __global__ void __launch_bounds__(kLSThreads) ls_bits_kernel(GraphDev g, LsArgs 
   const int valid = (int)min((int64_t)kTileEnvs, a.num_envs - env0);
   if (threadIdx.x == 0) {
     mbar_init(&sBar, 1);
-    if (a.finish && a.stage_sweep) stage_sweep_blob(g, sSweep, &sBar);
+    sNF = 0;
+    if (a.stage_sweep) stage_sweep_blob(g, sSweep, &sBar);
   }
   for (int i = threadIdx.x; i < g.np; i += kLSThreads) {
     const uint32_t w = a.packed[tile * g.np + i];
     sP[i] = w, sX[i] = w;
+  }
+  if (use_delta && a.num_iters > 0) {
+    const uint16_t* node = sweep_view(g, g.sweep_blob).sell.node;
+    for (int slot = threadIdx.x; slot < g.num_sweep_slices * 32; slot += kLSThreads) {
+      const uint32_t v = __ldg(node + slot);
+      if (v != 0xFFFFu) sInv[v] = (uint16_t)slot;
+    }
   }
   if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
   int64_t my_vs = 0;
@@ -713,22 +811,33 @@ __global__ void __launch_bounds__(kLSThreads) ls_bits_kernel(GraphDev g, LsArgs 
   const int blocks = (g.n + 31) >> 5;
   const uint64_t row = (uint64_t)(env0 + lane) * (uint64_t)g.n;     // first bit of the lane's env row
   const bool live = lane < valid;
+  uint16_t* flist = use_delta ? sF : nullptr;
+  int tk = 0;
+  stamp(a, tk);
   MaskChunk pre = mask_chunk_load(masks, row, warp, a.num_iters > 0 ? blocks : 0, live);
+  if (use_delta && a.stage_sweep && a.num_iters > 0) mbar_wait(&sBar, 0);   // the neighbour lists have landed
+  stamp(a, tk);
   for (int it = 0; it < a.num_iters; ++it) {
     const uint32_t* mask = masks + it * mask_words;
-    mask_chunk_apply(pre, row, warp, g.n, sP, sX);
+    mask_chunk_apply(pre, row, warp, g.n, sP, sX, flist, &sNF);
     for (int b0 = warp + 4 * kLSWarps; b0 < blocks; b0 += 4 * kLSWarps)
-      mask_chunk_apply(mask_chunk_load(mask, row, b0, blocks, live), row, b0, g.n, sP, sX);
+      mask_chunk_apply(mask_chunk_load(mask, row, b0, blocks, live), row, b0, g.n, sP, sX, flist, &sNF);
     ls_sync();
     pre = mask_chunk_load(mask + mask_words, row, warp, it + 1 < a.num_iters ? blocks : 0, live);
-    evaluate_and_accept(g, a, sP, sX, sCnt, &sAccept, valid, my_vs);
+    stamp(a, tk);
+    if (use_delta)
+      evaluate_delta_and_accept<P>(g, a, sSweep, sInv, sF, &sNF, sP, sX, sCnt, &sAccept, valid, my_vs);
+    else
+      evaluate_and_accept(g, a, sP, sX, sCnt, &sAccept, valid, my_vs);
+    stamp(a, tk);
   }
   const uint32_t vmask = valid == 32 ? kFull : ((1u << valid) - 1u);
   if (a.finish) {
-    finish_tile<P>(g, a, sP, sSweep, &sBar, sCnt, tile, valid);
+    finish_tile<P>(g, a, sP, sSweep, &sBar, sCnt, tile, valid, &tk);
   } else {
     if (warp == 0 && lane < valid) a.vs[env0 + lane] = my_vs;
   }
+  stamp(a, tk);
   for (int i = threadIdx.x; i < g.np; i += kLSThreads) a.packed[tile * g.np + i] = sP[i] & vmask;
 }
 
@@ -872,12 +981,16 @@ static int launch_generic(const GraphDev& g, LsArgs a, cudaStream_t st) {
 
 template <int P>
 static int launch_bits(const GraphDev& g, LsArgs a, const uint32_t* masks, cudaStream_t st) {
-  const size_t tiles_bytes = 2 * (size_t)g.np * sizeof(uint32_t);
-  a.stage_sweep = (a.finish && tiles_bytes + (size_t)g.sweep_blob_bytes <= kSmemBudget) ? 1 : 0;
+  const size_t tiles_bytes = 3 * (size_t)g.np * sizeof(uint32_t);     // two tile copies + node->slot map + flipped list
+  a.stage_sweep = ((a.finish || a.num_iters > 0) && tiles_bytes + (size_t)g.sweep_blob_bytes <= kSmemBudget) ? 1 : 0;
   const size_t smem = tiles_bytes + (a.stage_sweep ? (size_t)g.sweep_blob_bytes : 0);
+  RLSB_REQUIRE(smem <= kSmemBudget, RLSB_ERR_UNSUPPORTED, "ls_run_masks: %d nodes exceed the shared-memory tile", g.n);
   const int64_t tiles = (a.num_envs + kTileEnvs - 1) / kTileEnvs;
+  // slots of the sweep structure are addressed with 16 bits; RLSB_LS_FULL_CUT=1 keeps the full re-count (cross-check)
+  const char* env = getenv("RLSB_LS_FULL_CUT");
+  const int use_delta = (g.num_sweep_slices * 32 <= 65536 && !(env && env[0] == '1')) ? 1 : 0;
   if (int rc = allow_smem(ls_bits_kernel<P>, smem)) return rc;
-  ls_bits_kernel<P><<<(unsigned)tiles, kLSThreads, smem, st>>>(g, a, masks, ls_mask_words(a.num_envs, g.n));
+  ls_bits_kernel<P><<<(unsigned)tiles, kLSThreads, smem, st>>>(g, a, masks, ls_mask_words(a.num_envs, g.n), use_delta);
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }
@@ -1094,6 +1207,7 @@ int rlsb_ls_run_masks(const rlsb_graph_t* gh, int64_t num_envs, int64_t* vs, con
   a.packed = w.packed, a.vs = vs, a.num_iters = num_iters, a.num_envs = num_envs;
   a.finish = finish ? 1 : 0, a.xs_out = xs_out, a.unpack_vec4 = (xs_out && rows_vec4_ok(xs_out, g->n)) ? 1 : 0;
   a.cut_warps = cut_warps_for(g->m, kLSWarps), a.sweep_warps = sweep_warps_for(*g, kLSWarps);
+  a.times = ls_debug_times();
   auto st = static_cast<cudaStream_t>(stream);
   const int dc = degree_class(*g);
   return dc == 0 ? launch_bits<6>(*g, a, masks, st) : dc == 1 ? launch_bits<8>(*g, a, masks, st)
