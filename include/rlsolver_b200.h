@@ -175,6 +175,16 @@ int rlsb_rng_cursor_advance(uint64_t* rng_dev, uint64_t delta, void* stream);
  * this copies the 64 slots out (host pointer).  RLSB_ERR_INVALID when the variable is unset. */
 int rlsb_ls_debug_times(int64_t* out64);
 
+/* ---- relaxed (probabilistic) max-cut objective: SimulatorMaxcut.get_objectives (rlsolver/envs/env_k_spin.py:191-193)
+ * and PIGNN's hamiltonian_maxcut (rlsolver/methods/PIGNN/util.py:4-8):
+ *   out[e] = -sum over the ORIGINAL edge list (u, v) of  p[e][u] + p[e][v] - 2 p[e][u] p[e][v]      (weights ignored, as there)
+ * probs float32 [E][N], out float32 [E].  relaxed_cut_grad is its vector-Jacobian product: grad_probs[e][u] =
+ * -grad_out[e] * sum over edges incident to u of (1 - 2 p[e][other end]) (what autograd computes through the
+ * reference's gathers).  float32; results agree with the torch expression within 1e-5 relative. */
+int rlsb_relaxed_cut(const rlsb_graph_t* g, const float* probs, int64_t num_envs, float* out, void* stream);
+int rlsb_relaxed_cut_grad(const rlsb_graph_t* g, const float* probs, const float* grad_out, int64_t num_envs,
+                          float* grad_probs, void* stream);
+
 /* ---- the exhaustive single-flip pass alone, on packed tiles (vs is recomputed) */
 int rlsb_flip_sweep(const rlsb_graph_t* g, uint32_t* packed, int64_t* vs, int64_t num_envs, void* stream);
 

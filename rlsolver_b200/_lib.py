@@ -115,6 +115,8 @@ SIGNATURES = {
     "rlsb_ls_run_masks": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "rlsb_torch_randn": (C.c_int, [_vp, _i64, _u64, _u64, _vp, _i32, _i32, _i32, _vp]),
     "rlsb_flip_sweep": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "rlsb_relaxed_cut": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "rlsb_relaxed_cut_grad": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "rlsb_step_flip": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "rlsb_greedy_best_flip": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp]),
     "rlsb_torch_rand": (C.c_int, [_u64, _u64, _u32, _u32, _i64, _i64, _vp, _vp]),

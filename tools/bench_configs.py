@@ -87,6 +87,22 @@ def maxcut_config(tag, name, envs, dev, flush, with_samplers=False):
     ms = timeit(lambda: st.cut_eval_packed(packed, envs, out), flush)
     report(cfg, "K1 cut_eval (packed in)", "cut_eval_packed", ms, envs, envs * np_ // 8 + 8 * envs + 4 * m,
            note="working set is L2/SM resident: bounded by launch latency + integer ALU, not HBM")
+    # relaxed objective (env_k_spin.SimulatorMaxcut.get_objectives) and its gradient
+    from rlsolver_b200.relaxed import relaxed_cut
+    probs = th.rand((envs, n), device=dev)
+    ms = timeit(lambda: relaxed_cut(st, probs), flush)
+    report(cfg, "relaxed objective -(p0+p1-2p0p1) (fp32 rows in)", "SimulatorMaxcut.get_objectives", ms, envs,
+           4 * envs * n + 4 * m + 4 * envs)
+    pg = probs.clone().requires_grad_(True)
+    gout = th.ones(envs, device=dev)
+
+    def fwd_bwd():
+        pg.grad = None
+        (relaxed_cut(st, pg) * gout).sum().backward()
+    ms = timeit(fwd_bwd, flush)
+    report(cfg, "relaxed objective forward + backward", "get_objectives(...).backward()", ms, envs,
+           3 * 4 * envs * n + 8 * m + 8 * envs, note="includes torch's (obj * g).sum() and its backward")
+    del probs, pg
     # K2: exhaustive single-flip pass (N env-steps per env)
     vs = st.cut_eval_packed(packed, envs)
     pk = packed.clone()
