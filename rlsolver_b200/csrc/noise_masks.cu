@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256) noise_mask_fast_kernel(MaskArgs a, const 
   const uint32_t k = blockIdx.z;
   const PhiloxKey key = philox_key(r);
   const uint64_t ctr0 = key.offset4 + (uint64_t)k * r.iters_per_call;
-  const uint2 pkey = make_uint2((uint32_t)key.seed, (uint32_t)(key.seed >> 32));
+  const PhiloxKeys pkey = philox_keys(key.seed);
   const uint32_t T = r.threads;
   uint32_t* out = a.masks + (int64_t)k * a.mask_words;
   uint32_t* q = queue[warp];
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) noise_mask_fast_kernel(MaskArgs a, const 
   auto exact = [&](uint32_t ent) {      // one queued pair: bit 0 = second pair of the block
     const uint32_t jj = ent >> 8, src = idx - lane + ((ent >> 2) & 31u);
     const uint64_t ctr = ctr0 + jj;
-    const uint4 o = curand_Philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), src, 0u), pkey);
+    const uint4 o = philox10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), src, 0u), pkey);
     const bool second = (ent & 1u) != 0u;
     mask_exact_pair(a, out, second ? o.z : o.x, second ? o.w : o.y, src + T * (4u * jj + (second ? 2u : 0u)), T);
   };
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) noise_mask_fast_kernel(MaskArgs a, const 
     uint32_t can = 0, cbn = 0;
     if (j + jstep < r.iters_per_call) can = __ldg(bp), cbn = __ldg(bp + plane);   // next round's bytes travel during this Philox block
     const uint64_t ctr = ctr0 + j;
-    const uint4 o = curand_Philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), idx, 0u), pkey);
+    const uint4 o = philox10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), idx, 0u), pkey);
     const bool pa = (o.x >> 24) <= ca, pb = (o.z >> 24) <= cb;
     const uint32_t ba = __ballot_sync(kFull, pa), bb = __ballot_sync(kFull, pb);
     const uint32_t ent = (j << 8) | ((uint32_t)lane << 2);

@@ -37,6 +37,33 @@ __device__ __forceinline__ PhiloxKey philox_key(const TorchRng& r) {
   return k;
 }
 
+// Philox4x32-10 with the ten round keys precomputed (curand_Philox4x32_10 bumps the key inside every round;
+// in a loop over counters the compiler re-derives the warp-uniform key schedule each trip on the uniform
+// datapath, ~14 issue slots per call).  The keys are pinned in ordinary registers.
+struct PhiloxKeys {
+  uint32_t a[10], b[10];
+};
+__device__ __forceinline__ PhiloxKeys philox_keys(uint64_t seed) {
+  PhiloxKeys k;
+  uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    k.a[i] = a, k.b[i] = b;
+    asm volatile("" : "+r"(k.a[i]), "+r"(k.b[i]));      // opaque: keep them as per-thread registers
+    a += PHILOX_W32_0, b += PHILOX_W32_1;
+  }
+  return k;
+}
+__device__ __forceinline__ uint4 philox10(uint4 c, const PhiloxKeys& k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(PHILOX_M4x32_0, c.x), lo0 = PHILOX_M4x32_0 * c.x;
+    const uint32_t hi1 = __umulhi(PHILOX_M4x32_1, c.z), lo1 = PHILOX_M4x32_1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.a[i], lo1, hi0 ^ c.w ^ k.b[i], lo0);
+  }
+  return c;
+}
+
 // the uint32 element `li` of consecutive call number `call` receives
 __device__ __forceinline__ uint32_t torch_philox_u32(const TorchRng& r, uint64_t call, uint32_t li) {
   const uint32_t idx = li % r.threads, k = li / r.threads;

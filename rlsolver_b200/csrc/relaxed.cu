@@ -40,12 +40,25 @@ __global__ void __launch_bounds__(kRelaxThreads) relaxed_cut_kernel(GraphDev g, 
   float acc[ENVS];
 #pragma unroll
   for (int e = 0; e < ENVS; ++e) acc[e] = 0.f;
-  for (int k = threadIdx.x; k < g.m; k += kRelaxThreads) {
-    const uint32_t pr = __ldg(g.edge_pair + k);
-    const float* a = sp + (pr & 0xffffu) * ENVS;
-    const float* b = sp + (pr >> 16) * ENVS;
+  // four edges per 16-byte load (the list is zero-padded to whole quads), the next quad in flight while this
+  // one is evaluated; pad edges (k >= m) are skipped -- (0, 0) would add p0 + p0 - 2 p0^2
+  const int quads = (g.m + 3) >> 2;
+  const uint4* pairs = reinterpret_cast<const uint4*>(g.edge_pair);
+  uint4 cur = threadIdx.x < quads ? __ldg(pairs + threadIdx.x) : make_uint4(0, 0, 0, 0);
+  for (int q = threadIdx.x; q < quads; q += kRelaxThreads) {
+    const int qn = q + kRelaxThreads;
+    const uint4 nxt = qn < quads ? __ldg(pairs + qn) : make_uint4(0, 0, 0, 0);
+    const uint32_t pr[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
-    for (int e = 0; e < ENVS; ++e) acc[e] += fmaf(-2.f * a[e], b[e], a[e] + b[e]);
+    for (int c = 0; c < 4; ++c) {
+      if (4 * q + c < g.m) {
+        const float* a = sp + (pr[c] & 0xffffu) * ENVS;
+        const float* b = sp + (pr[c] >> 16) * ENVS;
+#pragma unroll
+        for (int e = 0; e < ENVS; ++e) acc[e] += fmaf(-2.f * a[e], b[e], a[e] + b[e]);
+      }
+    }
+    cur = nxt;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -94,6 +107,48 @@ __global__ void __launch_bounds__(kRelaxThreads) relaxed_cut_grad_kernel(GraphDe
   }
 }
 
+// Gradient by gathering (graphs without self loops): d/dp_u = deg_u - 2 * sum over the neighbours v of p_v.  One
+// lane per row of the full-neighbour SELL structure (the sweep's; short rows are padded with the node's own id,
+// subtracted again through the true degree), one LDS per neighbour for all ENVS envs, no atomics, deterministic.
+template <int ENVS>
+__global__ void __launch_bounds__(kRelaxThreads) relaxed_cut_grad_gather_kernel(GraphDev g, const float* __restrict__ probs,
+                                                                                const float* __restrict__ grad_out,
+                                                                                int64_t num_envs,
+                                                                                float* __restrict__ grad_probs) {
+  extern __shared__ float sp[];
+  const int64_t env0 = (int64_t)blockIdx.x * ENVS;
+  stage_rows<ENVS>(probs, num_envs, env0, g.n, sp);
+  __syncthreads();
+  const SweepView sv = sweep_view(g, g.sweep_blob);
+  float go[ENVS];
+#pragma unroll
+  for (int e = 0; e < ENVS; ++e) go[e] = env0 + e < num_envs ? -__ldg(grad_out + env0 + e) : 0.f;
+  for (int slot = threadIdx.x; slot < g.num_sweep_slices * 32; slot += kRelaxThreads) {
+    const uint32_t u = __ldg(sv.sell.node + slot);
+    if (u == 0xFFFFu) continue;
+    const int slice = slot >> 5;
+    const int gb = __ldg(sv.sell.off + slice), nb = __ldg(sv.sell.off + slice + 1) - gb;
+    const uint2* col = reinterpret_cast<const uint2*>(sv.sell.col) + (int64_t)gb * 32 + (slot & 31);
+    float sum[ENVS];
+#pragma unroll
+    for (int e = 0; e < ENVS; ++e) sum[e] = 0.f;
+    for (int b = 0; b < nb; ++b) {
+      const uint2 id = __ldg(col + b * 32);
+      const uint32_t ids[4] = {id.x & 0xffffu, id.x >> 16, id.y & 0xffffu, id.y >> 16};
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int e = 0; e < ENVS; ++e) sum[e] += sp[ids[c] * ENVS + e];
+    }
+    const int deg = __ldg(g.full_ptr + u + 1) - __ldg(g.full_ptr + u);
+    const float pad = (float)(4 * nb - deg), fdeg = (float)deg;
+#pragma unroll
+    for (int e = 0; e < ENVS; ++e)
+      if (env0 + e < num_envs)
+        grad_probs[(env0 + e) * (int64_t)g.n + u] = go[e] * (fdeg - 2.f * (sum[e] - pad * sp[u * ENVS + e]));
+  }
+}
+
 constexpr size_t kRelaxSmem = 200 * 1024;
 
 template <typename K>
@@ -139,6 +194,22 @@ int rlsb_relaxed_cut_grad(const rlsb_graph_t* gh, const float* probs, const floa
   if (num_envs == 0) return RLSB_OK;
   RLSB_REQUIRE(probs && grad_out && grad_probs, RLSB_ERR_INVALID, "relaxed_cut_grad: null pointer");
   auto st = static_cast<cudaStream_t>(stream);
+  if (g->m == g->mf / 2) {          // no self loops: every edge sits twice in the full-neighbour structure
+    const size_t row1 = (size_t)g->np * sizeof(float);
+    RLSB_REQUIRE(row1 <= kRelaxSmem, RLSB_ERR_UNSUPPORTED, "relaxed_cut_grad: %d nodes exceed the shared-memory row", g->n);
+#define RLSB_RELAX(E)                                                                                   \
+  {                                                                                                     \
+    if (int rc = relax_smem(relaxed_cut_grad_gather_kernel<E>, row1 * E)) return rc;                    \
+    relaxed_cut_grad_gather_kernel<E><<<(unsigned)((num_envs + E - 1) / E), kRelaxThreads, row1 * E, st>>>(             \
+        *g, probs, grad_out, num_envs, grad_probs);                                                     \
+  }
+    if (row1 * 4 <= 100 * 1024 && num_envs >= 4 * 2 * kNumSMs) RLSB_RELAX(4)
+    else if (row1 * 2 <= kRelaxSmem && num_envs >= 2 * 2 * kNumSMs) RLSB_RELAX(2)
+    else RLSB_RELAX(1)
+#undef RLSB_RELAX
+    RLSB_LAUNCH_OK();
+    return RLSB_OK;
+  }
   const size_t row = 2 * (size_t)g->np * sizeof(float);       // probabilities + gradient accumulators
   RLSB_REQUIRE(row <= kRelaxSmem, RLSB_ERR_UNSUPPORTED, "relaxed_cut_grad: %d nodes exceed the shared-memory rows", g->n);
 #define RLSB_RELAX(E)                                                                                   \
