@@ -251,6 +251,17 @@ int rlsb_metro_sampling(int32_t num_nodes, const float* probs, const float* star
                         int32_t max_iters, const int32_t* num_iters_dev, const int64_t* explicit_idx,
                         const float* explicit_u, uint64_t seed, uint64_t offset, uint32_t rng_threads,
                         uint32_t rng_iters, int32_t* acc, int32_t count_only, void* stream);
+/* The same sampler in split form (the default of the Python mirror): the draws of all iterations are computed in
+ * parallel first, the chain runs once over all max_iters iterations logging its accepted moves, the stop rule
+ * `accepted moves before iteration t >= stop_count` (MCPG.py:101-103, stop_count = C * max_transfer_time) gives the
+ * number of executed iterations *num_iters_dev (device int32, output) and the moves of the iterations that were not
+ * executed are taken back (flips commute).  Same result as rlsb_metro_sampling's count + apply passes; the caller
+ * advances the generator by 2 calls per executed iteration.  workspace: rlsb_metro_workspace_bytes(N, C, max_iters)
+ * bytes of device memory, 256-byte aligned. */
+int64_t rlsb_metro_workspace_bytes(int32_t num_nodes, int64_t num_chains, int32_t max_iters);
+int rlsb_metro_sampling_split(int32_t num_nodes, const float* probs, const float* start, float* out, int64_t num_chains,
+                              int32_t max_iters, int64_t stop_count, uint64_t seed, uint64_t offset, uint32_t rng_threads,
+                              uint32_t rng_iters, int32_t* num_iters_dev, void* workspace, void* stream);
 
 /* sub_set_sampling, the resampling loop (rlsolver/methods/L2A/transformer.py:346-352):
  * xs[row][ids[row % S][k]] = rand_k[row] < vals[row % S][k] for k < top_k, one rand_like draw of

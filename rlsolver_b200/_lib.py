@@ -127,6 +127,9 @@ SIGNATURES = {
     "rlsb_mcpg_sweeps": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _u64, _u64, _u32, _u32, _vp, _vp]),
     "rlsb_metro_sampling": (C.c_int, [_i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _u64, _u64, _u32, _u32, _vp,
                                       _i32, _vp]),
+    "rlsb_metro_workspace_bytes": (_i64, [_i32, _i64, _i32]),
+    "rlsb_metro_sampling_split": (C.c_int, [_i32, _vp, _vp, _vp, _i64, _i32, _i64, _u64, _u64, _u32, _u32, _vp, _vp,
+                                            _vp]),
     "rlsb_subset_sampling": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _u64, _u64, _u32, _u32, _vp]),
     "rlsb_qubo_create": (C.c_int, [_vp, _i32, _i32, C.POINTER(_vp), _vp]),
     "rlsb_qubo_destroy": (C.c_int, [_vp]),

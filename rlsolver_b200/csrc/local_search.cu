@@ -599,9 +599,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(GraphDev g, Ls
   }
 
   // ---------------- consumer warps
-  for (int i = threadIdx.x; i < g.np; i += kLSThreads) {
-    const uint32_t w = a.packed[tile * g.np + i];
-    sP[i] = w, sX[i] = w;        // padding nodes stay equal in both copies
+  const bool thresh_only = has_thresh && a.num_iters == 0 && !a.finish;   // no candidate, no state change: skip the tile
+  if (!thresh_only) {
+    for (int i = threadIdx.x; i < g.np; i += kLSThreads) {
+      const uint32_t w = a.packed[tile * g.np + i];
+      sP[i] = w, sX[i] = w;        // padding nodes stay equal in both copies
+    }
   }
   if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
   int64_t my_vs = 0;   // warp 0: lane e owns env e's value
@@ -645,7 +648,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(GraphDev g, Ls
     if (warp == 0 && lane < valid) a.vs[env0 + lane] = my_vs;
   }
   stamp(a, tk);
-  for (int i = threadIdx.x; i < g.np; i += kLSThreads) a.packed[tile * g.np + i] = sP[i] & vmask;
+  if (!thresh_only)
+    for (int i = threadIdx.x; i < g.np; i += kLSThreads) a.packed[tile * g.np + i] = sP[i] & vmask;
 }
 
 // ---- generic kernel (any N / alignment): direct global loads, thresh precomputed by

@@ -207,6 +207,225 @@ __global__ void __launch_bounds__(kMetroWarps * 32) metro_kernel(int n, int np, 
   }
 }
 
+// ---------------------------------------------------------------------------- metro_sampling, split form
+// metro_kernel above is a chain of up to 5*max_transfer dependent iterations per warp with two Philox blocks
+// inside every one of them, run twice (count, then apply): 1.8 ms for 4096 chains x 1000 iterations, almost
+// all of it latency.  What is sequential is only the state lookup; the draws are not.  The split form
+//   1. metro_draws_kernel  every (iteration, chain) in parallel: the randint node and the uniform torch's
+//                          calls 2t and 2t+1 would return                           (Philox bound, one pass)
+//   2. metro_rates_kernel  (1-q)/q for both values of the bit, per node, with the float ops of MCPG.py:107-109
+//   0. metro_pack_kernel   float32 [N][C] -> lane-private packed tiles (and metro_unpack_kernel back at the end)
+//   3. metro_pass_kernel   the chain, once, over ALL iterations: state word lookup, rate lookup, compare,
+//                          flip; logs the accept ballot of every (iteration, tile) and counts per iteration
+//   4. metro_scan_kernel   the reference's stop rule (MCPG.py:101-103): number of executed iterations
+//   5. metro_undo_kernel   flips commute: state(T*) = final state ^ the accepted flips of iterations >= T*,
+//                          applied in parallel; writes the float32 [N, C] result
+constexpr int kMetroPF = 8;    // iterations of draws in flight per lane
+
+// draws of (iteration t, chain c) as one 8-byte record {node, bits of the uniform}; grid = (chain blocks, iterations).
+// With C <= T (every call of the reference fits one round of torch's grid: always below 303104 chains) element c of a
+// call is output 0 of the Philox block (counter of the call, subsequence c): no index arithmetic at all.
+__global__ void __launch_bounds__(256) metro_draws_kernel(TorchRng rng, int iters, int64_t num_chains, uint32_t n,
+                                                          uint2* __restrict__ draws) {
+  const int64_t chain = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (chain >= num_chains) return;
+  const bool direct = num_chains <= (int64_t)rng.threads;
+  const uint2 key = make_uint2((uint32_t)rng.seed, (uint32_t)(rng.seed >> 32));
+  for (int t = blockIdx.y; t < iters; t += gridDim.y) {
+    uint32_t x0, x1;
+    if (direct) {
+      const uint64_t c0 = rng.offset4 + 2 * (uint64_t)t * rng.iters_per_call, c1 = c0 + rng.iters_per_call;
+      x0 = curand_Philox4x32_10(make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), (uint32_t)chain, 0u), key).x;
+      x1 = curand_Philox4x32_10(make_uint4((uint32_t)c1, (uint32_t)(c1 >> 32), (uint32_t)chain, 0u), key).x;
+    } else {
+      x0 = torch_philox_u32(rng, 2 * (uint64_t)t, (uint32_t)chain);
+      x1 = torch_philox_u32(rng, 2 * (uint64_t)t + 1, (uint32_t)chain);
+    }
+    // torch.randint(0, N, [C]) = x % N, torch.rand(C) = curand_uniform with the (0,1] -> [0,1) reversal
+    draws[(int64_t)t * num_chains + chain] = make_uint2(x0 % n, __float_as_uint(torch_uniform_from_u32(x1)));
+  }
+}
+
+__global__ void metro_rates_kernel(int n, const float* __restrict__ probs, float* __restrict__ rates) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float p = __ldg(probs + i);
+#pragma unroll
+  for (int bit = 0; bit < 2; ++bit) {
+    const float q = bit ? p : __fsub_rn(1.f, p);
+    rates[2 * i + bit] = __fdiv_rn(__fsub_rn(1.f, q), q);       // (1 - q) / q, IEEE division like torch
+  }
+}
+
+// float32 [N][C] (node-major, the reference's layout) <-> lane-private packed tiles [tile][N/32][32 lanes], by the
+// whole GPU: thread (tile, b, lane) converts nodes 32b .. 32b+31 of chain 32*tile + lane; every warp access is one
+// coalesced 128-byte row segment.  (The chain kernel itself runs on 4 warps per SM: converting there cost 350 us.)
+__global__ void __launch_bounds__(256) metro_pack_kernel(int n, int np, const float* __restrict__ start, int64_t num_chains,
+                                                         int64_t tiles, uint32_t* __restrict__ packed) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = (int)(gid & 31);
+  const int nb = np >> 5;
+  const int64_t tile = (gid >> 5) / nb;
+  const int b = (int)((gid >> 5) - tile * nb);
+  if (tile >= tiles) return;
+  const int64_t chain = tile * kTileEnvs + lane;
+  const bool live = chain < num_chains;
+  uint32_t mine = 0;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int i = 32 * b + k;
+    const float v = (live && i < n) ? __ldg(start + (int64_t)i * num_chains + chain) : 0.f;
+    mine |= (v != 0.f ? 1u : 0u) << k;                           // start_status.bool()
+  }
+  packed[gid] = mine;
+}
+
+__global__ void __launch_bounds__(256) metro_unpack_kernel(int n, int np, const uint32_t* __restrict__ packed,
+                                                           int64_t num_chains, int64_t tiles, float* __restrict__ out) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = (int)(gid & 31);
+  const int nb = np >> 5;
+  const int64_t tile = (gid >> 5) / nb;
+  const int b = (int)((gid >> 5) - tile * nb);
+  if (tile >= tiles) return;
+  const int64_t chain = tile * kTileEnvs + lane;
+  if (chain >= num_chains) return;
+  const uint32_t w = __ldg(packed + gid);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int i = 32 * b + k;
+    if (i < n) out[(int64_t)i * num_chains + chain] = (float)((w >> k) & 1u);
+  }
+}
+
+// State of a tile in LANE-PRIVATE form: word [b][lane] holds nodes 32b .. 32b+31 of chain `lane`, so a chain
+// reads and flips its bits with plain shared-memory loads / stores (no atomics, no bank conflicts, no ordering
+// between lanes).  The chain loop is branch-free and padded to groups of 32 iterations; the accept ballots of
+// a group are handed out one per lane and leave as one store + one counter add per lane and group.
+__global__ void __launch_bounds__(kMetroWarps * 32) metro_pass_kernel(int n, int np, int64_t num_chains, int iters,
+                                                                       const uint2* __restrict__ draws,
+                                                                       const float* __restrict__ rates,
+                                                                       uint32_t* __restrict__ bits, int32_t* __restrict__ acc,
+                                                                       uint32_t* __restrict__ fin) {
+  extern __shared__ uint32_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* sL = smem + (size_t)warp * np;
+  float* sRates = reinterpret_cast<float*>(smem + (size_t)kMetroWarps * np);      // [N][2], shared by the warps
+  for (int i = threadIdx.x; i < 2 * n; i += kMetroWarps * 32) sRates[i] = __ldg(rates + i);
+  __syncthreads();
+  const int64_t tiles = (num_chains + kTileEnvs - 1) / kTileEnvs;
+  for (int64_t tile = (int64_t)blockIdx.x * kMetroWarps + warp; tile < tiles; tile += (int64_t)gridDim.x * kMetroWarps) {
+    const int64_t c0 = tile * kTileEnvs;
+    const bool live = c0 + lane < num_chains;
+    const int64_t chain = c0 + lane;
+    for (int b = 0; b < np / 32; ++b) sL[b * 32 + lane] = fin[tile * np + b * 32 + lane];      // packed by metro_pack_kernel
+    const uint2* dp = draws + chain;
+    uint2 ring[kMetroPF];
+#pragma unroll
+    for (int k = 0; k < kMetroPF; ++k) {
+      ring[k] = make_uint2(0u, 0x7F800000u);                    // u = +inf: never accepted (idle chain / past the end)
+      if (live && k < iters) ring[k] = __ldg(dp + (int64_t)k * num_chains);
+    }
+    const uint2* dnext = dp + (int64_t)kMetroPF * num_chains;
+    const int padded = (iters + 31) / 32 * 32;
+    for (int t0 = 0; t0 < padded; t0 += 32) {
+      uint32_t myword = 0;
+#pragma unroll
+      for (int g = 0; g < 32 / kMetroPF; ++g) {
+#pragma unroll
+        for (int k = 0; k < kMetroPF; ++k) {
+          const int t = t0 + g * kMetroPF + k;
+          const uint2 d = ring[k];
+          ring[k] = make_uint2(0u, 0x7F800000u);
+          if (live && t + kMetroPF < iters) ring[k] = __ldg(dnext);
+          dnext += num_chains;
+          const uint32_t r = d.x;
+          uint32_t* wp = sL + (r >> 5) * 32 + lane;
+          const uint32_t w = *wp, sh = r & 31u;
+          const bool accept = __uint_as_float(d.y) < sRates[2 * r + ((w >> sh) & 1u)];
+          if (accept) *wp = w ^ (1u << sh);
+          const uint32_t word = __ballot_sync(kFull, accept);
+          if (lane == g * kMetroPF + k) myword = word;
+        }
+      }
+      const int t = t0 + lane;
+      if (t < iters) {
+        bits[(int64_t)t * tiles + tile] = myword;
+        if (myword) atomicAdd(acc + t, __popc(myword));
+      }
+    }
+    for (int b = 0; b < np / 32; ++b) fin[tile * np + b * 32 + lane] = sL[b * 32 + lane];
+  }
+}
+
+// num_iters = #{t : accepted moves before iteration t < thresh}  (the reference tests the count BEFORE every iteration)
+__global__ void metro_scan_kernel(const int32_t* __restrict__ acc, int iters, int64_t thresh, int32_t* __restrict__ num_iters) {
+  const int lane = threadIdx.x;
+  int64_t before = 0;
+  int count = 0;
+  for (int t0 = 0; t0 < iters; t0 += 32) {
+    const int t = t0 + lane;
+    int64_t v = t < iters ? (int64_t)acc[t] : 0;
+    int64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t y = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += y;
+    }
+    const int64_t mine = before + incl - v;                     // accepted moves before iteration t
+    count += __popc(__ballot_sync(kFull, t < iters && mine < thresh));
+    before += __shfl_sync(kFull, incl, 31);
+  }
+  if (lane == 0) *num_iters = count;
+}
+
+// flips commute and every (iteration, chain) pair touches its own bit: the moves of the iterations that were not
+// executed are taken back by the whole GPU, one thread per pair, with one atomic XOR on the packed tile in L2
+__global__ void __launch_bounds__(256) metro_undo_kernel(int np, int64_t num_chains, int iters, int64_t tiles,
+                                                         const int32_t* __restrict__ num_iters_dev,
+                                                         const uint2* __restrict__ draws, const uint32_t* __restrict__ bits,
+                                                         uint32_t* __restrict__ fin) {
+  const int first = min(iters, *num_iters_dev);
+  const int64_t total = (int64_t)(iters - first) * num_chains;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = (int64_t)first * num_chains + k;
+    const int64_t t = e / num_chains, chain = e - t * num_chains;
+    const int64_t tile = chain >> 5;
+    const int lane = (int)(chain & 31);
+    if ((__ldg(bits + t * tiles + tile) >> lane) & 1u) {
+      const uint32_t r = __ldg(draws + e).x;
+      atomicXor(fin + tile * np + (r >> 5) * 32 + lane, 1u << (r & 31u));
+    }
+  }
+}
+
+struct MetroWs {
+  uint2* draws;
+  uint32_t* bits;
+  int32_t* acc;
+  uint32_t* fin;
+  float* rates;
+  size_t bytes;
+};
+static MetroWs metro_carve(int n, int64_t num_chains, int iters, void* base) {
+  const int np = (n + 31) / 32 * 32;
+  const int64_t tiles = (num_chains + kTileEnvs - 1) / kTileEnvs;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? static_cast<char*>(base) + off : nullptr;
+    off += (bytes + 255) / 256 * 256;
+    return p;
+  };
+  MetroWs w;
+  w.draws = reinterpret_cast<uint2*>(take((size_t)iters * num_chains * 8));
+  w.bits = reinterpret_cast<uint32_t*>(take((size_t)iters * tiles * 4));
+  w.acc = reinterpret_cast<int32_t*>(take((size_t)iters * 4));
+  w.fin = reinterpret_cast<uint32_t*>(take((size_t)tiles * np * 4));
+  w.rates = reinterpret_cast<float*>(take((size_t)2 * n * 4));
+  w.bytes = off + 256;
+  return w;
+}
+
 // ---------------------------------------------------------------------------- sub_set_sampling
 // xs[row][ids[row % S][k]] = rand_k[row] < vals[row % S][k]   for every (row, k); ids of one row are distinct
 __global__ void subset_kernel(uint8_t* __restrict__ xs, int64_t rows, int n, int64_t num_sims, int top_k,
@@ -237,6 +456,7 @@ __global__ void torch_randint_kernel(TorchRng rng, int64_t calls, int64_t numel,
 static TorchRng make_rng(uint64_t seed, uint64_t offset, uint32_t threads, uint32_t iters) {
   TorchRng r;
   r.seed = seed, r.offset4 = offset / 4, r.threads = threads ? threads : 1, r.iters_per_call = iters ? iters : 1;
+  r.dev = nullptr;
   return r;
 }
 
@@ -464,6 +684,62 @@ int rlsb_torch_randint(uint64_t seed, uint64_t offset, uint32_t rng_threads, uin
   RLSB_REQUIRE(out != nullptr, RLSB_ERR_INVALID, "torch_randint: null pointer");
   torch_randint_kernel<<<(unsigned)((calls * numel + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       make_rng(seed, offset, rng_threads, rng_iters), calls, numel, range, out);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+int64_t rlsb_metro_workspace_bytes(int32_t num_nodes, int64_t num_chains, int32_t max_iters) {
+  if (num_nodes <= 0 || num_chains < 0 || max_iters < 0) return -1;
+  return (int64_t)rlsb::metro_carve(num_nodes, num_chains, max_iters, nullptr).bytes;
+}
+
+int rlsb_metro_sampling_split(int32_t num_nodes, const float* probs, const float* start, float* out, int64_t num_chains,
+                              int32_t max_iters, int64_t stop_count, uint64_t seed, uint64_t offset, uint32_t rng_threads,
+                              uint32_t rng_iters, int32_t* num_iters_dev, void* workspace, void* stream) {
+  using namespace rlsb;
+  RLSB_REQUIRE(num_nodes > 0 && num_chains >= 0 && max_iters >= 0, RLSB_ERR_INVALID, "metro_sampling_split: bad size");
+  RLSB_REQUIRE(num_chains < (int64_t(1) << 31), RLSB_ERR_UNSUPPORTED, "metro_sampling_split: more than 2^31 chains");
+  if (num_chains == 0) return RLSB_OK;
+  RLSB_REQUIRE(probs && start && out && num_iters_dev && workspace, RLSB_ERR_INVALID, "metro_sampling_split: null pointer");
+  RLSB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, RLSB_ERR_INVALID,
+               "metro_sampling_split: workspace must be 256-byte aligned");
+  RLSB_REQUIRE(rng_threads > 0 && rng_iters > 0, RLSB_ERR_INVALID, "metro_sampling_split: no random source");
+  const int np = (num_nodes + 31) / 32 * 32;
+  const size_t smem = (size_t)kMetroWarps * np * 4 + (size_t)2 * num_nodes * 4;      // state tiles + the rate table
+  RLSB_REQUIRE(smem <= 220 * 1024, RLSB_ERR_UNSUPPORTED, "metro_sampling_split: %d nodes exceed the shared-memory tiles",
+               num_nodes);
+  auto st = static_cast<cudaStream_t>(stream);
+  const MetroWs w = metro_carve(num_nodes, num_chains, max_iters, workspace);
+  const TorchRng rng = make_rng(seed, offset, rng_threads, rng_iters);
+  if (max_iters > 0) {
+    const dim3 dgrid((unsigned)((num_chains + 255) / 256), (unsigned)(max_iters < 65535 ? max_iters : 65535));
+    metro_draws_kernel<<<dgrid, 256, 0, st>>>(rng, max_iters, num_chains, (uint32_t)num_nodes, w.draws);
+    RLSB_LAUNCH_OK();
+    RLSB_CUDA_OK(cudaMemsetAsync(w.acc, 0, (size_t)max_iters * 4, st));
+  }
+  metro_rates_kernel<<<(num_nodes + 255) / 256, 256, 0, st>>>(num_nodes, probs, w.rates);
+  RLSB_LAUNCH_OK();
+  if (smem > 48 * 1024) {
+    RLSB_CUDA_OK(cudaFuncSetAttribute(metro_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  const int64_t tiles = (num_chains + kTileEnvs - 1) / kTileEnvs;
+  const int64_t ctas = (tiles + kMetroWarps - 1) / kMetroWarps;
+  const unsigned grid = (unsigned)(ctas < 32 * kNumSMs ? ctas : 32 * kNumSMs);
+  const int64_t words = tiles * np;
+  metro_pack_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(num_nodes, np, start, num_chains, tiles, w.fin);
+  RLSB_LAUNCH_OK();
+  metro_pass_kernel<<<grid, kMetroWarps * 32, smem, st>>>(num_nodes, np, num_chains, max_iters, w.draws, w.rates, w.bits,
+                                                          w.acc, w.fin);
+  RLSB_LAUNCH_OK();
+  metro_scan_kernel<<<1, 32, 0, st>>>(w.acc, max_iters, stop_count, num_iters_dev);
+  RLSB_LAUNCH_OK();
+  if (max_iters > 0) {
+    const int64_t total = (int64_t)max_iters * num_chains;
+    const unsigned ugrid = (unsigned)((total + 255) / 256 < 32 * kNumSMs ? (total + 255) / 256 : 32 * kNumSMs);
+    metro_undo_kernel<<<ugrid, 256, 0, st>>>(np, num_chains, max_iters, tiles, num_iters_dev, w.draws, w.bits, w.fin);
+  }
+  RLSB_LAUNCH_OK();
+  metro_unpack_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(num_nodes, np, w.fin, num_chains, tiles, out);
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }

@@ -24,6 +24,9 @@ from .config import MyGraph
 
 TEN = th.Tensor
 
+# scratch of the split metro_sampling (8 bytes per chain and iteration); beyond this the two-pass kernel is used
+_METRO_SPLIT_MAX_BYTES = 8 << 30
+
 
 class McpgData:
     """What maxcut_dataloader returns, reduced to the fields the samplers read
@@ -83,12 +86,15 @@ def metro_sampling(probs: TEN, start_status: TEN, max_transfer_time: int, device
     device = require_cuda(start_status.device if device is None else device)
     lib = _lib.lib()
     num_node, num_chain = len(probs), start_status.shape[1]
-    start = _as_chains(start_status.bool(), device)
+    if start_status.dtype == th.float32 and start_status.device == device and start_status.is_contiguous():
+        start = start_status            # the kernels read `value != 0` (== start_status.bool()): no conversion pass
+    else:
+        start = _as_chains(start_status.bool(), device)
     p = probs.detach().to(device=device, dtype=th.float32).contiguous()
     tmax = int(max_transfer_time) * 5
     out = th.empty_like(start)
     if tmax <= 0 or num_chain == 0:
-        return start
+        return _as_chains(start_status.bool(), device)
     seed, offset, threads, iters = rng.peek(device, num_chain)
     idx_ptr = u_ptr = C.c_void_p(0)
     if _explicit is not None:
@@ -96,12 +102,23 @@ def metro_sampling(probs: TEN, start_status: TEN, max_transfer_time: int, device
         assert e_idx.dtype == th.int64 and e_u.dtype == th.float32 and e_idx.shape[0] >= 1
         tmax = min(tmax, e_idx.shape[0])
         idx_ptr, u_ptr = _ptr(e_idx), _ptr(e_u)
-    acc = th.zeros((tmax,), dtype=th.int32, device=device)
     st = _stream_ptr(device)
+    thresh = num_chain * int(max_transfer_time)
+    if _explicit is None:
+        need = int(lib.rlsb_metro_workspace_bytes(num_node, num_chain, tmax))
+        if 0 <= need <= _METRO_SPLIT_MAX_BYTES:
+            # split form: draws in parallel, one pass of the chain, stop rule on the device, surplus moves undone
+            ws = th.empty((need,), dtype=th.uint8, device=device)
+            num_iters = th.empty((1,), dtype=th.int32, device=device)
+            _lib.check(lib.rlsb_metro_sampling_split(num_node, _ptr(p), _ptr(start), _ptr(out), num_chain, tmax, thresh,
+                                                     seed, offset, threads, iters, _ptr(num_iters), _ptr(ws), st),
+                       "metro_sampling_split")
+            rng.advance(device, num_chain, 2 * int(num_iters.item()))   # one randint + one rand per executed iteration
+            return out
+    acc = th.zeros((tmax,), dtype=th.int32, device=device)
     _lib.check(lib.rlsb_metro_sampling(num_node, _ptr(p), _ptr(start), None, num_chain, tmax, None, idx_ptr, u_ptr,
                                        seed, offset, threads, iters, _ptr(acc), 1, st), "metro_sampling(count)")
     # the reference checks `count >= num_chain * max_transfer_time` BEFORE every iteration (MCPG.py:101-103)
-    thresh = num_chain * int(max_transfer_time)
     before = th.cat([acc.new_zeros(1), acc.cumsum(0)[:-1]])
     num_iters = (before < thresh).sum().to(th.int32).reshape(1)
     _lib.check(lib.rlsb_metro_sampling(num_node, _ptr(p), _ptr(start), _ptr(out), num_chain, tmax, _ptr(num_iters),

@@ -162,3 +162,28 @@ def test_subset_same_seed_as_reference_calls(cuda_device):
     assert gen.get_offset() == off1
     want = oq.sub_set_sampling(_np(top_ids), _np(top_values), _np(start), repeats, u)
     assert np.array_equal(_np(xs), want)
+
+
+@pytest.mark.parametrize("n,c,max_transfer,lo,hi", [(2000, 4096, 200, 0.2, 0.8), (37, 33, 6, 0.05, 0.5),
+                                                    (800, 1000, 40, 0.4, 0.6), (100, 70, 3, 0.45, 0.55)])
+def test_metro_split_equals_two_pass(n, c, max_transfer, lo, hi, cuda_device, monkeypatch):
+    """The split form of metro_sampling (draws in parallel, one pass of the chain, surplus moves undone) against
+    the two-pass kernel from the same generator state: same samples, same number of executed iterations (the
+    generator ends at the same offset) -- with early stops (probabilities near 0.5 accept almost every move) and
+    runs that use all 5 * max_transfer iterations."""
+    import rlsolver_b200.methods.MCPG as M
+    from rlsolver_b200 import rng
+    dev = cuda_device
+    th.manual_seed(11)
+    probs = th.rand(n, device=dev) * (hi - lo) + lo
+    start = th.randint(0, 2, (n, c), device=dev).float()
+    gen = rng.generator(dev)
+    off0 = gen.get_offset()
+    got = M.metro_sampling(probs, start, max_transfer, device=dev)
+    off_split = gen.get_offset()
+    gen.set_offset(off0)
+    monkeypatch.setattr(M, "_METRO_SPLIT_MAX_BYTES", -1)
+    want = M.metro_sampling(probs, start, max_transfer, device=dev)
+    assert gen.get_offset() == off_split
+    assert th.equal(got, want)
+    assert not th.equal(got, start)

@@ -196,10 +196,16 @@ def maxcut_config(tag, name, envs, dev, flush, with_samplers=False):
         chains = total * rep
         probs = th.rand(n, device=dev) * 0.6 + 0.2
         start = (th.rand(n, chains, device=dev) < 0.5).float()
+        import rlsolver_b200.methods.MCPG as _M
         ms = timeit(lambda: metro_sampling(probs, start, n // 10, dev), flush)
         iters = 5 * (n // 10)
+        cap, _M._METRO_SPLIT_MAX_BYTES = _M._METRO_SPLIT_MAX_BYTES, -1
+        ms_two = timeit(lambda: metro_sampling(probs, start, n // 10, dev), flush)
+        _M._METRO_SPLIT_MAX_BYTES = cap
+        report(cfg, "K6 metro_sampling, two-pass chain kernel (round 1e form)", f"metro_sampling(max_transfer_time={n // 10})",
+               ms_two, chains * iters, note="count pass + apply pass, two Philox blocks inside every dependent iteration")
         report(cfg, "K6 metro_sampling", f"metro_sampling(max_transfer_time={n // 10}), <= {iters} iterations", ms,
-               chains * iters, 2 * 4 * n * chains, note="Philox-bound: two in-kernel draws per chain-iteration")
+               chains * iters, 2 * 4 * n * chains, note="split form: draws of all iterations in parallel, one pass of the chain, surplus moves undone")
         xs_s = metro_sampling(probs, start, n // 10, dev)
         ms = timeit(lambda: sampler_func(data, xs_s, 8, total, rep), flush)
         report(cfg, "K5 MCPG sweeps", "sampler_func(num_ls=8): 8 Gauss-Seidel sweeps + expected cut", ms,
