@@ -68,6 +68,24 @@ __device__ __forceinline__ void planes_cmp(const uint32_t (&z)[Q], uint32_t k, u
   }
 }
 
+// Ones among a slot's neighbours with the first kPlanPre id blocks already in registers (ids of short rows point at
+// the zero word `pad`): the loads left on the critical path are the state words themselves.
+constexpr int kPlanPre = 6;
+template <int P>
+__device__ __forceinline__ void cross_prefetched(const uint2 (&id)[kPlanPre], int nb, const uint2* __restrict__ col,
+                                                 const uint32_t* sP, uint32_t pad, VCount<P>& vc) {
+  vc.clear();
+  auto add_pair = [&](uint2 i0, uint2 i1) {
+    vc.add8(sP[i0.x & 0xffffu], sP[i0.x >> 16], sP[i0.y & 0xffffu], sP[i0.y >> 16], sP[i1.x & 0xffffu], sP[i1.x >> 16],
+            sP[i1.y & 0xffffu], sP[i1.y >> 16]);
+  };
+  const uint2 none = make_uint2(pad | (pad << 16), pad | (pad << 16));
+#pragma unroll
+  for (int b = 0; b < kPlanPre; b += 2)
+    if (b < nb) add_pair(id[b], b + 1 < nb ? id[b + 1] : none);
+  for (int b = kPlanPre; b < nb; b += 2) add_pair(__ldg(col + b * 32), b + 1 < nb ? __ldg(col + (b + 1) * 32) : none);
+}
+
 // ---------------------------------------------------------------------------- sampler_func sweeps
 constexpr int kMcpgThreads = 128;
 
@@ -88,23 +106,67 @@ __global__ void __launch_bounds__(kMcpgThreads) mcpg_sweeps_kernel(GraphDev g, r
     const uint32_t vmask = valid == 32 ? kFull : ((1u << valid) - 1u);
     if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
     // pack: one coalesced 128-byte row segment per node
-    for (int i = warp; i < g.np + 32; i += nwarps) {
-      float v = 0.f;
-      if (i < g.n && lane < valid) v = xs[(int64_t)i * num_chains + c0 + lane];
-      const uint32_t w = __ballot_sync(kFull, v != 0.f);
-      if (lane == 0) sP[i] = w;
+    for (int i0 = warp * 16; i0 < g.np + 32; i0 += nwarps * 16) {      // 16 row loads in flight, then their ballots
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        v[k] = (i0 + k < g.n && lane < valid) ? __ldg(xs + (int64_t)(i0 + k) * num_chains + c0 + lane) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const uint32_t w = __ballot_sync(kFull, v[k] != 0.f);
+        if (lane == 0 && i0 + k < g.np + 32) sP[i0 + k] = w;
+      }
     }
     __syncthreads();
+    // Everything a level needs that does not depend on the state -- its slice range, the slot's node / degree /
+    // position and the first neighbour-id blocks of both lists -- is fetched one level ahead (the plan lives in
+    // L2: four dependent round trips per level otherwise, and a level is only a handful of warps wide).
+    struct Pre {
+      int sb, se, nbe, nbl;
+      uint32_t node, deg, nlater, pos;
+      const uint2 *cole, *coll;
+      uint2 ide[kPlanPre], idl[kPlanPre];
+    };
+    auto fetch = [&](int l, Pre& p) {
+      p.sb = __ldg(plan.level_slice + l), p.se = __ldg(plan.level_slice + l + 1);
+      const int s = p.sb + warp;
+      p.nbe = p.nbl = 0, p.node = 0xFFFFu, p.deg = p.nlater = p.pos = 0u, p.cole = p.coll = nullptr;
+      if (s < p.se) {
+        p.node = __ldg(plan.earlier.node + s * 32 + lane);
+        p.deg = __ldg(plan.deg + s * 32 + lane);
+        p.nlater = __ldg(plan.nlater + s * 32 + lane);
+        p.pos = __ldg(plan.pos + s * 32 + lane);
+        const int ge = __ldg(plan.earlier.off + s), gl = __ldg(plan.later.off + s);
+        p.nbe = __ldg(plan.earlier.off + s + 1) - ge, p.nbl = __ldg(plan.later.off + s + 1) - gl;
+        p.cole = reinterpret_cast<const uint2*>(plan.earlier.col) + (int64_t)ge * 32 + lane;
+        p.coll = reinterpret_cast<const uint2*>(plan.later.col) + (int64_t)gl * 32 + lane;
+#pragma unroll
+        for (int b = 0; b < kPlanPre; ++b) {
+          p.ide[b] = b < p.nbe ? __ldg(p.cole + b * 32) : make_uint2(0u, 0u);
+          p.idl[b] = b < p.nbl ? __ldg(p.coll + b * 32) : make_uint2(0u, 0u);
+        }
+      }
+    };
+    Pre cur;
+    if (num_ls > 0 && plan.levels > 0) fetch(0, cur);
     for (int sweep = 0; sweep < num_ls; ++sweep) {
       for (int l = 0; l < plan.levels; ++l) {
-        const int sb = __ldg(plan.level_slice + l), se = __ldg(plan.level_slice + l + 1);
-        for (int s = sb + warp; s < se; s += nwarps) {
-          const uint32_t node = __ldg(plan.earlier.node + s * 32 + lane);
+        Pre nxt;
+        const int ln = l + 1 < plan.levels ? l + 1 : 0;
+        if (l + 1 < plan.levels || sweep + 1 < num_ls) fetch(ln, nxt);
+        for (int s = cur.sb + warp; s < cur.se; s += nwarps) {
+          const bool first = s == cur.sb + warp;
+          const uint32_t node = first ? cur.node : __ldg(plan.earlier.node + s * 32 + lane);
           const bool active = node != 0xFFFFu;
           VCount<P> a, b;
-          sell_cross<P, false>(plan.earlier, s, lane, sP, 0u, a);     // ones among already-visited neighbours
-          sell_cross<P, false>(plan.later, s, lane, sP, 0u, b);       // ones among not-yet-visited neighbours
-          const uint32_t deg = __ldg(plan.deg + s * 32 + lane);
+          if (first) {
+            cross_prefetched<P>(cur.ide, cur.nbe, cur.cole, sP, (uint32_t)g.np, a);   // ones among already-visited neighbours
+            cross_prefetched<P>(cur.idl, cur.nbl, cur.coll, sP, (uint32_t)g.np, b);   // ones among not-yet-visited neighbours
+          } else {
+            sell_cross<P, false>(plan.earlier, s, lane, sP, 0u, a);
+            sell_cross<P, false>(plan.later, s, lane, sP, 0u, b);
+          }
+          const uint32_t deg = first ? cur.deg : __ldg(plan.deg + s * 32 + lane);
           // 2*S = 2a + 4b - later  (first sweep: unvisited entries still hold {-0.5, 1.5}, MCPG.py:132-133)
           //     = 2a + 2b          (afterwards);   set iff S + rand/4 < (deg + 1/4) / 2
           uint32_t z[P + 3];
@@ -113,14 +175,15 @@ __global__ void __launch_bounds__(kMcpgThreads) mcpg_sweeps_kernel(GraphDev g, r
           planes_add_shifted<P + 3, P, 1>(z, a);
           if (sweep == 0) planes_add_shifted<P + 3, P, 2>(z, b);
           else planes_add_shifted<P + 3, P, 1>(z, b);
-          const uint32_t k = deg + (sweep == 0 ? (uint32_t)__ldg(plan.nlater + s * 32 + lane) : 0u);
+          const uint32_t nlater = first ? cur.nlater : (uint32_t)__ldg(plan.nlater + s * 32 + lane);
+          const uint32_t k = deg + (sweep == 0 ? nlater : 0u);
           uint32_t lt, eq;
           planes_cmp<P + 3>(z, k, lt, eq);
           uint32_t word = lt;
           uint32_t ties = active ? (eq & vmask) : 0u;
           if (ties) {       // S == deg/2: the coin decides, in float32 exactly as the reference adds it
             const float sf = 0.5f * (float)deg, tf = sf + 0.125f;
-            const uint64_t call = (uint64_t)sweep * g.n + __ldg(plan.pos + s * 32 + lane);
+            const uint64_t call = (uint64_t)sweep * g.n + (first ? cur.pos : (uint32_t)__ldg(plan.pos + s * 32 + lane));
             while (ties) {
               const int bpos = __ffs(ties) - 1;
               ties &= ties - 1;
@@ -133,6 +196,7 @@ __global__ void __launch_bounds__(kMcpgThreads) mcpg_sweeps_kernel(GraphDev g, r
           if (active) sP[node] = word & vmask;
         }
         __syncthreads();
+        cur = nxt;
       }
     }
     // expected_cut = sum_e (2x_u - 1)(2x_v - 1) = M - 2 * cut   (MCPG.py:148-154)
