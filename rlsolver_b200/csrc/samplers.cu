@@ -23,6 +23,11 @@ struct rlsb_mcpg_plan {
   rlsb_graph::Sell earlier, later;
   std::vector<uint16_t> deg, nlater, pos;
   void* dev_blob = nullptr;
+  // scratch owned by the plan (allocated on first use, grown on demand, freed with the plan): the tie-break words of
+  // one rlsb_mcpg_sweeps call and the node degrees in visiting order
+  mutable uint32_t* coin = nullptr;
+  mutable size_t coin_words = 0;
+  mutable uint16_t* degpos = nullptr;
   const rlsb_graph_t* graph = nullptr;
   struct Dev {
     int32_t levels, num_slices;
@@ -68,6 +73,53 @@ __device__ __forceinline__ void planes_cmp(const uint32_t (&z)[Q], uint32_t k, u
   }
 }
 
+// Tie-breaks of sampler_func.  A node is set iff S + rand/4 < (deg + 1/4)/2 (MCPG.py:140-142): the random number only
+// matters when S == deg/2 exactly, and then the outcome depends on nothing but (deg, rand).  Inside the level loop a
+// lane met its ties one after the other -- a dozen dependent Philox blocks on the critical path of every level, two
+// thirds of the kernel's stall samples.  Here the coin of every (sweep, node, chain) that can tie is decided by the
+// whole GPU beforehand, in float32 exactly as the reference adds it, from the uniform torch's call number
+// sweep*N + position returns; the sweep kernel ANDs its tie mask with the word.  coin[call][tile] bit c <-> chain
+// 32*tile + c.  After the first sweep S is an integer, so odd degrees cannot tie (no Philox for them); in the first
+// sweep the unvisited entries still hold {-0.5, 1.5} and every degree can.   grid = (tile groups, position groups, sweep).
+constexpr int kCoinPos = 32;     // node positions per block of mcpg_coins_kernel
+__global__ void __launch_bounds__(256) mcpg_coins_kernel(int n, int64_t num_chains, int64_t tiles,
+                                                         const uint16_t* __restrict__ degpos,
+                                                         const float* __restrict__ explicit_u, TorchRng rng,
+                                                         uint32_t* __restrict__ coin) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tile >= tiles) return;
+  const uint32_t sweep = blockIdx.z;
+  const int64_t chain = tile * kTileEnvs + lane;
+  const bool live = chain < num_chains;
+  const bool direct = num_chains <= (int64_t)rng.threads;
+  const uint2 pkey = make_uint2((uint32_t)rng.seed, (uint32_t)(rng.seed >> 32));
+  for (uint32_t pos = blockIdx.y * kCoinPos; pos < min((uint32_t)n, (blockIdx.y + 1) * kCoinPos); ++pos) {
+    const uint64_t call = (uint64_t)sweep * n + pos;
+    const uint32_t deg = __ldg(degpos + pos);
+    uint32_t word = 0;
+    if (sweep == 0 || !(deg & 1u)) {                       // warp-uniform
+      bool bit = false;
+      if (live) {
+        float u;
+        if (explicit_u) {
+          u = __ldg(explicit_u + call * num_chains + chain);
+        } else if (direct) {                               // element `chain` of a call = output 0 of (its counter, subsequence chain)
+          const uint64_t ctr = rng.offset4 + call * rng.iters_per_call;
+          u = torch_uniform_from_u32(
+              curand_Philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)chain, 0u), pkey).x);
+        } else {
+          u = torch_uniform_from_u32(torch_philox_u32(rng, call, (uint32_t)chain));
+        }
+        const float sf = 0.5f * (float)deg, tf = sf + 0.125f;
+        bit = __fadd_rn(sf, __fmul_rn(u, 0.25f)) < tf;
+      }
+      word = __ballot_sync(kFull, bit);
+    }
+    if (lane == 0) coin[call * tiles + tile] = word;
+  }
+}
+
 // Ones among a slot's neighbours with the first kPlanPre id blocks already in registers (ids of short rows point at
 // the zero word `pad`): the loads left on the critical path are the state words themselves.
 constexpr int kPlanPre = 6;
@@ -90,16 +142,38 @@ __device__ __forceinline__ void cross_prefetched(const uint2 (&id)[kPlanPre], in
 constexpr int kMcpgThreads = 128;
 
 // xs: float32 [N][C] node-major (values 0/1), in place.  expected: float32 [C].
-template <int P>
+// COINS: the tie-breaks come from mcpg_coins_kernel (few tiles: a level is latency bound and its ties would sit on
+// the critical path); otherwise a lane computes the coins of its ties in place (many tiles: other warps hide them,
+// and only ~9 % of the coins are ever needed).
+template <int P, bool COINS>
 __global__ void __launch_bounds__(kMcpgThreads) mcpg_sweeps_kernel(GraphDev g, rlsb_mcpg_plan::Dev plan,
                                                                    float* __restrict__ xs, int64_t num_chains,
-                                                                   int num_ls, const float* __restrict__ explicit_u,
-                                                                   TorchRng rng, float* __restrict__ expected,
-                                                                   int cut_warps) {
+                                                                   int num_ls, const uint32_t* __restrict__ coin,
+                                                                   const float* __restrict__ explicit_u, TorchRng rng,
+                                                                   float* __restrict__ expected, int cut_warps) {
   extern __shared__ uint32_t sP[];               // np + 32 words; [np] stays zero (padding target)
   __shared__ int sCnt[kTileEnvs];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int64_t tiles = (num_chains + kTileEnvs - 1) / kTileEnvs;
+  // The small static arrays of the plan live in shared memory for the whole kernel, so that fetching a level ahead
+  // is ONE round trip to L2 (neighbour ids + coin word) instead of a chain of three (slice range -> offsets -> ids).
+  const bool direct = num_chains <= (int64_t)rng.threads;
+  const uint2 pkey = make_uint2((uint32_t)rng.seed, (uint32_t)(rng.seed >> 32));
+  const int S = plan.num_slices;
+  int32_t* sLvs = reinterpret_cast<int32_t*>(sP + g.np + 32);
+  int32_t* sOffE = sLvs + plan.levels + 1;
+  int32_t* sOffL = sOffE + S + 1;
+  uint16_t* sNode = reinterpret_cast<uint16_t*>(sOffL + S + 1);
+  uint16_t* sDeg = sNode + 32 * S;
+  uint16_t* sNl = sDeg + 32 * S;
+  uint16_t* sPos = sNl + 32 * S;
+  for (int i = threadIdx.x; i <= plan.levels; i += blockDim.x) sLvs[i] = __ldg(plan.level_slice + i);
+  for (int i = threadIdx.x; i <= S; i += blockDim.x) sOffE[i] = __ldg(plan.earlier.off + i), sOffL[i] = __ldg(plan.later.off + i);
+  for (int i = threadIdx.x; i < 32 * S; i += blockDim.x) {
+    sNode[i] = __ldg(plan.earlier.node + i), sDeg[i] = __ldg(plan.deg + i);
+    sNl[i] = __ldg(plan.nlater + i), sPos[i] = __ldg(plan.pos + i);
+  }
+  __syncthreads();
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t c0 = tile * kTileEnvs;
     const int valid = (int)min((int64_t)kTileEnvs, num_chains - c0);
@@ -123,21 +197,24 @@ __global__ void __launch_bounds__(kMcpgThreads) mcpg_sweeps_kernel(GraphDev g, r
     // L2: four dependent round trips per level otherwise, and a level is only a handful of warps wide).
     struct Pre {
       int sb, se, nbe, nbl;
-      uint32_t node, deg, nlater, pos;
+      uint32_t node, deg, nlater, coin;
       const uint2 *cole, *coll;
       uint2 ide[kPlanPre], idl[kPlanPre];
     };
-    auto fetch = [&](int l, Pre& p) {
-      p.sb = __ldg(plan.level_slice + l), p.se = __ldg(plan.level_slice + l + 1);
+    auto coin_of = [&](int sweep, int slot) {           // tie-break word of the slot's node in this sweep, this tile
+      return COINS ? __ldg(coin + ((int64_t)sweep * g.n + sPos[slot]) * tiles + tile) : 0u;
+    };
+    auto fetch = [&](int l, int sweep, Pre& p) {
+      p.sb = sLvs[l], p.se = sLvs[l + 1];
       const int s = p.sb + warp;
-      p.nbe = p.nbl = 0, p.node = 0xFFFFu, p.deg = p.nlater = p.pos = 0u, p.cole = p.coll = nullptr;
+      p.nbe = p.nbl = 0, p.node = 0xFFFFu, p.deg = p.nlater = p.coin = 0u, p.cole = p.coll = nullptr;
       if (s < p.se) {
-        p.node = __ldg(plan.earlier.node + s * 32 + lane);
-        p.deg = __ldg(plan.deg + s * 32 + lane);
-        p.nlater = __ldg(plan.nlater + s * 32 + lane);
-        p.pos = __ldg(plan.pos + s * 32 + lane);
-        const int ge = __ldg(plan.earlier.off + s), gl = __ldg(plan.later.off + s);
-        p.nbe = __ldg(plan.earlier.off + s + 1) - ge, p.nbl = __ldg(plan.later.off + s + 1) - gl;
+        p.node = sNode[s * 32 + lane];
+        p.deg = sDeg[s * 32 + lane];
+        p.nlater = sNl[s * 32 + lane];
+        p.coin = p.node != 0xFFFFu ? coin_of(sweep, s * 32 + lane) : 0u;
+        const int ge = sOffE[s], gl = sOffL[s];
+        p.nbe = sOffE[s + 1] - ge, p.nbl = sOffL[s + 1] - gl;
         p.cole = reinterpret_cast<const uint2*>(plan.earlier.col) + (int64_t)ge * 32 + lane;
         p.coll = reinterpret_cast<const uint2*>(plan.later.col) + (int64_t)gl * 32 + lane;
 #pragma unroll
@@ -148,15 +225,15 @@ __global__ void __launch_bounds__(kMcpgThreads) mcpg_sweeps_kernel(GraphDev g, r
       }
     };
     Pre cur;
-    if (num_ls > 0 && plan.levels > 0) fetch(0, cur);
+    if (num_ls > 0 && plan.levels > 0) fetch(0, 0, cur);
     for (int sweep = 0; sweep < num_ls; ++sweep) {
       for (int l = 0; l < plan.levels; ++l) {
         Pre nxt;
         const int ln = l + 1 < plan.levels ? l + 1 : 0;
-        if (l + 1 < plan.levels || sweep + 1 < num_ls) fetch(ln, nxt);
+        if (l + 1 < plan.levels || sweep + 1 < num_ls) fetch(ln, l + 1 < plan.levels ? sweep : sweep + 1, nxt);
         for (int s = cur.sb + warp; s < cur.se; s += nwarps) {
           const bool first = s == cur.sb + warp;
-          const uint32_t node = first ? cur.node : __ldg(plan.earlier.node + s * 32 + lane);
+          const uint32_t node = first ? cur.node : (uint32_t)sNode[s * 32 + lane];
           const bool active = node != 0xFFFFu;
           VCount<P> a, b;
           if (first) {
@@ -166,7 +243,7 @@ __global__ void __launch_bounds__(kMcpgThreads) mcpg_sweeps_kernel(GraphDev g, r
             sell_cross<P, false>(plan.earlier, s, lane, sP, 0u, a);
             sell_cross<P, false>(plan.later, s, lane, sP, 0u, b);
           }
-          const uint32_t deg = first ? cur.deg : __ldg(plan.deg + s * 32 + lane);
+          const uint32_t deg = first ? cur.deg : (uint32_t)sDeg[s * 32 + lane];
           // 2*S = 2a + 4b - later  (first sweep: unvisited entries still hold {-0.5, 1.5}, MCPG.py:132-133)
           //     = 2a + 2b          (afterwards);   set iff S + rand/4 < (deg + 1/4) / 2
           uint32_t z[P + 3];
@@ -175,22 +252,35 @@ __global__ void __launch_bounds__(kMcpgThreads) mcpg_sweeps_kernel(GraphDev g, r
           planes_add_shifted<P + 3, P, 1>(z, a);
           if (sweep == 0) planes_add_shifted<P + 3, P, 2>(z, b);
           else planes_add_shifted<P + 3, P, 1>(z, b);
-          const uint32_t nlater = first ? cur.nlater : (uint32_t)__ldg(plan.nlater + s * 32 + lane);
+          const uint32_t nlater = first ? cur.nlater : (uint32_t)sNl[s * 32 + lane];
           const uint32_t k = deg + (sweep == 0 ? nlater : 0u);
           uint32_t lt, eq;
           planes_cmp<P + 3>(z, k, lt, eq);
+          // S == deg/2: the coin decides, in float32 exactly as the reference adds it
           uint32_t word = lt;
-          uint32_t ties = active ? (eq & vmask) : 0u;
-          if (ties) {       // S == deg/2: the coin decides, in float32 exactly as the reference adds it
-            const float sf = 0.5f * (float)deg, tf = sf + 0.125f;
-            const uint64_t call = (uint64_t)sweep * g.n + (first ? cur.pos : (uint32_t)__ldg(plan.pos + s * 32 + lane));
-            while (ties) {
-              const int bpos = __ffs(ties) - 1;
-              ties &= ties - 1;
-              const uint32_t chain = (uint32_t)(c0 + bpos);
-              const float u = explicit_u ? __ldg(explicit_u + call * num_chains + chain)
-                                         : torch_uniform_from_u32(torch_philox_u32(rng, call, chain));
-              if (__fadd_rn(sf, __fmul_rn(u, 0.25f)) < tf) word |= 1u << bpos;
+          if (COINS) {
+            word |= eq & (first ? cur.coin : (active ? coin_of(sweep, s * 32 + lane) : 0u));
+          } else {
+            uint32_t ties = active ? (eq & vmask) : 0u;
+            if (ties) {
+              const float sf = 0.5f * (float)deg, tf = sf + 0.125f;
+              const uint64_t call = (uint64_t)sweep * g.n + sPos[s * 32 + lane];
+              while (ties) {
+                const int bpos = __ffs(ties) - 1;
+                ties &= ties - 1;
+                const uint32_t chain = (uint32_t)(c0 + bpos);
+                float u;
+                if (explicit_u) {
+                  u = __ldg(explicit_u + call * num_chains + chain);
+                } else if (direct) {    // C <= T: element `chain` of a call is output 0 of (counter of the call, subsequence chain)
+                  const uint64_t ctr = rng.offset4 + call * rng.iters_per_call;
+                  u = torch_uniform_from_u32(
+                      curand_Philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), chain, 0u), pkey).x);
+                } else {
+                  u = torch_uniform_from_u32(torch_philox_u32(rng, call, chain));
+                }
+                if (__fadd_rn(sf, __fmul_rn(u, 0.25f)) < tf) word |= 1u << bpos;
+              }
             }
           }
           if (active) sP[node] = word & vmask;
@@ -639,6 +729,8 @@ int rlsb_mcpg_plan_create(const rlsb_graph_t* g, const int32_t* h_order, rlsb_mc
 int rlsb_mcpg_plan_destroy(rlsb_mcpg_plan_t* p) {
   if (!p) return RLSB_OK;
   if (p->dev_blob) cudaFree(p->dev_blob);
+  if (p->coin) cudaFree(p->coin);
+  if (p->degpos) cudaFree(p->degpos);
   delete p;
   return RLSB_OK;
 }
@@ -657,24 +749,56 @@ int rlsb_mcpg_sweeps(const rlsb_graph_t* gh, const rlsb_mcpg_plan_t* plan, float
   if (num_chains == 0 || g->n == 0) return RLSB_OK;
   RLSB_REQUIRE(xs && expected, RLSB_ERR_INVALID, "mcpg_sweeps: null pointer");
   RLSB_REQUIRE(explicit_u || (rng_threads > 0 && rng_iters > 0), RLSB_ERR_INVALID, "mcpg_sweeps: no random source");
-  const size_t smem = ((size_t)g->np + 32) * 4;
+  const size_t smem = ((size_t)g->np + 32) * 4 + (size_t)(plan->levels + 1) * 4 + 2 * (size_t)(plan->num_slices + 1) * 4 +
+                      4 * (size_t)plan->num_slices * 64 + 16;      // state tile + the plan's small static arrays
+  RLSB_REQUIRE(smem <= 220 * 1024, RLSB_ERR_UNSUPPORTED, "mcpg_sweeps: %d nodes exceed the shared-memory tile", g->n);
   const int64_t tiles = (num_chains + kTileEnvs - 1) / kTileEnvs;
   const unsigned grid = (unsigned)(tiles < 16 * kNumSMs ? tiles : 16 * kNumSMs);
   auto st = static_cast<cudaStream_t>(stream);
   const TorchRng rng = make_rng(seed, offset, rng_threads, rng_iters);
   const int cw = cut_warps_for(g->m, kMcpgThreads / 32);
-#define RLSB_MCPG(P)                                                                                        \
+  RLSB_REQUIRE(g->n <= 65535 && num_ls <= 65535, RLSB_ERR_UNSUPPORTED, "mcpg_sweeps: more than 65535 nodes or sweeps");
+  // few tiles: tie-breaks decided beforehand by the whole GPU, words [num_ls * N][tiles] in the plan's scratch
+  const bool coins = num_ls > 0 && tiles <= 4 * kNumSMs;
+  if (coins) {
+    const size_t need = (size_t)num_ls * g->n * tiles;
+    if (plan->coin_words < need) {
+      if (plan->coin) RLSB_CUDA_OK(cudaFree(plan->coin));
+      plan->coin = nullptr, plan->coin_words = 0;
+      RLSB_CUDA_OK(cudaMalloc(&plan->coin, need * sizeof(uint32_t)));
+      plan->coin_words = need;
+    }
+    if (!plan->degpos) {
+      std::vector<uint16_t> degpos((size_t)g->n, 0);
+      for (size_t slot = 0; slot < plan->deg.size(); ++slot)
+        if (plan->earlier.node[slot] != 0xFFFFu) degpos[plan->pos[slot]] = plan->deg[slot];
+      RLSB_CUDA_OK(cudaMalloc(&plan->degpos, degpos.size() * sizeof(uint16_t)));
+      RLSB_CUDA_OK(cudaMemcpy(plan->degpos, degpos.data(), degpos.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
+    const dim3 cgrid((unsigned)((tiles + 7) / 8), (unsigned)((g->n + kCoinPos - 1) / kCoinPos), (unsigned)num_ls);
+    mcpg_coins_kernel<<<cgrid, 256, 0, st>>>(g->n, num_chains, tiles, plan->degpos, explicit_u, rng, plan->coin);
+    RLSB_LAUNCH_OK();
+  }
+#define RLSB_MCPG_K(P, C)                                                                                   \
   do {                                                                                                      \
     if (smem > 48 * 1024)                                                                                   \
-      RLSB_CUDA_OK(cudaFuncSetAttribute(mcpg_sweeps_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      RLSB_CUDA_OK(cudaFuncSetAttribute(mcpg_sweeps_kernel<P, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         (int)smem));                                                        \
-    mcpg_sweeps_kernel<P><<<grid, kMcpgThreads, smem, st>>>(*g, plan->dev, xs, num_chains, num_ls, explicit_u, \
-                                                            rng, expected, cw);                             \
+    mcpg_sweeps_kernel<P, C><<<grid, kMcpgThreads, smem, st>>>(*g, plan->dev, xs, num_chains, num_ls, plan->coin, \
+                                                               explicit_u, rng, expected, cw);              \
+  } while (0)
+#define RLSB_MCPG(P)          \
+  do {                        \
+    if (coins)                \
+      RLSB_MCPG_K(P, true);   \
+    else                      \
+      RLSB_MCPG_K(P, false);  \
   } while (0)
   if (plan->max_deg <= 63) RLSB_MCPG(6);
   else if (plan->max_deg <= 255) RLSB_MCPG(8);
   else RLSB_MCPG(12);
 #undef RLSB_MCPG
+#undef RLSB_MCPG_K
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }
