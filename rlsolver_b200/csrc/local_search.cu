@@ -230,7 +230,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // the level's slice range, the slot's node / half / own word and its first 32 neighbour ids -- is fetched one
 // level ahead, before the barrier; after the barrier only the neighbour-word gathers, the counter adds, the
 // compare and the store remain.  That form is used when the structure is read from global memory / L2
-// (rlsb_flip_sweep: 116 -> 54 us at G22 x 4096).
+// (rlsb_flip_sweep with many tiles: 116 -> 54 us at G22 x 4096 before it staged the structure for few tiles).
 constexpr int kSweepPre = 8;     // neighbour-id blocks (of 4 ids) fetched ahead per slot
 
 template <int P, bool SMEM>
@@ -925,11 +925,20 @@ __global__ void __launch_bounds__(kLSThreads) ls_bits_kernel(GraphDev g, LsArgs 
 template <int P>
 __global__ void __launch_bounds__(kLSThreads) flip_sweep_kernel(GraphDev g, uint32_t* __restrict__ packed,
                                                                 int64_t* __restrict__ vs, int64_t num_envs,
-                                                                int cut_warps, int sweep_warps) {
-  extern __shared__ uint32_t sP[];
+                                                                int cut_warps, int sweep_warps, int stage) {
+  extern __shared__ __align__(1024) uint32_t sP[];
   __shared__ int sCnt[kTileEnvs];
+  __shared__ __align__(8) uint64_t sBar;
+  char* sSweep = reinterpret_cast<char*>(sP + g.np);       // stage: the sweep structure, copied once per CTA (TMA)
   const int lane = threadIdx.x & 31;
   const int64_t tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;
+  if (stage) {
+    if (threadIdx.x == 0) {
+      mbar_init(&sBar, 1);
+      stage_sweep_blob(g, sSweep, &sBar);
+    }
+    __syncthreads();
+  }
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t env0 = tile * kTileEnvs;
     const int valid = (int)min((int64_t)kTileEnvs, num_envs - env0);
@@ -937,7 +946,12 @@ __global__ void __launch_bounds__(kLSThreads) flip_sweep_kernel(GraphDev g, uint
     for (int i = threadIdx.x; i < g.np; i += blockDim.x) sP[i] = packed[tile * g.np + i];
     if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
     __syncthreads();
-    sweep_tile<P, false>(g, sweep_view(g, g.sweep_blob), sP, sweep_warps);
+    if (stage) {
+      mbar_wait(&sBar, 0);
+      sweep_tile<P, true>(g, sweep_view(g, sSweep), sP, sweep_warps);
+    } else {
+      sweep_tile<P, false>(g, sweep_view(g, g.sweep_blob), sP, sweep_warps);
+    }
     __syncthreads();
     const int cnt = tile_cut_partial(g, sP, cut_warps);
     if (cnt) atomicAdd(&sCnt[lane], cnt);
@@ -1314,16 +1328,21 @@ int rlsb_flip_sweep(const rlsb_graph_t* gh, uint32_t* packed, int64_t* vs, int64
   RLSB_REQUIRE(num_envs >= 0, RLSB_ERR_INVALID, "flip_sweep: negative num_envs");
   if (num_envs == 0 || g->n == 0) return RLSB_OK;
   RLSB_REQUIRE(packed && vs, RLSB_ERR_INVALID, "flip_sweep: null pointer");
-  const size_t smem = (size_t)g->np * sizeof(uint32_t);
   const int64_t tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;
-  const unsigned grid = (unsigned)(tiles < 4 * kNumSMs ? tiles : 4 * kNumSMs);
+  // few tiles (a level is latency bound): the sweep structure is staged into shared memory, one CTA per SM; many
+  // tiles: several CTAs per SM hide the L2 latency of the structure instead
+  const size_t tile_bytes = (size_t)g->np * sizeof(uint32_t);
+  const int stage = (tiles <= 2 * kNumSMs && tile_bytes + (size_t)g->sweep_blob_bytes <= kSmemBudget) ? 1 : 0;
+  const size_t smem = tile_bytes + (stage ? (size_t)g->sweep_blob_bytes : 0);
+  const int64_t max_ctas = stage ? kNumSMs : 4 * kNumSMs;
+  const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
   auto st = static_cast<cudaStream_t>(stream);
   const int cw = cut_warps_for(g->m, kLSThreads / 32);
   const int dc = g->max_full_deg <= 63 ? 0 : g->max_full_deg <= 255 ? 1 : 2;
   int rc;
 #define RLSB_SWEEP(P)                                                \
   if ((rc = allow_smem(flip_sweep_kernel<P>, smem))) return rc;      \
-  flip_sweep_kernel<P><<<grid, kLSThreads, smem, st>>>(*g, packed, vs, num_envs, cw, sweep_warps_for(*g, kLSThreads / 32))
+  flip_sweep_kernel<P><<<grid, kLSThreads, smem, st>>>(*g, packed, vs, num_envs, cw, sweep_warps_for(*g, kLSThreads / 32), stage)
   if (dc == 0) { RLSB_SWEEP(6); } else if (dc == 1) { RLSB_SWEEP(8); } else { RLSB_SWEEP(12); }
 #undef RLSB_SWEEP
   RLSB_LAUNCH_OK();

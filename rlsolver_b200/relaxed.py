@@ -6,8 +6,6 @@ backward are the CUDA kernels of csrc/relaxed.cu; autograd sees a normal functio
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import torch as th
 
 from . import _lib
@@ -55,4 +53,4 @@ def relaxed_cut(store: GraphStore, probs: TEN) -> TEN:
     return _RelaxedCut.apply(probs, store)
 
 
-__all__ = ["relaxed_cut", "C"]
+__all__ = ["relaxed_cut"]
