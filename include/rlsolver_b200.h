@@ -235,6 +235,9 @@ int rlsb_torch_randint(uint64_t seed, uint64_t offset, uint32_t rng_threads, uin
 int rlsb_mcpg_plan_create(const rlsb_graph_t* g, const int32_t* h_order, rlsb_mcpg_plan_t** out);
 int rlsb_mcpg_plan_destroy(rlsb_mcpg_plan_t* plan);
 int32_t rlsb_mcpg_plan_num_levels(const rlsb_mcpg_plan_t* plan);
+/* Note on rlsb_mcpg_sweeps: the plan owns device scratch for the tie-break words of a call (allocated on first use
+ * and when a larger chain count arrives -- cudaMalloc, so not inside a CUDA-graph capture; freed by
+ * rlsb_mcpg_plan_destroy).  Calls that share a plan must be ordered on one stream. */
 int rlsb_mcpg_sweeps(const rlsb_graph_t* g, const rlsb_mcpg_plan_t* plan, float* xs, int64_t num_chains,
                      int32_t num_ls, const float* explicit_u, uint64_t seed, uint64_t offset, uint32_t rng_threads,
                      uint32_t rng_iters, float* expected, void* stream);
