@@ -142,3 +142,17 @@ def test_sell_structures_model_the_reference(lib, path):
     want_xs, want_vs = z["xs"].copy(), om.cut_values(g, z["xs"]).astype(np.int64)
     om.sweep_literal(g, want_xs, want_vs)
     assert np.array_equal(cur[:, :n], want_xs)
+
+
+def test_metro_workspace_bytes_is_host_arithmetic():
+    """rlsb_metro_workspace_bytes needs no device: 8 bytes of draws per (iteration, chain), the accept words, the
+    per-iteration counters, the packed tiles and the rate table, each section rounded up to 256 bytes."""
+    import rlsolver_b200
+    lib = rlsolver_b200.lib()
+    n, c, t = 2000, 4096, 1000
+    np_, tiles = 2016, 128
+    up = lambda b: (b + 255) // 256 * 256          # noqa: E731
+    want = up(t * c * 8) + up(t * tiles * 4) + up(t * 4) + up(tiles * np_ * 4) + up(2 * n * 4) + 256
+    assert lib.rlsb_metro_workspace_bytes(n, c, t) == want
+    assert lib.rlsb_metro_workspace_bytes(0, c, t) == -1 and lib.rlsb_metro_workspace_bytes(n, -1, t) == -1
+    assert lib.rlsb_metro_workspace_bytes(37, 33, 0) > 0
