@@ -13,10 +13,20 @@ from typing import Tuple
 import torch as th
 
 
+_MAX_GRID = {}      # device index -> SMs * (max threads per SM // 256): ATen's cap on the grid of a distribution kernel
+
+
+def _max_grid(device: th.device) -> int:
+    key = device.index if device.index is not None else th.cuda.current_device()
+    cap = _MAX_GRID.get(key)
+    if cap is None:
+        props = th.cuda.get_device_properties(key)
+        cap = _MAX_GRID[key] = props.multi_processor_count * (props.max_threads_per_multi_processor // 256)
+    return cap
+
+
 def torch_call_geometry(device: th.device, numel: int) -> Tuple[int, int]:
-    props = th.cuda.get_device_properties(device)
-    blocks_per_sm = props.max_threads_per_multi_processor // 256
-    grid = min(props.multi_processor_count * blocks_per_sm, (numel + 255) // 256)
+    grid = min(_max_grid(device), (numel + 255) // 256)
     threads = 256 * max(grid, 1)
     iters = (max(numel, 1) - 1) // (threads * 4) + 1
     return threads, iters
