@@ -42,6 +42,16 @@ typedef struct rlsb_qubo rlsb_qubo_t;
 int rlsb_version(void);
 const char* rlsb_last_error(void);
 
+/* Diagnostic switches (cross-check paths of the tests and the profiling tools; none changes a result).
+ * The word is initialised ONCE, when the library is loaded, from the environment variables named below;
+ * afterwards only this call changes it: new = (old & ~clear_mask) | set_mask.  Returns the new word.
+ * Nothing on the data path reads the environment. */
+#define RLSB_DEBUG_PLAIN_MASKS 1 /* RLSB_LS_PLAIN_MASKS=1: rlsb_ls_noise_masks evaluates every normal (no early-out bytes) */
+#define RLSB_DEBUG_FULL_CUT 2    /* RLSB_LS_FULL_CUT=1: rlsb_ls_run_masks re-counts all edges for every candidate */
+#define RLSB_DEBUG_LS_SKIP 4     /* RLSB_LS_SKIP=1: rlsb_ls_run consumers skip the arithmetic (streaming-rate probe) */
+#define RLSB_DEBUG_LS_TIMES 8    /* RLSB_LS_TIMES=1: CTA 0 of the local-search kernels stamps clock64 per phase */
+int32_t rlsb_debug_flags(int32_t set_mask, int32_t clear_mask);
+
 /* ---- graph store: replaces EnvMaxcut.__init__ (rlsolver/envs/env_L2A.py:25-52),
  * build_adjacency_indies (rlsolver/methods/util_read_data.py:144-187) and
  * calc_num_nodes_in_mygraph (rlsolver/methods/util.py:35-40).

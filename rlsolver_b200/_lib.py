@@ -83,6 +83,7 @@ _u32, _u64 = C.c_uint32, C.c_uint64
 SIGNATURES = {
     "rlsb_version": (C.c_int, []),
     "rlsb_last_error": (C.c_char_p, []),
+    "rlsb_debug_flags": (_i32, [_i32, _i32]),
     "rlsb_graph_create": (C.c_int, [_i32, _i64, _vp, _vp, _vp, _i32, _i32, C.POINTER(_vp)]),
     "rlsb_graph_destroy": (C.c_int, [_vp]),
     "rlsb_graph_num_nodes": (_i32, [_vp]),
@@ -145,6 +146,14 @@ SIGNATURES = {
     "rlsb_best_pick": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "rlsb_pick_best": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
 }
+
+
+DEBUG_PLAIN_MASKS, DEBUG_FULL_CUT, DEBUG_LS_SKIP, DEBUG_LS_TIMES = 1, 2, 4, 8
+
+
+def debug_flags(set_mask: int = 0, clear_mask: int = 0) -> int:
+    """rlsb_debug_flags: diagnostic switches of the library (tests / profiling tools)."""
+    return int(lib().rlsb_debug_flags(int(set_mask), int(clear_mask)))
 
 
 class RlsbError(RuntimeError):

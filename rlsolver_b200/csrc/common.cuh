@@ -14,6 +14,7 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxTileNodes = 49152;   // padded nodes a shared-memory tile may hold (uint16 ids, <= 192 KB of words)
 
 void set_error(const char* fmt, ...);
+int debug_flags();   // rlsb_debug_flags word (environment read once at load time)
 
 #define RLSB_CUDA_OK(expr)                                                              \
   do {                                                                                  \

@@ -3,6 +3,8 @@
 // (rlsolver/methods/util_read_data.py:144-187) and calc_num_nodes_in_mygraph
 // (rlsolver/methods/util.py:35-40).  Host side is plain C++; the device image is a
 // handful of int32 arrays that stay L2-resident (<= a few hundred KB for Gset).
+#include <atomic>
+#include <stdlib.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -101,6 +103,21 @@ void build_sell(const std::vector<int32_t>& order, const std::vector<int32_t>& g
   }
 }
 
+static int debug_flags_from_env() {
+  int f = 0;
+  const struct { const char* name; int bit; } vars[] = {{"RLSB_LS_PLAIN_MASKS", RLSB_DEBUG_PLAIN_MASKS},
+                                                        {"RLSB_LS_FULL_CUT", RLSB_DEBUG_FULL_CUT},
+                                                        {"RLSB_LS_SKIP", RLSB_DEBUG_LS_SKIP},
+                                                        {"RLSB_LS_TIMES", RLSB_DEBUG_LS_TIMES}};
+  for (const auto& v : vars) {
+    const char* e = getenv(v.name);
+    if (e && e[0] == '1') f |= v.bit;
+  }
+  return f;
+}
+static std::atomic<int> g_debug_flags{debug_flags_from_env()};
+int debug_flags() { return g_debug_flags.load(std::memory_order_relaxed); }
+
 }  // namespace rlsb
 
 using rlsb::build_csr;
@@ -110,6 +127,12 @@ extern "C" {
 
 int rlsb_version(void) { return 100; }
 const char* rlsb_last_error(void) { return rlsb::g_last_error.c_str(); }
+int32_t rlsb_debug_flags(int32_t set_mask, int32_t clear_mask) {
+  int old = rlsb::g_debug_flags.load(), now;
+  do now = (old & ~clear_mask) | set_mask;
+  while (!rlsb::g_debug_flags.compare_exchange_weak(old, now));
+  return now;
+}
 
 int rlsb_graph_create(int32_t num_nodes, int64_t num_edges, const int32_t* h_n0, const int32_t* h_n1,
                       const int32_t* h_w, int32_t bidirectional, int32_t device, rlsb_graph_t** out) {

@@ -1081,8 +1081,7 @@ static int launch_bits(const GraphDev& g, LsArgs a, const uint32_t* masks, cudaS
   RLSB_REQUIRE(smem <= kSmemBudget, RLSB_ERR_UNSUPPORTED, "ls_run_masks: %d nodes exceed the shared-memory tile", g.n);
   const int64_t tiles = (a.num_envs + kTileEnvs - 1) / kTileEnvs;
   // slots of the sweep structure are addressed with 16 bits; RLSB_LS_FULL_CUT=1 keeps the full re-count (cross-check)
-  const char* env = getenv("RLSB_LS_FULL_CUT");
-  const int use_delta = (g.num_sweep_slices * 32 <= 65536 && !(env && env[0] == '1')) ? 1 : 0;
+  const int use_delta = (g.num_sweep_slices * 32 <= 65536 && !(debug_flags() & RLSB_DEBUG_FULL_CUT)) ? 1 : 0;
   if (int rc = allow_smem(ls_bits_kernel<P>, smem)) return rc;
   ls_bits_kernel<P><<<(unsigned)tiles, kLSThreads, smem, st>>>(g, a, masks, ls_mask_words(a.num_envs, g.n), use_delta);
   RLSB_LAUNCH_OK();
@@ -1107,17 +1106,17 @@ static int launch_thresh(const GraphDev& g, const LsWorkspace& w, int mult, cons
 // RLSB_LS_TIMES=1: CTA 0 of every pipe launch writes clock64 phase stamps into a device buffer
 // that rlsb_ls_debug_times() copies out (profiling aid, tools/ls_phase_times.py)
 static long long* ls_debug_times() {
-  static long long* buf = nullptr;
-  static int init = 0;
-  if (!init) {
-    init = 1;
-    const char* e = getenv("RLSB_LS_TIMES");
-    if (e && e[0] == '1' && cudaMalloc(&buf, 64 * sizeof(long long)) == cudaSuccess)
-      cudaMemset(buf, 0, 64 * sizeof(long long));
+  static long long* bufs[64] = {};      // one buffer per device (the kernels run on the current device)
+  if (!(debug_flags() & RLSB_DEBUG_LS_TIMES)) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!bufs[dev]) {
+    if (cudaMalloc(&bufs[dev], 64 * sizeof(long long)) == cudaSuccess)
+      cudaMemset(bufs[dev], 0, 64 * sizeof(long long));
     else
-      buf = nullptr;
+      bufs[dev] = nullptr;
   }
-  return buf;
+  return bufs[dev];
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -1161,12 +1160,7 @@ static int run_search(const GraphDev& g, int64_t num_envs, int64_t* vs, int ws_m
     a.sweep_warps = sweep_warps_for(g, kLSWarps), a.negmult = -ws_mult;
     a.times = ls_debug_times();
     {
-      static int skip = -1;
-      if (skip < 0) {
-        const char* e = getenv("RLSB_LS_SKIP");
-        skip = (e && e[0] == '1') ? 1 : 0;
-      }
-      a.skip = skip;
+      a.skip = (debug_flags() & RLSB_DEBUG_LS_SKIP) ? 1 : 0;
     }
     int rc;
     if (pipe) {

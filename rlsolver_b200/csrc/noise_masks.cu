@@ -281,9 +281,8 @@ int rlsb_ls_noise_masks(const rlsb_graph_t* gh, int64_t num_envs, int32_t ws_mul
   TorchRng r{seed, offset / 4, (uint32_t)rng_threads, (uint32_t)rng_iters, rng_dev};
   dim3 grid((unsigned)(rng_threads / 256), (unsigned)rng_iters, 1);
   auto st = static_cast<cudaStream_t>(stream);
-  // RLSB_LS_PLAIN_MASKS=1: evaluate every normal (cross-check of the early-out form; read per call)
-  const char* env = getenv("RLSB_LS_PLAIN_MASKS");
-  if (env && env[0] == '1') {
+  // RLSB_DEBUG_PLAIN_MASKS: evaluate every normal (cross-check of the early-out form)
+  if (debug_flags() & RLSB_DEBUG_PLAIN_MASKS) {
     grid.z = (unsigned)num_draws;
     noise_mask_kernel<<<grid, 256, 0, st>>>(a, r);
     RLSB_LAUNCH_OK();

@@ -66,16 +66,24 @@ __global__ void __launch_bounds__(128) pick_best_kernel(const uint8_t* __restric
   copy_row(out_xs + sim * (int64_t)n, xs + ((int64_t)r * num_sims + sim) * (int64_t)n, n, threadIdx.x, blockDim.x);
 }
 
-// The per-rank record of the multi-GPU best-cut exchange: int64 key (cut << 32 | 0xFFFFFFFF - global
-// env id) of the best local row, followed by that row.  One CTA: block-wide max, then the row copy.
+// The per-rank record of the multi-GPU best-cut exchange: 64-bit key of the best local row followed by that
+// row.  key = (value + 2^31) << 32 | (0xFFFFFFFF - global env id), compared UNSIGNED: the bias makes negative
+// values (weighted cuts, QUBO energies) order below positive ones, ties go to the lowest env id.  Values are
+// saturated to the int32 range (the Python mirror applies the same rule).  One CTA: block-wide max, row copy.
+__device__ __forceinline__ unsigned long long best_key(int64_t v, unsigned long long gid) {
+  v = v > 2147483647ll ? 2147483647ll : (v < -2147483648ll ? -2147483648ll : v);
+  return ((unsigned long long)(v + 2147483648ll) << 32) | (0xFFFFFFFFull - gid);
+}
+__device__ __forceinline__ int64_t best_key_value(unsigned long long key) {
+  return (int64_t)(key >> 32) - 2147483648ll;
+}
 __global__ void __launch_bounds__(1024) best_record_kernel(const int64_t* __restrict__ vs, const uint8_t* __restrict__ xs,
                                                            int64_t num_envs, int n, int64_t env_offset,
                                                            uint8_t* __restrict__ record) {
   __shared__ unsigned long long sBest[32];
   unsigned long long best = 0;
   for (int64_t e = threadIdx.x; e < num_envs; e += blockDim.x) {
-    const unsigned long long key =
-        ((unsigned long long)vs[e] << 32) | (unsigned long long)(0xFFFFFFFFull - (unsigned long long)(env_offset + e));
+    const unsigned long long key = best_key(vs[e], (unsigned long long)(env_offset + e));
     best = key > best ? key : best;
   }
 #pragma unroll
@@ -105,7 +113,7 @@ __global__ void __launch_bounds__(256) best_pick_kernel(const uint8_t* __restric
     if (r == 0 || key > best) best = key, win = r;
   }
   if (threadIdx.x == 0) {
-    out[0] = (int64_t)(best >> 32);
+    out[0] = best_key_value(best);
     out[1] = (int64_t)(0xFFFFFFFFull - (best & 0xFFFFFFFFull));
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) row[i] = gathered[win * stride + 8 + i];

@@ -2,8 +2,9 @@
 box: the best cut, its argmax and the winner's spins.
 
 ONE collective and no host synchronisation: every rank contributes a record of 8 + N bytes -- the
-int64 key `(cut << 32) | (0xFFFFFFFF - global_env_id)` of its local best row (ties go to the lowest
-global env id) followed by that row -- to an all-gather over NCCL/NVLink; every rank then picks
+64-bit key `((cut + 2^31) << 32) | (0xFFFFFFFF - global_env_id)` of its local best row (compared
+unsigned: negative values order below positive ones, ties go to the lowest global env id; values are
+saturated to the int32 range) followed by that row -- to an all-gather over NCCL/NVLink; every rank then picks
 the record with the largest key locally.  Latency-bound (world * (8 + N) bytes); the results stay
 device tensors, so the step loop never waits on the host.
 """
@@ -14,18 +15,35 @@ from typing import Tuple
 import torch as th
 import torch.distributed as dist
 
+from .graph_store import on_device
+
 TEN = th.Tensor
 _LOW = 0xFFFFFFFF
 
 
-def local_best_key(vs: TEN, rank: int, envs_per_rank: int) -> TEN:
-    """int64 [1]: max over local envs of (cut << 32) | (0xFFFFFFFF - global_env_id)."""
+_BIAS = 1 << 31
+
+
+def _keys(vs: TEN, rank: int, envs_per_rank: int) -> TEN:
+    """int64 [E] holding the 64-bit keys MINUS 2^63 (so signed int64 order == unsigned key order)."""
     gid = th.arange(vs.shape[0], device=vs.device, dtype=th.int64) + rank * envs_per_rank
-    return ((vs.to(th.int64) << 32) | (_LOW - gid)).max().reshape(1)
+    v = vs.to(th.int64).clamp(-_BIAS, _BIAS - 1)
+    return (v << 32) | (_LOW - gid)          # ((v + 2^31) << 32 | low) - 2^63 == (v << 32) | low in two's complement
+
+
+def local_best_key(vs: TEN, rank: int, envs_per_rank: int) -> TEN:
+    """int64 [1]: the largest local key (in the signed form of _keys)."""
+    return _keys(vs, rank, envs_per_rank).max().reshape(1)
 
 
 def decode_key(key: int) -> Tuple[int, int]:
+    """(value, global env id) of a signed-form key (see _keys)."""
     return key >> 32, _LOW - (key & _LOW)
+
+
+def _to_wire(signed_keys: TEN) -> TEN:
+    """signed form -> the unsigned wire form the kernels write (adds 2^63 = flips the top bit)."""
+    return signed_keys ^ th.iinfo(th.int64).min
 
 
 def _local_record(vs: TEN, xs: TEN, rank: int, envs_per_rank: int) -> TEN:
@@ -34,14 +52,14 @@ def _local_record(vs: TEN, xs: TEN, rank: int, envs_per_rank: int) -> TEN:
     if vs.is_cuda and vs.dtype == th.int64 and xs.dtype == th.bool and vs.is_contiguous() and xs.is_contiguous():
         from . import _lib                      # one kernel instead of a dozen tiny torch ops
         record = th.empty((8 + n,), dtype=th.uint8, device=vs.device)
-        _lib.check(_lib.lib().rlsb_best_record(vs.data_ptr(), xs.data_ptr(), vs.shape[0], n, rank * envs_per_rank,
-                                               record.data_ptr(), th.cuda.current_stream(vs.device).cuda_stream),
-                   "best_record")
+        with on_device(vs.device):
+            _lib.check(_lib.lib().rlsb_best_record(vs.data_ptr(), xs.data_ptr(), vs.shape[0], n, rank * envs_per_rank,
+                                                   record.data_ptr(), th.cuda.current_stream(vs.device).cuda_stream),
+                       "best_record")
         return record
-    gid = th.arange(vs.shape[0], device=vs.device, dtype=th.int64) + rank * envs_per_rank
-    keys = (vs.to(th.int64) << 32) | (_LOW - gid)
+    keys = _keys(vs, rank, envs_per_rank)
     local = keys.argmax()                         # keys are distinct (they embed the env id)
-    return th.cat([keys[local].reshape(1).view(th.uint8), xs[local].view(th.uint8)])
+    return th.cat([_to_wire(keys[local].reshape(1)).view(th.uint8), xs[local].view(th.uint8)])
 
 
 def best_allreduce(vs: TEN, xs: TEN, rank: int, world: int, envs_per_rank: int, group=None):
@@ -57,10 +75,11 @@ def best_allreduce(vs: TEN, xs: TEN, rank: int, world: int, envs_per_rank: int, 
         from . import _lib
         out2 = th.empty((2,), dtype=th.int64, device=vs.device)
         row = th.empty((xs.shape[1],), dtype=th.bool, device=vs.device)
-        _lib.check(_lib.lib().rlsb_best_pick(gathered.data_ptr(), gathered.shape[0], xs.shape[1], out2.data_ptr(),
-                                             row.data_ptr(), th.cuda.current_stream(vs.device).cuda_stream), "best_pick")
+        with on_device(vs.device):
+            _lib.check(_lib.lib().rlsb_best_pick(gathered.data_ptr(), gathered.shape[0], xs.shape[1], out2.data_ptr(),
+                                                 row.data_ptr(), th.cuda.current_stream(vs.device).cuda_stream), "best_pick")
         return out2[0], out2[1], row
-    all_keys = gathered[:, :8].contiguous().view(th.int64).reshape(-1)
+    all_keys = _to_wire(gathered[:, :8].reshape(-1).clone().view(th.int64))     # wire -> signed form
     win = all_keys.argmax()
     key = all_keys[win]
     return key >> 32, _LOW - (key & _LOW), gathered[win, 8:].view(th.bool)

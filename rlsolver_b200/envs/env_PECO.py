@@ -22,7 +22,7 @@ import numpy as np
 import torch as th
 
 from .. import _lib
-from ..graph_store import _ptr, _stream_ptr, require_cuda
+from ..graph_store import _ptr, _stream_ptr, on_device, require_cuda
 
 TEN = th.Tensor
 
@@ -220,8 +220,9 @@ class SpinSystemUnbiased:
         fields = th.empty((e, n), dtype=th.float32, device=self.device)
         as_ = th.empty((e, n), dtype=th.float32, device=self.device) if want_as else None
         cut = th.empty((e,), dtype=th.float32, device=self.device) if want_cut else None
-        _lib.check(self._lib.rlsb_peco_fields(_ptr(self.matrix), _ptr(spins), e, n, _ptr(as_), _ptr(fields), _ptr(cut),
-                                              _stream_ptr(self.device)), "peco_fields")
+        with on_device(self.device):
+            _lib.check(self._lib.rlsb_peco_fields(_ptr(self.matrix), _ptr(spins), e, n, _ptr(as_), _ptr(fields), _ptr(cut),
+                                                  _stream_ptr(self.device)), "peco_fields")
         return fields, as_, cut
 
     def _get_immeditate_cuts_avaialable(self, spins: TEN, matrix: Optional[TEN] = None) -> TEN:
@@ -296,14 +297,15 @@ class SpinSystemUnbiased:
         term = np.float32(max(np.float32(0.), np.float32((self.current_step - self.max_steps) / self.horizon_length)
                               + np.float32(1.)))
         use_stag, use_basin = self.stag_punishment is not None, self.basin_reward is not None
-        _lib.check(self._lib.rlsb_peco_step(
-            _ptr(self.matrix), _ptr(self.state), _ptr(self._as), _ptr(action), _ptr(self.score), _ptr(self.best_score),
-            _ptr(self.best_spins), _ptr(self.max_local_reward_available_), _ptr(rew), _ptr(self._history),
-            self._hist_len, _ptr(self._bad), self.num_envs, self.n_spins, len(self.observables),
-            self._rows.ctypes.data, self.reward_signal.value, int(bool(self.norm_rewards)),
-            float(np.float32(1. / self.max_steps)), float(term), int(use_stag),
-            float(self.stag_punishment or 0.0), int(use_basin), float(self.basin_reward or 0.0),
-            int(bool(self.scalar_div_as_cuda)), _stream_ptr(self.device)), "peco_step")
+        with on_device(self.device):
+            _lib.check(self._lib.rlsb_peco_step(
+                _ptr(self.matrix), _ptr(self.state), _ptr(self._as), _ptr(action), _ptr(self.score), _ptr(self.best_score),
+                _ptr(self.best_spins), _ptr(self.max_local_reward_available_), _ptr(rew), _ptr(self._history),
+                self._hist_len, _ptr(self._bad), self.num_envs, self.n_spins, len(self.observables),
+                self._rows.ctypes.data, self.reward_signal.value, int(bool(self.norm_rewards)),
+                float(np.float32(1. / self.max_steps)), float(term), int(use_stag),
+                float(self.stag_punishment or 0.0), int(use_basin), float(self.basin_reward or 0.0),
+                int(bool(self.scalar_div_as_cuda)), _stream_ptr(self.device)), "peco_step")
         if self._history is not None:
             self._hist_len += 1
         self.best_obs_score = self.best_score           # infinite memory (spinsystem_PECO.py:427-429)

@@ -59,20 +59,47 @@ class OpTimer:
         return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.spans.items()}
 
 
-class _Span:
+class on_device:
+    """Makes `device` the current CUDA device for the duration of a library call (and restores the previous
+    one).  The C ABI launches on the stream it is handed and calls cudaFuncSetAttribute / cudaMalloc on the
+    CURRENT device, so a simulator built for cuda:1 must not launch while cuda:0 is current."""
+    __slots__ = ("index", "prev")
+
+    def __init__(self, device: Optional[th.device]):
+        self.index = None if device is None else device.index
+
+    def __enter__(self):
+        self.prev = None
+        if self.index is not None:
+            cur = th.cuda.current_device()
+            if cur != self.index:
+                self.prev = cur
+                th.cuda.set_device(self.index)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            th.cuda.set_device(self.prev)
+        return False
+
+
+class _Span(on_device):
+    """One library call of a GraphStore: device guard + optional per-op timing."""
     __slots__ = ("timer", "name", "launches", "tok")
 
-    def __init__(self, timer, name, launches):
+    def __init__(self, timer, name, launches, device=None):
+        on_device.__init__(self, device)
         self.timer, self.name, self.launches = timer, name, launches
 
     def __enter__(self):
+        on_device.__enter__(self)
         if self.timer is not None:
             self.tok = self.timer.begin(self.name)
 
     def __exit__(self, *exc):
         if self.timer is not None:
             self.timer.end(self.tok, self.launches)
-        return False
+        return on_device.__exit__(self, *exc)
 
 
 class GraphStore:
@@ -112,7 +139,7 @@ class GraphStore:
 
     def _op(self, name: str, launches: int = 1) -> _Span:
         self.launch_count += launches
-        return _Span(self.timer, name, launches)
+        return _Span(self.timer, name, launches, self.device)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -209,8 +236,9 @@ class GraphStore:
         out = th.empty((xs.shape[0], self.num_listed), dtype=th.bool, device=self.device)
         for lo in range(0, xs.shape[0], 32768):
             part = xs[lo:lo + 32768]
-            _lib.check(self._lib.rlsb_cut_edges(self._h, _ptr(part), part.shape[0], _ptr(out[lo:lo + 32768]),
-                                                _stream_ptr(self.device)), "cut_edges")
+            with self._op("cut_edges"):
+                _lib.check(self._lib.rlsb_cut_edges(self._h, _ptr(part), part.shape[0], _ptr(out[lo:lo + 32768]),
+                                                    _stream_ptr(self.device)), "cut_edges")
         return out
 
     def cross_counts(self, packed: TEN, num_envs: int, want_minmax: bool = True):
@@ -429,9 +457,10 @@ def select_rows(xs0: TEN, vs0: TEN, xs1: TEN, vs1: TEN, if_maximize: bool = True
     if vs0.dtype != th.int64:
         raise TypeError("select_rows: vs0 must be int64")
     vs1 = vs1.to(th.int64)
-    _lib.check(lib.rlsb_select_rows(_ptr(xs0), _ptr(vs0), _ptr(xs1.contiguous()), _ptr(vs1.contiguous()),
-                                    xs0.shape[0], xs0.shape[1], int(bool(if_maximize)), _stream_ptr(dev)),
-               "select_rows")
+    with on_device(dev):
+        _lib.check(lib.rlsb_select_rows(_ptr(xs0), _ptr(vs0), _ptr(xs1.contiguous()), _ptr(vs1.contiguous()),
+                                        xs0.shape[0], xs0.shape[1], int(bool(if_maximize)), _stream_ptr(dev)),
+                   "select_rows")
 
 
 def pick_best(xs: TEN, vs: TEN, num_repeats: int, if_maximize: bool = True) -> Tuple[TEN, TEN]:
@@ -445,6 +474,7 @@ def pick_best(xs: TEN, vs: TEN, num_repeats: int, if_maximize: bool = True) -> T
     vs64 = vs.to(th.int64).contiguous()
     out_xs = th.empty((sims, n), dtype=th.bool, device=dev)
     out_vs = th.empty((sims,), dtype=th.int64, device=dev)
-    _lib.check(lib.rlsb_pick_best(_ptr(xs), _ptr(vs64), int(num_repeats), sims, n, int(bool(if_maximize)),
-                                  _ptr(out_xs), _ptr(out_vs), _stream_ptr(dev)), "pick_best")
+    with on_device(dev):
+        _lib.check(lib.rlsb_pick_best(_ptr(xs), _ptr(vs64), int(num_repeats), sims, n, int(bool(if_maximize)),
+                                      _ptr(out_xs), _ptr(out_vs), _stream_ptr(dev)), "pick_best")
     return out_xs, out_vs.to(vs.dtype)

@@ -10,7 +10,7 @@ from typing import Optional, Tuple
 import torch as th
 
 from ... import _lib, rng
-from ...graph_store import _ptr, _stream_ptr, require_cuda
+from ...graph_store import _ptr, _stream_ptr, on_device, require_cuda
 
 TEN = th.Tensor
 
@@ -35,9 +35,10 @@ def sub_set_sampling(probs: TEN, start_xs: TEN, num_repeats: int, top_k: int,
         if _explicit_u is not None:
             u = _explicit_u.to(device=device, dtype=th.float32).contiguous()
             assert u.shape == (k, rows)
-        _lib.check(_lib.lib().rlsb_subset_sampling(_ptr(xs), rows, max_k, num_sims, k, _ptr(top_ids.contiguous()),
-                                                   _ptr(top_values.float().contiguous()), _ptr(u), seed, offset,
-                                                   threads, iters, _stream_ptr(device)), "subset_sampling")
+        with on_device(device):
+            _lib.check(_lib.lib().rlsb_subset_sampling(_ptr(xs), rows, max_k, num_sims, k, _ptr(top_ids.contiguous()),
+                                                       _ptr(top_values.float().contiguous()), _ptr(u), seed, offset,
+                                                       threads, iters, _stream_ptr(device)), "subset_sampling")
         if u is None:
             rng.advance(device, rows, k)              # one rand_like(_prob) per resampled column
     return xs, probs

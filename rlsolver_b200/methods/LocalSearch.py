@@ -18,10 +18,16 @@ def update_xs_by_vs(xs0, vs0, xs1, vs1, if_maximize: bool = True):
     return _update_xs_by_vs(xs0, vs0, xs1, vs1, if_maximize)
 
 
-def update_vs_only(vs0: TEN, vs1: TEN) -> int:
-    """Value half of update_xs_by_vs when the rows were already written in place."""
-    th.maximum(vs0, vs1, out=vs0)
-    return vs0.shape[0]
+def merge_searched(good_xs: TEN, good_vs: TEN, backup_xs: TEN, prev_vs: TEN) -> int:
+    """update_xs_by_vs(good, prev) (LocalSearch.py:85) when the search ran IN PLACE on good_xs and
+    `backup_xs` holds the rows as they were: a row keeps its old spins exactly where the reference
+    keeps them, i.e. where prev_vs < good_vs.  That only happens when the caller's good_vs is larger
+    than the cut of its good_xs row (a stale value) -- every accepted move has vs' >= vs -- so for
+    consistent inputs no row moves and this is two tiny kernels."""
+    bar = prev_vs + 1                      # good_vs >= prev_vs + 1  <=>  prev_vs < good_vs (integers)
+    _update_xs_by_vs(good_xs, bar, backup_xs, good_vs, True)     # restores the stale rows
+    th.maximum(good_vs, prev_vs, out=good_vs)
+    return good_vs.shape[0]
 
 
 class LocalSearch:
@@ -64,15 +70,16 @@ class LocalSearch:
         shape = (num_sims, sim.num_nodes)
         if not (self.good_xs.is_contiguous() and self.good_vs.is_contiguous() and self.good_vs.dtype == th.int64):
             raise RuntimeError("random_search updates good_xs / good_vs in place: contiguous bool / int64 needed")
-        # prev_xs = good_xs.clone(), prev_vs = cut(prev_xs).  Every accepted move has vs' >= vs, so the
-        # final update_xs_by_vs(good, prev) (LocalSearch.py:85) always takes prev: the search runs in
-        # place on good_xs / good_vs (a row of good_vs that disagrees with its good_xs row is re-evaluated).
+        # The reference searches on prev_xs = good_xs.clone() and merges with update_xs_by_vs(good, prev)
+        # (LocalSearch.py:57, 85).  Here the search runs in place on good_xs and the clone is the backup:
+        # rows whose searched value stays below a (stale, larger) good_vs are restored from it.
+        backup_xs = self.good_xs.clone()
         ws = st.ls_workspace(num_sims)
         prev_vs = st.ls_begin(self.good_xs, None, 2, noise_std, ws)
         if getattr(sim, "fused_rng", False) and num_sims > 0 and num_iters > 0 and st.ls_mask_words(num_sims) >= 0:
             # the threshold comes from the first draw, which also drives iteration 0 (LocalSearch.py:66-68)
             st.ls_fused(prev_vs, 2, num_spin, num_iters, True, self.good_xs, ws)
-            num_update = update_vs_only(self.good_vs, prev_vs)
+            num_update = merge_searched(self.good_xs, self.good_vs, backup_xs, prev_vs)
             return self.good_xs, self.good_vs, num_update
         done = 0
         first = True
@@ -85,5 +92,5 @@ class LocalSearch:
             first = False
         if num_iters <= 0:
             st.ls_search(prev_vs, 2, [], True, self.good_xs, ws)
-        num_update = update_vs_only(self.good_vs, prev_vs)
+        num_update = merge_searched(self.good_xs, self.good_vs, backup_xs, prev_vs)
         return self.good_xs, self.good_vs, num_update

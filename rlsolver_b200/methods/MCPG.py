@@ -19,7 +19,7 @@ import numpy as np
 import torch as th
 
 from .. import _lib, rng
-from ..graph_store import GraphStore, _ptr, _stream_ptr, require_cuda
+from ..graph_store import GraphStore, _ptr, _stream_ptr, on_device, require_cuda
 from .config import MyGraph
 
 TEN = th.Tensor
@@ -46,8 +46,9 @@ class McpgData:
         self.store = GraphStore(mygraph, True, device=self.device, num_nodes=self.num_nodes)
         order = np.ascontiguousarray(self.sorted_degree_nodes.numpy(), dtype=np.int32)
         handle = C.c_void_p()
-        _lib.check(_lib.lib().rlsb_mcpg_plan_create(self.store.handle, order.ctypes.data, C.byref(handle)),
-                   "mcpg_plan_create")
+        with on_device(self.device):
+            _lib.check(_lib.lib().rlsb_mcpg_plan_create(self.store.handle, order.ctypes.data, C.byref(handle)),
+                       "mcpg_plan_create")
         self._plan = handle
         self.num_levels = int(_lib.lib().rlsb_mcpg_plan_num_levels(handle))
 
@@ -110,20 +111,23 @@ def metro_sampling(probs: TEN, start_status: TEN, max_transfer_time: int, device
             # split form: draws in parallel, one pass of the chain, stop rule on the device, surplus moves undone
             ws = th.empty((need,), dtype=th.uint8, device=device)
             num_iters = th.empty((1,), dtype=th.int32, device=device)
-            _lib.check(lib.rlsb_metro_sampling_split(num_node, _ptr(p), _ptr(start), _ptr(out), num_chain, tmax, thresh,
-                                                     seed, offset, threads, iters, _ptr(num_iters), _ptr(ws), st),
-                       "metro_sampling_split")
+            with on_device(device):
+                _lib.check(lib.rlsb_metro_sampling_split(num_node, _ptr(p), _ptr(start), _ptr(out), num_chain, tmax, thresh,
+                                                         seed, offset, threads, iters, _ptr(num_iters), _ptr(ws), st),
+                           "metro_sampling_split")
             rng.advance(device, num_chain, 2 * int(num_iters.item()))   # one randint + one rand per executed iteration
             return out
     acc = th.zeros((tmax,), dtype=th.int32, device=device)
-    _lib.check(lib.rlsb_metro_sampling(num_node, _ptr(p), _ptr(start), None, num_chain, tmax, None, idx_ptr, u_ptr,
-                                       seed, offset, threads, iters, _ptr(acc), 1, st), "metro_sampling(count)")
+    with on_device(device):
+        _lib.check(lib.rlsb_metro_sampling(num_node, _ptr(p), _ptr(start), None, num_chain, tmax, None, idx_ptr, u_ptr,
+                                           seed, offset, threads, iters, _ptr(acc), 1, st), "metro_sampling(count)")
     # the reference checks `count >= num_chain * max_transfer_time` BEFORE every iteration (MCPG.py:101-103)
     before = th.cat([acc.new_zeros(1), acc.cumsum(0)[:-1]])
     num_iters = (before < thresh).sum().to(th.int32).reshape(1)
-    _lib.check(lib.rlsb_metro_sampling(num_node, _ptr(p), _ptr(start), _ptr(out), num_chain, tmax, _ptr(num_iters),
-                                       idx_ptr, u_ptr, seed, offset, threads, iters, None, 0, st),
-               "metro_sampling(apply)")
+    with on_device(device):
+        _lib.check(lib.rlsb_metro_sampling(num_node, _ptr(p), _ptr(start), _ptr(out), num_chain, tmax, _ptr(num_iters),
+                                           idx_ptr, u_ptr, seed, offset, threads, iters, None, 0, st),
+                   "metro_sampling(apply)")
     if _explicit is None:
         rng.advance(device, num_chain, 2 * int(num_iters.item()))      # one randint + one rand per executed iteration
     return out
@@ -150,9 +154,10 @@ def sampler_func(data: McpgData, xs_sample: TEN, num_ls: int, total_mcmc_num: in
         if _explicit_u is not None:
             u = _explicit_u.to(device=device, dtype=th.float32).contiguous()
             assert u.shape == (num_ls * data.num_nodes, num_chain)
-        _lib.check(lib.rlsb_mcpg_sweeps(data.store.handle, data._plan, _ptr(xs_loc), num_chain, int(num_ls), _ptr(u),
-                                        seed, offset, threads, iters, _ptr(expected), _stream_ptr(device)),
-                   "mcpg_sweeps")
+        with on_device(device):
+            _lib.check(lib.rlsb_mcpg_sweeps(data.store.handle, data._plan, _ptr(xs_loc), num_chain, int(num_ls), _ptr(u),
+                                            seed, offset, threads, iters, _ptr(expected), _stream_ptr(device)),
+                       "mcpg_sweeps")
         if u is None:
             rng.advance(device, num_chain, int(num_ls) * data.num_nodes)   # one torch.rand(C) per node visit
     expected_reshape = expected.reshape((-1, total_mcmc_num))

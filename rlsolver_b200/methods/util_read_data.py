@@ -88,11 +88,14 @@ def build_adjacency_indies(mygraph: MyGraph, if_bidirectional: bool = False) -> 
 def update_xs_by_vs(xs0: TEN, vs0: TEN, xs1: TEN, vs1: TEN, if_maximize: bool) -> int:
     """Rows of (xs1, vs1) replace rows of (xs0, vs0) where not worse; in place; returns the
     batch size like the reference (`good_is.shape[0]`)."""
-    if vs0.dtype == th.int64 and xs0.is_contiguous() and vs0.is_contiguous():
+    int_types = (th.int64, th.int32, th.int16, th.int8, th.uint8)
+    fast = (xs0.is_cuda and xs0.dtype == th.bool and xs1.dtype == th.bool and xs0.shape == xs1.shape
+            and xs0.is_contiguous() and vs0.dtype == th.int64 and vs0.is_contiguous() and vs1.dtype in int_types)
+    if fast:
         select_rows(xs0, vs0, xs1, vs1, if_maximize)
-    else:  # other value dtypes (the reference allows any): same semantics through a CUDA mask kernel
+    else:  # any other dtype combination the reference accepts (float values, non-bool rows): same semantics, torch ops
         good = vs1.ge(vs0) if if_maximize else vs1.le(vs0)
-        xs0.copy_(th.where(good[:, None], xs1, xs0))
+        xs0.copy_(th.where(good[:, None], xs1.to(xs0.dtype), xs0))
         vs0.copy_(th.where(good, vs1.to(vs0.dtype), vs0))
     return xs0.shape[0]
 

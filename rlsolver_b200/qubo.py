@@ -12,7 +12,7 @@ from typing import Tuple
 import torch as th
 
 from . import _lib
-from .graph_store import _ptr, _stream_ptr, require_cuda
+from .graph_store import _ptr, _stream_ptr, on_device, require_cuda
 
 TEN = th.Tensor
 
@@ -26,8 +26,9 @@ class QuboModel:
         self.nvar = int(Q.shape[0])
         self._lib = _lib.lib()
         handle = C.c_void_p()
-        _lib.check(self._lib.rlsb_qubo_create(_ptr(self.Q), self.nvar, self.device.index, C.byref(handle),
-                                              _stream_ptr(self.device)), "qubo_create")
+        with on_device(self.device):
+            _lib.check(self._lib.rlsb_qubo_create(_ptr(self.Q), self.nvar, self.device.index, C.byref(handle),
+                                                  _stream_ptr(self.device)), "qubo_create")
         self._h = handle
         self._ws = None
 
@@ -51,8 +52,9 @@ class QuboModel:
         need = int(self._lib.rlsb_qubo_workspace_bytes(self._h, c))
         if self._ws is None or self._ws.numel() < need:
             self._ws = th.empty((need,), dtype=th.uint8, device=self.device)
-        _lib.check(self._lib.rlsb_qubo_energy(self._h, _ptr(X), c, _ptr(out), _ptr(self._ws),
-                                              _stream_ptr(self.device)), "qubo_energy")
+        with on_device(self.device):
+            _lib.check(self._lib.rlsb_qubo_energy(self._h, _ptr(X), c, _ptr(out), _ptr(self._ws),
+                                                  _stream_ptr(self.device)), "qubo_energy")
         return out
 
     def sweeps(self, X: TEN, num_sweeps: int, binary: bool = False) -> TEN:
@@ -66,8 +68,9 @@ class QuboModel:
         need = int(self._lib.rlsb_qubo_workspace_bytes(self._h, c))
         if self._ws is None or self._ws.numel() < need:
             self._ws = th.empty((need,), dtype=th.uint8, device=self.device)
-        _lib.check(self._lib.rlsb_qubo_sweeps(self._h, _ptr(self.Q), _ptr(X), c, int(num_sweeps), int(bool(binary)),
-                                              _ptr(self._ws), _stream_ptr(self.device)), "qubo_sweeps")
+        with on_device(self.device):
+            _lib.check(self._lib.rlsb_qubo_sweeps(self._h, _ptr(self.Q), _ptr(X), c, int(num_sweeps), int(bool(binary)),
+                                                  _ptr(self._ws), _stream_ptr(self.device)), "qubo_sweeps")
         return X
 
 

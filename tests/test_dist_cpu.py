@@ -43,3 +43,18 @@ def test_key_roundtrip():
     vs = th.tensor([5, 9, 9, 1])
     k = int(local_best_key(vs, rank=2, envs_per_rank=4).item())
     assert decode_key(k) == (9, 2 * 4 + 1)
+
+
+def test_negative_values_order_below_positive_ones():
+    """Weighted cuts / QUBO energies can be negative: the key is biased so they rank below positive values
+    (kernel and torch path use the same rule, csrc/select.cu best_key)."""
+    vs = th.tensor([-7, -2, -2, -100])
+    assert decode_key(int(local_best_key(vs, rank=1, envs_per_rank=4).item())) == (-2, 4 + 1)
+    vs = th.tensor([-7, 3, -2, 0])
+    assert decode_key(int(local_best_key(vs, rank=0, envs_per_rank=4).item())) == (3, 1)
+    xs = th.arange(4 * 5).reshape(4, 5).remainder(2).bool()
+    cut, gid, row = best_allreduce(th.tensor([-7, -3, -3, -9]), xs, rank=0, world=1, envs_per_rank=4)
+    assert int(cut) == -3 and int(gid) == 1 and th.equal(row, xs[1])
+    # saturation to the int32 range
+    big = th.tensor([2 ** 40, 5])
+    assert decode_key(int(local_best_key(big, 0, 2).item())) == (2 ** 31 - 1, 0)

@@ -12,6 +12,7 @@ import torch as th  # noqa: E402
 from synth import gset_like  # noqa: E402
 
 import rlsolver_b200  # noqa: E402
+from rlsolver_b200 import _lib  # noqa: E402
 from rlsolver_b200.envs.env_L2A import EnvMaxcut  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "G22"
@@ -20,7 +21,7 @@ dev = th.device("cuda:0")
 sim = EnvMaxcut(mygraph=gset_like(name), device=dev, if_bidirectional=True)
 xs = sim.generate_xs_randomly(envs)
 for full in ("0", "1"):
-    os.environ["RLSB_LS_FULL_CUT"] = full
+    _lib.debug_flags(*((_lib.DEBUG_FULL_CUT, 0) if full == "1" else (0, _lib.DEBUG_FULL_CUT)))
     for _ in range(3):
         sim.local_search_inplace(xs.clone(), th.empty(()))
     th.cuda.synchronize()

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import torch as th  # noqa: E402
 
-from rlsolver_b200 import rng  # noqa: E402
+from rlsolver_b200 import _lib, rng  # noqa: E402
 from rlsolver_b200.envs.env_L2A import EnvMaxcut  # noqa: E402
 from rlsolver_b200.graph_store import OpTimer  # noqa: E402
 from synth import gset_like  # noqa: E402
@@ -69,9 +69,9 @@ for spec in (sys.argv[1:] or ["G22:4096", "G70:16384", "G14:256"]):
     seed, offset, threads, iters = rng.peek(dev, envs * n)
     t_randn = timed(lambda: th.randn((envs, n), device=dev))
     t_own = timed(lambda: st.torch_randn(envs * n, 1, seed, offset, threads, iters))
-    os.environ["RLSB_LS_PLAIN_MASKS"] = "1"
+    _lib.debug_flags(_lib.DEBUG_PLAIN_MASKS, 0)
     t_plain = timed(lambda: st.ls_noise_masks(envs, 1, 8, seed, offset, threads, iters, wsb))
-    os.environ["RLSB_LS_PLAIN_MASKS"] = "0"
+    _lib.debug_flags(0, _lib.DEBUG_PLAIN_MASKS)
     t_fast = timed(lambda: st.ls_noise_masks(envs, 1, 8, seed, offset, threads, iters, wsb))
     t_fast1 = timed(lambda: st.ls_noise_masks(envs, 1, 1, seed, offset, threads, iters, wsb))
     masks = st.ls_noise_masks(envs, 1, 8, seed, offset, threads, iters, wsb)
