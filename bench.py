@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Benchmark of the max-cut environment hot path (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--configs 1,3,4,5|none]
 
-Workload (BASELINE.json configs[1]): G22-shaped max-cut (2000 nodes, 19990 edges, synthetic,
+Headline workload (BASELINE.json configs[1]): G22-shaped max-cut (2000 nodes, 19990 edges, synthetic,
 seed 74), 4096 environments per GPU, one dREINFORCE sampling step of local search =
 `EnvMaxcut.local_search_inplace(xs, ())` with the reference defaults (8 noisy multi-flip
 iterations + the 2000-node single-flip pass).  1 env-step = one (environment, candidate move)
@@ -11,8 +11,14 @@ whose cut value is produced: E * (1 + num_iters + N) per step.
 
 One JSON line on rank 0.  `value` = env-steps/s with inputs resident in HBM, CUDA-event timed,
 L2 flushed between steps; `e2e` = the same through the public API from pinned HOST buffers
-(H2D of the spins, D2H of spins + values inside the timed region).  `--impl reference` times
-the CPU restatement of the reference's own algorithm (oracle/torch_port.py) on the host cores.
+(H2D of the spins, D2H of spins + values inside the timed region).  The same line carries
+  * `configs`: the other four BASELINE configurations (1: G14 x 256, 3: G70 x 16384 strong-scaled over the
+    ranks, 4: 10^6 per-env BA/ER-100 graphs, 5: dense QUBO N = 4096 with 8192 chains split over the ranks),
+    each with its own time, env-steps/s, roofline entry and clocks;
+  * `gpu_reference`: the torch restatement of the reference's algorithm (oracle/torch_port.py: index-gather
+    objective, one full re-evaluation per candidate flip) on the SAME GPU, the FULL headline workload;
+  * `cpu_baseline`: the same restatement on the host cores on a bounded sample.
+`--impl reference` times the CPU restatement alone.
 """
 import argparse
 import json
@@ -42,6 +48,15 @@ def env_steps_per_call(envs, n, num_iters, sweep_nodes):
     return envs * (1 + num_iters + sweep_nodes)
 
 
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "tensor": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "tensor_burst": d["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "tensor": 1400.0, "tensor_burst": 1650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -62,14 +77,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
-    def stop(self, t0, t1):
+    def window(self, t0, t1):
+        """Clock summary of the samples taken in [t0, t1] (the sampler keeps running)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.rows:
+        for ts, line in list(self.rows):
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7 or not (t0 - 0.05 <= ts <= t1 + 0.15):
                 continue
@@ -84,8 +98,16 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return self.window(t0, t1)
+        time.sleep(0.15)
+        out = self.window(t0, t1)
+        self.proc.terminate()
+        return out
 
-# ----------------------------------------------------------------------------- reference arm
+
+# ----------------------------------------------------------------------------- reference arm (host cores)
 def cpu_reference_run(steps, warmup, budget_s=3.0):
     """The reference's algorithm on the host cores: torch restatement (index-gather objective,
     one full re-evaluation per candidate flip).  Each step is a bounded sample of the workload:
@@ -118,10 +140,16 @@ def cpu_reference_run(steps, warmup, budget_s=3.0):
             times.append(dt)
     total = sum(times)
     value = per_call * len(times) / total
+    full_per_call = env_steps_per_call(NUM_ENVS, sim.num_nodes, NUM_ITERS, sim.num_nodes)
     sample = (f"{envs} envs of the same graph, {NUM_ITERS} noisy iters + first {sweep_nodes} of 2000 sweep nodes "
               f"per step ({per_call} env-steps), torch CPU ops as the reference uses them")
+    basis = (f"every env-step of this path is one full objective evaluation of one env in the reference, so the rate is "
+             f"per evaluation: the full workload ({NUM_ENVS} envs, all {sim.num_nodes} sweep nodes = {full_per_call} "
+             f"env-steps per step) would take {full_per_call / value:.1f} s per step at this rate; sampled because it "
+             f"is {full_per_call / per_call:.0f}x the sample")
     return {"value": value, "unit": UNIT, "cores": th.get_num_threads(), "kind": "port", "sample": sample,
-            "ms_per_step": 1e3 * total / len(times), "steps": len(times)}
+            "ms_per_step": 1e3 * total / len(times), "steps": len(times), "same_config_basis": basis,
+            "full_workload_seconds_per_step_extrapolated": full_per_call / value}
 
 
 def run_reference(args):
@@ -133,33 +161,379 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": workload_name(NUM_ENVS), "cpu_sample": r["sample"]},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": {"workload": workload_name(NUM_ENVS), "cpu_sample": r["sample"],
+                       "same_config_basis": r["same_config_basis"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "same_config_basis",
+                                               "full_workload_seconds_per_step_extrapolated")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
 
 
+# ----------------------------------------------------------------------------- shared helpers of the B200 arm
+class Ctx:
+    """Per-process state shared by the headline and the per-config blocks."""
+
+    def __init__(self, args):
+        import torch as th
+        import torch.distributed as dist
+        self.th, self.dist, self.args = th, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not th.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (rlsolver_b200 has no CPU fallback)")
+        th.cuda.set_device(self.local)
+        self.dev = th.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = th.empty(256 << 20, dtype=th.uint8, device=self.dev)       # > 126 MB L2
+        self.peaks = peaks()
+        self.clocks = ClockSampler(self.local) if self.rank == 0 else None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.th.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        t = self.th.tensor([x], dtype=self.th.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, reps, warm=3, flush=True, prepare=None):
+        """CUDA-event time of `fn` per repetition (ms, list).  `prepare` runs untimed before each repetition;
+        the L2 is evicted between repetitions (256 MiB write) unless flush=False."""
+        th = self.th
+        for _ in range(warm):
+            if prepare:
+                prepare()
+            fn()
+        self.barrier()
+        evs = []
+        for _ in range(reps):
+            if prepare:
+                prepare()
+            if flush:
+                self.flush.zero_()
+            a, b = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        self.barrier()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    def job_ms(self, ms_list):
+        """Per-repetition time of the whole job: sum over the repetitions, max over the ranks, / repetitions."""
+        return self.max_over_ranks(sum(ms_list)) / len(ms_list)
+
+    def window_clocks(self, t0, t1):
+        return self.clocks.window(t0, t1) if self.clocks else None
+
+
+def roof(bound, achieved, peak, unit, kernel, traffic=None, **extra):
+    d = {"kernel": kernel, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+         "frac": achieved / peak if peak else None, "traffic": traffic}
+    d.update(extra)
+    return d
+
+
+def dram_traffic():
+    p = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+def ls_alg_bytes(st, envs, n, m, num_iters):
+    """Algorithmic HBM bytes per launch group of the local-search path (DESIGN.md "Kernels")."""
+    np_ = st.padded_nodes
+    cb = 1 if max(st.max_listed_degree, st.max_full_degree) <= 255 else 2   # cross-count bytes
+    graph_b = 4 * m + 2 * st.num_full + 12 * np_
+    return {
+        "ls_search": 4 * envs * n + cb * envs * np_ + 2 * envs * np_ // 8 + 20 * envs + 8 * np_,
+        "ls_thresh": 4 * envs * n + cb * envs * np_ + 4 * envs + 8 * np_,
+        # early-out pass (cross counts in, one byte per Box-Muller pair out) + per draw those bytes in, one bit per
+        # element out (zeroed, then OR-ed).  The float32 noise itself (4 B per element and draw) never exists.
+        "ls_noise_masks": envs * np_ + envs * n // 2 + num_iters * (envs * n // 2 + 2 * envs * n // 8) + 4 * envs
+                          + 8 * np_,
+        # packed tile in/out, one mask bit per element and iteration, bool rows + values out, graph once
+        "ls_run_masks": 2 * envs * np_ // 8 + num_iters * envs * n // 8 + envs * n + 16 * envs + graph_b,
+        "ls_fused_search": 2 * envs * np_ // 8 + envs * n + envs * np_ + 16 * envs + graph_b,
+        "torch_randn": 4 * envs * n,
+        "rng_cursor_advance": 16,
+        "ls_begin": envs * n + envs * np_ // 8 + cb * envs * np_ + 8 * envs + graph_b,
+        "pack_spins": envs * n + envs * np_ // 8,
+        "unpack_spins": envs * n + envs * np_ // 8,
+        "cut_eval_packed": envs * np_ // 8 + 8 * envs + 4 * m,
+        "cut_eval": envs * n + 8 * envs + 4 * m,
+        "greedy_best_flip": 2 * envs * n + 8 * envs + graph_b,
+        "select_rows": 16 * envs,
+    }
+
+
+def per_kernel_pass(ctx, store, fn, reps, prepare=None):
+    """CUDA events around every call of this library made by `fn` (eager launches): {op: ms per launch},
+    {op: share of the summed kernel time}."""
+    from rlsolver_b200.graph_store import OpTimer
+    store.timer = OpTimer()
+    for _ in range(reps):
+        if prepare:
+            prepare()
+        ctx.flush.zero_()
+        fn()
+    spans = store.timer.summary()
+    store.timer = None
+    total = sum(v[1] for v in spans.values()) or 1e-9
+    return ({k: v[1] / v[0] for k, v in spans.items()}, {k: round(v[1] / total, 4) for k, v in spans.items()},
+            {k: v[0] / reps for k, v in spans.items()})
+
+
+# ----------------------------------------------------------------------------- config 1: G14 x 256
+def config1(ctx):
+    """check_local_search_maxcut (rlsolver/envs/env_L2A.py:178-230) shape: calculate_obj_values x100,
+    local_search_inplace x4, then greedy best-flip to a local optimum, 256 envs on the G14 shape."""
+    th = ctx.th
+    from synth import gset_like
+    from rlsolver_b200.envs.env_L2A import EnvMaxcut
+    edges = gset_like("G14")
+    sim = EnvMaxcut(mygraph=edges, device=ctx.dev, if_bidirectional=True)
+    st, n, m, envs = sim.store, sim.num_nodes, sim.num_edges, 256
+    th.manual_seed(74)
+    xs0 = sim.generate_xs_randomly(envs)
+    xs = xs0.clone()
+    sentinel = th.empty(())
+
+    def block():
+        for _ in range(100):
+            sim.calculate_obj_values(xs)
+        gx, gv = xs, sentinel
+        for _ in range(4):
+            gx, gv = sim.local_search_inplace(gx, gv, NUM_ITERS, NUM_SPIN, NOISE_STD)
+        st.greedy_best_flip(gx, n, True)
+
+    t0 = time.time()
+    ms = ctx.timed(block, reps=10, warm=3, prepare=lambda: xs.copy_(xs0))
+    t1 = time.time()
+    ms_job = sum(ms) / len(ms)
+    steps = envs * (100 + 4 * (1 + NUM_ITERS + n))            # greedy's flips are data dependent: not counted
+    kms, share, per_rep = per_kernel_pass(ctx, st, block, 3, prepare=lambda: xs.copy_(xs0))
+    alg = ls_alg_bytes(st, envs, n, m, NUM_ITERS)
+    dom = max(share, key=share.get)
+    gbs = alg.get(dom, 0) / (kms[dom] * 1e-3) / 1e9
+    return {"workload": f"G14-shaped maxcut (N={n}, M={m}, synthetic seed 74), {envs} envs: calculate_obj_values x100 + "
+                        f"local_search_inplace x4 + greedy best-flip to a local optimum (check_local_search_maxcut)",
+            "n_gpus": 1, "ms": ms_job, "env_steps": steps, "env_steps_per_s": steps / (ms_job * 1e-3),
+            "roofline": roof("hbm", gbs, ctx.peaks["hbm"], "GB/s", dom, algorithmic_bytes_per_launch=alg.get(dom),
+                             ms_per_launch=kms[dom], share_of_block=share,
+                             note="8 tiles on 148 SMs: every kernel of this configuration sits at the launch / latency "
+                                  "floor (working set 205 KB, L2 resident); the HBM fraction is reported for the record"),
+            "kernel_us": {k: round(v * 1e3, 2) for k, v in kms.items()}, "launches_per_block": per_rep,
+            "clocks": ctx.window_clocks(t0, t1)}
+
+
+# ----------------------------------------------------------------------------- config 3: G70 x 16384, strong scaling
+def config3(ctx, inner=4, outer=2):
+    """env_MCPG.py:449-476 (search_and_evaluate_local_search): broadcast the best row, 16 random flips per env,
+    then `inner` x {LocalSearch.random_search(64, 4) + update_xs_by_vs}; one best-cut exchange per outer
+    iteration.  16384 envs in total, split over the ranks (strong scaling)."""
+    th = ctx.th
+    from synth import gset_like
+    from rlsolver_b200.dist import best_allreduce
+    from rlsolver_b200.envs.env_MCPG import EnvMaxcut, LocalSearch, update_xs_by_vs
+    total_envs = 16384
+    envs = total_envs // ctx.world
+    edges = gset_like("G70")
+    sim = EnvMaxcut(mygraph=edges, device=ctx.dev, if_bidirectional=False)     # as env_MCPG.py:435 builds it
+    st, n, m = sim.store, sim.num_nodes, sim.num_edges
+    solver = LocalSearch(sim, n)
+    th.manual_seed(74 + ctx.rank)
+    best_xs = sim.generate_xs_randomly(envs)
+    best_vs = sim.calculate_obj_values(best_xs)
+    sim_ids = th.arange(envs, device=ctx.dev)
+    iters, spin = 64, 4
+
+    def outer_iteration():
+        # the exchange: global best row (all-gather of 8 + N byte records), broadcast to every env of every rank
+        cut, gid, row = best_allreduce(best_vs, best_xs, ctx.rank, ctx.world, envs)
+        best_xs[:] = row
+        best_vs[:] = cut
+        xs = best_xs.clone()
+        for _ in range(16):
+            ids = th.randint(0, n, size=(envs,), device=ctx.dev)
+            xs[sim_ids, ids] = th.logical_not(xs[sim_ids, ids])
+        solver.reset(xs)
+        for _ in range(inner):
+            solver.random_search(num_iters=iters, num_spin=spin)
+            update_xs_by_vs(best_xs, best_vs, solver.good_xs, solver.good_vs, True)
+
+    t0 = time.time()
+    ms = ctx.timed(outer_iteration, reps=outer, warm=1, flush=False)
+    t1 = time.time()
+    ms_job = ctx.job_ms(ms)
+    steps = total_envs * (1 + inner * (iters + n))
+    kms, share, per_rep = per_kernel_pass(ctx, st, lambda: solver.random_search(num_iters=iters, num_spin=spin), 1)
+    alg = ls_alg_bytes(st, envs, n, m, iters)
+    dom = max(share, key=share.get)
+    gbs = alg.get(dom, 0) / (kms[dom] * 1e-3) / 1e9
+    gen = next((k for k in ("ls_noise_masks", "ls_fused_search") if k in kms), None)
+    noise_eq = iters * 4 * envs * n / (kms[gen] * 1e-3) / 1e9 if gen else None
+    return {"workload": f"G70-shaped maxcut (N={n}, M={m}, synthetic seed 74), {total_envs} envs over {ctx.world} GPU(s) "
+                        f"({envs}/GPU): outer iteration of env_MCPG.py:449-476 with {inner} x "
+                        f"LocalSearch.random_search(num_iters=64, num_spin=4) (the reference runs 16) + one best-cut "
+                        f"exchange",
+            "n_gpus": ctx.world, "scaling": "strong", "ms": ms_job, "env_steps": steps,
+            "env_steps_per_s": steps / (ms_job * 1e-3),
+            "exchange": "best_record kernel + ncclAllGather of world x (8 + N) bytes + best_pick kernel, once per outer iteration",
+            "roofline": roof("hbm", gbs, ctx.peaks["hbm"], "GB/s", dom, algorithmic_bytes_per_launch=alg.get(dom),
+                             ms_per_launch=kms[dom], share_of_random_search=share, noise_equivalent_gbs=noise_eq,
+                             traffic=dram_traffic().get("config3_" + dom),
+                             note="one random_search(64, 4) call: the mask generator recomputes 64 draws of randn "
+                                  "[E, N] in registers (issue bound); noise_equivalent_gbs = the float32 noise a "
+                                  "streaming implementation reads over the same time"),
+            "kernel_ms": {k: round(v, 4) for k, v in kms.items()}, "clocks": ctx.window_clocks(t0, t1)}
+
+
+# ----------------------------------------------------------------------------- config 4: 10^6 BA / ER instances
+def config4(ctx, total_envs):
+    """Distribution-wise pattern-I step: one graph per env (BA m=4 and ER p=0.15, N=100, +-1 weights),
+    SpinSystemUnbiased.step with uniformly random actions, BLS reward (spinsystem_PECO.py:306-486)."""
+    th = ctx.th
+    from rlsolver_b200.envs import env_PECO as P
+    n = 100
+    envs = total_envs // ctx.world
+    out = {}
+    for kind in ("BA", "ER"):
+        t_gen = time.time()
+        if kind == "BA":
+            gg = P.RandomBAGraphGenerator(n_spins=n, m_insertion_edges=4, edge_type=P.EdgeType.DISCRETE, num_envs=envs,
+                                          device=ctx.dev)
+        else:
+            gg = P.RandomERGraphGenerator(n_spins=n, p_connection=0.15, edge_type=P.EdgeType.DISCRETE, num_envs=envs,
+                                          device=ctx.dev)
+        th.manual_seed(74 + ctx.rank)
+        env = P.SpinSystemFactory.get(gg, 2 * n, observables=P.ECO_PECO_OBSERVABLES, reward_signal=P.RewardSignal.BLS,
+                                      extra_action=P.ExtraAction.NONE, optimisation_target=P.OptimisationTarget.CUT,
+                                      spin_basis=P.SpinBasis.BINARY, norm_rewards=True, memory_length=None,
+                                      horizon_length=None, stag_punishment=None, basin_reward=None,
+                                      reversible_spins=True, device=ctx.dev, num_envs=envs)
+        th.cuda.synchronize()
+        gen_s = time.time() - t_gen
+        acts = [th.randint(0, n, (envs,), device=ctx.dev) for _ in range(8)]
+        k = [0]
+
+        def step():
+            env.step(acts[k[0] % 8], return_observation=False)
+            k[0] += 1
+
+        t0 = time.time()
+        ms = ctx.timed(step, reps=20, warm=3, flush=False)         # state >> L2: every step streams from HBM
+        t1 = time.time()
+        ms_job = ctx.job_ms(ms)
+        alg = env.step_algorithmic_bytes() if hasattr(env, "step_algorithmic_bytes") else \
+            envs * (4 * n + 8 * n + 2 * 4 * n * 4 + 40)
+        gbs = alg / (ms_job * 1e-3) / 1e9
+        deg = float(env.mean_degree()) if hasattr(env, "mean_degree") else \
+            float((env.matrix[:1024] != 0).float().sum() / min(envs, 1024) / n)
+        out[kind] = {"workload": f"{kind}-100 per-env graphs (+-1 weights), {total_envs} envs over {ctx.world} GPU(s) "
+                                 f"({envs}/GPU), mean degree {deg:.1f}: SpinSystemUnbiased.step, random actions, BLS reward",
+                     "n_gpus": ctx.world, "scaling": "strong", "ms": ms_job, "env_steps": total_envs,
+                     "env_steps_per_s": total_envs / (ms_job * 1e-3), "graph_generation_s": round(gen_s, 2),
+                     "state_layout": getattr(env, "state_layout", "dense float32 matrix [E,N,N] + state [E,7,N]"),
+                     "roofline": roof("hbm", gbs, ctx.peaks["hbm"], "GB/s", "peco_step",
+                                      algorithmic_bytes_per_launch=alg, bytes_per_env_step=alg / envs,
+                                      traffic=dram_traffic().get("config4_peco_step_" + kind)),
+                     "clocks": ctx.window_clocks(t0, t1)}
+        del env, gg, acts
+        th.cuda.empty_cache()
+    return out
+
+
+# ----------------------------------------------------------------------------- config 5: dense QUBO
+def config5(ctx, total_chains=8192):
+    """Dense float QUBO, N = 4096: x^T Q x for every chain on the tensor cores (MCPG/sampling.py:339-340) and one
+    coordinate-ascent sweep (sampling.py:331-337); chains split over the ranks, Q replicated."""
+    th = ctx.th
+    from rlsolver_b200.qubo import QuboModel
+    n = 4096
+    chains = total_chains // ctx.world
+    th.manual_seed(0)
+    u = th.randn(n, n, device=ctx.dev)
+    q = th.triu(u) + th.triu(u, 1).T
+    model = QuboModel(q)
+    th.manual_seed(1 + ctx.rank)
+    x = th.randint(0, 2, (n, chains), device=ctx.dev).float() * 2 - 1
+    out = {}
+    t0 = time.time()
+    ms = ctx.timed(lambda: model.energy(x), reps=10, warm=3)
+    ms_e = ctx.job_ms(ms)
+    xs_ = x.clone()
+    ms = ctx.timed(lambda: model.sweeps(xs_, 1), reps=3, warm=1)
+    ms_s = ctx.job_ms(ms)
+    ms = ctx.timed(lambda: (x * (q @ x)).sum(0), reps=3, warm=1)
+    ms_t = ctx.job_ms(ms)
+    t1 = time.time()
+    flops = 3 * 2.0 * n * n * chains                      # bf16 issued per GPU: 3 limbs of Q
+    for tag, ms_k, steps, what in (("energy", ms_e, total_chains, "QuboModel.energy (x^T Q x per chain)"),
+                                   ("sweep", ms_s, total_chains * n, "QuboModel.sweeps(1): N coordinate updates per chain")):
+        tf = flops / (ms_k * 1e-3) / 1e12
+        out[tag] = {"workload": f"dense QUBO N={n} fp32 (3 exact bf16 limbs), {total_chains} chains over {ctx.world} GPU(s) "
+                                f"({chains}/GPU): {what}",
+                    "n_gpus": ctx.world, "scaling": "strong", "ms": ms_k, "env_steps": steps,
+                    "env_steps_per_s": steps / (ms_k * 1e-3),
+                    "roofline": roof("tensor", tf, ctx.peaks["tensor"], "TFLOP/s", "qubo_" + tag + "_kernel",
+                                     flops_issued_per_launch=flops, useful_tflops=tf / 3,
+                                     peak_note="sustained cuBLAS bf16 (MEASURED_PEAKS.json bf16_tflops_sustained); "
+                                               "useful fp32-accurate flops are 1/3 of the issued bf16 flops")}
+    out["torch_fp32_same_gpu_ms"] = ms_t
+    out["clocks"] = ctx.window_clocks(t0, t1)
+    return out
+
+
+# ----------------------------------------------------------------------------- same-GPU reference arm
+def gpu_reference(ctx, envs):
+    """The reference's algorithm, op for op in torch (oracle/torch_port.py), on the SAME B200: the FULL headline
+    workload (4096 envs, all 8 iterations, all 2000 sweep nodes).  Isolates 'GPU vs CPU' from the algorithm."""
+    th = ctx.th
+    from oracle import torch_port as tp
+    from synth import gset_like
+    edges = gset_like(GRAPH)
+    sim = tp.TorchSim(edges, True, device=ctx.dev)
+    th.manual_seed(74)
+    xs0 = sim.random_xs(envs)
+    times = []
+    for it in range(2):
+        xs = xs0.clone()
+        th.cuda.synchronize()
+        a, b = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        a.record()
+        sim.local_search_inplace(xs, None, NUM_ITERS, NUM_SPIN, NOISE_STD)
+        b.record()
+        th.cuda.synchronize()
+        if it >= 1:
+            times.append(a.elapsed_time(b))
+    ms = sum(times) / len(times)
+    per_call = env_steps_per_call(envs, sim.num_nodes, NUM_ITERS, sim.num_nodes)
+    peak_mem = th.cuda.max_memory_allocated(ctx.dev)
+    del sim
+    th.cuda.empty_cache()
+    return {"impl": "oracle/torch_port.py (torch ops as the reference uses them: 3 int64 [E, Md] index tensors, one full "
+                    "objective evaluation per candidate flip) on the same GPU, full workload, 1 warm-up + 1 timed step",
+            "ms_per_step": ms, "value": per_call / (ms * 1e-3), "unit": UNIT, "envs": envs,
+            "peak_memory_gb": round(peak_mem / 2 ** 30, 2)}
+
+
 # ----------------------------------------------------------------------------- B200 arm
 def run_b200(args):
-    import torch as th
-    import torch.distributed as dist
+    ctx = Ctx(args)
+    th, dist = ctx.th, ctx.dist
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
     from synth import gset_like
 
     import rlsolver_b200
-    from rlsolver_b200.dist import best_allreduce
+    from rlsolver_b200.dist import BestExchange
     from rlsolver_b200.envs.env_L2A import EnvMaxcut
-    from rlsolver_b200.graph_store import OpTimer
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not th.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (rlsolver_b200 has no CPU fallback)")
-    th.cuda.set_device(local)
-    dev = th.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     rlsolver_b200.build()
 
     envs = args.envs
@@ -170,28 +544,27 @@ def run_b200(args):
     xs0 = sim.generate_xs_randomly(envs)
     xs = xs0.clone()
     sentinel = th.empty(())
-    flush = th.empty(256 << 20, dtype=th.uint8, device=dev)       # > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        th.cuda.synchronize()
+    flush = ctx.flush
+    barrier = ctx.barrier
+    exchange = BestExchange(n, rank, world, envs, dev) if world > 1 else None
 
     def local_part():
         return sim.local_search_inplace(xs, sentinel, NUM_ITERS, NUM_SPIN, NOISE_STD)
+
+    def step_body():
+        """One step: the local search and -- with several ranks -- the path's only exchange (best cut, its argmax,
+        the winner's spins), issued right behind it on the same stream."""
+        gx, gv = local_part()
+        best = exchange(gv, gx) if exchange is not None else None
+        return gx, gv, best
 
     state = {"graph": None, "out": None}
 
     def one_step():
         if state["graph"] is not None:
             state["graph"].replay()
-            gx, gv = state["out"]
-        else:
-            gx, gv = local_part()
-        best = None
-        if world > 1:     # the path's only exchange: best cut + its argmax + the winner's spins (eager: 1 kernel + 1 all-gather)
-            best = best_allreduce(gv, gx, rank, world, envs)
-        return gx, gv, best
+            return state["out"]
+        return step_body()
 
     def timed_steps(k):
         evs = []
@@ -207,9 +580,9 @@ def run_b200(args):
         return [a.elapsed_time(b) for a, b in evs]
 
     def try_capture():
-        """The local part of the step is a fixed sequence of 14 launches (torch's RNG kernels and this
-        library's kernels): capture it once into a CUDA graph so its host cost is one replay.  torch's
-        graph-safe Philox state keeps the random stream identical to eager execution."""
+        """The step is a fixed sequence of launches (this library's kernels, and with several ranks the NCCL
+        all-gather of the exchange): capture it once into a CUDA graph so its host cost is one replay.  The
+        device-resident generator cursor keeps the random stream identical to eager execution."""
         if args.no_graph:
             return "disabled (--no-graph)"
         try:
@@ -217,28 +590,27 @@ def run_b200(args):
             side.wait_stream(th.cuda.current_stream(dev))
             with th.cuda.stream(side):
                 for _ in range(3):
-                    local_part()
+                    step_body()
             th.cuda.current_stream(dev).wait_stream(side)
             th.cuda.synchronize()
             sim.store.rng_cursor_sync()        # the captured kernels read the generator state from device memory
             g = th.cuda.CUDAGraph()
             with th.cuda.graph(g):
-                out = local_part()
+                out = step_body()
             th.cuda.synchronize()
             state["graph"], state["out"] = g, out
-            return "captured"
+            return "captured (local search" + (" + best-cut exchange incl. ncclAllGather)" if world > 1 else ")")
         except Exception as exc:                                   # noqa: BLE001 - eager remains correct
             state["graph"] = None
             th.cuda.synchronize()
             return f"eager ({type(exc).__name__}: {str(exc)[:80]})"
 
-    clocks = ClockSampler(local) if rank == 0 else None
     # warm-up: W steps plus a fixed number of settle steps (~0.5 s of load so the clocks settle).  The
     # count must not depend on wall time: every rank has to issue the same sequence of collectives.
     t_w = time.time()
     launches_before = sim.store.launch_count
     timed_steps(1)
-    launches_per_step = sim.store.launch_count - launches_before
+    launches_per_step = sim.store.launch_count - launches_before + (2 if world > 1 else 0)
     graph_status = try_capture()
     if world > 1:       # all ranks must agree on the mode (the collective sequence is part of it)
         flag = th.tensor([1 if state["graph"] is not None else 0], device=dev)
@@ -248,166 +620,193 @@ def run_b200(args):
     for _ in range(max(3, args.warmup) + SETTLE_STEPS):
         timed_steps(1)
     barrier()
-    launches0 = sim.store.launch_count
     t0 = time.time()
     ms = timed_steps(args.steps)
     barrier()
     t1 = time.time()
     launches = launches_per_step * args.steps          # kernels of this library per step (counted on an eager step)
-    total_ms = th.tensor([sum(ms)], dtype=th.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
+    total_ms = ctx.max_over_ranks(sum(ms))
     per_call = env_steps_per_call(envs, n, NUM_ITERS, n)
     value = per_call * world * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end from pinned host buffers through the public API.  Every step copies its spins from pinned host
-    # memory to the device, runs the step, and copies spins + values back.  Two measurements: `serial` (copy in,
-    # compute, copy out, one after the other, one event pair per step) and `pipelined` (three streams, double
-    # buffered: the H2D of step i+1 and the D2H of step i-1 run under the compute of step i; one event pair around
-    # all K steps, fill and drain included) -- the headline, since that is how a host-fed loop runs the device.
-    h_xs = xs0.cpu().pin_memory()
-    h_out_xs = th.empty_like(h_xs).pin_memory()
-    h_out_vs = th.empty((envs,), dtype=th.int64).pin_memory()
-
-    def e2e_step():
-        xs.copy_(h_xs, non_blocking=True)                          # H2D into the step's input buffer
-        gx, gv, _ = one_step()
-        h_out_xs.copy_(gx, non_blocking=True)
-        h_out_vs.copy_(gv, non_blocking=True)
-
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    e2e_ms = []
-    for _ in range(args.steps):
-        flush.zero_()
-        a, b = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
-        a.record()
-        e2e_step()
-        b.record()
-        th.cuda.synchronize()
-        e2e_ms.append(a.elapsed_time(b))
-    barrier()
-    serial_total = th.tensor([sum(e2e_ms)], dtype=th.float64, device=dev)
+    # exchange cost alone (multi-GPU): record kernel + all-gather + pick kernel, eager, CUDA events
+    exch_us = None
     if world > 1:
-        dist.all_reduce(serial_total, op=dist.ReduceOp.MAX)
-    serial_ms = float(serial_total.item()) / args.steps
+        gx, gv = xs, sim.calculate_obj_values(xs)
+        ex_ms = ctx.timed(lambda: exchange(gv, gx), reps=50, warm=5, flush=False)
+        exch_us = 1e3 * ctx.job_ms(ex_ms)
 
+    # ---- end to end from pinned host buffers through the public API.  Every step copies its spins from pinned host
+    # memory to the device, runs the step, and copies spins + values back.  Two host layouts: `bool` = the
+    # reference's bool [E, N] rows (one byte per spin, what EnvMaxcut.local_search_inplace takes), and `packed` =
+    # the library's packed tiles (uint32 [E/32, Np], one bit per spin: rlsb_ls_begin_packed in, the workspace's
+    # packed section out), through EnvMaxcut.local_search_packed.  For each: `serial` (copy in, compute, copy out,
+    # one event pair per step) and `pipelined` (three streams, double buffered: H2D(i+1) | step(i) | D2H(i-1), one
+    # event pair around all K steps, fill and drain included).  The headline e2e is pipelined / bool (the
+    # reference-facing call); the packed figures are reported next to it.
     cur = th.cuda.current_stream(dev)
     s_in, s_out = th.cuda.Stream(device=dev), th.cuda.Stream(device=dev)
-    st_in = [th.empty_like(xs) for _ in range(2)]
-    st_xs = [th.empty_like(xs) for _ in range(2)]
-    st_vs = [th.empty((envs,), dtype=th.int64, device=dev) for _ in range(2)]
     small_flush = flush[:160 << 20]                                # > 126 MB L2, inside the timed region
+    pk0 = sim.store.pack(xs0)
 
-    def e2e_pipelined(k):
-        in_ready = [th.cuda.Event() for _ in range(2)]
-        in_free = [th.cuda.Event() for _ in range(2)]
-        out_ready = [th.cuda.Event() for _ in range(2)]
-        out_free = [th.cuda.Event() for _ in range(2)]
-        for e in in_free + out_free:
-            e.record(cur)
-        s_in.wait_stream(cur)
-        s_out.wait_stream(cur)
-        t0, t1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
-        t0.record(cur)
-        s_in.wait_event(t0)
-        for i in range(k):
-            b = i & 1
-            with th.cuda.stream(s_in):
-                s_in.wait_event(in_free[b])
-                st_in[b].copy_(h_xs, non_blocking=True)            # H2D of step i
-                in_ready[b].record(s_in)
-            cur.wait_event(in_ready[b])
-            xs.copy_(st_in[b])
-            in_free[b].record(cur)
-            small_flush.zero_()                                    # evict L2 between steps (timed)
-            gx, gv, _ = one_step()
-            cur.wait_event(out_free[b])
-            st_xs[b].copy_(gx)
-            st_vs[b].copy_(gv)
-            out_ready[b].record(cur)
-            with th.cuda.stream(s_out):
-                s_out.wait_event(out_ready[b])
-                h_out_xs.copy_(st_xs[b], non_blocking=True)        # D2H of step i
-                h_out_vs.copy_(st_vs[b], non_blocking=True)
-                out_free[b].record(s_out)
-        cur.wait_stream(s_out)
-        cur.wait_stream(s_in)
-        t1.record(cur)
-        th.cuda.synchronize()
-        return t0.elapsed_time(t1)
+    def make_layout(kind):
+        if kind == "bool":
+            h_in = xs0.cpu().pin_memory()
+            d_in = [th.empty_like(xs0) for _ in range(2)]
+            d_out = [th.empty_like(xs0) for _ in range(2)]
 
-    e2e_pipelined(4)
-    barrier()
-    e2e_total = th.tensor([e2e_pipelined(args.steps)], dtype=th.float64, device=dev)
-    barrier()
-    if world > 1:
-        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
-    e2e_value = per_call * world * args.steps / (float(e2e_total.item()) * 1e-3)
-    clock_info = clocks.stop(t_w, time.time()) if clocks else None
+            def run(src):
+                xs.copy_(src)
+                gx, gv, _ = one_step()
+                return gx, gv
+        else:
+            h_in = pk0.cpu().pin_memory()
+            d_in = [th.empty_like(pk0) for _ in range(2)]
+            d_out = [th.empty_like(pk0) for _ in range(2)]
+
+            def run(src):
+                pk, gv = sim.local_search_packed(src, NUM_ITERS, NUM_SPIN, NOISE_STD)
+                if exchange is not None:
+                    exchange.packed(gv, pk, sim.store)
+                return pk, gv
+        h_out = th.empty_like(h_in).pin_memory()
+        h_vs = th.empty((envs,), dtype=th.int64).pin_memory()
+        d_vs = [th.empty((envs,), dtype=th.int64, device=dev) for _ in range(2)]
+        return h_in, h_out, h_vs, d_in, d_out, d_vs, run
+
+    def e2e_measure(kind):
+        h_in, h_out, h_vs, d_in, d_out, d_vs, run = make_layout(kind)
+
+        def serial_step():
+            d_in[0].copy_(h_in, non_blocking=True)
+            gx, gv = run(d_in[0])
+            h_out.copy_(gx, non_blocking=True)
+            h_vs.copy_(gv, non_blocking=True)
+
+        for _ in range(3):
+            serial_step()
+        barrier()
+        ser = []
+        for _ in range(args.steps):
+            flush.zero_()
+            a, b = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+            a.record()
+            serial_step()
+            b.record()
+            th.cuda.synchronize()
+            ser.append(a.elapsed_time(b))
+        barrier()
+        serial_ms = ctx.max_over_ranks(sum(ser)) / args.steps
+
+        def pipelined(k):
+            in_ready = [th.cuda.Event() for _ in range(2)]
+            in_free = [th.cuda.Event() for _ in range(2)]
+            out_ready = [th.cuda.Event() for _ in range(2)]
+            out_free = [th.cuda.Event() for _ in range(2)]
+            for e in in_free + out_free:
+                e.record(cur)
+            s_in.wait_stream(cur)
+            s_out.wait_stream(cur)
+            ta, tb = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+            ta.record(cur)
+            s_in.wait_event(ta)
+            for i in range(k):
+                b = i & 1
+                with th.cuda.stream(s_in):
+                    s_in.wait_event(in_free[b])
+                    d_in[b].copy_(h_in, non_blocking=True)             # H2D of step i
+                    in_ready[b].record(s_in)
+                cur.wait_event(in_ready[b])
+                small_flush.zero_()                                    # evict L2 between steps (timed)
+                gx, gv = run(d_in[b])
+                in_free[b].record(cur)
+                cur.wait_event(out_free[b])
+                d_out[b].copy_(gx)
+                d_vs[b].copy_(gv)
+                out_ready[b].record(cur)
+                with th.cuda.stream(s_out):
+                    s_out.wait_event(out_ready[b])
+                    h_out.copy_(d_out[b], non_blocking=True)           # D2H of step i
+                    h_vs.copy_(d_vs[b], non_blocking=True)
+                    out_free[b].record(s_out)
+            cur.wait_stream(s_out)
+            cur.wait_stream(s_in)
+            tb.record(cur)
+            th.cuda.synchronize()
+            return ta.elapsed_time(tb)
+
+        pipelined(4)
+        barrier()
+        pipe_ms = ctx.max_over_ranks(pipelined(args.steps)) / args.steps
+        barrier()
+        nbytes = h_in.numel() * h_in.element_size()
+        return {"ms_per_step": pipe_ms, "value": per_call * world / (pipe_ms * 1e-3), "serial_ms_per_step": serial_ms,
+                "serial_value": per_call * world / (serial_ms * 1e-3), "h2d_bytes_per_step": nbytes,
+                "d2h_bytes_per_step": nbytes + 8 * envs}
+
+    e2e_bool = e2e_measure("bool")
+    e2e_packed = e2e_measure("packed")
+    t_headline_end = time.time()
 
     # ---- per-kernel pass (CUDA events around every launch of this library) for the roofline
     saved_graph, state["graph"] = state["graph"], None          # per-kernel events need eager launches
-    sim.store.timer = OpTimer()
-    timed_steps(args.steps)
+    kernel_ms, share, _ = per_kernel_pass(ctx, sim.store, lambda: step_body(), args.steps,
+                                          prepare=lambda: xs.copy_(xs0))
     state["graph"] = saved_graph
-    spans = sim.store.timer.summary()
-    sim.store.timer = None
-    step_ms_prof = sum(v[1] for v in spans.values()) / args.steps
-    share = {k: round(v[1] / args.steps / max(step_ms_prof, 1e-9), 4) for k, v in spans.items()}
-    kernel_ms = {k: v[1] / v[0] for k, v in spans.items()}
-    dom = max(spans, key=lambda k: spans[k][1])
-    np_ = sim.store.padded_nodes
-    cb = 1 if max(sim.store.max_listed_degree, sim.store.max_full_degree) <= 255 else 2   # cross-count bytes
-    graph_b = 4 * sim.num_edges + 2 * sim.store.num_full + 12 * np_
-    alg_bytes = {   # algorithmic bytes per launch group, DESIGN.md "Kernels"
-        # ls_run: noise + cross counts per pass (threshold pass + NUM_ITERS iterations); packed tile in/out,
-        # thresholds, bool rows + values out, graph once
-        # ls_run here = the threshold pass only (noise of draw 0 + cross counts in, thresholds out)
-        "ls_search": 4 * envs * n + cb * envs * np_ + 2 * envs * np_ // 8 + 20 * envs + 8 * np_,
-        "ls_thresh": 4 * envs * n + cb * envs * np_ + 4 * envs + 8 * np_,
-        # early-out pass (cross counts in, one byte per Box-Muller pair out) + per draw those bytes in, one bit per
-        # element out (zeroed, then OR-ed).  The float32 noise itself (4 B per element and draw) never exists.
-        "ls_noise_masks": envs * np_ + envs * n // 2 + NUM_ITERS * (envs * n // 2 + 2 * envs * n // 8) + 4 * envs
-                          + 8 * np_,
-        # packed tile in/out, one mask bit per element and iteration, bool rows + values out, graph once
-        "ls_run_masks": 2 * envs * np_ // 8 + NUM_ITERS * envs * n // 8 + envs * n + 16 * envs + graph_b,
-        "torch_randn": 4 * envs * n,
-        "rng_cursor_advance": 16,
-        "ls_begin": envs * n + envs * np_ // 8 + cb * envs * np_ + 8 * envs + graph_b,
-        "pack_spins": envs * n + envs * np_ // 8,
-        "unpack_spins": envs * n + envs * np_ // 8,
-        "cut_eval_packed": envs * np_ // 8 + 8 * envs + 4 * sim.num_edges,
-        "cut_eval": envs * n + 8 * envs + 4 * sim.num_edges,
-    }
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    dom = max(share, key=share.get)
+    alg_bytes = ls_alg_bytes(sim.store, envs, n, sim.num_edges, NUM_ITERS)
+    peak, peak_src = ctx.peaks["hbm"], ctx.peaks["source"] + " hbm_gbs"
     achieved = alg_bytes[dom] / (kernel_ms[dom] * 1e-3) / 1e9
+    gen = next((k for k in ("ls_noise_masks", "ls_fused_search") if k in kernel_ms), None)
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": dram_traffic().get(dom), "peak_source": peak_src,
                 "ms_per_launch": kernel_ms[dom], "algorithmic_bytes_per_launch": alg_bytes[dom],
                 "share_of_step": share,
                 "all_kernels_gbs": {k: alg_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9 for k in kernel_ms if k in alg_bytes},
                 "pass": "separate K-step pass with CUDA events around each call of this library, single stream",
-                "note": ("the step no longer streams noise: ls_noise_masks recomputes torch's Philox/Box-Muller stream in "
-                         "registers (issue-bound, see profiles/), its algorithmic HBM bytes are the early-out bytes and "
-                         "the mask bits; noise_equivalent_gbs = the 4 B per element and draw a streaming implementation "
-                         "reads, over the same time"),
-                "noise_equivalent_gbs": (NUM_ITERS * 4 * envs * n / (kernel_ms["ls_noise_masks"] * 1e-3) / 1e9
-                                         if "ls_noise_masks" in kernel_ms else None)}
-    traffic_path = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.exists(traffic_path):
-        roofline["traffic"] = json.load(open(traffic_path)).get(dom)
+                "note": ("the step does not stream noise: torch's Philox/Box-Muller stream is recomputed in registers "
+                         "(issue-bound, see profiles/), the algorithmic HBM bytes of that kernel are the early-out bytes "
+                         "and the mask bits; noise_equivalent_gbs = the 4 B per element and draw a streaming "
+                         "implementation reads, over the same time"),
+                "noise_equivalent_gbs": (NUM_ITERS * 4 * envs * n / (kernel_ms[gen] * 1e-3) / 1e9 if gen else None),
+                "whole_step_noise_equivalent_frac": ((1 + NUM_ITERS) * 4 * envs * n / (total_ms / args.steps * 1e-3)
+                                                     / 1e9 / peak)}
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(steps=3, warmup=1, budget_s=4.0)
-        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    cpu = gpu_ref = None
+    if world == 1 and not args.no_cpu_baseline:
+        if rank == 0:
+            r = cpu_reference_run(steps=3, warmup=1, budget_s=4.0)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "same_config_basis",
+                                     "full_workload_seconds_per_step_extrapolated")}
+            try:
+                gpu_ref = gpu_reference(ctx, envs)
+                gpu_ref["device_timed_ratio"] = value / gpu_ref["value"]
+            except Exception as exc:                               # noqa: BLE001
+                gpu_ref = {"unavailable": f"{type(exc).__name__}: {str(exc)[:120]}"}
+                th.cuda.empty_cache()
+
+    # ---- the other BASELINE configurations
+    want = set() if args.configs == "none" else set(args.configs.split(","))
+    configs = {}
+
+    def attempt(name, fn):
+        try:
+            barrier()
+            configs[name] = fn()
+        except Exception as exc:                                   # noqa: BLE001 - one config must not sink the line
+            configs[name] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+            th.cuda.empty_cache()
+
+    del flush
+    if "1" in want and world == 1:
+        attempt("config1_G14_256", lambda: config1(ctx))
+    if "3" in want:
+        attempt("config3_G70_16384", lambda: config3(ctx))
+    if "5" in want:
+        attempt("config5_QUBO_4096_8192", lambda: config5(ctx))
+    if "4" in want:
+        attempt("config4_BA_ER_100_1M", lambda: config4(ctx, args.peco_envs))
+    clock_info = ctx.clocks.stop(t_w, t_headline_end) if ctx.clocks else None
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -416,16 +815,22 @@ def run_b200(args):
                 "data": "synthetic",
                 "config": {"workload": workload_name(envs), "envs_per_gpu": envs, "nodes": n, "edges": sim.num_edges,
                            "env_steps_per_step_per_gpu": per_call, "l2": "flushed between steps (256 MiB write)", "cuda_graph": graph_status,
-                           "rng": "torch's CUDA Philox stream, 1+8 draws of randn [E,N] f32 per step inside the timed region: draw 0 "
-                                  "(threshold) as a tensor, draws 1-8 recomputed in place by ls_noise_masks (flip bits only)",
-                           "multi_gpu": "env batch sharded, graph replicated, one best-cut exchange per step (all-gather of 8+N byte records, no host sync)"},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": envs * n,
-                        "d2h_bytes_per_step": envs * n + 8 * envs, "ms_per_step": float(e2e_total.item()) / args.steps,
+                           "rng": "torch's CUDA Philox stream, 1+8 draws of randn [E,N] f32 per step inside the timed region, "
+                                  "recomputed in place (only thresholds / flip bits leave the kernels)",
+                           "multi_gpu": ("env batch sharded, graph replicated, one best-cut exchange per step inside the "
+                                         "captured graph: best_record kernel + ncclAllGather of world x (8+N) B + "
+                                         "best_pick kernel, no host sync"),
+                           "exchange_us": exch_us},
+                "e2e": {"value": e2e_bool["value"], "unit": UNIT, "h2d_bytes_per_step": e2e_bool["h2d_bytes_per_step"],
+                        "d2h_bytes_per_step": e2e_bool["d2h_bytes_per_step"], "ms_per_step": e2e_bool["ms_per_step"],
+                        "layout": "bool [E, N] rows (the reference's layout), EnvMaxcut.local_search_inplace",
                         "mode": ("pipelined: H2D(i+1) | step(i) | D2H(i-1) on three streams, double buffered, one event "
                                  "pair around all K steps (fill + drain and a 160 MiB L2-evicting write per step included)"),
-                        "serial_ms_per_step": serial_ms,
-                        "serial_value": per_call * world / (serial_ms * 1e-3)},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info}
+                        "serial_ms_per_step": e2e_bool["serial_ms_per_step"], "serial_value": e2e_bool["serial_value"],
+                        "packed": dict(e2e_packed, layout="packed tiles uint32 [E/32, Np] (one bit per spin), "
+                                                          "EnvMaxcut.local_search_packed / rlsb_ls_begin_packed")},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "gpu_reference": gpu_ref,
+                "configs": configs, "clocks": clock_info}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -462,6 +867,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=NUM_ENVS)
+    ap.add_argument("--configs", default="1,3,4,5", help="other BASELINE configs to measure ('none' to skip)")
+    ap.add_argument("--peco-envs", type=int, default=1 << 20, help="total envs of config 4 (10^6 instances)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -172,6 +172,22 @@ int rlsb_ls_noise_masks(const rlsb_graph_t* g, int64_t num_envs, int32_t ws_mult
                         int32_t reuse_bound, uint32_t* masks, void* workspace, void* stream);
 int rlsb_ls_run_masks(const rlsb_graph_t* g, int64_t num_envs, int64_t* vs, const uint32_t* masks, int32_t num_iters,
                       int32_t finish, uint8_t* xs_out, void* workspace, void* stream);
+/* Noisy iterations + single-flip pass with the generator running NEXT TO the tile kernel (round 2): same
+ * arguments and results as rlsb_ls_noise_masks(num_draws = num_iters) followed by rlsb_ls_run_masks, issued as
+ * early-out bytes + zeroing on `stream`, then the tile kernel on `stream` and the streaming generator on a side
+ * stream of the graph handle (joined back into `stream` before the call returns; capturable in a CUDA graph).
+ * The generator finishes the draws in groups of two; a tile CTA starts iteration k when the group of draw k is
+ * complete (counters in the workspace).  masks: scratch, uint32 [num_iters][rlsb_ls_mask_words].  xs_out may be
+ * NULL when only the packed tiles (workspace section 0) and vs are wanted; also for rlsb_ls_run_masks. */
+int rlsb_ls_fused_search(const rlsb_graph_t* g, int64_t num_envs, int64_t* vs, int32_t ws_mult, uint64_t seed,
+                         uint64_t offset, const uint64_t* rng_dev, int32_t rng_threads, int32_t rng_iters,
+                         int32_t num_iters, int32_t finish, uint8_t* xs_out, uint32_t* masks, void* workspace,
+                         void* stream);
+/* rlsb_ls_begin for a state handed over as packed tiles (uint32 [ceil(E/32)][Np], bit b of word [t][i] = node i
+ * of env 32t + b; bits of envs >= E must be 0): what a host that keeps spins packed sends, 1 bit instead of
+ * 1 byte per spin.  packed_in may be the workspace's own packed section (no copy then). */
+int rlsb_ls_begin_packed(const rlsb_graph_t* g, const uint32_t* packed_in, int64_t num_envs, int64_t* vs,
+                         int32_t compute_vs, int32_t ws_mult, float noise_std, void* workspace, void* stream);
 int rlsb_torch_randn(float* out, int64_t numel, uint64_t seed, uint64_t offset, const uint64_t* rng_dev,
                      int32_t rng_threads, int32_t rng_iters, int32_t num_draws, void* stream);
 /* Device-resident generator state for CUDA-graph replays: rng_dev -> {seed, offset} (2 x uint64 in device
@@ -350,14 +366,21 @@ int rlsb_pick_best(const uint8_t* xs, const int64_t* vs, int32_t num_repeats, in
                    int32_t maximize, uint8_t* out_xs, int64_t* out_vs, void* stream);
 
 /* ---- multi-GPU best-cut exchange (new; the reference is single-process): the record a rank
- * contributes to the all-gather -- int64 key (cut << 32) | (0xFFFFFFFF - global_env_id) of its best
- * row (cut values must be >= 0; ties go to the lowest global env id), then the row's N bytes.
+ * contributes to the all-gather -- 64-bit key ((cut + 2^31) << 32) | (0xFFFFFFFF - global_env_id) of its best
+ * row, compared unsigned (negative values order below positive ones, values saturate to the int32 range; ties
+ * go to the lowest global env id), then the row's N bytes.
  * vs int64 [E], xs bool [E][N], record uint8 [8 + N] (8-byte aligned); env_offset = rank * E. */
 int rlsb_best_record(const int64_t* vs, const uint8_t* xs, int64_t num_envs, int32_t num_nodes, int64_t env_offset,
                      uint8_t* record, void* stream);
+/* the same record taken from packed tiles (uint32 [ceil(E/32)][Np]); the row is expanded to one byte per node */
+int rlsb_best_record_packed(const int64_t* vs, const uint32_t* packed, int64_t num_envs, int32_t num_nodes,
+                            int32_t padded_nodes, int64_t env_offset, uint8_t* record, void* stream);
 /* winner of `world` gathered records (uint8 [world][8 + N]): out2[0] = best cut, out2[1] = its global
  * env id, row = its N spin bytes. */
 int rlsb_best_pick(const uint8_t* gathered, int32_t world, int32_t num_nodes, int64_t* out2, uint8_t* row, void* stream);
+/* the same for records `stride` bytes apart (stride >= 8 + N; padded so that every record is 8-byte aligned) */
+int rlsb_best_pick_strided(const uint8_t* gathered, int32_t world, int32_t num_nodes, int64_t stride, int64_t* out2,
+                           uint8_t* row, void* stream);
 
 #ifdef __cplusplus
 }

@@ -221,12 +221,23 @@ def sweep_delta(g: GraphStore, xs: np.ndarray, vs: np.ndarray) -> None:
         vs[acc] += gain[acc].astype(vs.dtype)
 
 
+def batch_rd_std(g: GraphStore, xs: np.ndarray, mult: int, noise_std: float) -> np.ndarray:
+    """float32 [1, N]: `(max_e ws - min_e ws) * noise_std` over the WHOLE batch `xs` (env_L2A.py:92-95 with
+    mult = 2 if bi else 1; LocalSearch.py:64-66 with mult = 4 if bi else 2).  The spread couples the envs of a
+    batch; everything after it is per env, so a test can replay a SUBSET of the rows of a large batch by
+    handing this to local_search_inplace / LocalSearch.random_search as `rd_std`."""
+    ws = g.listed_degree[None, :] - mult * obj_values_for_loop(g, xs, if_sum=False)
+    ws_std = ws.max(axis=0, keepdims=True) - ws.min(axis=0, keepdims=True)
+    return (ws_std.astype(np.float32) * np.float32(noise_std)).astype(np.float32)
+
+
 def local_search_inplace(g: GraphStore, good_xs: np.ndarray, good_vs, noises: Sequence[np.ndarray],
                          num_iters: int = 8, num_spin: int = 8, noise_std: float = 0.3,
-                         literal: bool = True):
+                         literal: bool = True, rd_std: np.ndarray = None):
     """EnvMaxcut.local_search_inplace (env_L2A.py:87-116).
     `noises` holds the 1 + num_iters recorded randn draws (float32 [E, N]).
-    `good_vs=None` stands for the reference's `()` sentinel (line 91)."""
+    `good_vs=None` stands for the reference's `()` sentinel (line 91).
+    `rd_std`: see batch_rd_std (rows of a larger batch); None = computed from this batch, as the reference does."""
     vs_raw = obj_values_for_loop(g, good_xs, if_sum=False)
     if good_vs is None:
         good_vs = vs_raw.sum(axis=1).astype(np.int64)
@@ -234,8 +245,9 @@ def local_search_inplace(g: GraphStore, good_xs: np.ndarray, good_vs, noises: Se
         good_vs = good_vs.astype(np.int64)
     mult = 2 if g.bidirectional else 1
     ws = g.listed_degree[None, :] - mult * vs_raw           # float32 (bi) / int64 (uni)
-    ws_std = ws.max(axis=0, keepdims=True) - ws.min(axis=0, keepdims=True)
-    rd_std = (ws_std.astype(np.float32) * np.float32(noise_std)).astype(np.float32)
+    if rd_std is None:
+        ws_std = ws.max(axis=0, keepdims=True) - ws.min(axis=0, keepdims=True)
+        rd_std = (ws_std.astype(np.float32) * np.float32(noise_std)).astype(np.float32)
     thresh = kth_smallest(_spin_rand(ws, noises[0], rd_std), g.num_nodes - num_spin)[:, None]
     for it in range(num_iters):
         mask = _spin_rand(ws, noises[1 + it], rd_std) > thresh
@@ -261,7 +273,7 @@ class LocalSearch:
         return vs
 
     def random_search(self, noises: Sequence[np.ndarray], num_iters: int = 8, num_spin: int = 8,
-                      noise_std: float = 0.3, literal: bool = True):
+                      noise_std: float = 0.3, literal: bool = True, rd_std: np.ndarray = None):
         g = self.g
         kth = g.num_nodes - num_spin
         prev_xs = self.good_xs.copy()
@@ -269,8 +281,9 @@ class LocalSearch:
         prev_vs = raw.sum(axis=1)                             # int64 (uni) / float32 (bi)
         mult = 4 if g.bidirectional else 2
         ws = g.listed_degree[None, :] - mult * raw            # constant across iterations (raw is not refreshed)
-        ws_std = ws.max(axis=0, keepdims=True) - ws.min(axis=0, keepdims=True)
-        rd_std = (ws_std.astype(np.float32) * np.float32(noise_std)).astype(np.float32)
+        if rd_std is None:                                    # else: rows of a larger batch, see batch_rd_std
+            ws_std = ws.max(axis=0, keepdims=True) - ws.min(axis=0, keepdims=True)
+            rd_std = (ws_std.astype(np.float32) * np.float32(noise_std)).astype(np.float32)
         thresh = None
         for it in range(num_iters):
             sr = _spin_rand(ws, noises[it], rd_std)

@@ -114,6 +114,8 @@ SIGNATURES = {
     "rlsb_ls_noise_masks": (C.c_int, [_vp, _i64, _i32, _u64, _u64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "rlsb_rng_cursor_advance": (C.c_int, [_vp, _u64, _vp]),
     "rlsb_ls_run_masks": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "rlsb_ls_fused_search": (C.c_int, [_vp, _i64, _vp, _i32, _u64, _u64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "rlsb_ls_begin_packed": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _f32, _vp, _vp]),
     "rlsb_torch_randn": (C.c_int, [_vp, _i64, _u64, _u64, _vp, _i32, _i32, _i32, _vp]),
     "rlsb_flip_sweep": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "rlsb_relaxed_cut": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
@@ -143,6 +145,8 @@ SIGNATURES = {
                                  _i32, _i32, _f32, _f32, _i32, _f32, _i32, _f32, _i32, _vp]),
     "rlsb_select_rows": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "rlsb_best_record": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp]),
+    "rlsb_best_record_packed": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i64, _vp, _vp]),
+    "rlsb_best_pick_strided": (C.c_int, [_vp, _i32, _i32, _i64, _vp, _vp, _vp]),
     "rlsb_best_pick": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "rlsb_pick_best": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
 }

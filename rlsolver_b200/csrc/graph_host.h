@@ -20,6 +20,10 @@ struct rlsb_graph {
   } sell_listed, sell_sweep;
   void* dev_blob = nullptr;   // one allocation holding every device array
   rlsb::GraphDev dev{};
+  // side stream + fork / join events for work that runs next to the caller's stream (the streaming mask
+  // generator of rlsb_ls_fused_search); created with the device blob
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "graph_host.h"
+#include "ls_workspace.cuh"
 
 namespace rlsb {
 
@@ -42,6 +43,12 @@ int graph_check(const rlsb_graph_t* g, const GraphDev** out, const char* what) {
                "%s: graph outside the shared-memory tile kernels (padded nodes %d > %d or degree > 4095)", what, g->np,
                kMaxTileNodes);
   *out = &g->dev;
+  return RLSB_OK;
+}
+
+int graph_side(const rlsb_graph_t* g, GraphSide* out) {
+  RLSB_REQUIRE(g && g->side_stream && g->ev_fork && g->ev_join, RLSB_ERR_NODEVICE, "graph has no side stream (host-only graph)");
+  out->stream = g->side_stream, out->fork = g->ev_fork, out->join = g->ev_join;
   return RLSB_OK;
 }
 
@@ -282,6 +289,9 @@ int rlsb_graph_create(int32_t num_nodes, int64_t num_edges, const int32_t* h_n0,
     }
     const int b_sweep = add(sblob.data(), sblob.size());
     if (e == cudaSuccess) e = cudaMalloc(&g->dev_blob, total);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->side_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming);
     for (size_t a = 0; a < blobs.size() && e == cudaSuccess; ++a)
       if (blobs[a].bytes)
         e = cudaMemcpy((char*)g->dev_blob + blobs[a].off, blobs[a].src, blobs[a].bytes, cudaMemcpyHostToDevice);
@@ -318,6 +328,9 @@ int rlsb_graph_create(int32_t num_nodes, int64_t num_edges, const int32_t* h_n0,
 
 int rlsb_graph_destroy(rlsb_graph_t* g) {
   if (!g) return RLSB_OK;
+  if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+  if (g->ev_join) cudaEventDestroy(g->ev_join);
+  if (g->side_stream) cudaStreamDestroy(g->side_stream);
   if (g->dev_blob) cudaFree(g->dev_blob);
   delete g;
   return RLSB_OK;

@@ -362,6 +362,7 @@ __device__ __forceinline__ void finish_tile(const GraphDev& g, const LsArgs& a, 
   ls_sync();
   if (tk) stamp(a, *tk);
   if (threadIdx.x < valid) a.vs[tile * kTileEnvs + threadIdx.x] = sCnt[threadIdx.x];
+  if (!a.xs_out) return;        // packed output only (the caller reads the workspace's packed tiles)
   if (a.unpack_vec4)
     unpack_tile_from_smem<4>(sP, a.xs_out, a.num_envs, g.n, g.np, tile, kLSWarps);
   else
@@ -746,7 +747,7 @@ __device__ __forceinline__ MaskChunk mask_chunk_load(const uint32_t* __restrict_
     c.lo[u] = c.hi[u] = 0;
     if (live && b < blocks) {
       const uint64_t o = row + 32u * (uint32_t)b;
-      c.lo[u] = __ldg(mask + (o >> 5)), c.hi[u] = __ldg(mask + (o >> 5) + 1);
+      c.lo[u] = __ldcg(mask + (o >> 5)), c.hi[u] = __ldcg(mask + (o >> 5) + 1);   // L2: written by another kernel
     }
   }
   return c;
@@ -851,9 +852,23 @@ __device__ __forceinline__ void evaluate_delta_and_accept(const GraphDev& g, con
   ls_sync();
 }
 
+// Hand-shake with the streaming mask generator (noise_masks.cu): the draws of group g are complete when
+// ctl[2g + 1] == units.  One thread polls (acquire at gpu scope), the CTA barrier that follows publishes it.
+__device__ __forceinline__ bool gen_group_ready(const uint32_t* ctl, int group, uint32_t units) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctl + 2 * group + 1) : "memory");
+  return v >= units;
+}
+__device__ __forceinline__ void gen_group_wait(const uint32_t* ctl, int group, uint32_t units) {
+  while (!gen_group_ready(ctl, group, units)) __nanosleep(200);
+}
+
+// 96 registers: a CTA (512 threads) leaves a quarter of the register file to the generator block that runs
+// on the same SM (rlsb_ls_fused_search); the kernel needs ~100 without spilling anything that matters.
 template <int P>
-__global__ void __launch_bounds__(kLSThreads) ls_bits_kernel(GraphDev g, LsArgs a, const uint32_t* __restrict__ masks,
-                                                             int64_t mask_words, int use_delta) {
+__global__ void __maxnreg__(96) ls_bits_kernel(GraphDev g, LsArgs a, const uint32_t* __restrict__ masks,
+                                               int64_t mask_words, int use_delta, const uint32_t* __restrict__ ctl,
+                                               uint32_t units) {
   extern __shared__ __align__(1024) uint32_t smem[];
   uint32_t* sP = smem;
   uint32_t* sX = smem + g.np;
@@ -863,6 +878,7 @@ __global__ void __launch_bounds__(kLSThreads) ls_bits_kernel(GraphDev g, LsArgs 
   __shared__ int sCnt[kTileEnvs];
   __shared__ uint32_t sAccept;
   __shared__ int sNF;
+  __shared__ int sNextReady;
   __shared__ __align__(8) uint64_t sBar;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t tile = blockIdx.x;
@@ -871,6 +887,7 @@ __global__ void __launch_bounds__(kLSThreads) ls_bits_kernel(GraphDev g, LsArgs 
   if (threadIdx.x == 0) {
     mbar_init(&sBar, 1);
     sNF = 0;
+    sNextReady = 0;
     if (a.stage_sweep) stage_sweep_blob(g, sSweep, &sBar);
   }
   for (int i = threadIdx.x; i < g.np; i += kLSThreads) {
@@ -887,6 +904,7 @@ __global__ void __launch_bounds__(kLSThreads) ls_bits_kernel(GraphDev g, LsArgs 
   if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
   int64_t my_vs = 0;
   if (warp == 0 && lane < valid) my_vs = a.vs[env0 + lane];
+  if (ctl && a.num_iters > 0 && threadIdx.x == 0) gen_group_wait(ctl, 0, units);     // the first group of draws
   ls_sync();
   const int blocks = (g.n + 31) >> 5;
   const uint64_t row = (uint64_t)(env0 + lane) * (uint64_t)g.n;     // first bit of the lane's env row
@@ -895,15 +913,27 @@ __global__ void __launch_bounds__(kLSThreads) ls_bits_kernel(GraphDev g, LsArgs 
   int tk = 0;
   stamp(a, tk);
   MaskChunk pre = mask_chunk_load(masks, row, warp, a.num_iters > 0 ? blocks : 0, live);
+  bool have_pre = true;
   if (use_delta && a.stage_sweep && a.num_iters > 0) mbar_wait(&sBar, 0);   // the neighbour lists have landed
   stamp(a, tk);
   for (int it = 0; it < a.num_iters; ++it) {
     const uint32_t* mask = masks + it * mask_words;
+    if (!have_pre) {      // the draw was not complete when the previous iteration could have fetched ahead
+      if (threadIdx.x == 0) gen_group_wait(ctl, it / kGenGroup, units);
+      ls_sync();
+      pre = mask_chunk_load(mask, row, warp, blocks, live);
+    }
     mask_chunk_apply(pre, row, warp, g.n, sP, sX, flist, &sNF);
     for (int b0 = warp + 4 * kLSWarps; b0 < blocks; b0 += 4 * kLSWarps)
       mask_chunk_apply(mask_chunk_load(mask, row, b0, blocks, live), row, b0, g.n, sP, sX, flist, &sNF);
+    // fetch ahead only when the next draw's group is known to be complete (same group: it is; next group: one
+    // poll, published by the barrier below)
+    const bool more = it + 1 < a.num_iters;
+    const bool same_group = !ctl || (it + 1) / kGenGroup == it / kGenGroup;
+    if (more && !same_group && threadIdx.x == 0) sNextReady = gen_group_ready(ctl, (it + 1) / kGenGroup, units) ? 1 : 0;
     ls_sync();
-    pre = mask_chunk_load(mask + mask_words, row, warp, it + 1 < a.num_iters ? blocks : 0, live);
+    have_pre = !more || same_group || sNextReady != 0;
+    if (have_pre) pre = mask_chunk_load(mask + mask_words, row, warp, more ? blocks : 0, live);
     stamp(a, tk);
     if (use_delta)
       evaluate_delta_and_accept<P>(g, a, sSweep, sInv, sF, &sNF, sP, sX, sCnt, &sAccept, valid, my_vs);
@@ -1073,17 +1103,20 @@ static int launch_generic(const GraphDev& g, LsArgs a, cudaStream_t st) {
   return RLSB_OK;
 }
 
+// smem_budget: the fused search leaves room for the generator block on the same SM
 template <int P>
-static int launch_bits(const GraphDev& g, LsArgs a, const uint32_t* masks, cudaStream_t st) {
+static int launch_bits(const GraphDev& g, LsArgs a, const uint32_t* masks, cudaStream_t st, const uint32_t* ctl = nullptr,
+                       uint32_t units = 0, size_t smem_budget = kSmemBudget) {
   const size_t tiles_bytes = 3 * (size_t)g.np * sizeof(uint32_t);     // two tile copies + node->slot map + flipped list
-  a.stage_sweep = ((a.finish || a.num_iters > 0) && tiles_bytes + (size_t)g.sweep_blob_bytes <= kSmemBudget) ? 1 : 0;
+  a.stage_sweep = ((a.finish || a.num_iters > 0) && tiles_bytes + (size_t)g.sweep_blob_bytes <= smem_budget) ? 1 : 0;
   const size_t smem = tiles_bytes + (a.stage_sweep ? (size_t)g.sweep_blob_bytes : 0);
-  RLSB_REQUIRE(smem <= kSmemBudget, RLSB_ERR_UNSUPPORTED, "ls_run_masks: %d nodes exceed the shared-memory tile", g.n);
+  RLSB_REQUIRE(smem <= smem_budget, RLSB_ERR_UNSUPPORTED, "ls_run_masks: %d nodes exceed the shared-memory tile", g.n);
   const int64_t tiles = (a.num_envs + kTileEnvs - 1) / kTileEnvs;
-  // slots of the sweep structure are addressed with 16 bits; RLSB_LS_FULL_CUT=1 keeps the full re-count (cross-check)
+  // slots of the sweep structure are addressed with 16 bits; RLSB_DEBUG_FULL_CUT keeps the full re-count (cross-check)
   const int use_delta = (g.num_sweep_slices * 32 <= 65536 && !(debug_flags() & RLSB_DEBUG_FULL_CUT)) ? 1 : 0;
   if (int rc = allow_smem(ls_bits_kernel<P>, smem)) return rc;
-  ls_bits_kernel<P><<<(unsigned)tiles, kLSThreads, smem, st>>>(g, a, masks, ls_mask_words(a.num_envs, g.n), use_delta);
+  ls_bits_kernel<P><<<(unsigned)tiles, kLSThreads, smem, st>>>(g, a, masks, ls_mask_words(a.num_envs, g.n), use_delta, ctl,
+                                                                units);
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }
@@ -1288,8 +1321,7 @@ int rlsb_ls_run_masks(const rlsb_graph_t* gh, int64_t num_envs, int64_t* vs, con
   if (int rc = ls_check(gh, &g, "ls_run_masks", num_envs, 1)) return rc;
   RLSB_REQUIRE(num_iters >= 0, RLSB_ERR_INVALID, "ls_run_masks: negative num_iters");
   if (num_envs == 0 || g->n == 0) return RLSB_OK;
-  RLSB_REQUIRE(vs && workspace && (num_iters == 0 || masks) && (!finish || xs_out), RLSB_ERR_INVALID,
-               "ls_run_masks: null pointer");
+  RLSB_REQUIRE(vs && workspace && (num_iters == 0 || masks), RLSB_ERR_INVALID, "ls_run_masks: null pointer");
   const LsWorkspace w = carve(*g, num_envs, workspace);
   LsArgs a{};
   a.packed = w.packed, a.vs = vs, a.num_iters = num_iters, a.num_envs = num_envs;
@@ -1300,6 +1332,85 @@ int rlsb_ls_run_masks(const rlsb_graph_t* gh, int64_t num_envs, int64_t* vs, con
   const int dc = degree_class(*g);
   return dc == 0 ? launch_bits<6>(*g, a, masks, st) : dc == 1 ? launch_bits<8>(*g, a, masks, st)
                                                               : launch_bits<12>(*g, a, masks, st);
+}
+
+// Noisy iterations + single-flip pass with the generator running NEXT TO the tile kernel: the streaming mask
+// generator (noise_masks.cu) on the graph's side stream, the tile kernel on the caller's stream, coupled through
+// per-group counters in the workspace.  Both kernels fit on an SM together (96 + 64 registers per thread, the
+// generator's 5 KB of shared memory), the generator never waits for a tile CTA, so any interleaving the
+// hardware picks makes progress.  Same masks, same decisions, same results as rlsb_ls_noise_masks followed by
+// rlsb_ls_run_masks.
+int rlsb_ls_fused_search(const rlsb_graph_t* gh, int64_t num_envs, int64_t* vs, int32_t ws_mult, uint64_t seed,
+                         uint64_t offset, const uint64_t* rng_dev, int32_t rng_threads, int32_t rng_iters,
+                         int32_t num_iters, int32_t finish, uint8_t* xs_out, uint32_t* masks, void* workspace,
+                         void* stream) {
+  using namespace rlsb;
+  const GraphDev* g;
+  if (int rc = ls_check(gh, &g, "ls_fused_search", num_envs, ws_mult)) return rc;
+  RLSB_REQUIRE(num_iters >= 0 && num_iters <= kLsMaxFusedDraws, RLSB_ERR_INVALID,
+               "ls_fused_search: num_iters must be in [0, %d]", kLsMaxFusedDraws);
+  if (num_envs == 0 || g->n == 0) return RLSB_OK;
+  RLSB_REQUIRE(vs && workspace && (num_iters == 0 || masks), RLSB_ERR_INVALID, "ls_fused_search: null pointer");
+  auto st = static_cast<cudaStream_t>(stream);
+  const LsWorkspace w = carve(*g, num_envs, workspace);
+  LsArgs a{};
+  a.packed = w.packed, a.vs = vs, a.num_iters = num_iters, a.num_envs = num_envs;
+  a.finish = finish ? 1 : 0, a.xs_out = xs_out, a.unpack_vec4 = (xs_out && rows_vec4_ok(xs_out, g->n)) ? 1 : 0;
+  a.cut_warps = cut_warps_for(g->m, kLSWarps), a.sweep_warps = sweep_warps_for(*g, kLSWarps);
+  a.times = ls_debug_times();
+  const int dc = degree_class(*g);
+  const uint32_t* ctl = nullptr;
+  uint32_t units = 0;
+  GraphSide side{};
+  MaskPlan plan;
+  if (num_iters > 0) {
+    if (int rc = graph_side(gh, &side)) return rc;
+    if (int rc = mask_plan(*g, "ls_fused_search", num_envs, ws_mult, seed, offset, rng_dev, rng_threads, rng_iters,
+                           num_iters, masks, workspace, &plan))
+      return rc;
+    if (int rc = mask_prepare(plan, true, true, st)) return rc;
+    RLSB_CUDA_OK(cudaEventRecord(side.fork, st));
+    ctl = plan.ctl, units = (uint32_t)rng_threads / 256u;
+  }
+  // the tile kernel first: its CTAs take their SMs, the generator blocks fill in beside them
+  constexpr size_t kFusedSmem = 212 * 1024;
+  if (int rc = dc == 0 ? launch_bits<6>(*g, a, masks, st, ctl, units, kFusedSmem)
+               : dc == 1 ? launch_bits<8>(*g, a, masks, st, ctl, units, kFusedSmem)
+                         : launch_bits<12>(*g, a, masks, st, ctl, units, kFusedSmem))
+    return rc;
+  if (num_iters > 0) {
+    RLSB_CUDA_OK(cudaStreamWaitEvent(side.stream, side.fork, 0));
+    if (int rc = mask_stream_launch(plan, side.stream)) return rc;
+    RLSB_CUDA_OK(cudaEventRecord(side.join, side.stream));
+    RLSB_CUDA_OK(cudaStreamWaitEvent(st, side.join, 0));
+  }
+  return RLSB_OK;
+}
+
+// rlsb_ls_begin with the state given as packed tiles (uint32 [ceil(E/32)][Np], bit b of word [t][i] = node i of
+// env 32t + b): the layout a host that keeps its spins packed hands over (1 bit instead of 1 byte per spin on
+// the wire).  packed_in may be the workspace's own packed section (rlsb_ls_workspace_offset(.., 0)): no copy.
+int rlsb_ls_begin_packed(const rlsb_graph_t* gh, const uint32_t* packed_in, int64_t num_envs, int64_t* vs,
+                         int32_t compute_vs, int32_t ws_mult, float noise_std, void* workspace, void* stream) {
+  using namespace rlsb;
+  const GraphDev* g;
+  if (int rc = ls_check(gh, &g, "ls_begin_packed", num_envs, ws_mult)) return rc;
+  if (num_envs == 0 || g->n == 0) return RLSB_OK;
+  RLSB_REQUIRE(packed_in && workspace && (vs || !compute_vs), RLSB_ERR_INVALID, "ls_begin_packed: null pointer");
+  RLSB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, RLSB_ERR_INVALID,
+               "ls_begin_packed: workspace must be 256-byte aligned");
+  auto st = static_cast<cudaStream_t>(stream);
+  const LsWorkspace w = carve(*g, num_envs, workspace);
+  const int64_t tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;
+  if (packed_in != w.packed)
+    RLSB_CUDA_OK(cudaMemcpyAsync(w.packed, packed_in, (size_t)tiles * g->np * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  if (int rc = prepare_tiles(*g, nullptr, w.packed, num_envs, nullptr, w.cross, degree_class(*g) != 2 ? 1 : 2,
+                             w.cross_rows, w.col_min, w.col_max, compute_vs ? vs : nullptr, st))
+    return rc;
+  ls_rdstd_kernel<<<(g->np + 255) / 256, 256, 0, st>>>(*g, w.col_min, w.col_max, ws_mult, noise_std, w.rd_std, w.degm,
+                                                       w.nd);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
 }
 
 int rlsb_ls_debug_times(int64_t* out64) {

@@ -3,6 +3,7 @@
 // floating-point expression of the path, spin_rand (env_L2A.py:94-95, LocalSearch.py:66-67).
 #pragma once
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace rlsb {
 
@@ -29,6 +30,11 @@ inline int degree_class(const GraphDev& g) {
 // on each of the 148 SMs (ATen calc_execution_policy on a B200).
 inline int64_t ls_bound_bytes(int64_t numel) { return (numel + 4 * (int64_t)kNumSMs * 2048) / 2 + 256; }
 
+// Streaming mask generator <-> tile kernel hand-shake (rlsb_ls_fused_search): per group of draws two counters,
+// ctl[2g] = units handed out, ctl[2g + 1] = units finished.
+constexpr int kLsMaxFusedDraws = 1024;
+constexpr size_t kLsCtlBytes = (size_t)(kLsMaxFusedDraws + 2) * 2 * sizeof(uint32_t);
+
 // workspace carving (all sections 256-byte aligned)
 struct LsWorkspace {
   uint32_t* packed;
@@ -38,6 +44,7 @@ struct LsWorkspace {
   uint32_t* nd;
   uint8_t* cross_rows;   // [E][Np] uint8 row-major copy of the cross counts (mask generator); null for uint16 counts
   uint8_t* bound;        // early-out bytes of the mask generator (noise_masks.cu: two planes of one byte per thread-round)
+  uint32_t* ctl;         // unit counters of the streaming generator (kLsCtlBytes)
   size_t bytes;
 };
 
@@ -59,6 +66,7 @@ inline LsWorkspace carve(const GraphDev& g, int64_t num_envs, void* base) {
   w.rd_std = reinterpret_cast<float*>(take((size_t)g.np * 4));
   w.thresh = reinterpret_cast<float*>(take((size_t)num_envs * 4));
   w.nd = reinterpret_cast<uint32_t*>(take((size_t)g.np * 8));
+  w.ctl = reinterpret_cast<uint32_t*>(take(kLsCtlBytes));
   w.cross_rows = nullptr;
   w.bound = nullptr;
   if (cross_elt == 1) {
@@ -74,5 +82,39 @@ inline LsWorkspace carve(const GraphDev& g, int64_t num_envs, void* base) {
 inline int64_t ls_mask_words(int64_t num_envs, int n) {
   return (((num_envs * n + 31) / 32 + 2) + 3) / 4 * 4;
 }
+
+// ---- mask generator (noise_masks.cu), shared with the fused search entry point (local_search.cu)
+struct MaskArgs {
+  const uint8_t* cross_rows;   // [E][Np] cross counts, row-major (ls_begin)
+  const float* rd_std;         // [Np]
+  const int32_t* degm;         // [Np] listed degree + kMagicI
+  const float* thresh;         // [E]
+  uint32_t* masks;             // [draws][mask_words]
+  int64_t mask_words;
+  uint32_t numel, n, np;
+  uint32_t step_e, step_n;     // T / N, T % N
+  uint32_t div_m, div_s;       // floor(l / N) = (l * div_m) >> (31 + div_s) for every l < 2^31
+  int negmult;
+};
+struct MaskPlan {
+  MaskArgs a;
+  TorchRng r;
+  uint8_t* bound;
+  uint32_t* ctl;
+  int num_draws;
+};
+int mask_plan(const GraphDev& g, const char* what, int64_t num_envs, int ws_mult, uint64_t seed, uint64_t offset,
+              const uint64_t* rng_dev, int rng_threads, int rng_iters, int num_draws, uint32_t* masks, void* workspace,
+              MaskPlan* plan);
+int mask_prepare(const MaskPlan& p, bool write_bound, bool zero_ctl, cudaStream_t st);
+int mask_stream_launch(const MaskPlan& p, cudaStream_t st);
+constexpr int kGenGroup = 2;   // draws the streaming generator finishes together (= what a tile iteration waits for)
+
+// side stream + fork / join events of a graph handle (graph_store.cu): the generator runs there
+struct GraphSide {
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+};
+int graph_side(const rlsb_graph_t* g, GraphSide* out);
 
 }  // namespace rlsb

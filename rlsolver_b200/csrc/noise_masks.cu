@@ -33,18 +33,6 @@
 
 namespace rlsb {
 
-struct MaskArgs {
-  const uint8_t* cross_rows;   // [E][Np] cross counts, row-major (ls_begin)
-  const float* rd_std;         // [Np]
-  const int32_t* degm;         // [Np] listed degree + kMagicI
-  const float* thresh;         // [E]
-  uint32_t* masks;             // [draws][mask_words]
-  int64_t mask_words;
-  uint32_t numel, n, np;
-  uint32_t step_e, step_n;     // T / N, T % N
-  uint32_t div_m, div_s;       // floor(l / N) = (l * div_m) >> (31 + div_s) for every l < 2^31
-  int negmult;
-};
 
 // exact floor(l / n) for l < 2^31 (Granlund-Montgomery, 31-bit dividends: the magic number fits 32 bits)
 __device__ __forceinline__ uint32_t div_n(const MaskArgs& a, uint32_t l) {
@@ -208,6 +196,96 @@ __global__ void __launch_bounds__(256) noise_mask_fast_kernel(MaskArgs a, const 
   if (lane < cnt) exact(q[lane]);
 }
 
+// ---- streaming generator: the form that runs NEXT TO the tile kernel (rlsb_ls_fused_search).
+//
+// The masks do not depend on what the tile kernel accepts, so the generator can run a group of draws ahead of
+// the tile CTAs on the same SMs.  One persistent block of 8 warps per SM (64 registers: it fits beside a tile CTA of
+// 512 threads x 96 registers and its 170 KB of shared memory).  Work is handed out dynamically: the draws are
+// processed in GROUPS of kGenGroup consecutive draws; a unit is one 256-thread slice of torch's call geometry
+// for every round j and every draw of the group; `ctl[2g]` hands out the units of group g, `ctl[2g + 1]` counts
+// the finished ones.  A tile CTA starts iteration it only when ctl[2 (it / kGenGroup) + 1] == units (release /
+// acquire through a gpu-scope fence around the counter).  No block ever waits for another block, so the kernel
+// makes progress whatever part of the grid is resident.
+//
+// Inside a unit a thread handles the kGenGroup draws of round j together: the two early-out bytes are loaded
+// once per round, the Philox blocks of the draws are independent instruction streams (the latency of one
+// hides behind the other: two warps per scheduler are enough), and passing pairs go to the warp's queue
+// exactly as in noise_mask_fast_kernel.
+constexpr int kGenQueue = 32 + 64 * kGenGroup;
+
+__global__ void __maxnreg__(64) noise_mask_stream_kernel(MaskArgs a, const uint8_t* __restrict__ planes, TorchRng r,
+                                                         uint32_t* __restrict__ ctl, int num_draws, uint32_t units) {
+  __shared__ uint32_t queue[8][kGenQueue];
+  __shared__ uint32_t sUnit;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  const PhiloxKey key = philox_key(r);
+  const PhiloxKeys pkey = philox_keys(key.seed);
+  const uint32_t T = r.threads, iters = r.iters_per_call;
+  const uint64_t plane = (uint64_t)iters * T;
+  uint32_t* q = queue[warp];
+  const int groups = (num_draws + kGenGroup - 1) / kGenGroup;
+  for (int g = 0; g < groups; ++g) {
+    const int k0 = g * kGenGroup;
+    const int nd = min(kGenGroup, num_draws - k0);
+    for (;;) {
+      if (threadIdx.x == 0) sUnit = atomicAdd(ctl + 2 * g, 1u);
+      __syncthreads();
+      const uint32_t unit = sUnit;
+      __syncthreads();                                // everybody has read it before thread 0 claims the next one
+      if (unit >= units) break;                       // uniform: every thread read the same value
+      const uint32_t idx = unit * 256 + threadIdx.x;
+      const uint8_t* bp = planes + idx;
+      int cnt = 0;
+
+      auto exact = [&](uint32_t ent) {                // one queued pair: bit 0 = second pair, bit 1 = draw in the group
+        const uint32_t jj = ent >> 8, src = idx - lane + ((ent >> 2) & 31u), d = (ent >> 1) & 1u;
+        const uint64_t ctr = key.offset4 + (uint64_t)(k0 + d) * iters + jj;
+        const uint4 o = philox10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), src, 0u), pkey);
+        const bool second = (ent & 1u) != 0u;
+        mask_exact_pair(a, a.masks + (int64_t)(k0 + d) * a.mask_words, second ? o.z : o.x, second ? o.w : o.y,
+                        src + T * (4u * jj + (second ? 2u : 0u)), T);
+      };
+
+      uint32_t ca = __ldg(bp), cb = __ldg(bp + plane);
+      for (uint32_t j = 0; j < iters; ++j) {
+        bp += T;
+        uint32_t can = 0, cbn = 0;
+        if (j + 1 < iters) can = __ldg(bp), cbn = __ldg(bp + plane);
+        uint4 o[kGenGroup];
+#pragma unroll
+        for (int d = 0; d < kGenGroup; ++d) {
+          const uint64_t ctr = key.offset4 + (uint64_t)(k0 + d) * iters + j;
+          o[d] = philox10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), idx, 0u), pkey);
+        }
+#pragma unroll
+        for (int d = 0; d < kGenGroup; ++d) {
+          const bool pa = d < nd && (o[d].x >> 24) <= ca, pb = d < nd && (o[d].z >> 24) <= cb;
+          const uint32_t ba = __ballot_sync(kFull, pa), bb = __ballot_sync(kFull, pb);
+          const uint32_t ent = (j << 8) | ((uint32_t)lane << 2) | ((uint32_t)d << 1);
+          if (pa) q[cnt + __popc(ba & lt)] = ent;
+          if (pb) q[cnt + __popc(ba) + __popc(bb & lt)] = ent | 1u;
+          cnt += __popc(ba) + __popc(bb);
+        }
+        __syncwarp();
+        while (cnt >= 32) {
+          cnt -= 32;
+          const uint32_t mine = q[cnt + lane];
+          __syncwarp();
+          exact(mine);
+        }
+        ca = can, cb = cbn;
+      }
+      if (lane < cnt) exact(q[lane]);
+      __syncthreads();                                // every flip bit of the unit has been issued
+      if (threadIdx.x == 0) {
+        __threadfence();                              // ... and is visible device-wide before the count moves
+        atomicAdd(ctl + 2 * g + 1, 1u);
+      }
+    }
+  }
+}
+
 // the same draws as explicit float32 tensors (tests: must equal torch.randn bit for bit)
 __global__ void __launch_bounds__(256) noise_values_kernel(float* __restrict__ out, uint32_t numel, TorchRng r) {
   const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
@@ -242,6 +320,58 @@ static int rng_check(const char* what, int64_t numel, uint64_t offset, int32_t r
   return RLSB_OK;
 }
 
+// ---- host pieces shared by rlsb_ls_noise_masks and rlsb_ls_fused_search (local_search.cu)
+int mask_plan(const GraphDev& g, const char* what, int64_t num_envs, int ws_mult, uint64_t seed, uint64_t offset,
+              const uint64_t* rng_dev, int rng_threads, int rng_iters, int num_draws, uint32_t* masks, void* workspace,
+              MaskPlan* plan) {
+  RLSB_REQUIRE(num_envs > 0, RLSB_ERR_INVALID, "%s: num_envs must be positive", what);
+  RLSB_REQUIRE(ws_mult == 1 || ws_mult == 2, RLSB_ERR_INVALID, "%s: ws_mult must be 1 or 2", what);
+  RLSB_REQUIRE(degree_class(g) != 2, RLSB_ERR_UNSUPPORTED,
+               "%s: degrees above 255 keep uint16 counts (use rlsb_ls_run with noise tensors)", what);
+  const int64_t numel = num_envs * (int64_t)g.n;
+  if (int rc = rng_check(what, numel, offset, rng_threads, rng_iters, num_draws)) return rc;
+  RLSB_REQUIRE(masks && workspace, RLSB_ERR_INVALID, "%s: null pointer", what);
+  const LsWorkspace w = carve(g, num_envs, workspace);
+  RLSB_REQUIRE(w.bound != nullptr, RLSB_ERR_INVALID, "%s: workspace without the bound section", what);
+  RLSB_REQUIRE((int64_t)rng_threads * rng_iters * 2 <= ls_bound_bytes(numel), RLSB_ERR_INVALID,
+               "%s: call geometry (threads %d, iters %d) larger than a B200's", what, rng_threads, rng_iters);
+  MaskArgs& a = plan->a;
+  a.cross_rows = w.cross_rows, a.rd_std = w.rd_std, a.degm = w.degm, a.thresh = w.thresh;
+  a.masks = masks, a.mask_words = ls_mask_words(num_envs, g.n);
+  a.numel = (uint32_t)numel, a.n = (uint32_t)g.n, a.np = (uint32_t)g.np;
+  a.step_e = (uint32_t)rng_threads / a.n, a.step_n = (uint32_t)rng_threads % a.n;
+  a.negmult = -ws_mult;
+  a.div_s = 0;
+  while ((1u << a.div_s) < a.n) ++a.div_s;
+  a.div_m = (uint32_t)(((uint64_t(1) << (31 + a.div_s)) + a.n - 1) / a.n);
+  plan->r = TorchRng{seed, offset / 4, (uint32_t)rng_threads, (uint32_t)rng_iters, rng_dev};
+  plan->bound = w.bound, plan->ctl = w.ctl, plan->num_draws = num_draws;
+  return RLSB_OK;
+}
+
+// early-out bytes (unless still valid) + zeroed mask arrays (+ zeroed unit counters of the streaming form)
+int mask_prepare(const MaskPlan& p, bool write_bound, bool zero_ctl, cudaStream_t st) {
+  const uint32_t T = p.r.threads, iters = p.r.iters_per_call;
+  if (write_bound) {
+    if (p.a.n % 4 == 0)
+      mask_bound_kernel<true><<<dim3((T + 1023) / 1024, iters, 2), 256, 0, st>>>(p.a, p.bound, T, iters);
+    else
+      mask_bound_kernel<false><<<dim3(T / 256, iters, 2), 256, 0, st>>>(p.a, p.bound, T, iters);
+    RLSB_LAUNCH_OK();
+  }
+  RLSB_CUDA_OK(cudaMemsetAsync(p.a.masks, 0, (size_t)p.num_draws * p.a.mask_words * sizeof(uint32_t), st));
+  if (zero_ctl) RLSB_CUDA_OK(cudaMemsetAsync(p.ctl, 0, kLsCtlBytes, st));
+  return RLSB_OK;
+}
+
+// the streaming generator: one persistent block per SM on `st` (the tile kernel polls ctl)
+int mask_stream_launch(const MaskPlan& p, cudaStream_t st) {
+  RLSB_REQUIRE(p.num_draws <= kLsMaxFusedDraws, RLSB_ERR_INVALID, "fused search: at most %d draws per call", kLsMaxFusedDraws);
+  noise_mask_stream_kernel<<<kNumSMs, 256, 0, st>>>(p.a, p.bound, p.r, p.ctl, p.num_draws, p.r.threads / 256);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
 }  // namespace rlsb
 
 extern "C" {
@@ -260,53 +390,26 @@ int rlsb_ls_noise_masks(const rlsb_graph_t* gh, int64_t num_envs, int32_t ws_mul
   using namespace rlsb;
   const GraphDev* g;
   if (int rc = graph_check(gh, &g, "ls_noise_masks")) return rc;
-  RLSB_REQUIRE(num_envs >= 0, RLSB_ERR_INVALID, "ls_noise_masks: negative num_envs");
-  RLSB_REQUIRE(ws_mult == 1 || ws_mult == 2, RLSB_ERR_INVALID, "ls_noise_masks: ws_mult must be 1 or 2");
   if (num_envs == 0 || g->n == 0 || num_draws == 0) return RLSB_OK;
-  RLSB_REQUIRE(degree_class(*g) != 2, RLSB_ERR_UNSUPPORTED,
-               "ls_noise_masks: degrees above 255 keep uint16 counts (use rlsb_ls_run with noise tensors)");
-  const int64_t numel = num_envs * (int64_t)g->n;
-  if (int rc = rng_check("ls_noise_masks", numel, offset, rng_threads, rng_iters, num_draws)) return rc;
-  RLSB_REQUIRE(masks && workspace, RLSB_ERR_INVALID, "ls_noise_masks: null pointer");
-  const LsWorkspace w = carve(*g, num_envs, workspace);
-  MaskArgs a;
-  a.cross_rows = w.cross_rows, a.rd_std = w.rd_std, a.degm = w.degm, a.thresh = w.thresh;
-  a.masks = masks, a.mask_words = ls_mask_words(num_envs, g->n);
-  a.numel = (uint32_t)numel, a.n = (uint32_t)g->n, a.np = (uint32_t)g->np;
-  a.step_e = (uint32_t)rng_threads / a.n, a.step_n = (uint32_t)rng_threads % a.n;
-  a.negmult = -ws_mult;
-  a.div_s = 0;
-  while ((1u << a.div_s) < a.n) ++a.div_s;
-  a.div_m = (uint32_t)(((uint64_t(1) << (31 + a.div_s)) + a.n - 1) / a.n);
-  TorchRng r{seed, offset / 4, (uint32_t)rng_threads, (uint32_t)rng_iters, rng_dev};
-  dim3 grid((unsigned)(rng_threads / 256), (unsigned)rng_iters, 1);
+  MaskPlan plan;
+  if (int rc = mask_plan(*g, "ls_noise_masks", num_envs, ws_mult, seed, offset, rng_dev, rng_threads, rng_iters, num_draws,
+                         masks, workspace, &plan))
+    return rc;
   auto st = static_cast<cudaStream_t>(stream);
-  // RLSB_DEBUG_PLAIN_MASKS: evaluate every normal (cross-check of the early-out form)
-  if (debug_flags() & RLSB_DEBUG_PLAIN_MASKS) {
-    grid.z = (unsigned)num_draws;
-    noise_mask_kernel<<<grid, 256, 0, st>>>(a, r);
+  if (debug_flags() & RLSB_DEBUG_PLAIN_MASKS) {   // evaluate every normal (cross-check of the early-out form)
+    const dim3 grid((unsigned)(rng_threads / 256), (unsigned)rng_iters, (unsigned)num_draws);
+    noise_mask_kernel<<<grid, 256, 0, st>>>(plan.a, plan.r);
     RLSB_LAUNCH_OK();
     return RLSB_OK;
   }
-  RLSB_REQUIRE(w.bound != nullptr, RLSB_ERR_INVALID, "ls_noise_masks: workspace without the bound section");
-  RLSB_REQUIRE((int64_t)rng_threads * rng_iters * 2 <= ls_bound_bytes(numel), RLSB_ERR_INVALID,
-               "ls_noise_masks: call geometry (threads %d, iters %d) larger than a B200's", rng_threads, rng_iters);
-  if (!reuse_bound) {
-    if (g->n % 4 == 0)
-      mask_bound_kernel<true><<<dim3((unsigned)((rng_threads + 1023) / 1024), (unsigned)rng_iters, 2), 256, 0, st>>>(
-          a, w.bound, (uint32_t)rng_threads, (uint32_t)rng_iters);
-    else
-      mask_bound_kernel<false><<<dim3((unsigned)(rng_threads / 256), (unsigned)rng_iters, 2), 256, 0, st>>>(
-          a, w.bound, (uint32_t)rng_threads, (uint32_t)rng_iters);
-    RLSB_LAUNCH_OK();
-  }
-  RLSB_CUDA_OK(cudaMemsetAsync(masks, 0, (size_t)num_draws * a.mask_words * sizeof(uint32_t), st));
+  if (int rc = mask_prepare(plan, !reuse_bound, false, st)) return rc;
   // rounds are split over blockIdx.y only when there would be too few blocks to fill the GPU otherwise
+  dim3 grid((unsigned)(rng_threads / 256), 1, (unsigned)num_draws);
   int jsplit = 1;
   while ((int64_t)grid.x * jsplit * num_draws < 4 * 8 * kNumSMs && jsplit < rng_iters) jsplit *= 2;
   if (jsplit > rng_iters) jsplit = rng_iters;
-  grid.y = (unsigned)jsplit, grid.z = (unsigned)num_draws;
-  noise_mask_fast_kernel<<<grid, 256, 0, st>>>(a, w.bound, r);
+  grid.y = (unsigned)jsplit;
+  noise_mask_fast_kernel<<<grid, 256, 0, st>>>(plan.a, plan.bound, plan.r);
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }

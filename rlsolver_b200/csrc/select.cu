@@ -101,10 +101,38 @@ __global__ void __launch_bounds__(1024) best_record_kernel(const int64_t* __rest
   for (int i = threadIdx.x; i < n; i += blockDim.x) record[8 + i] = row[i];
 }
 
+// the same record from packed tiles (uint32 [ceil(E/32)][Np], bit b of word [t][i] = node i of env 32t + b):
+// the row is expanded to the record's one-byte-per-node form, so best_pick_kernel serves both layouts
+__global__ void __launch_bounds__(1024) best_record_packed_kernel(const int64_t* __restrict__ vs,
+                                                                  const uint32_t* __restrict__ packed, int64_t num_envs,
+                                                                  int n, int np, int64_t env_offset,
+                                                                  uint8_t* __restrict__ record) {
+  __shared__ unsigned long long sBest[32];
+  unsigned long long best = 0;
+  for (int64_t e = threadIdx.x; e < num_envs; e += blockDim.x) {
+    const unsigned long long key = best_key(vs[e], (unsigned long long)(env_offset + e));
+    best = key > best ? key : best;
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(kFull, best, off);
+    best = o > best ? o : best;
+  }
+  if ((threadIdx.x & 31) == 0) sBest[threadIdx.x >> 5] = best;
+  __syncthreads();
+  best = sBest[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = sBest[w] > best ? sBest[w] : best;
+  const int64_t local = (int64_t)(0xFFFFFFFFull - (best & 0xFFFFFFFFull)) - env_offset;
+  if (threadIdx.x == 0) *reinterpret_cast<unsigned long long*>(record) = best;
+  const uint32_t* tile = packed + (local >> 5) * (int64_t)np;
+  const int bit = (int)(local & 31);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) record[8 + i] = (uint8_t)((tile[i] >> bit) & 1u);
+}
+
 // winner of the gathered records: out[0] = cut, out[1] = global env id, row = its spins
 __global__ void __launch_bounds__(256) best_pick_kernel(const uint8_t* __restrict__ gathered, int world, int n,
-                                                        int64_t* __restrict__ out, uint8_t* __restrict__ row) {
-  const int64_t stride = 8 + (int64_t)n;
+                                                        int64_t stride, int64_t* __restrict__ out,
+                                                        uint8_t* __restrict__ row) {
   unsigned long long best = 0;
   int win = 0;
   for (int r = 0; r < world; ++r) {
@@ -127,7 +155,19 @@ int rlsb_best_pick(const uint8_t* gathered, int32_t world, int32_t num_nodes, in
   using namespace rlsb;
   RLSB_REQUIRE(world > 0 && num_nodes >= 0, RLSB_ERR_INVALID, "best_pick: bad shape");
   RLSB_REQUIRE(gathered && out2 && row, RLSB_ERR_INVALID, "best_pick: null pointer");
-  best_pick_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(gathered, world, num_nodes, out2, row);
+  best_pick_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(gathered, world, num_nodes, 8 + (int64_t)num_nodes,
+                                                                     out2, row);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+int rlsb_best_pick_strided(const uint8_t* gathered, int32_t world, int32_t num_nodes, int64_t stride, int64_t* out2,
+                           uint8_t* row, void* stream) {
+  using namespace rlsb;
+  RLSB_REQUIRE(world > 0 && num_nodes >= 0 && stride >= 8 + (int64_t)num_nodes, RLSB_ERR_INVALID,
+               "best_pick_strided: bad shape");
+  RLSB_REQUIRE(gathered && out2 && row, RLSB_ERR_INVALID, "best_pick_strided: null pointer");
+  best_pick_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(gathered, world, num_nodes, stride, out2, row);
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }
@@ -140,6 +180,21 @@ int rlsb_best_record(const int64_t* vs, const uint8_t* xs, int64_t num_envs, int
   RLSB_REQUIRE(vs && xs && record, RLSB_ERR_INVALID, "best_record: null pointer");
   RLSB_REQUIRE((reinterpret_cast<uintptr_t>(record) & 7u) == 0, RLSB_ERR_INVALID, "best_record: record must be 8-byte aligned");
   best_record_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(vs, xs, num_envs, num_nodes, env_offset, record);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+int rlsb_best_record_packed(const int64_t* vs, const uint32_t* packed, int64_t num_envs, int32_t num_nodes,
+                            int32_t padded_nodes, int64_t env_offset, uint8_t* record, void* stream) {
+  using namespace rlsb;
+  RLSB_REQUIRE(num_envs > 0 && num_nodes >= 0 && padded_nodes >= num_nodes && env_offset >= 0 &&
+                   env_offset + num_envs <= 0xFFFFFFFFll,
+               RLSB_ERR_INVALID, "best_record_packed: bad shape (global env ids must fit 32 bits, at least one env)");
+  RLSB_REQUIRE(vs && packed && record, RLSB_ERR_INVALID, "best_record_packed: null pointer");
+  RLSB_REQUIRE((reinterpret_cast<uintptr_t>(record) & 7u) == 0, RLSB_ERR_INVALID,
+               "best_record_packed: record must be 8-byte aligned");
+  best_record_packed_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(vs, packed, num_envs, num_nodes,
+                                                                               padded_nodes, env_offset, record);
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }

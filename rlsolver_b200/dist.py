@@ -83,3 +83,55 @@ def best_allreduce(vs: TEN, xs: TEN, rank: int, world: int, envs_per_rank: int, 
     win = all_keys.argmax()
     key = all_keys[win]
     return key >> 32, _LOW - (key & _LOW), gathered[win, 8:].view(th.bool)
+
+
+
+class BestExchange:
+    """The exchange with every buffer allocated once, so that record kernel -> ncclAllGather -> pick kernel is a
+    fixed launch sequence: it can be captured into the CUDA graph of the step (NCCL collectives are capturable)
+    and replays with no host work at all.  `ex(vs, xs)` takes bool rows [E, N]; `ex.packed(vs, packed, store)`
+    takes packed tiles.  Returns (best_cut int64 [], global_env_id int64 [], best_x bool [N]) -- views of
+    buffers owned by this object, overwritten by the next call."""
+
+    def __init__(self, num_nodes: int, rank: int, world: int, envs_per_rank: int, device, group=None):
+        self.n, self.rank, self.world, self.envs, self.group = int(num_nodes), rank, world, envs_per_rank, group
+        self.device = th.device(device)
+        stride = (8 + self.n + 7) // 8 * 8                 # records stay 8-byte aligned inside the gathered buffer
+        self.stride = stride
+        self.record = th.zeros((stride,), dtype=th.uint8, device=self.device)
+        self.gathered = th.zeros((world, stride), dtype=th.uint8, device=self.device)
+        self.out2 = th.zeros((2,), dtype=th.int64, device=self.device)
+        self.row = th.zeros((self.n,), dtype=th.bool, device=self.device)
+
+    def _finish(self):
+        from . import _lib
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.record.unsqueeze(0), group=self.group)
+            src = self.gathered
+        else:
+            src = self.record.unsqueeze(0)
+        with on_device(self.device):
+            _lib.check(_lib.lib().rlsb_best_pick_strided(src.data_ptr(), src.shape[0], self.n, self.stride,
+                                                         self.out2.data_ptr(), self.row.data_ptr(),
+                                                         th.cuda.current_stream(self.device).cuda_stream), "best_pick")
+        return self.out2[0], self.out2[1], self.row
+
+    def __call__(self, vs: TEN, xs: TEN):
+        from . import _lib
+        assert vs.dtype == th.int64 and xs.dtype == th.bool and vs.is_contiguous() and xs.is_contiguous()
+        with on_device(self.device):
+            _lib.check(_lib.lib().rlsb_best_record(vs.data_ptr(), xs.data_ptr(), vs.shape[0], self.n,
+                                                   self.rank * self.envs, self.record.data_ptr(),
+                                                   th.cuda.current_stream(self.device).cuda_stream), "best_record")
+        return self._finish()
+
+    def packed(self, vs: TEN, packed: TEN, store):
+        from . import _lib
+        assert vs.dtype == th.int64 and packed.dtype == th.int32 and packed.is_contiguous()
+        with on_device(self.device):
+            _lib.check(_lib.lib().rlsb_best_record_packed(vs.data_ptr(), packed.data_ptr(), vs.shape[0], self.n,
+                                                          store.padded_nodes, self.rank * self.envs,
+                                                          self.record.data_ptr(),
+                                                          th.cuda.current_stream(self.device).cuda_stream),
+                       "best_record_packed")
+        return self._finish()

@@ -130,4 +130,23 @@ class EnvMaxcut:
         return good_xs, good_vs
 
 
+    def local_search_packed(self, packed: TEN, num_iters: int = 8, num_spin: int = 8, noise_std: float = 0.3,
+                            num_sims: Optional[int] = None, good_vs: Optional[TEN] = None):
+        """`local_search_inplace` for a batch kept as packed tiles: `packed` int32 [ceil(E/32), Np] with bit b of
+        word [t][i] = node i of env 32t + b (`store.pack(xs)` / `rlsb_pack_spins` produce it, `store.unpack`
+        reads it).  Same algorithm, same RNG use; nothing is expanded to one byte per spin on the way in or out,
+        so a host that ships spins across PCIe moves N/8 bytes per env.  Returns `(packed_out, vs)`; `packed_out`
+        is a view of the simulator's workspace, valid until its next local-search call."""
+        st = self.store
+        num_sims = packed.shape[0] * 32 if num_sims is None else int(num_sims)
+        if not (self.fused_rng and num_sims > 0 and st.ls_mask_words(num_sims) >= 0):
+            raise NotImplementedError("local_search_packed needs the fused generator path (degrees <= 255, "
+                                      "fewer than 2^31 elements per draw)")
+        ws = st.ls_workspace(num_sims)
+        vs = st.ls_begin_packed(packed, num_sims, None if good_vs is None else good_vs.long().contiguous(), 1,
+                                noise_std, ws)
+        st.ls_fused(vs, 1, num_spin, num_iters, False, None, ws)
+        return st.ls_section(ws, num_sims, "packed").view(st.tiles(num_sims), st.padded_nodes), vs
+
+
 __all__ = ["EnvMaxcut", "update_xs_by_vs"]

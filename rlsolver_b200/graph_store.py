@@ -383,14 +383,56 @@ class GraphStore:
                                                    int(finish), _ptr(xs_out), _ptr(workspace),
                                                    _stream_ptr(self.device)), "ls_run_masks")
 
+    # overlap=True: the mask generator runs next to the tile kernel (rlsb_ls_fused_search); False: one after the
+    # other (rlsb_ls_noise_masks, then rlsb_ls_run_masks) -- same results, kept as the cross-check
+    overlap_generator = True
+
+    def _mask_scratch(self, num_draws: int, words: int) -> TEN:
+        m = getattr(self, "_masks", None)
+        if m is None or m.shape[0] < num_draws or m.shape[1] != words:
+            m = self._masks = th.empty((max(num_draws, 1), words), dtype=th.int32, device=self.device)
+        return m
+
+    def ls_fused_search(self, vs: TEN, ws_mult: int, num_iters: int, seed: int, offset: int, threads: int, iters: int,
+                        finish: bool, xs_out: Optional[TEN], workspace: TEN, cursor: Optional[TEN] = None) -> None:
+        """Noisy iterations (draws recomputed from (seed, offset) or the device cursor) + single-flip pass, the
+        generator streaming next to the tile kernel."""
+        e = vs.shape[0]
+        words = self.ls_mask_words(e)
+        if words < 0:
+            _lib.check(3, "ls_mask_words")
+        masks = self._mask_scratch(num_iters, words)
+        with self._op("ls_fused_search", 4):
+            _lib.check(self._lib.rlsb_ls_fused_search(self._h, e, _ptr(vs), int(ws_mult), int(seed), int(offset),
+                                                      _ptr(cursor), int(threads), int(iters), int(num_iters),
+                                                      int(finish), _ptr(xs_out), _ptr(masks), _ptr(workspace),
+                                                      _stream_ptr(self.device)), "ls_fused_search")
+
+    def ls_begin_packed(self, packed: TEN, num_envs: int, vs: Optional[TEN], ws_mult: int, noise_std: float,
+                        workspace: TEN) -> TEN:
+        """ls_begin for a state given as packed tiles (uint32 [ceil(E/32), Np]).  Returns vs (int64 [E])."""
+        if packed.dtype != th.int32 or tuple(packed.shape) != (self.tiles(num_envs), self.padded_nodes) \
+                or not packed.is_contiguous() or packed.device != self.device:
+            raise TypeError(f"packed must be a contiguous int32 [{self.tiles(num_envs)}, {self.padded_nodes}] tensor "
+                            f"on {self.device}")
+        compute = vs is None
+        if compute:
+            vs = th.empty((num_envs,), dtype=th.int64, device=self.device)
+        with self._op("ls_begin", 3):
+            _lib.check(self._lib.rlsb_ls_begin_packed(self._h, _ptr(packed), num_envs, _ptr(vs), int(compute),
+                                                      int(ws_mult), float(noise_std), _ptr(workspace),
+                                                      _stream_ptr(self.device)), "ls_begin_packed")
+        return vs
+
     def ls_fused(self, vs: TEN, ws_mult: int, num_spin: int, num_iters: int, first_draw_is_iter: bool,
-                 xs_out: TEN, workspace: TEN) -> None:
+                 xs_out: Optional[TEN], workspace: TEN) -> None:
         """Threshold + noisy iterations + single-flip pass with the generator consumed in place.
         RNG use == the reference's: one randn [E, N] for the threshold -- which is also the first
         iteration's noise when `first_draw_is_iter` (LocalSearch.py:66-68) -- then one per iteration.
         Eager: torch draws the threshold noise, the rest is recomputed from (seed, offset) and torch's
         generator is advanced past it.  While a CUDA graph is captured every draw comes from the device
-        cursor (rng_cursor_sync before, rng_cursor_commit after the replays)."""
+        cursor (rng_cursor_sync before, rng_cursor_commit after the replays).  xs_out None: the result
+        stays in the workspace's packed tiles."""
         e, n = vs.shape[0], self.num_nodes
         numel = e * n
         threads, iters = rng.torch_call_geometry(self.device, numel)
@@ -408,9 +450,22 @@ class GraphStore:
             seed, base, _, _ = rng.peek(self.device, numel)
             noise0 = th.randn((e, n), dtype=th.float32, device=self.device)
         self.ls_run(vs, ws_mult, noise0, num_spin, [], False, None, workspace)
-        masks = self.ls_noise_masks(e, ws_mult, num_iters, seed, base + 4 * iters * first, threads, iters, workspace,
-                                    cursor=cur)
-        self.ls_run_masks(vs, masks, num_iters, True, xs_out, workspace)
+        done = 0
+        chunk = 1024 if self.overlap_generator else 16384           # kLsMaxFusedDraws per fused launch
+        while True:
+            now = min(chunk, num_iters - done)
+            last = done + now == num_iters
+            off = base + 4 * iters * (first + done)
+            if self.overlap_generator:
+                self.ls_fused_search(vs, ws_mult, now, seed, off, threads, iters, last, xs_out if last else None,
+                                     workspace, cursor=cur)
+            else:
+                masks = self.ls_noise_masks(e, ws_mult, now, seed, off, threads, iters, workspace, cursor=cur,
+                                            out=self._mask_scratch(now, self.ls_mask_words(e)))
+                self.ls_run_masks(vs, masks, now, last, xs_out if last else None, workspace)
+            done += now
+            if last:
+                break
         if capturing:
             self.rng_cursor_advance(4 * iters * draws)
         else:

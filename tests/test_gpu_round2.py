@@ -1,0 +1,309 @@
+"""Round-2 parity tests of the CUDA path (through the C ABI / the reference-mirroring classes):
+
+* the generator streaming NEXT TO the tile kernel (rlsb_ls_fused_search) against the sequential form and the oracle;
+* the BASELINE config-3 shape at full size (G70-like, 16384 envs) against the NumPy oracle on sampled rows;
+* packed-tile entry points (rlsb_ls_begin_packed, packed best-cut record) against the bool-row ones;
+* the RNG first-use self-check;
+* a 2-rank NCCL run against the single-GPU run of each shard (needs 2 GPUs: `gpurun --gpus 2`).
+Integer / bool results must be bit-exact.  Needs a B200: run with `-m gpu`.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch as th
+
+from oracle import maxcut as om
+from synth import gset_like, random_graph
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _rand_xs(e, n, seed):
+    rng = np.random.default_rng(seed)
+    xs = rng.integers(0, 2, size=(e, n)).astype(bool)
+    xs[:, 0] = False
+    return xs
+
+
+# ------------------------------------------------------------------ generator next to the tile kernel
+@pytest.mark.parametrize("name,envs,iters,bidir", [("G22", 4096, 8, True), ("G14", 256, 8, True), ("G70", 9600, 5, False),
+                                                   ("N37", 45, 3, False), ("N100", 33, 7, True), ("G22", 1, 8, True),
+                                                   ("G22", 4097, 2, False), ("G14", 6000, 9, True)])
+def test_overlapped_generator_equals_sequential(name, envs, iters, bidir, cuda_device):
+    """rlsb_ls_fused_search (generator on the side stream, tile CTAs waiting per group of draws) against
+    rlsb_ls_noise_masks followed by rlsb_ls_run_masks: same states, same values, same generator state."""
+    from rlsolver_b200.envs.env_L2A import EnvMaxcut
+    from rlsolver_b200.methods.LocalSearch import LocalSearch
+    edges = (random_graph(37, 90, seed=3) if name == "N37" else random_graph(100, 320, seed=8) if name == "N100"
+             else gset_like(name))
+    out = []
+    for overlap in (False, True):
+        sim = EnvMaxcut(mygraph=edges, device=cuda_device, if_bidirectional=bidir)
+        sim.store.overlap_generator = overlap
+        th.manual_seed(5)
+        xs = sim.generate_xs_randomly(envs)
+        xs, vs = sim.local_search_inplace(xs, th.empty(()), num_iters=iters, num_spin=6, noise_std=0.3)
+        xs, vs = sim.local_search_inplace(xs, vs, num_iters=iters + 1, num_spin=3, noise_std=0.4)
+        res = [xs.clone(), vs.clone()]
+        if not bidir:
+            solver = LocalSearch(sim, sim.num_nodes)
+            solver.reset(xs.clone())
+            x2, v2, _ = solver.random_search(num_iters=iters, num_spin=4)
+            res += [x2.clone(), v2.clone()]
+        res.append(th.cuda.get_rng_state(cuda_device))
+        out.append(res)
+        assert th.equal(sim.calculate_obj_values(res[0]), res[1])
+    assert all(th.equal(a, b) for a, b in zip(*out))
+
+
+def test_overlapped_generator_many_calls_and_graph_replay(cuda_device):
+    """Back-to-back fused calls reuse the side stream, the events and the counters; replays of a captured call
+    continue the random stream like eager calls."""
+    from rlsolver_b200.envs.env_L2A import EnvMaxcut
+    edges = gset_like("G22")
+    sims = [EnvMaxcut(mygraph=edges, device=cuda_device, if_bidirectional=True) for _ in range(2)]
+    sims[0].store.overlap_generator = False
+    envs = 1024
+    th.manual_seed(11)
+    x0 = sims[0].generate_xs_randomly(envs)
+    sentinel = th.empty(())
+    # eager reference: 5 consecutive calls of the sequential form
+    th.manual_seed(3)
+    xa = x0.clone()
+    for _ in range(5):
+        xa, va = sims[0].local_search_inplace(xa, sentinel)
+    state_a = th.cuda.get_rng_state(cuda_device)
+    # overlapped form: 2 eager calls, then one captured call replayed 3 times
+    th.manual_seed(3)
+    xb = x0.clone()
+    for _ in range(2):
+        sims[1].local_search_inplace(xb, sentinel)
+    sims[1].store.rng_cursor_sync()
+    side = th.cuda.Stream(device=cuda_device)
+    side.wait_stream(th.cuda.current_stream(cuda_device))
+    g = th.cuda.CUDAGraph()
+    with th.cuda.stream(side):
+        with th.cuda.graph(g, stream=side):
+            gx, gv = sims[1].local_search_inplace(xb, sentinel)
+    th.cuda.current_stream(cuda_device).wait_stream(side)
+    th.cuda.synchronize()
+    for _ in range(3):
+        g.replay()
+    th.cuda.synchronize()
+    sims[1].store.rng_cursor_commit()
+    assert th.equal(xa, gx) and th.equal(va, gv)
+    assert th.equal(th.cuda.get_rng_state(cuda_device), state_a)
+
+
+# ------------------------------------------------------------------ config 3 at full size vs the oracle
+def _g70_setup(cuda_device, envs):
+    from rlsolver_b200.envs.env_L2A import EnvMaxcut
+    edges = gset_like("G70")
+    g = om.build_graph_store(edges, False)
+    sim = EnvMaxcut(mygraph=edges, device=cuda_device, if_bidirectional=False)
+    xs_np = _rand_xs(envs, g.num_nodes, 70)
+    rows = np.arange(7, envs, 128)                     # 128 sampled envs, every tile position hit
+    return g, sim, xs_np, rows
+
+
+def _sampled_draws(cuda_device, envs, n, count, rows, seed):
+    """The rows `rows` of the `count` draws torch.randn((envs, n)) returns from `seed` (one draw resident at a time)."""
+    th.manual_seed(seed)
+    idx = th.from_numpy(rows).to(cuda_device)
+    out = []
+    for _ in range(count):
+        out.append(th.randn((envs, n), device=cuda_device)[idx].cpu().numpy())
+    return out, th.cuda.get_rng_state(cuda_device)
+
+
+def test_local_search_inplace_g70_16384_vs_oracle(cuda_device):
+    """BASELINE config 3 shape at full size: G70-like (10000 nodes), 16384 envs, local_search_inplace with the
+    defaults.  The oracle replays 128 sampled envs with the whole batch's spread (oracle.maxcut.batch_rd_std);
+    every other row is checked through the size-independent properties (value == cut of the row, not worse)."""
+    envs = 16384
+    g, sim, xs_np, rows = _g70_setup(cuda_device, envs)
+    n = g.num_nodes
+    draws, after = _sampled_draws(cuda_device, envs, n, 9, rows, seed=74)
+    th.manual_seed(74)
+    xs = th.from_numpy(xs_np.copy()).to(cuda_device)
+    gx, gv = sim.local_search_inplace(xs, th.empty(()))
+    assert th.equal(th.cuda.get_rng_state(cuda_device), after)
+    rd = om.batch_rd_std(g, xs_np, 1, 0.3)
+    want_xs, want_vs = om.local_search_inplace(g, xs_np[rows].copy(), None, draws, 8, 8, 0.3, literal=False, rd_std=rd)
+    got_xs, got_vs = _np(gx), _np(gv)
+    assert np.array_equal(got_xs[rows], want_xs) and np.array_equal(got_vs[rows], want_vs)
+    assert np.array_equal(om.cut_values(g, got_xs), got_vs)
+    assert (got_vs >= om.cut_values(g, xs_np)).all()
+
+
+def test_random_search_64_4_g70_16384_vs_oracle(cuda_device):
+    """The inner call of config 3's loop (env_MCPG.py:463): LocalSearch.random_search(num_iters=64, num_spin=4) on
+    16384 envs of the G70 shape, 128 sampled envs replayed by the oracle with the 64 draws torch returns."""
+    from rlsolver_b200.methods.LocalSearch import LocalSearch
+    envs = 16384
+    g, sim, xs_np, rows = _g70_setup(cuda_device, envs)
+    n = g.num_nodes
+    draws, after = _sampled_draws(cuda_device, envs, n, 64, rows, seed=75)
+    th.manual_seed(75)
+    solver = LocalSearch(sim, n)
+    vs0 = solver.reset(th.from_numpy(xs_np.copy()).to(cuda_device))
+    assert np.array_equal(_np(vs0), om.cut_values(g, xs_np))
+    gx, gv, _ = solver.random_search(num_iters=64, num_spin=4)
+    assert th.equal(th.cuda.get_rng_state(cuda_device), after)
+    rd = om.batch_rd_std(g, xs_np, 2, 0.3)
+    ref = om.LocalSearch(g)
+    ref.reset(xs_np[rows].copy())
+    want_xs, want_vs, _ = ref.random_search(draws, 64, 4, 0.3, literal=False, rd_std=rd)
+    got_xs, got_vs = _np(gx), _np(gv)
+    assert np.array_equal(got_xs[rows], want_xs) and np.array_equal(got_vs[rows], want_vs)
+    assert np.array_equal(om.cut_values(g, got_xs), got_vs)
+    assert (got_vs >= om.cut_values(g, xs_np)).all()
+
+
+# ------------------------------------------------------------------ packed-tile entry points
+@pytest.mark.parametrize("name,envs", [("G22", 4096), ("G14", 250), ("N37", 45)])
+def test_local_search_packed_equals_bool_rows(name, envs, cuda_device):
+    from rlsolver_b200.envs.env_L2A import EnvMaxcut
+    edges = random_graph(37, 90, seed=3) if name == "N37" else gset_like(name)
+    sim = EnvMaxcut(mygraph=edges, device=cuda_device, if_bidirectional=True)
+    th.manual_seed(2)
+    x0 = sim.generate_xs_randomly(envs)
+    th.manual_seed(9)
+    xa, va = sim.local_search_inplace(x0.clone(), th.empty(()))
+    state = th.cuda.get_rng_state(cuda_device)
+    th.manual_seed(9)
+    pk, vb = sim.local_search_packed(sim.store.pack(x0), num_sims=envs)
+    assert th.equal(th.cuda.get_rng_state(cuda_device), state)
+    assert th.equal(va, vb) and th.equal(sim.store.unpack(pk.contiguous(), envs), xa)
+    # second call starting from the packed result with the values handed in
+    th.manual_seed(10)
+    xa2, va2 = sim.local_search_inplace(xa.clone(), va.clone(), num_iters=3, num_spin=5)
+    th.manual_seed(10)
+    pk2, vb2 = sim.local_search_packed(pk.clone(), 3, 5, num_sims=envs, good_vs=vb)
+    assert th.equal(va2, vb2) and th.equal(sim.store.unpack(pk2.contiguous(), envs), xa2)
+
+
+def test_best_exchange_object_matches_best_allreduce(cuda_device):
+    from rlsolver_b200.dist import BestExchange, best_allreduce
+    from rlsolver_b200.envs.env_L2A import EnvMaxcut
+    th.manual_seed(0)
+    for envs, edges in ((37, random_graph(100, 320, seed=8)), (4096, gset_like("G22")), (1, random_graph(37, 90, seed=3))):
+        sim = EnvMaxcut(mygraph=edges, device=cuda_device, if_bidirectional=False)
+        n = sim.num_nodes
+        xs = sim.generate_xs_randomly(envs)
+        vs = sim.calculate_obj_values(xs) - 500            # negative values too
+        if envs > 3:
+            vs[3] = vs[envs - 1] = 9000                    # tie -> lowest global env id
+        want = best_allreduce(vs, xs, rank=3, world=1, envs_per_rank=envs)
+        ex = BestExchange(n, rank=3, world=1, envs_per_rank=envs, device=cuda_device)
+        got = ex(vs, xs)
+        assert all(th.equal(a, b) for a, b in zip(want, got))
+        got = ex.packed(vs, sim.store.pack(xs), sim.store)
+        assert all(th.equal(a, b) for a, b in zip(want, got))
+
+
+# ------------------------------------------------------------------ RNG self-check
+def test_rng_self_check_detects_a_foreign_geometry(cuda_device, monkeypatch):
+    """rng.self_check passes on this torch build and raises when the modelled call geometry is not torch's."""
+    from rlsolver_b200 import rng
+    rng._CHECKED.discard(cuda_device.index)
+    state = th.cuda.get_rng_state(cuda_device)
+    rng.self_check(cuda_device)
+    assert cuda_device.index in rng._CHECKED
+    assert th.equal(th.cuda.get_rng_state(cuda_device), state)          # the caller's generator is untouched
+    rng._CHECKED.discard(cuda_device.index)
+    real = rng._max_grid(cuda_device)
+    monkeypatch.setitem(rng._MAX_GRID, cuda_device.index, real // 2)   # a torch that sized its grids differently
+    with pytest.raises(RuntimeError, match="rlsolver_b200.rng"):
+        rng.self_check(cuda_device)
+    monkeypatch.setitem(rng._MAX_GRID, cuda_device.index, real)
+    rng.self_check(cuda_device)
+
+
+# ------------------------------------------------------------------ 2 ranks over NCCL
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _nccl_worker(rank, world, port, envs, out):
+    import torch.distributed as dist
+    from rlsolver_b200.dist import BestExchange, best_allreduce
+    from rlsolver_b200.envs.env_L2A import EnvMaxcut
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    th.cuda.set_device(rank)
+    dev = th.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    edges = gset_like("G22")
+    sim = EnvMaxcut(mygraph=edges, device=dev, if_bidirectional=True)
+    th.manual_seed(74 + rank)
+    xs = sim.generate_xs_randomly(envs)
+    xs, vs = sim.local_search_inplace(xs, th.empty(()))
+    cut, gid, row = best_allreduce(vs, xs, rank, world, envs)
+    ex = BestExchange(sim.num_nodes, rank, world, envs, dev)
+    cut2, gid2, row2 = ex(vs, xs)
+    # the exchange captured in a CUDA graph with the local search (what bench.py replays)
+    sim.store.rng_cursor_sync()
+    side = th.cuda.Stream(device=dev)
+    side.wait_stream(th.cuda.current_stream(dev))
+    g = th.cuda.CUDAGraph()
+    xg = xs.clone()
+    with th.cuda.stream(side):
+        for _ in range(2):
+            ex(vs, xs)
+        with th.cuda.graph(g, stream=side):
+            gx, gv = sim.local_search_inplace(xg, th.empty(()))
+            best = ex(gv, gx)
+    th.cuda.current_stream(dev).wait_stream(side)
+    g.replay()
+    th.cuda.synchronize()
+    out[rank] = {"xs": xs.cpu(), "vs": vs.cpu(), "cut": int(cut), "gid": int(gid), "row": row.cpu(),
+                 "cut2": int(cut2), "gid2": int(gid2), "row2": row2.cpu(),
+                 "g_vs": gv.cpu(), "g_xs": gx.cpu(), "g_cut": int(best[0]), "g_gid": int(best[1]), "g_row": best[2].cpu()}
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(th.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_rank_nccl_shards_equal_single_gpu_runs():
+    """Rank r's (xs, vs) equal the single-GPU run of shard r with seed 74 + r (bit-exactness is per shard,
+    SURVEY.md 8e) and best_allreduce / BestExchange return the global argmax on both ranks, eagerly and when the
+    step (local search + exchange) is replayed from a CUDA graph."""
+    import torch.multiprocessing as mp
+    from rlsolver_b200.envs.env_L2A import EnvMaxcut
+    world, envs = 2, 1024
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_nccl_worker, args=(world, _free_port(), envs, out), nprocs=world, join=True)
+        res = [out[r] for r in range(world)]
+    dev = th.device("cuda:0")
+    sim = EnvMaxcut(mygraph=gset_like("G22"), device=dev, if_bidirectional=True)
+    all_vs = []
+    for r in range(world):
+        th.manual_seed(74 + r)
+        xs = sim.generate_xs_randomly(envs)
+        xs, vs = sim.local_search_inplace(xs, th.empty(()))
+        assert th.equal(xs.cpu(), res[r]["xs"]) and th.equal(vs.cpu(), res[r]["vs"])
+        all_vs.append(vs.cpu())
+    flat = th.cat(all_vs)
+    best = int(flat.max())
+    gid = int((flat == best).nonzero()[0])
+    want_row = res[gid // envs]["xs"][gid % envs]
+    for r in range(world):
+        for tag in ("", "2"):
+            assert res[r]["cut" + tag] == best and res[r]["gid" + tag] == gid and th.equal(res[r]["row" + tag], want_row)
+        # graph replay: a second local search from the first one's result, then the exchange, same on both ranks
+        assert res[r]["g_cut"] == res[0]["g_cut"] and res[r]["g_gid"] == res[0]["g_gid"]
+        assert th.equal(res[r]["g_row"], res[0]["g_row"])
+    g_flat = th.cat([res[r]["g_vs"] for r in range(world)])
+    assert res[0]["g_cut"] == int(g_flat.max()) and res[0]["g_gid"] == int((g_flat == g_flat.max()).nonzero()[0])
+    owner = res[0]["g_gid"] // envs
+    assert th.equal(res[0]["g_row"], res[owner]["g_xs"][res[0]["g_gid"] % envs])
