@@ -99,6 +99,21 @@ int rlsb_cut_eval(const rlsb_graph_t* g, const uint8_t* xs, int64_t num_envs, in
 int rlsb_cut_eval_packed(const rlsb_graph_t* g, const uint32_t* packed, int64_t num_envs, int64_t* vs, void* stream);
 int rlsb_cut_edges(const rlsb_graph_t* g, const uint8_t* xs, int64_t num_envs, uint8_t* out, void* stream);
 
+/* ---- integer-weighted objective (row W of the scope table).  The reference's EnvMaxcut ignores edge weights
+ * (env_L2A.py:54-66 counts XORs); its callers that do not are PISCO's adjacency energy -1/4 s^T A s
+ * (rlsolver/envs/env_ISCO.py:436-444) and MCPG's weighted sampler (rlsolver/methods/MCPG/sampling.py:89-127).
+ * A graph created with weights other than 1 additionally holds its edges bucketed by (bit of |w|, sign):
+ * the weighted cut is sum_k scale_k * popcount-per-env(bucket k), +-1 weights (Gset) being two buckets.
+ *   cut_eval_weighted   : vs[e] = sum over edges of w * [x_u != x_v]; xs bool [E][N] OR packed tiles (the other NULL).
+ *   node_fields_weighted: out[e][i] = sum_j w_ij [x_i != x_j] over the undirected neighbourhood (int32 [E][Np]);
+ *                         the gain of flipping node i is wdeg_i - 2 out[e][i].
+ * |w| < 2^24; self loops never count.  RLSB_ERR_INVALID on a graph whose weights are all 1. */
+int rlsb_graph_is_weighted(const rlsb_graph_t* g);
+int rlsb_cut_eval_weighted(const rlsb_graph_t* g, const uint8_t* xs, const uint32_t* packed, int64_t num_envs,
+                           int64_t* vs, void* stream);
+int rlsb_node_fields_weighted(const rlsb_graph_t* g, const uint32_t* packed, int64_t num_envs, int32_t* out,
+                              void* stream);
+
 /* ---- per-node cross counts: integer core of calculate_obj_values_for_loop
  * (env_L2A.py:68-80).  cross is uint16 [E][Np] (row-major, rows padded to Np):
  * number of LISTED neighbours of node i on the other side in env e.
@@ -381,6 +396,22 @@ int rlsb_best_pick(const uint8_t* gathered, int32_t world, int32_t num_nodes, in
 /* the same for records `stride` bytes apart (stride >= 8 + N; padded so that every record is 8-byte aligned) */
 int rlsb_best_pick_strided(const uint8_t* gathered, int32_t world, int32_t num_nodes, int64_t stride, int64_t* out2,
                            uint8_t* row, void* stream);
+
+/* ---- weighted max-cut sampler of MCPG: the local-search sweeps + expected cut of mcpg_sampling_maxcut
+ * (rlsolver/methods/MCPG/sampling.py:101-121) for float edge weights (MCPG/dataloader.py:53-103).
+ * xs float32 [N][C] node-major, in: the 0/1 output of metro_sampling, out: the states after the sweeps (0/1).
+ * order int32 [N] (data.sorted_degree_nodes); nbr_* = data.neighbors / data.neighbor_edges as CSR (edge order, both
+ * directions); thr[i] = float32(data.weighted_degree[i] / 2 + 0.125); edge_* = data.edge_index / edge_attr.
+ * The kernel applies the symmetry-breaking XOR with row order[0] (:102-104), runs num_sweeps >= 1 Gauss-Seidel
+ * sweeps `x_i <- [sum_j w_ij x_j + rand / 4 < thr_i]` and writes expected[c] = sum_e (2x_u - 1)(2x_v - 1) w_e.
+ * Random numbers: explicit_u float32 [num_sweeps * N][C] (replayed draws), or torch's CUDA Philox stream from
+ * (seed, offset) with the call geometry of torch.rand(C) -- one call per node visit; the caller advances the
+ * generator by 4 * rng_iters * num_sweeps * N. */
+int rlsb_mcpg_weighted_sweeps(int32_t num_nodes, int64_t num_chains, const int32_t* order, const int32_t* nbr_ptr,
+                              const int32_t* nbr_col, const float* nbr_w, const float* thr, int32_t num_edges,
+                              const int32_t* edge_u, const int32_t* edge_v, const float* edge_w, float* xs,
+                              int32_t num_sweeps, const float* explicit_u, uint64_t seed, uint64_t offset,
+                              uint32_t rng_threads, uint32_t rng_iters, float* expected, void* stream);
 
 #ifdef __cplusplus
 }

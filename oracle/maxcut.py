@@ -167,6 +167,32 @@ def evolutionary_replacement(xs, vs, low_k: int, if_maximize: bool, perm: np.nda
     vs[rep] = vs[low_ids]
 
 
+# --------------------------------------------------------------------------- integer-weighted objective
+
+def cut_values_weighted(edges: Sequence[Edge], xs: np.ndarray) -> np.ndarray:
+    """int64 [E]: sum of w over the edges whose ends differ -- obj_maxcut (rlsolver/methods/util_obj.py:31-39,
+    `obj += adj[i, j]` for i < j with result[i] != result[j]) for a batch of rows; self loops never count.
+    Equivalently PISCO's energy: -1/4 s^T A s = cut_w - sum(A) / 4 (rlsolver/envs/env_ISCO.py:436-444)."""
+    arr = np.asarray(list(edges), dtype=np.int64).reshape(-1, 3)
+    u, v, w = arr[:, 0], arr[:, 1], arr[:, 2]
+    return ((xs[:, u] ^ xs[:, v]).astype(np.int64) * w[None, :]).sum(axis=1)
+
+
+def node_fields_weighted(edges: Sequence[Edge], num_nodes: int, xs: np.ndarray) -> np.ndarray:
+    """int64 [E, N]: per node the total weight of its incident cut edges (each undirected edge seen from both
+    ends).  With d = 2x - 1: d_i (A d)_i = wdeg_i - 2 * this, the quantity PISCO's gradient carries
+    ((1 - 2x_i) grad_i = (A d)_i d_i / 2 up to the temperature, env_ISCO.py:412-418, 436-444)."""
+    arr = np.asarray(list(edges), dtype=np.int64).reshape(-1, 3)
+    out = np.zeros((xs.shape[0], num_nodes), np.int64)
+    for a, b, w in arr:
+        if a == b:
+            continue
+        cut = (xs[:, a] ^ xs[:, b]).astype(np.int64) * w
+        out[:, a] += cut
+        out[:, b] += cut
+    return out
+
+
 # --------------------------------------------------------------------------- local search
 
 def kth_smallest(a: np.ndarray, k: int) -> np.ndarray:

@@ -3,6 +3,8 @@
   metro_sampling     rlsolver/methods/MCPG.py:88-117 (== MCPG/sampling.py:67-86)
   sampler_func       rlsolver/methods/MCPG.py:120-166 with the data fields of maxcut_dataloader (187-232)
   sub_set_sampling   rlsolver/methods/L2A/transformer.py:335-353
+  weighted_sampler   rlsolver/methods/MCPG/sampling.py:89-127 (mcpg_sampling_maxcut, float `edge_attr`) with the data
+                     fields of rlsolver/methods/MCPG/dataloader.py:53-103, 106-124
 
 Random draws are passed in (recorded from the reference, or regenerated from torch's generator by
 the tests), so every function is deterministic.  Layout as in the reference: node-major [N, C]."""
@@ -73,6 +75,54 @@ def sampler_func(num_nodes: int, edges: Sequence[Tuple[int, int, int]], order: n
     vs_good = (f32(len(edges)) - max_cut) / f32(2)
     value = expected - expected.mean(dtype=f32)
     return vs_good, xs[:, index], value, xs, expected
+
+
+def weighted_fields(num_nodes: int, edges: np.ndarray, weights: np.ndarray):
+    """append_neighbors + the degree fields of MCPG/dataloader.py:75-85, 106-124: per node the neighbour ids and
+    edge weights in edge order (both directions), weighted_degree = float(sum of the float32 row)."""
+    nb: List[List[int]] = [[] for _ in range(num_nodes)]
+    nw: List[List[float]] = [[] for _ in range(num_nodes)]
+    for (a, b), w in zip(edges, weights):
+        nb[a].append(int(b)), nw[a].append(w)
+        nb[b].append(int(a)), nw[b].append(w)
+    nb_a = [np.asarray(x, dtype=np.int64) for x in nb]
+    nw_a = [np.asarray(x, dtype=f32) for x in nw]
+    wdeg = [float(x.sum(dtype=f32)) if x.size else 0.0 for x in nw_a]
+    return nb_a, nw_a, wdeg
+
+
+def weighted_sampler(num_nodes: int, edges: np.ndarray, weights: np.ndarray, order: np.ndarray, metro_out: np.ndarray,
+                     num_ls: int, total_mcmc_num: int, rands: np.ndarray):
+    """mcpg_sampling_maxcut after its metro_sampling call (sampling.py:101-127).  metro_out float32 [N, C] (0/1);
+    rands float32 [max(num_ls, 1) * N, C].  Returns (vs_good [T], xs_good [N, T], value [C], expected [C]).
+    The neighbour sum is accumulated in float32 in neighbour order; torch.mm's order is its own, so bit-exactness
+    against the reference holds for weights whose partial sums are exact (integers, k/8, ...)."""
+    nb, nw, wdeg = weighted_fields(num_nodes, edges, weights)
+    xs = metro_out.astype(f32).copy()
+    xs = (xs + xs[order[0]].copy()) % f32(2)                  # :102-104 symmetry breaking on the top-degree node
+    xs = ((xs - f32(0.5)) * f32(2) + f32(0.5)).astype(f32)    # :105  {0, 1} -> {-0.5, 1.5}
+    draw = 0
+    cnt = 0
+    while True:                                               # :109-121 (at least one sweep)
+        cnt += 1
+        for node in order:
+            s = np.zeros(xs.shape[1], f32)
+            for j, w in zip(nb[node], nw[node]):
+                s = (s + f32(w) * xs[j]).astype(f32)
+            v = (s + (rands[draw].astype(f32) / f32(4)).astype(f32)).astype(f32)
+            xs[node] = (v < f32(wdeg[node] / 2 + 0.125)).astype(f32)
+            draw += 1
+        if cnt >= num_ls:
+            break
+    e = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+    terms = (f32(2) * xs[e[:, 0]] - f32(1)) * (f32(2) * xs[e[:, 1]] - f32(1)) * weights.astype(f32)[:, None]
+    expected = terms.sum(axis=0, dtype=f32)
+    index = expected.reshape(-1, total_mcmc_num).argmin(axis=0)
+    index = np.arange(total_mcmc_num) + index * total_mcmc_num
+    wsum = f32(float(weights.astype(f32).sum(dtype=f32)))
+    vs_good = (wsum - expected[index]) / f32(2)
+    value = expected - expected.mean(dtype=f32)
+    return vs_good, xs[:, index], value, expected
 
 
 def sub_set_sampling(top_ids: np.ndarray, top_values: np.ndarray, start_xs: np.ndarray, num_repeats: int,

@@ -101,6 +101,9 @@ SIGNATURES = {
     "rlsb_unpack_spins": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "rlsb_cut_eval": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "rlsb_cut_eval_packed": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "rlsb_graph_is_weighted": (C.c_int, [_vp]),
+    "rlsb_cut_eval_weighted": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "rlsb_node_fields_weighted": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "rlsb_cut_edges": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "rlsb_node_cross_counts": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "rlsb_ls_workspace_bytes": (_i64, [_vp, _i64]),
@@ -128,6 +131,8 @@ SIGNATURES = {
     "rlsb_mcpg_plan_destroy": (C.c_int, [_vp]),
     "rlsb_mcpg_plan_num_levels": (_i32, [_vp]),
     "rlsb_mcpg_sweeps": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _u64, _u64, _u32, _u32, _vp, _vp]),
+    "rlsb_mcpg_weighted_sweeps": (C.c_int, [_i32, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp,
+                                            _u64, _u64, _u32, _u32, _vp, _vp]),
     "rlsb_metro_sampling": (C.c_int, [_i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _u64, _u64, _u32, _u32, _vp,
                                       _i32, _vp]),
     "rlsb_metro_workspace_bytes": (_i64, [_i32, _i64, _i32]),

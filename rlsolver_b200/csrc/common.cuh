@@ -35,6 +35,16 @@ int debug_flags();   // rlsb_debug_flags word (environment read once at load tim
 
 #define RLSB_LAUNCH_OK() RLSB_CUDA_OK(cudaGetLastError())
 
+// RLSB_REQUIRE that runs `cleanup` before returning
+#define RLSB_REQUIRE_CLEAN(cond, cleanup, code, ...) \
+  do {                                               \
+    if (!(cond)) {                                   \
+      rlsb::set_error(__VA_ARGS__);                  \
+      cleanup;                                       \
+      return (code);                                 \
+    }                                                \
+  } while (0)
+
 // Sliced-ELL neighbour lists ("SELL-32"): a slice is 32 node slots (one per lane).  Column ids
 // are stored in blocks of 4 rounds, lane-major inside a block, so a lane reads 4 neighbour ids
 // with one 8-byte load and a warp reads 256 contiguous bytes.  Short rows are padded with the
@@ -72,6 +82,12 @@ struct GraphDev {
   const char* sweep_blob;
   int32_t sweep_blob_bytes, num_sweep_slices, max_level_slices;
   int32_t sweep_lvs, sweep_off, sweep_node, sweep_half, sweep_col;   // byte offsets inside the blob
+  // weighted objective (null / 0 when every weight is 1): see rlsb_graph::wpair / wmeta / full_w / wdeg
+  const uint32_t* wpair;
+  const int4* wmeta;           // [wbuckets] {first quad, quads, signed scale, edges}
+  const int32_t* full_w;       // [mf]
+  const int32_t* wdeg;         // [np]
+  int32_t wbuckets;
 };
 
 // the sweep structure seen through a base pointer (global blob or its shared-memory copy)

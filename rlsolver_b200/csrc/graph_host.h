@@ -18,6 +18,14 @@ struct rlsb_graph {
     std::vector<int32_t> off;
     std::vector<uint16_t> node, half, col;
   } sell_listed, sell_sweep;
+  // weighted objective (weights other than 1 present): edges bucketed by (bit of |w|, sign), each bucket a
+  // zero-padded list of u | v << 16 words; meta[k] = {first quad, quads, signed scale (+-2^bit), edges}
+  bool weighted = false;
+  std::vector<uint32_t> wpair;
+  std::vector<int32_t> wmeta;
+  std::vector<int32_t> full_w;          // weight of every full-neighbourhood slot (aligned with full_col)
+  std::vector<int32_t> wdeg;            // [np] sum of the weights of a node's (non-loop) edges
+  int64_t weight_sum = 0, abs_weight_sum = 0;
   void* dev_blob = nullptr;   // one allocation holding every device array
   rlsb::GraphDev dev{};
   // side stream + fork / join events for work that runs next to the caller's stream (the streaming mask

@@ -198,6 +198,56 @@ int rlsb_graph_create(int32_t num_nodes, int64_t num_edges, const int32_t* h_n0,
   }
   build_csr(g->n, src, dst, g->full_ptr, g->full_col);
 
+  // weights: only materialised when some weight differs from 1 (the reference's EnvMaxcut ignores them; the
+  // weighted entry points serve the callers that do not: PISCO's adjacency energy, MCPG's weighted sampler)
+  for (int64_t k = 0; k < num_edges && h_w; ++k) g->weighted = g->weighted || h_w[k] != 1;
+  if (g->weighted) {
+    int32_t max_abs = 0;
+    for (int64_t k = 0; k < num_edges; ++k) {
+      const int64_t w = h_w[k];
+      RLSB_REQUIRE_CLEAN(w > -(int64_t(1) << 24) && w < (int64_t(1) << 24), delete g, RLSB_ERR_UNSUPPORTED,
+                         "graph_create: |weight| of edge %lld is 2^24 or more", (long long)k);
+      if (g->edge_u[k] != g->edge_v[k]) g->weight_sum += w, g->abs_weight_sum += w < 0 ? -w : w;
+      max_abs = std::max<int32_t>(max_abs, int32_t(w < 0 ? -w : w));
+    }
+    // full_w aligned with full_col: build_csr orders a row by neighbour id, stably; replay that order
+    {
+      std::vector<std::vector<std::pair<int32_t, int32_t>>> rows(g->n);
+      for (int64_t k = 0; k < num_edges; ++k) {
+        if (g->edge_u[k] == g->edge_v[k]) continue;
+        rows[g->edge_u[k]].push_back({g->edge_v[k], h_w[k]});
+        rows[g->edge_v[k]].push_back({g->edge_u[k], h_w[k]});
+      }
+      g->full_w.assign(g->full_col.size(), 0);
+      g->wdeg.assign(g->np, 0);
+      for (int32_t i = 0; i < g->n; ++i) {
+        auto& r = rows[i];
+        std::stable_sort(r.begin(), r.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+        for (size_t t = 0; t < r.size(); ++t) {
+          // duplicates of one neighbour may carry different weights: any assignment of them to the equal
+          // column entries gives the same sums
+          g->full_w[g->full_ptr[i] + t] = r[t].second;
+          g->wdeg[i] += r[t].second;
+        }
+      }
+    }
+    for (int bit = 0; (1 << bit) <= max_abs; ++bit)
+      for (int sign = 0; sign < 2; ++sign) {
+        std::vector<uint32_t> list;
+        for (int64_t k = 0; k < num_edges; ++k) {
+          const int32_t w = h_w[k], a = w < 0 ? -w : w;
+          if (((a >> bit) & 1) && (w < 0) == (sign == 1) && g->edge_u[k] != g->edge_v[k])
+            list.push_back(uint32_t(g->edge_u[k]) | (uint32_t(g->edge_v[k]) << 16));
+        }
+        if (list.empty()) continue;
+        const int32_t first = int32_t(g->wpair.size() / 4), edges = int32_t(list.size());
+        list.resize((list.size() + 3) / 4 * 4, 0u);
+        g->wpair.insert(g->wpair.end(), list.begin(), list.end());
+        const int32_t scale = sign ? -(1 << bit) : (1 << bit);
+        g->wmeta.insert(g->wmeta.end(), {first, int32_t(list.size() / 4), scale, edges});
+      }
+  }
+
   for (int32_t i = 0; i < g->n; ++i) {
     g->max_listed_deg = std::max(g->max_listed_deg, g->listed_ptr[i + 1] - g->listed_ptr[i]);
     g->max_full_deg = std::max(g->max_full_deg, g->full_ptr[i + 1] - g->full_ptr[i]);
@@ -288,8 +338,14 @@ int rlsb_graph_create(int32_t num_nodes, int64_t num_edges, const int32_t* h_n0,
       s_col = put(g->sell_sweep.col.data(), g->sell_sweep.col.size() * 2);
     }
     const int b_sweep = add(sblob.data(), sblob.size());
+    const int b_wpair = add(g->wpair.data(), g->wpair.size() * 4), b_wmeta = addv32(g->wmeta);
+    const int b_fullw = addv32(g->full_w), b_wdeg = addv32(g->wdeg);
     if (e == cudaSuccess) e = cudaMalloc(&g->dev_blob, total);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->side_stream, cudaStreamNonBlocking);
+    // the side stream never synchronises with the legacy default stream (non-blocking) and its blocks are
+    // dispatched ahead of pending blocks of the caller's stream (highest priority)
+    int prio_least = 0, prio_greatest = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&g->side_stream, cudaStreamNonBlocking, prio_greatest);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming);
     for (size_t a = 0; a < blobs.size() && e == cudaSuccess; ++a)
@@ -318,6 +374,11 @@ int rlsb_graph_create(int32_t num_nodes, int64_t num_edges, const int32_t* h_n0,
     d.sweep_lvs = int32_t(s_lvs), d.sweep_off = int32_t(s_off), d.sweep_node = int32_t(s_node);
     d.sweep_half = int32_t(s_half), d.sweep_col = int32_t(s_col);
     d.num_sweep_slices = int32_t(g->sell_sweep.off.size()) - 1;
+    d.wbuckets = g->weighted ? int32_t(g->wmeta.size() / 4) : 0;
+    d.wpair = g->weighted ? reinterpret_cast<const uint32_t*>(i32(b_wpair)) : nullptr;
+    d.wmeta = g->weighted ? reinterpret_cast<const int4*>(i32(b_wmeta)) : nullptr;
+    d.full_w = g->weighted ? i32(b_fullw) : nullptr;
+    d.wdeg = g->weighted ? i32(b_wdeg) : nullptr;
     d.max_level_slices = 0;
     for (size_t l = 0; l + 1 < g->level_slice.size(); ++l)
       d.max_level_slices = std::max(d.max_level_slices, g->level_slice[l + 1] - g->level_slice[l]);

@@ -207,7 +207,7 @@ struct LsArgs {
 };
 
 __device__ __forceinline__ void stamp(const LsArgs& a, int& k) {
-  if (a.times && blockIdx.x == 0 && threadIdx.x == 0) a.times[k] = clock64();
+  if (a.times && blockIdx.x == 0 && threadIdx.x == 0 && k < 64) a.times[k] = clock64();
   ++k;
 }
 
@@ -881,18 +881,12 @@ __global__ void __maxnreg__(96) ls_bits_kernel(GraphDev g, LsArgs a, const uint3
   __shared__ int sNextReady;
   __shared__ __align__(8) uint64_t sBar;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t tile = blockIdx.x;
-  const int64_t env0 = tile * kTileEnvs;
-  const int valid = (int)min((int64_t)kTileEnvs, a.num_envs - env0);
+  const int64_t tiles = (a.num_envs + kTileEnvs - 1) / kTileEnvs;
   if (threadIdx.x == 0) {
     mbar_init(&sBar, 1);
     sNF = 0;
     sNextReady = 0;
     if (a.stage_sweep) stage_sweep_blob(g, sSweep, &sBar);
-  }
-  for (int i = threadIdx.x; i < g.np; i += kLSThreads) {
-    const uint32_t w = a.packed[tile * g.np + i];
-    sP[i] = w, sX[i] = w;
   }
   if (use_delta && a.num_iters > 0) {
     const uint16_t* node = sweep_view(g, g.sweep_blob).sell.node;
@@ -901,54 +895,67 @@ __global__ void __maxnreg__(96) ls_bits_kernel(GraphDev g, LsArgs a, const uint3
       if (v != 0xFFFFu) sInv[v] = (uint16_t)slot;
     }
   }
-  if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
-  int64_t my_vs = 0;
-  if (warp == 0 && lane < valid) my_vs = a.vs[env0 + lane];
-  if (ctl && a.num_iters > 0 && threadIdx.x == 0) gen_group_wait(ctl, 0, units);     // the first group of draws
-  ls_sync();
   const int blocks = (g.n + 31) >> 5;
-  const uint64_t row = (uint64_t)(env0 + lane) * (uint64_t)g.n;     // first bit of the lane's env row
-  const bool live = lane < valid;
   uint16_t* flist = use_delta ? sF : nullptr;
   int tk = 0;
-  stamp(a, tk);
-  MaskChunk pre = mask_chunk_load(masks, row, warp, a.num_iters > 0 ? blocks : 0, live);
-  bool have_pre = true;
-  if (use_delta && a.stage_sweep && a.num_iters > 0) mbar_wait(&sBar, 0);   // the neighbour lists have landed
-  stamp(a, tk);
-  for (int it = 0; it < a.num_iters; ++it) {
-    const uint32_t* mask = masks + it * mask_words;
-    if (!have_pre) {      // the draw was not complete when the previous iteration could have fetched ahead
-      if (threadIdx.x == 0) gen_group_wait(ctl, it / kGenGroup, units);
-      ls_sync();
-      pre = mask_chunk_load(mask, row, warp, blocks, live);
+  // PERSISTENT over tiles: the grid never exceeds one CTA per SM, so every CTA of this kernel and every block of
+  // the generator is resident at the same time whatever order the two grids are dispatched in -- a CTA that
+  // waits for a group of draws can never keep the generator's blocks from being scheduled.
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t env0 = tile * kTileEnvs;
+    const int valid = (int)min((int64_t)kTileEnvs, a.num_envs - env0);
+    for (int i = threadIdx.x; i < g.np; i += kLSThreads) {
+      const uint32_t w = a.packed[tile * g.np + i];
+      sP[i] = w, sX[i] = w;
     }
-    mask_chunk_apply(pre, row, warp, g.n, sP, sX, flist, &sNF);
-    for (int b0 = warp + 4 * kLSWarps; b0 < blocks; b0 += 4 * kLSWarps)
-      mask_chunk_apply(mask_chunk_load(mask, row, b0, blocks, live), row, b0, g.n, sP, sX, flist, &sNF);
-    // fetch ahead only when the next draw's group is known to be complete (same group: it is; next group: one
-    // poll, published by the barrier below)
-    const bool more = it + 1 < a.num_iters;
-    const bool same_group = !ctl || (it + 1) / kGenGroup == it / kGenGroup;
-    if (more && !same_group && threadIdx.x == 0) sNextReady = gen_group_ready(ctl, (it + 1) / kGenGroup, units) ? 1 : 0;
+    if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
+    int64_t my_vs = 0;
+    if (warp == 0 && lane < valid) my_vs = a.vs[env0 + lane];
+    if (ctl && a.num_iters > 0 && threadIdx.x == 0) gen_group_wait(ctl, 0, units);     // the first group of draws
     ls_sync();
-    have_pre = !more || same_group || sNextReady != 0;
-    if (have_pre) pre = mask_chunk_load(mask + mask_words, row, warp, more ? blocks : 0, live);
+    const uint64_t row = (uint64_t)(env0 + lane) * (uint64_t)g.n;     // first bit of the lane's env row
+    const bool live = lane < valid;
     stamp(a, tk);
-    if (use_delta)
-      evaluate_delta_and_accept<P>(g, a, sSweep, sInv, sF, &sNF, sP, sX, sCnt, &sAccept, valid, my_vs);
-    else
-      evaluate_and_accept(g, a, sP, sX, sCnt, &sAccept, valid, my_vs);
+    MaskChunk pre = mask_chunk_load(masks, row, warp, a.num_iters > 0 ? blocks : 0, live);
+    bool have_pre = true;
+    if (use_delta && a.stage_sweep && a.num_iters > 0) mbar_wait(&sBar, 0);   // the neighbour lists have landed
     stamp(a, tk);
+    for (int it = 0; it < a.num_iters; ++it) {
+      const uint32_t* mask = masks + it * mask_words;
+      if (!have_pre) {      // the draw was not complete when the previous iteration could have fetched ahead
+        if (threadIdx.x == 0) gen_group_wait(ctl, it / kGenGroup, units);
+        ls_sync();
+        pre = mask_chunk_load(mask, row, warp, blocks, live);
+      }
+      mask_chunk_apply(pre, row, warp, g.n, sP, sX, flist, &sNF);
+      for (int b0 = warp + 4 * kLSWarps; b0 < blocks; b0 += 4 * kLSWarps)
+        mask_chunk_apply(mask_chunk_load(mask, row, b0, blocks, live), row, b0, g.n, sP, sX, flist, &sNF);
+      // fetch ahead only when the next draw's group is known to be complete (same group: it is; next group: one
+      // poll, published by the barrier below)
+      const bool more = it + 1 < a.num_iters;
+      const bool same_group = !ctl || (it + 1) / kGenGroup == it / kGenGroup;
+      if (more && !same_group && threadIdx.x == 0)
+        sNextReady = gen_group_ready(ctl, (it + 1) / kGenGroup, units) ? 1 : 0;
+      ls_sync();
+      have_pre = !more || same_group || sNextReady != 0;
+      if (have_pre) pre = mask_chunk_load(mask + mask_words, row, warp, more ? blocks : 0, live);
+      stamp(a, tk);
+      if (use_delta)
+        evaluate_delta_and_accept<P>(g, a, sSweep, sInv, sF, &sNF, sP, sX, sCnt, &sAccept, valid, my_vs);
+      else
+        evaluate_and_accept(g, a, sP, sX, sCnt, &sAccept, valid, my_vs);
+      stamp(a, tk);
+    }
+    const uint32_t vmask = valid == 32 ? kFull : ((1u << valid) - 1u);
+    if (a.finish) {
+      finish_tile<P>(g, a, sP, sSweep, &sBar, sCnt, tile, valid, &tk);
+    } else {
+      if (warp == 0 && lane < valid) a.vs[env0 + lane] = my_vs;
+    }
+    stamp(a, tk);
+    for (int i = threadIdx.x; i < g.np; i += kLSThreads) a.packed[tile * g.np + i] = sP[i] & vmask;
+    ls_sync();          // the tile copies are free for the next tile
   }
-  const uint32_t vmask = valid == 32 ? kFull : ((1u << valid) - 1u);
-  if (a.finish) {
-    finish_tile<P>(g, a, sP, sSweep, &sBar, sCnt, tile, valid, &tk);
-  } else {
-    if (warp == 0 && lane < valid) a.vs[env0 + lane] = my_vs;
-  }
-  stamp(a, tk);
-  for (int i = threadIdx.x; i < g.np; i += kLSThreads) a.packed[tile * g.np + i] = sP[i] & vmask;
 }
 
 // single-flip pass on packed tiles only (rlsb_flip_sweep)
@@ -1115,8 +1122,9 @@ static int launch_bits(const GraphDev& g, LsArgs a, const uint32_t* masks, cudaS
   // slots of the sweep structure are addressed with 16 bits; RLSB_DEBUG_FULL_CUT keeps the full re-count (cross-check)
   const int use_delta = (g.num_sweep_slices * 32 <= 65536 && !(debug_flags() & RLSB_DEBUG_FULL_CUT)) ? 1 : 0;
   if (int rc = allow_smem(ls_bits_kernel<P>, smem)) return rc;
-  ls_bits_kernel<P><<<(unsigned)tiles, kLSThreads, smem, st>>>(g, a, masks, ls_mask_words(a.num_envs, g.n), use_delta, ctl,
-                                                                units);
+  // persistent: at most one CTA per SM (96 registers x 512 threads: a second one would not fit anyway)
+  const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+  ls_bits_kernel<P><<<grid, kLSThreads, smem, st>>>(g, a, masks, ls_mask_words(a.num_envs, g.n), use_delta, ctl, units);
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }

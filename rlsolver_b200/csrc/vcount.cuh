@@ -143,13 +143,13 @@ __device__ __forceinline__ uint32_t pair_xor(const uint32_t* sP, uint32_t pr) {
 }
 
 // `warp` = this warp's index among the `warps` that take edges (default: its index in the CTA).
-__device__ __forceinline__ int tile_cut_partial(const GraphDev& g, const uint32_t* sP, int warps, int warp = -1) {
+// `pairs` / `quads`: a zero-padded list of u | v << 16 words, four per 16-byte element.
+__device__ __forceinline__ int tile_cut_range(const uint4* __restrict__ pairs, int quads, const uint32_t* sP, int warps,
+                                              int warp = -1) {
   const int lane = threadIdx.x & 31;
   if (warp < 0) warp = threadIdx.x >> 5;
   if (warp >= warps) return 0;
   const int T = warps * 32;
-  const int quads = (g.m + 3) >> 2;                     // the list is zero-padded to whole quads
-  const uint4* pairs = reinterpret_cast<const uint4*>(g.edge_pair);
   int total = 0;
   VCount<8> vc;
   vc.clear();
@@ -184,6 +184,23 @@ __device__ __forceinline__ int tile_cut_partial(const GraphDev& g, const uint32_
     }
   }
   total += vc.flush_warp(lane);
+  return total;
+}
+
+__device__ __forceinline__ int tile_cut_partial(const GraphDev& g, const uint32_t* sP, int warps, int warp = -1) {
+  return tile_cut_range(reinterpret_cast<const uint4*>(g.edge_pair), (g.m + 3) >> 2, sP, warps, warp);
+}
+
+// Weighted cut of one tile: sum over the (bit of |w|, sign) buckets of scale * (cut edges of the bucket) -- a
+// weighted popcount of the XORed words.  +-1 weights are two buckets, i.e. two passes of the unweighted loop.
+__device__ __forceinline__ long long tile_cut_weighted_partial(const GraphDev& g, const uint32_t* sP, int warps,
+                                                               int warp = -1) {
+  long long total = 0;
+  const uint4* base = reinterpret_cast<const uint4*>(g.wpair);
+  for (int k = 0; k < g.wbuckets; ++k) {
+    const int4 meta = __ldg(g.wmeta + k);                 // {first quad, quads, scale, edges}
+    total += (long long)meta.z * tile_cut_range(base + meta.x, meta.y, sP, warps, warp);
+  }
   return total;
 }
 

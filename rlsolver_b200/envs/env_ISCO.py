@@ -16,7 +16,8 @@ own sequence of torch ops, so a replayed uniform stream reproduces its choices.
 Numerics: PISCO's energy and flip gains reproduce the reference's fp16/fp32 roundings exactly
 (small integers, one division); ISCO's autograd accumulates +-0.5/T per edge with atomics, so its
 gains carry a few ulp of order-dependent noise in the reference itself -- parity there is to
-1e-6 relative (tests/test_gpu_isco.py).  Unit edge weights only (all shipped graphs)."""
+1e-6 relative (tests/test_gpu_isco.py).  ISCO_maxcut takes the edge list and ignores weights like the reference;
+PISCO_maxcut's adjacency may carry integer weights (rlsb_cut_eval_weighted / rlsb_node_fields_weighted)."""
 from __future__ import annotations
 
 import torch as th
@@ -112,9 +113,30 @@ class PISCO_maxcut(_PathAuxMaxcut):
         super().__init__(params_dict)
         self.adj_matrix = params_dict['adj_matrix']
         self.sum_A = th.sum(self.adj_matrix)
-        a = self.adj_matrix[:self.max_num_nodes, :self.max_num_nodes]
+        a = self.adj_matrix[:self.max_num_nodes, :self.max_num_nodes].float()
+        if not bool((a == a.round()).all()):
+            raise NotImplementedError("PISCO_maxcut: integer edge weights only (the packed-spin kernels count "
+                                      "weighted edges exactly)")
+        self._wdeg = None
         if not bool(((a == 0) | (a == 1)).all()):
-            raise NotImplementedError("PISCO_maxcut: unit edge weights only (the packed-spin kernels count edges)")
+            # weighted adjacency (Gset's +-1 instances): the energy is -1/4 s^T A s with A the WEIGHT matrix
+            # (env_ISCO.py:436-444), so the integer core is the weighted cut and the weighted local fields
+            iu = th.triu(a, diagonal=1).nonzero()
+            w = a[iu[:, 0], iu[:, 1]].long()
+            graph = th.stack([iu[:, 0], iu[:, 1], w], dim=1).cpu().numpy()
+            self.store = GraphStore(graph, True, device=self.device, num_nodes=self.max_num_nodes)
+            self._wdeg = a.sum(dim=1).long()[None, :]
+
+    def _int_fields(self, sample: TEN):
+        if self._wdeg is None:
+            return super()._int_fields(sample)
+        n = self.max_num_nodes
+        bits = (sample[:, :n] != 0).contiguous()
+        b = bits.shape[0]
+        packed = self.store.pack(bits)
+        cut = self.store.cut_eval_weighted(packed=packed, num_envs=b)
+        cross = self.store.node_fields_weighted(packed, b)[:, :n].long()
+        return cut, self._wdeg - 2 * cross
 
     def random_gen_init_sample(self):
         return th.bernoulli(th.full((cfg.BATCH_SIZE, self.max_num_nodes), 0.5, device=self.device)).to(th.float16)

@@ -134,6 +134,11 @@ class GraphStore:
         self.max_listed_degree = int(L.rlsb_graph_max_listed_degree(handle))
         self.max_full_degree = int(L.rlsb_graph_max_full_degree(handle))
         self.if_bidirectional = bool(if_bidirectional)
+        # weights other than 1: the weighted entry points apply (the unweighted ones keep ignoring weights,
+        # like the reference's EnvMaxcut)
+        self.weighted = bool(arr.shape[0]) and bool((arr[:, 2] != 1).any())
+        loops = arr[:, 0] == arr[:, 1]
+        self.weight_sum = int(arr[~loops, 2].sum()) if arr.shape[0] else 0
         self.timer: Optional[OpTimer] = None      # set by bench.py for the per-kernel pass
         self.launch_count = 0                     # kernels of this library launched through this store
 
@@ -230,6 +235,28 @@ class GraphStore:
             _lib.check(self._lib.rlsb_cut_eval_packed(self._h, _ptr(packed), num_envs, _ptr(vs),
                                                       _stream_ptr(self.device)), "cut_eval_packed")
         return vs
+
+    def cut_eval_weighted(self, xs: Optional[TEN] = None, packed: Optional[TEN] = None,
+                          num_envs: Optional[int] = None) -> TEN:
+        """int64 [E]: sum of w over the cut edges, from bool rows `xs` or from packed tiles."""
+        if (xs is None) == (packed is None):
+            raise ValueError("cut_eval_weighted takes bool rows OR packed tiles")
+        if xs is not None:
+            xs = self._check_xs(xs)
+            num_envs = xs.shape[0]
+        vs = th.empty((num_envs,), dtype=th.int64, device=self.device)
+        with self._op("cut_eval_weighted"):
+            _lib.check(self._lib.rlsb_cut_eval_weighted(self._h, _ptr(xs), _ptr(packed), num_envs, _ptr(vs),
+                                                        _stream_ptr(self.device)), "cut_eval_weighted")
+        return vs
+
+    def node_fields_weighted(self, packed: TEN, num_envs: int) -> TEN:
+        """int32 [E, Np]: per node the weight of its incident edges that are cut."""
+        out = th.empty((num_envs, self.padded_nodes), dtype=th.int32, device=self.device)
+        with self._op("node_fields_weighted"):
+            _lib.check(self._lib.rlsb_node_fields_weighted(self._h, _ptr(packed), num_envs, _ptr(out),
+                                                           _stream_ptr(self.device)), "node_fields_weighted")
+        return out
 
     def cut_edges(self, xs: TEN) -> TEN:
         xs = self._check_xs(xs)

@@ -169,3 +169,81 @@ def sampler_func(data: McpgData, xs_sample: TEN, num_ls: int, total_mcmc_num: in
     value = expected.float()
     value = value - value.mean()
     return vs_good, xs_good, value
+
+
+# ----------------------------------------------------------------------------- weighted sampler (MCPG/sampling.py)
+class WeightedMcpgData:
+    """What `maxcut_dataloader` of rlsolver/methods/MCPG/dataloader.py:53-103 returns, reduced to the fields
+    `mcpg_sampling_maxcut` reads: num_nodes, edge_index [2, M], edge_attr [M, 1] float32, edge_weight_sum,
+    neighbors / neighbor_edges (as CSR, edge order, both directions), weighted_degree (float(sum of the float32
+    row)), sorted_degree_nodes (descending |weighted| degree, torch CPU argsort as in the reference)."""
+
+    def __init__(self, edges, weights, num_nodes: int, device):
+        self.device = require_cuda(device)
+        e = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+        w = np.asarray(weights, dtype=np.float32).reshape(-1)
+        self.num_nodes, self.num_edges = int(num_nodes), int(e.shape[0])
+        self.edge_index = th.from_numpy(e.T.copy()).to(self.device)
+        self.edge_attr = th.from_numpy(w.copy()).reshape(-1, 1).to(self.device)
+        self.edge_weight_sum = float(th.sum(th.from_numpy(w.copy())))
+        src = np.concatenate([e[:, 0], e[:, 1]])
+        dst = np.concatenate([e[:, 1], e[:, 0]])
+        pos = np.concatenate([2 * np.arange(e.shape[0]), 2 * np.arange(e.shape[0]) + 1])     # edge order, (row, col) first
+        order = np.lexsort((pos, src))
+        ptr = np.zeros(self.num_nodes + 1, np.int64)
+        np.add.at(ptr, src + 1, 1)
+        ptr = np.cumsum(ptr)
+        col, nw = dst[order], np.concatenate([w, w])[order]
+        self.single_degree = np.diff(ptr).tolist()
+        rows = [th.from_numpy(nw[ptr[i]:ptr[i + 1]].copy()) for i in range(self.num_nodes)]
+        self.weighted_degree = [float(th.sum(r)) for r in rows]
+        abs_deg = th.tensor([float(th.sum(th.abs(r))) for r in rows])
+        self.sorted_degree_nodes = th.argsort(abs_deg, descending=True)
+        thr = np.asarray([np.float32(d / 2 + 0.125) for d in self.weighted_degree], dtype=np.float32)
+        to = lambda a, dt: th.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.device)   # noqa: E731
+        self._order = to(self.sorted_degree_nodes.numpy(), np.int32)
+        self._ptr, self._col, self._w, self._thr = to(ptr, np.int32), to(col, np.int32), to(nw, np.float32), to(thr, np.float32)
+        self._eu, self._ev, self._ew = to(e[:, 0], np.int32), to(e[:, 1], np.int32), to(w, np.float32)
+
+
+def weighted_maxcut_dataloader(path: str, device=None):
+    """`N M` header + 1-based `u v w` rows with float weights -> (data, num_nodes) (MCPG/dataloader.py:53-103)."""
+    with open(path) as fh:
+        first = fh.readline().split()
+        num_nodes, num_edges = int(first[0]), int(first[1])
+        rows = [ln.split() for ln in fh if ln.strip()]
+    assert len(rows) == num_edges, f"{path}: header says {num_edges} edges, file has {len(rows)}"
+    device = th.device("cuda", th.cuda.current_device()) if device is None else device
+    edges = [(int(r[0]) - 1, int(r[1]) - 1) for r in rows]
+    return WeightedMcpgData(edges, [float(r[2]) for r in rows], num_nodes, device), num_nodes
+
+
+def mcpg_sampling_maxcut(data: WeightedMcpgData, start_result: TEN, probs: TEN, num_ls: int, change_times: int,
+                         total_mcmc_num: int, device=None, _explicit=None, _explicit_u: Optional[TEN] = None):
+    """rlsolver/methods/MCPG/sampling.py:89-127: metro_sampling, then the weighted local-search sweeps and the
+    expected cut in one kernel (csrc/mcpg_weighted.cu).  Returns ((edge_weight_sum - cut) / 2 [T], xs [N, T],
+    the metro output [N, C], advantage [C])."""
+    device = data.device
+    lib = _lib.lib()
+    graph_probs = metro_sampling(probs, start_result.clone(), change_times, device, _explicit=_explicit)
+    start = graph_probs.clone()
+    num_chain = graph_probs.shape[1]
+    sweeps = max(int(num_ls), 1)                      # the reference's `while True` runs once for num_ls <= 1
+    expected = th.empty((num_chain,), dtype=th.float32, device=device)
+    seed, offset, threads, iters = rng.peek(device, num_chain)
+    u = None
+    if _explicit_u is not None:
+        u = _explicit_u.to(device=device, dtype=th.float32).contiguous()
+        assert u.shape == (sweeps * data.num_nodes, num_chain)
+    with on_device(device):
+        _lib.check(lib.rlsb_mcpg_weighted_sweeps(data.num_nodes, num_chain, _ptr(data._order), _ptr(data._ptr),
+                                                 _ptr(data._col), _ptr(data._w), _ptr(data._thr), data.num_edges,
+                                                 _ptr(data._eu), _ptr(data._ev), _ptr(data._ew), _ptr(graph_probs),
+                                                 sweeps, _ptr(u), seed, offset, threads, iters, _ptr(expected),
+                                                 _stream_ptr(device)), "mcpg_weighted_sweeps")
+    if u is None:
+        rng.advance(device, num_chain, sweeps * data.num_nodes)      # one torch.rand(C) per node visit
+    index = th.argmin(expected.reshape((-1, total_mcmc_num)), dim=0)
+    index = th.arange(total_mcmc_num, device=device) + index * total_mcmc_num
+    max_cut = expected[index]
+    return (data.edge_weight_sum - max_cut) / 2, graph_probs[:, index], start, expected - th.mean(expected)

@@ -43,8 +43,9 @@ def test_isco_step_matches_reference(path, cuda_device, monkeypatch):
     if pisco:
         npad = (n + 7) // 8 * 8
         A = th.zeros((npad, npad), dtype=th.float16, device=cuda_device)
-        A[ef, et] = 1
-        A[et, ef] = 1
+        w = th.from_numpy(z["edge_w"]).to(cuda_device).to(th.float16) if "edge_w" in z.files else 1   # weighted goldens
+        A[ef, et] = w
+        A[et, ef] = w
         params["adj_matrix"] = A
         sampler = env_ISCO.PISCO_maxcut(params)
     else:

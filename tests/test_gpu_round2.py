@@ -307,3 +307,101 @@ def test_two_rank_nccl_shards_equal_single_gpu_runs():
     assert res[0]["g_cut"] == int(g_flat.max()) and res[0]["g_gid"] == int((g_flat == g_flat.max()).nonzero()[0])
     owner = res[0]["g_gid"] // envs
     assert th.equal(res[0]["g_row"], res[owner]["g_xs"][res[0]["g_gid"] % envs])
+
+
+# ------------------------------------------------------------------ integer-weighted objective (row W)
+from conftest import golden_files  # noqa: E402
+
+
+@pytest.mark.parametrize("path", golden_files("weighted_cut_"), ids=os.path.basename)
+def test_weighted_cut_and_fields_match_reference(path, cuda_device):
+    """rlsb_cut_eval_weighted / rlsb_node_fields_weighted against obj_maxcut and PISCO's energy / gradient computed by
+    the reference (tools/make_goldens_r2.py): +-1 weights (two buckets), small integers (|w| bit buckets)."""
+    from rlsolver_b200.graph_store import GraphStore
+    z = np.load(path)
+    edges = [tuple(int(t) for t in row) for row in z["edges"]]
+    n = z["xs"].shape[1]
+    st = GraphStore(edges, True, device=cuda_device, num_nodes=n)
+    assert st.weighted
+    xs = th.from_numpy(z["xs"]).to(cuda_device)
+    envs = xs.shape[0]
+    assert np.array_equal(_np(st.cut_eval_weighted(xs=xs)), z["cuts"])
+    packed = st.pack(xs)
+    assert np.array_equal(_np(st.cut_eval_weighted(packed=packed, num_envs=envs)), z["cuts"])
+    fields = _np(st.node_fields_weighted(packed, envs))[:, :n].astype(np.int64)
+    assert np.array_equal(fields, om.node_fields_weighted(edges, n, z["xs"]))
+    # the unweighted entry points keep ignoring weights, like the reference's EnvMaxcut (env_L2A.py:54-66)
+    unit = om.build_graph_store(edges, True)
+    assert np.array_equal(_np(st.cut_eval(xs)), om.cut_values(unit, z["xs"]))
+
+
+@pytest.mark.parametrize("values,envs", [((-1, 1), 4096), ((-5, -1, 1, 2, 6), 333), ((1, 1, 1, 3), 64)])
+def test_weighted_cut_g22_shape_vs_oracle(values, envs, cuda_device):
+    from rlsolver_b200.graph_store import GraphStore
+    rng = np.random.default_rng(len(values))
+    edges = [(a, b, int(rng.choice(values))) for a, b, _ in gset_like("G22")]
+    n = 2000
+    st = GraphStore(edges, False, device=cuda_device, num_nodes=n)
+    xs_np = _rand_xs(envs, n, 3)
+    xs = th.from_numpy(xs_np).to(cuda_device)
+    assert np.array_equal(_np(st.cut_eval_weighted(xs=xs)), om.cut_values_weighted(edges, xs_np))
+    got = _np(st.node_fields_weighted(st.pack(xs), envs))[:, :n].astype(np.int64)
+    assert np.array_equal(got, om.node_fields_weighted(edges, n, xs_np))
+    with pytest.raises(ValueError):
+        GraphStore(gset_like("G14"), False, device=cuda_device).cut_eval_weighted(xs=th.zeros((2, 800), dtype=th.bool,
+                                                                                              device=cuda_device))
+
+
+# ------------------------------------------------------------------ weighted MCPG sampler (a12, float edge_attr)
+@pytest.mark.parametrize("path", golden_files("wmcpg_"), ids=os.path.basename)
+def test_weighted_mcpg_sampler_matches_reference(path, cuda_device):
+    """mcpg_sampling_maxcut (MCPG/sampling.py:89-127) with the reference's recorded draws replayed: +-1, integer and
+    dyadic weights bit-exact; arbitrary float weights within 1e-5 on every chain whose decisions agree."""
+    from rlsolver_b200.methods.MCPG import WeightedMcpgData, mcpg_sampling_maxcut
+    z = np.load(path)
+    n, t = int(z["num_nodes"]), int(z["total_mcmc"])
+    data = WeightedMcpgData(z["edges"], z["weights"], n, cuda_device)
+    assert np.array_equal(data.sorted_degree_nodes.numpy(), z["order"])
+    assert abs(data.edge_weight_sum - float(z["edge_weight_sum"])) < 1e-6
+    dev = cuda_device
+    explicit = (th.from_numpy(z["metro_idx"]).to(dev), th.from_numpy(z["metro_u"]).to(dev))
+    vs_good, xs_good, start, value = mcpg_sampling_maxcut(
+        data, th.from_numpy(z["start"]).to(dev), th.from_numpy(z["probs"]).to(dev), int(z["num_ls"]),
+        int(z["change_times"]), t, dev, _explicit=explicit, _explicit_u=th.from_numpy(z["ls_u"]).to(dev))
+    assert np.array_equal(_np(start), z["metro_out"])
+    if "float" in os.path.basename(path):
+        same = (_np(xs_good) == z["xs_good"]).all(axis=0)
+        assert same.mean() >= 0.8
+        np.testing.assert_allclose(_np(vs_good)[same], z["vs_good"][same], rtol=1e-5, atol=1e-5)
+        return
+    assert np.array_equal(_np(xs_good), z["xs_good"]) and np.array_equal(_np(vs_good), z["vs_good"])
+    np.testing.assert_allclose(_np(value), z["value"], rtol=0, atol=1e-4)
+
+
+def test_weighted_mcpg_sampler_same_seed_vs_oracle(cuda_device):
+    """Generator consumed in place: the kernel's decisions from torch's Philox stream equal the oracle fed with the
+    draws torch.rand returns for the same seed, and the generator ends where num_ls * N rand(C) calls leave it."""
+    from oracle import mcpg as oq
+    from rlsolver_b200.methods.MCPG import WeightedMcpgData, mcpg_sampling_maxcut
+    rng = np.random.default_rng(4)
+    edges = np.asarray([(a, b) for a, b, _ in random_graph(300, 1500, seed=9)], dtype=np.int64)
+    weights = rng.choice([-1.0, 1.0, 0.5, -2.0, 3.0], size=len(edges)).astype(np.float32)
+    n, t, rep, num_ls, change = 300, 64, 4, 3, 6
+    c = t * rep
+    data = WeightedMcpgData(edges, weights, n, cuda_device)
+    th.manual_seed(77)
+    probs = th.rand(n, device=cuda_device) * 0.6 + 0.2
+    start = th.randint(0, 2, (n, c), device=cuda_device).float()
+    th.manual_seed(78)
+    vs_good, xs_good, metro_out, value = mcpg_sampling_maxcut(data, start, probs, num_ls, change, t, cuda_device)
+    after = th.cuda.get_rng_state(cuda_device)
+    # replay: the metro part again from the same seed (it consumes a data-dependent number of draws), then the
+    # num_ls * N uniform draws of the sweeps
+    from rlsolver_b200.methods.MCPG import metro_sampling
+    th.manual_seed(78)
+    again = metro_sampling(probs, start.clone(), change, cuda_device)
+    assert th.equal(again, metro_out)
+    draws = np.stack([_np(th.rand(c, device=cuda_device)) for _ in range(num_ls * n)])
+    assert th.equal(th.cuda.get_rng_state(cuda_device), after)
+    want = oq.weighted_sampler(n, edges, weights, data.sorted_degree_nodes.numpy(), _np(metro_out), num_ls, t, draws)
+    assert np.array_equal(_np(xs_good), want[1]) and np.array_equal(_np(vs_good), want[0])

@@ -67,7 +67,8 @@ def run_case(kind, name, mygraph, batch, steps, seed):
     finally:
         th.rand = orig_rand
     ef, et = params["edge_from"].numpy(), params["edge_to"].numpy()
-    out = dict(edge_from=ef, edge_to=et, num_nodes=np.asarray(n), xs=np.stack(xs), energies=np.stack(energies),
+    adj = params["adj_matrix"].float().numpy()
+    out = dict(edge_from=ef, edge_to=et, edge_w=adj[ef, et].astype(np.int64), num_nodes=np.asarray(n), xs=np.stack(xs), energies=np.stack(energies),
                accs=np.stack(accs), paths=np.stack(paths), temps=np.asarray(temps, dtype=np.float64),
                draws=np.concatenate(draws).astype(np.float32), draw_sizes=np.asarray([d.size for d in draws]))
     path = os.path.join(OUT, f"{kind}_{name}_B{batch}.npz")

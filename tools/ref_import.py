@@ -31,6 +31,12 @@ def setup():
             def num_edges(self):
                 return self.edge_index.shape[1]
 
+            def to(self, device):   # torch_geometric moves every tensor attribute
+                for k, v in list(self.__dict__.items()):
+                    if hasattr(v, "to") and hasattr(v, "dtype"):
+                        self.__dict__[k] = v.to(device)
+                return self
+
         tgd.Data = Data
         tg.data = tgd
         sys.modules["torch_geometric"] = tg
