@@ -153,7 +153,7 @@ int64_t rlsb_ls_workspace_bytes(const rlsb_graph_t* g, int64_t num_envs);
 /* byte offset of a workspace section (tests / debugging): 0 packed u32 [W][Np], 1 cross counts
  * (uint8, or uint16 when a degree exceeds 255) tiled [W][Np/4][32 envs][4 nodes], 2 col_min i32 [Np], 3 col_max i32 [Np],
  * 4 listed degree + 0x4B400000 i32 [Np], 5 rd_std f32 [Np], 6 thresh f32 [E], 7 cross counts uint8 row-major
- * [32W][Np] (absent when a degree exceeds 255); -1 on error. */
+ * [32W][Np] (absent when a degree exceeds 255), 8 unit counters of the streaming generator (u32 pairs); -1 on error. */
 int64_t rlsb_ls_workspace_offset(const rlsb_graph_t* g, int64_t num_envs, int32_t section);
 int rlsb_ls_begin(const rlsb_graph_t* g, const uint8_t* xs, int64_t num_envs, int64_t* vs, int32_t compute_vs,
                   int32_t ws_mult, float noise_std, void* workspace, void* stream);
@@ -412,6 +412,55 @@ int rlsb_mcpg_weighted_sweeps(int32_t num_nodes, int64_t num_chains, const int32
                               const int32_t* edge_u, const int32_t* edge_v, const float* edge_w, float* xs,
                               int32_t num_sweeps, const float* explicit_u, uint64_t seed, uint64_t offset,
                               uint32_t rng_threads, uint32_t rng_iters, float* expected, void* stream);
+
+/* ---- pattern-I environment, COMPACT resident state (round 2; csrc/peco_compact.cu).  Same semantics as
+ * rlsb_peco_step for matrices with entries in {-1, 0, +1} (what util_envs_PECO.py:15-113 generates), with the
+ * state that lives in HBM reduced to bits and small integers:
+ *   adj uint32 [E][N][W] adjacency bit rows (W = ceil(N/32), diagonal bit = self loop); sgn uint32 bit = weight -1,
+ *   laid out [E][N][W] (sgn_stride = N*W), one shared [N][W] matrix (sgn_stride = 0) or NULL (all +1);
+ *   spins / best_spins uint32 [E][W] (bit = spin +1); fields int16 [E][Np] = (A s)_j; last_flip uint16 [E][Np];
+ *   score / best_score / max_local / reward float32 [E].
+ * compact_step    : SpinSystemUnbiased.step (spinsystem_PECO.py:306-486) for ExtraAction.NONE, reversible spins,
+ *                   infinite memory; `step` = 1-based index of this step.  Visited-state test (HistoryBuffer,
+ *                   util_envs_PECO.py:228-288) as a per-env open-addressing set of 64-bit Zobrist keys: hset uint64
+ *                   [E][hcap] (hcap a power of two >= 2 * (max_steps + 1), zeroed at reset), hkey uint64 [E] (0 at
+ *                   reset), zobrist uint64 [N] random constants; NULL when no stag / basin reward is used.
+ * compact_fields  : fields, cut (:601-607) and max_local (:163-171, from the all-ones state) for given spins;
+ *                   *empty_graphs counts envs whose all-ones fields are all zero or whose largest is zero (:166-171).
+ * compact_from_dense / expand_matrix : dense float32 [E][N][N] <-> bit rows (*bad_entries counts entries not in
+ *                   {-1, 0, 1}).  expand_state writes the reference's float32 state rows (obs row indices as in
+ *                   rlsb_peco_step; table[k] = k-fold float32 accumulation of 1/max_steps, k <= max_steps);
+ *                   *_env_stride = floats between consecutive envs of the destination (so both can write straight
+ *                   into an observation tensor [E][num_obs + N][N]).
+ * gen_er / gen_ba : RandomERGraphGenerator.get / RandomBAGraphGenerator.get (util_envs_PECO.py:40-52, 87-107)
+ *                   written as bit rows from torch's CUDA Philox stream (ER: the one rand(E, N, N) call; BA: the
+ *                   exponential_ call inside each torch.multinomial): same graphs as the reference's torch ops for
+ *                   the same seed.  The caller advances the generator (ER: 4 * rng_iters; BA: (N - m - 1) calls of
+ *                   E * N elements).  E * N * N (ER) and E * N (BA) must stay below 2^31 per call. */
+int rlsb_peco_compact_step(const uint32_t* adj, const uint32_t* sgn, int64_t sgn_stride, uint32_t* spins,
+                           int16_t* fields, uint16_t* last_flip, uint32_t* best_spins, float* score, float* best_score,
+                           const float* max_local, float* reward, const int64_t* action, uint64_t* hset,
+                           int32_t hcap, uint64_t* hkey, const uint64_t* zobrist, int32_t* bad_actions,
+                           int64_t num_envs, int32_t num_spins, int32_t step, int32_t reward_signal,
+                           int32_t norm_rewards, int32_t use_stag, float stag, int32_t use_basin, float basin,
+                           int32_t scalar_div_as_cuda, void* stream);
+int rlsb_peco_compact_fields(const uint32_t* adj, const uint32_t* sgn, int64_t sgn_stride, const uint32_t* spins,
+                             int64_t num_envs, int32_t num_spins, int16_t* fields, float* cut, float* max_local,
+                             int32_t* empty_graphs, void* stream);
+int rlsb_peco_compact_from_dense(const float* matrix, int64_t num_envs, int32_t num_spins, uint32_t* adj, uint32_t* sgn,
+                                 int32_t* bad_entries, void* stream);
+int rlsb_peco_compact_expand_matrix(const uint32_t* adj, const uint32_t* sgn, int64_t sgn_stride, int64_t num_envs,
+                                    int32_t num_spins, float* out, int64_t out_env_stride, void* stream);
+int rlsb_peco_compact_expand_state(const uint32_t* spins, const uint32_t* best_spins, const int16_t* fields,
+                                   const uint16_t* last_flip, const float* score, const float* best_score,
+                                   const float* max_local, const float* table, float* state, int64_t state_env_stride,
+                                   int64_t num_envs, int32_t num_spins, int32_t num_obs, const int32_t* h_obs_rows,
+                                   int32_t step, int32_t binary_spins, float termination, int32_t scalar_div_as_cuda,
+                                   int32_t at_reset, void* stream);
+int rlsb_peco_gen_er(uint32_t* adj, int64_t num_envs, int32_t num_spins, float p_connection, uint64_t seed,
+                     uint64_t offset, uint32_t rng_threads, uint32_t rng_iters, void* stream);
+int rlsb_peco_gen_ba(uint32_t* adj, int64_t num_envs, int32_t num_spins, int32_t m_insertion_edges, uint64_t seed,
+                     uint64_t offset, uint32_t rng_threads, uint32_t rng_iters, void* stream);
 
 #ifdef __cplusplus
 }

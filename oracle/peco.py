@@ -111,3 +111,46 @@ class SpinSystem:
         if binary:
             state[:, 0, :] = (1 - state[:, 0, :]) / 2
         return np.concatenate([state, self.m], axis=-2)
+
+
+# --------------------------------------------------------------------------- generators (torch restatement)
+def torch_edge_mask(edge_type: str, n: int, num_envs: int, device):
+    """util_envs_PECO.py:21-38 / 67-84, op for op: the edge-weight mask drawn per get() call.
+    edge_type in {"UNIFORM", "DISCRETE", "RANDOM"}.  TEST INFRASTRUCTURE: run on the same device and seed as the
+    generator kernels (csrc/peco_compact.cu) to check "same seed, same graphs"."""
+    import torch as th
+    if edge_type == "UNIFORM":
+        return th.ones((n, n), device=device)
+    if edge_type == "DISCRETE":
+        mask = 2. * th.randint(0, 2, (n, n), device=device) - 1.
+        return th.tril(mask) + th.triu(mask.T, 1)
+    mask = 2. * th.randint(0, 2, (num_envs, n, n), dtype=th.float32, device=device) - 1
+    return th.tril(mask, diagonal=0) + th.triu(mask.transpose(1, 2), diagonal=1)
+
+
+def torch_er_graphs(num_envs: int, n: int, p: float, edge_type: str, device):
+    """RandomERGraphGenerator.get (util_envs_PECO.py:40-52) with the reference's torch ops."""
+    import torch as th
+    adj = (th.rand(num_envs, n, n, device=device) < p).float()
+    adj = adj * (1 - th.eye(n, device=device).unsqueeze(0))
+    adj = th.triu(adj, diagonal=1)
+    adj = adj + adj.transpose(1, 2)
+    return adj * torch_edge_mask(edge_type, n, num_envs, device)
+
+
+def torch_ba_graphs(num_envs: int, n: int, m: int, edge_type: str, device):
+    """RandomBAGraphGenerator.get (util_envs_PECO.py:87-107) with the reference's torch ops, including the self loops
+    its initial clique loop sets."""
+    import torch as th
+    adj = th.zeros((num_envs, n, n), device=device)
+    for i in range(m + 1):
+        adj[:, i, :i + 1] = 1
+        adj[:, :i + 1, i] = 1
+    for new_node in range(m + 1, n):
+        degree = adj.sum(dim=-1)
+        prob = degree / degree.sum(dim=-1, keepdim=True)
+        chosen = th.multinomial(prob, num_samples=m, replacement=False)
+        batch = th.arange(num_envs, device=device).repeat_interleave(m)
+        adj[batch, new_node, chosen.view(-1)] = 1
+        adj[batch, chosen.view(-1), new_node] = 1
+    return adj * torch_edge_mask(edge_type, n, num_envs, device)

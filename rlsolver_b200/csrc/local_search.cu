@@ -1242,8 +1242,8 @@ int64_t rlsb_ls_workspace_offset(const rlsb_graph_t* gh, int64_t num_envs, int32
   if (graph_check(gh, &g, "ls_workspace_offset") || num_envs < 0) return -1;
   char* base = reinterpret_cast<char*>(uintptr_t(4096));
   const LsWorkspace w = carve(*g, num_envs, base);
-  const void* at[8] = {w.packed, w.cross, w.col_min, w.col_max, w.degm, w.rd_std, w.thresh, w.cross_rows};
-  if (section < 0 || section > 7 || !at[section]) return -1;
+  const void* at[9] = {w.packed, w.cross, w.col_min, w.col_max, w.degm, w.rd_std, w.thresh, w.cross_rows, w.ctl};
+  if (section < 0 || section > 8 || !at[section]) return -1;
   return static_cast<const char*>(at[section]) - base;
 }
 
@@ -1376,6 +1376,7 @@ int rlsb_ls_fused_search(const rlsb_graph_t* gh, int64_t num_envs, int64_t* vs, 
     if (int rc = mask_plan(*g, "ls_fused_search", num_envs, ws_mult, seed, offset, rng_dev, rng_threads, rng_iters,
                            num_iters, masks, workspace, &plan))
       return rc;
+    if (int rc = mask_stream_preload(plan, st)) return rc;
     if (int rc = mask_prepare(plan, true, true, st)) return rc;
     RLSB_CUDA_OK(cudaEventRecord(side.fork, st));
     ctl = plan.ctl, units = (uint32_t)rng_threads / 256u;

@@ -107,6 +107,7 @@ int mask_plan(const GraphDev& g, const char* what, int64_t num_envs, int ws_mult
               const uint64_t* rng_dev, int rng_threads, int rng_iters, int num_draws, uint32_t* masks, void* workspace,
               MaskPlan* plan);
 int mask_prepare(const MaskPlan& p, bool write_bound, bool zero_ctl, cudaStream_t st);
+int mask_stream_preload(const MaskPlan& p, cudaStream_t st);
 int mask_stream_launch(const MaskPlan& p, cudaStream_t st);
 constexpr int kGenGroup = 2;   // draws the streaming generator finishes together (= what a tile iteration waits for)
 

@@ -364,6 +364,28 @@ int mask_prepare(const MaskPlan& p, bool write_bound, bool zero_ctl, cudaStream_
   return RLSB_OK;
 }
 
+// CUDA loads a kernel's code lazily, at its first launch, and that load may need the context to go idle: a FIRST
+// launch of the generator while tile CTAs are already spinning on its counters would never start (CUDA Programming
+// Guide, "Lazy Loading": preload kernels that must run concurrently).  Called on the caller's stream before the
+// tile kernel of a fused search is launched: once per device it runs the generator with no work.
+int mask_stream_preload(const MaskPlan& p, cudaStream_t st) {
+  static bool loaded[64] = {};
+  int dev = 0;
+  RLSB_CUDA_OK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && loaded[dev]) return RLSB_OK;
+  cudaFuncAttributes attr;
+  RLSB_CUDA_OK(cudaFuncGetAttributes(&attr, noise_mask_stream_kernel));
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  RLSB_CUDA_OK(cudaStreamIsCapturing(st, &cap));
+  RLSB_REQUIRE(cap == cudaStreamCaptureStatusNone, RLSB_ERR_INVALID,
+               "fused search: the first call on a device must not be captured into a CUDA graph (run it once eagerly: "
+               "the generator kernel has to be loaded before it can run next to the tile kernel)");
+  noise_mask_stream_kernel<<<1, 256, 0, st>>>(p.a, p.bound, p.r, p.ctl, 0, 0u);     // no draws: returns at once
+  RLSB_LAUNCH_OK();
+  if (dev >= 0 && dev < 64) loaded[dev] = true;
+  return RLSB_OK;
+}
+
 // the streaming generator: one persistent block per SM on `st` (the tile kernel polls ctl)
 int mask_stream_launch(const MaskPlan& p, cudaStream_t st) {
   RLSB_REQUIRE(p.num_draws <= kLsMaxFusedDraws, RLSB_ERR_INVALID, "fused search: at most %d draws per call", kLsMaxFusedDraws);
