@@ -50,6 +50,8 @@ const char* rlsb_last_error(void);
 #define RLSB_DEBUG_FULL_CUT 2    /* RLSB_LS_FULL_CUT=1: rlsb_ls_run_masks re-counts all edges for every candidate */
 #define RLSB_DEBUG_LS_SKIP 4     /* RLSB_LS_SKIP=1: rlsb_ls_run consumers skip the arithmetic (streaming-rate probe) */
 #define RLSB_DEBUG_LS_TIMES 8    /* RLSB_LS_TIMES=1: CTA 0 of the local-search kernels stamps clock64 per phase */
+#define RLSB_DEBUG_CARVEOUT_DEFAULT 16 /* RLSB_CARVEOUT_DEFAULT=1: the fused search leaves the shared-memory carve-out of its two kernels to the driver (they then do not share SMs) */
+#define RLSB_DEBUG_GEN_PER_DRAW 32 /* RLSB_GEN_PER_DRAW=1: rlsb_ls_noise_masks uses the one-draw-per-thread generator (round-1 form) */
 int32_t rlsb_debug_flags(int32_t set_mask, int32_t clear_mask);
 
 /* ---- graph store: replaces EnvMaxcut.__init__ (rlsolver/envs/env_L2A.py:25-52),
@@ -198,6 +200,10 @@ int rlsb_ls_fused_search(const rlsb_graph_t* g, int64_t num_envs, int64_t* vs, i
                          uint64_t offset, const uint64_t* rng_dev, int32_t rng_threads, int32_t rng_iters,
                          int32_t num_iters, int32_t finish, uint8_t* xs_out, uint32_t* masks, void* workspace,
                          void* stream);
+/* Diagnostics of the last rlsb_ls_fused_search on this workspace (synchronises `stream`): h_out3 = {generator blocks
+ * that started, tile CTAs whose bounded wait for a group of draws ran out, units finished of the first group}.
+ * A non-zero second word means the two kernels were not scheduled together and the call's results are invalid. */
+int rlsb_ls_fused_status(const rlsb_graph_t* g, int64_t num_envs, const void* workspace, uint32_t* h_out3, void* stream);
 /* rlsb_ls_begin for a state handed over as packed tiles (uint32 [ceil(E/32)][Np], bit b of word [t][i] = node i
  * of env 32t + b; bits of envs >= E must be 0): what a host that keeps spins packed sends, 1 bit instead of
  * 1 byte per spin.  packed_in may be the workspace's own packed section (no copy then). */
@@ -461,6 +467,25 @@ int rlsb_peco_gen_er(uint32_t* adj, int64_t num_envs, int32_t num_spins, float p
                      uint64_t offset, uint32_t rng_threads, uint32_t rng_iters, void* stream);
 int rlsb_peco_gen_ba(uint32_t* adj, int64_t num_envs, int32_t num_spins, int32_t m_insertion_edges, uint64_t seed,
                      uint64_t offset, uint32_t rng_threads, uint32_t rng_iters, void* stream);
+
+/* ---- float tail of an ISCO / PISCO Metropolis-Hastings step (csrc/isco.cu), one CTA per chain:
+ * propose = get_local_dist + multinomial + the flip (rlsolver/envs/env_ISCO.py:37-63 / 394-418,
+ *           rlsolver/methods/ISCO/util.py:3-60); accept = get_local_dist(y) + ll_y2x + mh_step (env_ISCO.py:27-35, 65-77,
+ *           util.py:62-75).  x / y: [B][ld] float32 (is_half = 0) or float16 (1), entries {0, 1}; ld >= num_nodes, sites
+ *           >= num_nodes are padding with gain 0 (PISCO pads to a multiple of 8 and its softmax includes them).
+ * cross: per (chain, site) uint16 cross counts [B][cross_ld] of rlsb_node_cross_counts (weighted = 0) or the int32
+ *           sums of rlsb_node_fields_weighted (weighted = 1); deg int32 [N] = (weighted) degree; the flip gain is
+ *           (deg - 2 cross) / (2 T).  cut int64 [B] (ISCO energy = cut / T; pisco = 1: -1/4 fp16(sum of gains) / T).
+ * u: the uniform draws the reference makes (gumbel: [B][ld], then bernoulli_logp: [B]).  sel int32 [B][kmax]: the
+ *           chosen sites in order (-1 padded), kmax >= max path_length.  accept overwrites y with the next state. */
+int rlsb_isco_propose(const void* x, void* y, int32_t is_half, const void* cross, int32_t weighted, int32_t cross_ld,
+                      const int32_t* deg, const int64_t* cut, int32_t pisco, const float* temperature,
+                      const int64_t* path_length, const float* u, int32_t* sel, int32_t kmax, float* ll_x, float* ll_x2y,
+                      int32_t num_nodes, int32_t ld, int64_t num_chains, void* stream);
+int rlsb_isco_accept(const void* x, void* y, int32_t is_half, const void* cross_y, int32_t weighted, int32_t cross_ld,
+                     const int32_t* deg, const int64_t* cut_y, int32_t pisco, const float* temperature, const float* u,
+                     const int32_t* sel, int32_t kmax, const float* ll_x, const float* ll_x2y, float* ll_y_times_t,
+                     float* acc, int32_t num_nodes, int32_t ld, int64_t num_chains, void* stream);
 
 #ifdef __cplusplus
 }

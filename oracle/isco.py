@@ -1,9 +1,6 @@
-"""Path-auxiliary sampling helpers of ISCO (rlsolver/methods/ISCO/util.py:3-75), restated.
-
-These are small dense float32 ops on [B, N] tensors (sort / cumsum / exp / log); they stay torch
-calls in the reference's order so a replayed uniform stream gives the reference's choices.  The
-part of an ISCO step that touches the graph -- energies and per-node flip gains -- comes from the
-sm_100a kernels (see envs/env_ISCO.py)."""
+"""Torch restatement of the path-auxiliary sampling helpers of ISCO (rlsolver/methods/ISCO/util.py:3-75) and of the
+step built on them (rlsolver/envs/env_ISCO.py:27-77).  TEST INFRASTRUCTURE ONLY: the product path runs
+csrc/isco.cu (rlsb_isco_propose / rlsb_isco_accept); the tests feed both the same uniform draws and compare."""
 from __future__ import annotations
 
 from typing import Dict, Tuple
@@ -60,3 +57,33 @@ def mh_step(log_prob: TEN, current_sample: TEN, new_sample: TEN) -> Tuple[TEN, T
     """util.py:67-75: Metropolis-Hastings accept per chain."""
     accept = bernoulli_logp(log_prob)
     return th.where(accept.unsqueeze(-1).expand_as(new_sample), new_sample, current_sample), accept
+
+
+
+def step(log_prob_of, x: TEN, path_length: TEN, u_gumbel: TEN, u_accept: TEN):
+    """One MH step (env_ISCO.py:27-77) given `log_prob_of(state) -> (energy [B], log_prob [B, N])` and the two uniform
+    draws the reference makes (gumbel: [B, N], bernoulli_logp: [B]).  Returns (next state, ll_y, log_acc, ll_x2y,
+    ll_y2x, selected mask)."""
+    ll_x, log_prob = log_prob_of(x)
+    num_classes = log_prob.shape[-1]
+    perturbed = log_prob - th.log(-th.log(u_gumbel))
+    ascending, _ = th.sort(perturbed)
+    threshold = th.gather(ascending, 1, (num_classes - path_length).unsqueeze(1))
+    mask = (perturbed >= threshold.expand_as(perturbed)).int()
+    order = th.argsort(-perturbed, dim=-1)
+    ll_in_order = noreplacement_sampling_renormalize(th.gather(log_prob, dim=-1, index=order))
+    ll_selected = th.zeros_like(ll_in_order)
+    ll_selected.scatter_(1, order, ll_in_order)
+    ll_x2y = th.sum(ll_selected * mask, dim=-1)
+    y = x * (1 - mask) + mask * (1 - x)
+    ll_y, log_prob_y = log_prob_of(y)
+    backwd_idx = th.argsort(perturbed, dim=-1)
+    log_prob_y = th.where(mask.bool(), log_prob_y, th.tensor(-1e18, device=x.device))
+    backwd_ll = th.gather(log_prob_y, dim=-1, index=backwd_idx)
+    backwd_mask = th.gather(mask, dim=-1, index=backwd_idx)
+    ll_backwd = noreplacement_sampling_renormalize(backwd_ll)
+    ll_y2x = th.sum(th.where(backwd_mask.bool(), ll_backwd, th.tensor(0.0, device=x.device)), dim=-1)
+    log_acc = th.clamp(ll_y + ll_y2x - ll_x - ll_x2y, max=0.0)
+    accept = th.log(u_accept + 1e-24) < log_acc
+    nxt = th.where(accept.unsqueeze(-1).expand_as(y), y, x)
+    return nxt, ll_y, log_acc, ll_x2y, ll_y2x, mask

@@ -118,6 +118,7 @@ SIGNATURES = {
     "rlsb_rng_cursor_advance": (C.c_int, [_vp, _u64, _vp]),
     "rlsb_ls_run_masks": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "rlsb_ls_fused_search": (C.c_int, [_vp, _i64, _vp, _i32, _u64, _u64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "rlsb_ls_fused_status": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "rlsb_ls_begin_packed": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _f32, _vp, _vp]),
     "rlsb_torch_randn": (C.c_int, [_vp, _i64, _u64, _u64, _vp, _i32, _i32, _i32, _vp]),
     "rlsb_flip_sweep": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
@@ -157,6 +158,10 @@ SIGNATURES = {
                                                  _i32, _i32, _f32, _i32, _i32, _vp]),
     "rlsb_peco_gen_er": (C.c_int, [_vp, _i64, _i32, _f32, _u64, _u64, _u32, _u32, _vp]),
     "rlsb_peco_gen_ba": (C.c_int, [_vp, _i64, _i32, _i32, _u64, _u64, _u32, _u32, _vp]),
+    "rlsb_isco_propose": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp,
+                                    _i32, _i32, _i64, _vp]),
+    "rlsb_isco_accept": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
+                                   _vp, _i32, _i32, _i64, _vp]),
     "rlsb_select_rows": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "rlsb_best_record": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp]),
     "rlsb_best_record_packed": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i64, _vp, _vp]),

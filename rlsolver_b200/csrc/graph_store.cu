@@ -115,7 +115,9 @@ static int debug_flags_from_env() {
   const struct { const char* name; int bit; } vars[] = {{"RLSB_LS_PLAIN_MASKS", RLSB_DEBUG_PLAIN_MASKS},
                                                         {"RLSB_LS_FULL_CUT", RLSB_DEBUG_FULL_CUT},
                                                         {"RLSB_LS_SKIP", RLSB_DEBUG_LS_SKIP},
-                                                        {"RLSB_LS_TIMES", RLSB_DEBUG_LS_TIMES}};
+                                                        {"RLSB_LS_TIMES", RLSB_DEBUG_LS_TIMES},
+                                                        {"RLSB_CARVEOUT_DEFAULT", RLSB_DEBUG_CARVEOUT_DEFAULT},
+                                                        {"RLSB_GEN_PER_DRAW", RLSB_DEBUG_GEN_PER_DRAW}};
   for (const auto& v : vars) {
     const char* e = getenv(v.name);
     if (e && e[0] == '1') f |= v.bit;

@@ -859,8 +859,24 @@ __device__ __forceinline__ bool gen_group_ready(const uint32_t* ctl, int group, 
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctl + 2 * group + 1) : "memory");
   return v >= units;
 }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// bounded: a generator that never shows up (it would mean the two kernels were not scheduled together) must not hang
+// the device; the stall is recorded and reported by rlsb_ls_fused_status
 __device__ __forceinline__ void gen_group_wait(const uint32_t* ctl, int group, uint32_t units) {
-  while (!gen_group_ready(ctl, group, units)) __nanosleep(200);
+  if (gen_group_ready(ctl, group, units)) return;
+  if (*reinterpret_cast<const volatile uint32_t*>(ctl + kLsCtlStalled) != 0u) return;     // already given up
+  const unsigned long long t0 = global_ns();
+  while (!gen_group_ready(ctl, group, units)) {
+    __nanosleep(200);
+    if (global_ns() - t0 > kLsStallNs) {
+      atomicAdd(const_cast<uint32_t*>(ctl) + kLsCtlStalled, 1u);
+      return;
+    }
+  }
 }
 
 // 96 registers: a CTA (512 threads) leaves a quarter of the register file to the generator block that runs
@@ -1122,6 +1138,9 @@ static int launch_bits(const GraphDev& g, LsArgs a, const uint32_t* masks, cudaS
   // slots of the sweep structure are addressed with 16 bits; RLSB_DEBUG_FULL_CUT keeps the full re-count (cross-check)
   const int use_delta = (g.num_sweep_slices * 32 <= 65536 && !(debug_flags() & RLSB_DEBUG_FULL_CUT)) ? 1 : 0;
   if (int rc = allow_smem(ls_bits_kernel<P>, smem)) return rc;
+  if (ctl && !(debug_flags() & RLSB_DEBUG_CARVEOUT_DEFAULT))      // fused search: same carve-out as the generator (see there)
+    RLSB_CUDA_OK(cudaFuncSetAttribute(ls_bits_kernel<P>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
   // persistent: at most one CTA per SM (96 registers x 512 threads: a second one would not fit anyway)
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
   ls_bits_kernel<P><<<grid, kLSThreads, smem, st>>>(g, a, masks, ls_mask_words(a.num_envs, g.n), use_delta, ctl, units);
@@ -1393,6 +1412,23 @@ int rlsb_ls_fused_search(const rlsb_graph_t* gh, int64_t num_envs, int64_t* vs, 
     RLSB_CUDA_OK(cudaEventRecord(side.join, side.stream));
     RLSB_CUDA_OK(cudaStreamWaitEvent(st, side.join, 0));
   }
+  return RLSB_OK;
+}
+
+// diagnostics of the last fused search on this workspace: out3 = {generator blocks that started, tile CTAs whose wait
+// for a group of draws ran out (non-zero: the results of that call are invalid), units finished of the first group}
+int rlsb_ls_fused_status(const rlsb_graph_t* gh, int64_t num_envs, const void* workspace, uint32_t* h_out3, void* stream) {
+  using namespace rlsb;
+  const GraphDev* g;
+  if (int rc = graph_check(gh, &g, "ls_fused_status")) return rc;
+  RLSB_REQUIRE(workspace && h_out3, RLSB_ERR_INVALID, "ls_fused_status: null pointer");
+  const LsWorkspace w = carve(*g, num_envs, const_cast<void*>(workspace));
+  auto st = static_cast<cudaStream_t>(stream);
+  uint32_t tmp[3];
+  RLSB_CUDA_OK(cudaMemcpyAsync(&tmp[0], w.ctl + kLsCtlStarted, 8, cudaMemcpyDeviceToHost, st));
+  RLSB_CUDA_OK(cudaMemcpyAsync(&tmp[2], w.ctl + 1, 4, cudaMemcpyDeviceToHost, st));
+  RLSB_CUDA_OK(cudaStreamSynchronize(st));
+  h_out3[0] = tmp[0], h_out3[1] = tmp[1], h_out3[2] = tmp[2];
   return RLSB_OK;
 }
 

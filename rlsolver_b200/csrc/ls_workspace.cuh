@@ -33,7 +33,13 @@ inline int64_t ls_bound_bytes(int64_t numel) { return (numel + 4 * (int64_t)kNum
 // Streaming mask generator <-> tile kernel hand-shake (rlsb_ls_fused_search): per group of draws two counters,
 // ctl[2g] = units handed out, ctl[2g + 1] = units finished.
 constexpr int kLsMaxFusedDraws = 1024;
-constexpr size_t kLsCtlBytes = (size_t)(kLsMaxFusedDraws + 2) * 2 * sizeof(uint32_t);
+constexpr int kLsCtlWords = (kLsMaxFusedDraws + 2) * 2 + 4;
+constexpr size_t kLsCtlBytes = (size_t)kLsCtlWords * sizeof(uint32_t);
+// diagnostics at the end of the counter block: generator blocks that started, tile CTAs whose wait ran out
+constexpr int kLsCtlStarted = kLsCtlWords - 2, kLsCtlStalled = kLsCtlWords - 1;
+// a tile CTA gives up waiting for a group of draws after this many nanoseconds (the call then reports
+// RLSB_ERR_CUDA through rlsb_ls_fused_status instead of hanging the device)
+constexpr unsigned long long kLsStallNs = 4000000000ull;
 
 // workspace carving (all sections 256-byte aligned)
 struct LsWorkspace {

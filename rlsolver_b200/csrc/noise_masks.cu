@@ -213,77 +213,101 @@ __global__ void __launch_bounds__(256) noise_mask_fast_kernel(MaskArgs a, const 
 // exactly as in noise_mask_fast_kernel.
 constexpr int kGenQueue = 32 + 64 * kGenGroup;
 
+// one unit: the 256-thread slice `unit` of the call geometry, every round, the draws k0 .. k0 + nd - 1
+__device__ __forceinline__ void gen_unit(const MaskArgs& a, const uint8_t* __restrict__ planes, const PhiloxKey& key,
+                                         const PhiloxKeys& pkey, uint32_t T, uint32_t iters, uint32_t unit, int k0, int nd,
+                                         uint32_t* q) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint64_t plane = (uint64_t)iters * T;
+  const uint32_t idx = unit * 256 + threadIdx.x;
+  const uint8_t* bp = planes + idx;
+  int cnt = 0;
+
+  auto exact = [&](uint32_t ent) {                // one queued pair: bit 0 = second pair, bit 1 = draw in the group
+    const uint32_t jj = ent >> 8, src = idx - lane + ((ent >> 2) & 31u), d = (ent >> 1) & 1u;
+    const uint64_t ctr = key.offset4 + (uint64_t)(k0 + d) * iters + jj;
+    const uint4 o = philox10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), src, 0u), pkey);
+    const bool second = (ent & 1u) != 0u;
+    mask_exact_pair(a, a.masks + (int64_t)(k0 + d) * a.mask_words, second ? o.z : o.x, second ? o.w : o.y,
+                    src + T * (4u * jj + (second ? 2u : 0u)), T);
+  };
+
+  uint32_t ca = __ldg(bp), cb = __ldg(bp + plane);
+  for (uint32_t j = 0; j < iters; ++j) {
+    bp += T;
+    uint32_t can = 0, cbn = 0;
+    if (j + 1 < iters) can = __ldg(bp), cbn = __ldg(bp + plane);
+    uint4 o[kGenGroup];
+#pragma unroll
+    for (int d = 0; d < kGenGroup; ++d) {
+      const uint64_t ctr = key.offset4 + (uint64_t)(k0 + d) * iters + j;
+      o[d] = philox10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), idx, 0u), pkey);
+    }
+#pragma unroll
+    for (int d = 0; d < kGenGroup; ++d) {
+      const bool pa = d < nd && (o[d].x >> 24) <= ca, pb = d < nd && (o[d].z >> 24) <= cb;
+      const uint32_t ba = __ballot_sync(kFull, pa), bb = __ballot_sync(kFull, pb);
+      const uint32_t ent = (j << 8) | ((uint32_t)lane << 2) | ((uint32_t)d << 1);
+      if (pa) q[cnt + __popc(ba & lt)] = ent;
+      if (pb) q[cnt + __popc(ba) + __popc(bb & lt)] = ent | 1u;
+      cnt += __popc(ba) + __popc(bb);
+    }
+    __syncwarp();
+    while (cnt >= 32) {
+      cnt -= 32;
+      const uint32_t mine = q[cnt + lane];
+      __syncwarp();
+      exact(mine);
+    }
+    ca = can, cb = cbn;
+  }
+  if (lane < cnt) exact(q[lane]);
+}
+
 __global__ void __maxnreg__(64) noise_mask_stream_kernel(MaskArgs a, const uint8_t* __restrict__ planes, TorchRng r,
                                                          uint32_t* __restrict__ ctl, int num_draws, uint32_t units) {
   __shared__ uint32_t queue[8][kGenQueue];
-  __shared__ uint32_t sUnit;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t lt = (1u << lane) - 1u;
+  __shared__ uint32_t sUnit[2];
   const PhiloxKey key = philox_key(r);
   const PhiloxKeys pkey = philox_keys(key.seed);
-  const uint32_t T = r.threads, iters = r.iters_per_call;
-  const uint64_t plane = (uint64_t)iters * T;
-  uint32_t* q = queue[warp];
+  uint32_t* q = queue[threadIdx.x >> 5];
   const int groups = (num_draws + kGenGroup - 1) / kGenGroup;
+  if (threadIdx.x == 0 && groups > 0) atomicAdd(ctl + kLsCtlStarted, 1u);
   for (int g = 0; g < groups; ++g) {
     const int k0 = g * kGenGroup;
     const int nd = min(kGenGroup, num_draws - k0);
-    for (;;) {
-      if (threadIdx.x == 0) sUnit = atomicAdd(ctl + 2 * g, 1u);
-      __syncthreads();
-      const uint32_t unit = sUnit;
-      __syncthreads();                                // everybody has read it before thread 0 claims the next one
+    // units are claimed one ahead: the atomic of the next claim is in flight while the current unit is processed
+    if (threadIdx.x == 0) sUnit[0] = atomicAdd(ctl + 2 * g, 1u);
+    __syncthreads();
+    for (int cur = 0;; cur ^= 1) {
+      const uint32_t unit = sUnit[cur];
       if (unit >= units) break;                       // uniform: every thread read the same value
-      const uint32_t idx = unit * 256 + threadIdx.x;
-      const uint8_t* bp = planes + idx;
-      int cnt = 0;
-
-      auto exact = [&](uint32_t ent) {                // one queued pair: bit 0 = second pair, bit 1 = draw in the group
-        const uint32_t jj = ent >> 8, src = idx - lane + ((ent >> 2) & 31u), d = (ent >> 1) & 1u;
-        const uint64_t ctr = key.offset4 + (uint64_t)(k0 + d) * iters + jj;
-        const uint4 o = philox10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), src, 0u), pkey);
-        const bool second = (ent & 1u) != 0u;
-        mask_exact_pair(a, a.masks + (int64_t)(k0 + d) * a.mask_words, second ? o.z : o.x, second ? o.w : o.y,
-                        src + T * (4u * jj + (second ? 2u : 0u)), T);
-      };
-
-      uint32_t ca = __ldg(bp), cb = __ldg(bp + plane);
-      for (uint32_t j = 0; j < iters; ++j) {
-        bp += T;
-        uint32_t can = 0, cbn = 0;
-        if (j + 1 < iters) can = __ldg(bp), cbn = __ldg(bp + plane);
-        uint4 o[kGenGroup];
-#pragma unroll
-        for (int d = 0; d < kGenGroup; ++d) {
-          const uint64_t ctr = key.offset4 + (uint64_t)(k0 + d) * iters + j;
-          o[d] = philox10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), idx, 0u), pkey);
-        }
-#pragma unroll
-        for (int d = 0; d < kGenGroup; ++d) {
-          const bool pa = d < nd && (o[d].x >> 24) <= ca, pb = d < nd && (o[d].z >> 24) <= cb;
-          const uint32_t ba = __ballot_sync(kFull, pa), bb = __ballot_sync(kFull, pb);
-          const uint32_t ent = (j << 8) | ((uint32_t)lane << 2) | ((uint32_t)d << 1);
-          if (pa) q[cnt + __popc(ba & lt)] = ent;
-          if (pb) q[cnt + __popc(ba) + __popc(bb & lt)] = ent | 1u;
-          cnt += __popc(ba) + __popc(bb);
-        }
-        __syncwarp();
-        while (cnt >= 32) {
-          cnt -= 32;
-          const uint32_t mine = q[cnt + lane];
-          __syncwarp();
-          exact(mine);
-        }
-        ca = can, cb = cbn;
-      }
-      if (lane < cnt) exact(q[lane]);
-      __syncthreads();                                // every flip bit of the unit has been issued
+      uint32_t next_unit = 0;
+      if (threadIdx.x == 0) next_unit = atomicAdd(ctl + 2 * g, 1u);
+      gen_unit(a, planes, key, pkey, r.threads, r.iters_per_call, unit, k0, nd, q);
+      if (threadIdx.x == 0) sUnit[cur ^ 1] = next_unit;
+      __syncthreads();                                // every flip bit of the unit has been issued; the next claim is published
       if (threadIdx.x == 0) {
         __threadfence();                              // ... and is visible device-wide before the count moves
         atomicAdd(ctl + 2 * g + 1, 1u);
       }
     }
+    __syncthreads();                                  // sUnit is rewritten for the next group
   }
+}
+
+// The same unit loop as an ordinary grid (one block per unit and group of draws): the generator of the SEQUENTIAL
+// path.  Two draws per thread share the early-out bytes and give the scheduler two independent Philox blocks; the
+// ten round keys sit in registers.
+__global__ void __maxnreg__(64) noise_mask_group_kernel(MaskArgs a, const uint8_t* __restrict__ planes, TorchRng r,
+                                                        int num_draws) {
+  __shared__ uint32_t queue[8][kGenQueue];
+  const PhiloxKey key = philox_key(r);
+  const PhiloxKeys pkey = philox_keys(key.seed);
+  const int k0 = blockIdx.y * kGenGroup;
+  gen_unit(a, planes, key, pkey, r.threads, r.iters_per_call, blockIdx.x, k0, min(kGenGroup, num_draws - k0),
+           queue[threadIdx.x >> 5]);
 }
 
 // the same draws as explicit float32 tensors (tests: must equal torch.randn bit for bit)
@@ -389,6 +413,12 @@ int mask_stream_preload(const MaskPlan& p, cudaStream_t st) {
 // the streaming generator: one persistent block per SM on `st` (the tile kernel polls ctl)
 int mask_stream_launch(const MaskPlan& p, cudaStream_t st) {
   RLSB_REQUIRE(p.num_draws <= kLsMaxFusedDraws, RLSB_ERR_INVALID, "fused search: at most %d draws per call", kLsMaxFusedDraws);
+  // Two kernels only share an SM when they ask for the same shared-memory carve-out (measured: with the driver's
+  // per-kernel default the generator's blocks wait for the tile CTAs to leave, profiles/r02_fused_debug.log), so both
+  // kernels of the fused search ask for the largest one.
+  if (!(debug_flags() & RLSB_DEBUG_CARVEOUT_DEFAULT))
+    RLSB_CUDA_OK(cudaFuncSetAttribute(noise_mask_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
   noise_mask_stream_kernel<<<kNumSMs, 256, 0, st>>>(p.a, p.bound, p.r, p.ctl, p.num_draws, p.r.threads / 256);
   RLSB_LAUNCH_OK();
   return RLSB_OK;
@@ -425,6 +455,12 @@ int rlsb_ls_noise_masks(const rlsb_graph_t* gh, int64_t num_envs, int32_t ws_mul
     return RLSB_OK;
   }
   if (int rc = mask_prepare(plan, !reuse_bound, false, st)) return rc;
+  if (!(debug_flags() & RLSB_DEBUG_GEN_PER_DRAW) && (int64_t)(rng_threads / 256) * ((num_draws + kGenGroup - 1) / kGenGroup) >= 2 * kNumSMs) {
+    noise_mask_group_kernel<<<dim3((unsigned)(rng_threads / 256), (unsigned)((num_draws + kGenGroup - 1) / kGenGroup)), 256, 0, st>>>(
+        plan.a, plan.bound, plan.r, num_draws);
+    RLSB_LAUNCH_OK();
+    return RLSB_OK;
+  }
   // rounds are split over blockIdx.y only when there would be too few blocks to fill the GPU otherwise
   dim3 grid((unsigned)(rng_threads / 256), 1, (unsigned)num_draws);
   int jsplit = 1;

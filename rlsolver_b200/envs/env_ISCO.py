@@ -10,8 +10,11 @@ Both gradients are integers in disguise: with d = 2x-1, (1-2x_i) * grad_i / 2 = 
 / (2T) = (same-side neighbours - other-side neighbours) / (2T).  Here the integer part --
 cut[b] and cross[b][i] for all chains and nodes -- comes from the bit-packed tile kernels behind
 the C ABI (rlsb_pack_spins, rlsb_node_cross_counts, rlsb_cut_eval_packed); the float tail (one
-division by T, log_softmax, the Gumbel top-k path proposal and the MH accept) is the reference's
-own sequence of torch ops, so a replayed uniform stream reproduces its choices.
+division by T, log-softmax, the Gumbel top-k path proposal, the without-replacement renormalisation
+and the MH accept: 2 sorts, an argsort and ~15 elementwise launches per step in the reference,
+rlsolver/methods/ISCO/util.py:3-75) is two kernels with one CTA per chain (csrc/isco.cu:
+rlsb_isco_propose, rlsb_isco_accept).  The uniform draws are the reference's two torch.rand calls,
+made here in the same order and shape, so a seeded or replayed stream reproduces its choices.
 
 Numerics: PISCO's energy and flip gains reproduce the reference's fp16/fp32 roundings exactly
 (small integers, one division); ISCO's autograd accumulates +-0.5/T per edge with atomics, so its
@@ -22,9 +25,9 @@ from __future__ import annotations
 
 import torch as th
 
-from ..graph_store import GraphStore, require_cuda
+from .. import _lib
+from ..graph_store import GraphStore, _ptr, _stream_ptr, on_device, require_cuda
 from ..methods.ISCO import config_maxcut as cfg
-from ..methods.ISCO.util import mh_step, multinomial, noreplacement_sampling_renormalize
 
 TEN = th.Tensor
 
@@ -60,35 +63,66 @@ class _PathAuxMaxcut:
         cross = cross[:, :n].to(th.long) & 0xFFFF
         return cut, self._deg - 2 * cross
 
-    def step(self, x, path_length, temperature):
-        ll_x, y, trajectory = self.proposal(x, path_length, temperature)
-        ll_x2y = trajectory['ll_x2y']
-        ll_y, ll_y2x = self.ll_y2x(trajectory, y, temperature)
-        log_acc = th.clamp(ll_y + ll_y2x - ll_x - ll_x2y, max=0.0)
-        y = self.select_sample(log_acc, x, y)
-        return y, ll_y * temperature, log_acc.exp()
+    # ---- one MH step on the kernels (env_ISCO.py:27-77; util.py:3-75)
+    _pisco = False
+
+    def _raw_fields(self, sample: TEN):
+        """(cut int64 [B], per-site cross counts as the kernels take them, weighted flag, row stride)."""
+        n = self.max_num_nodes
+        bits = (sample[:, :n] != 0).contiguous()
+        b = bits.shape[0]
+        packed = self.store.pack(bits)
+        cross, _, _ = self.store.cross_counts(packed, b, want_minmax=False)
+        return self.store.cut_eval_packed(packed, b), cross, 0, self.store.padded_nodes
+
+    def _deg32(self) -> TEN:
+        d = getattr(self, "_deg_i32", None)
+        if d is None:
+            d = self._deg_i32 = self._deg.reshape(-1).to(th.int32).contiguous()
+        return d
+
+    def _temperature(self, temperature) -> TEN:
+        t = temperature if isinstance(temperature, th.Tensor) else th.tensor(float(temperature))
+        return t.to(device=self.device, dtype=th.float32).reshape(1).contiguous()
 
     def proposal(self, x, path_length, temperature):
-        ll_x, log_prob = self.get_local_dist(x, temperature)
-        selected_idx, ll_selected = multinomial(log_prob, path_length)
-        mask = selected_idx['selected_mask']
-        y = x * (1 - mask) + mask * (1 - x)
-        return ll_x, y, {'ll_x2y': th.sum(ll_selected, dim=-1), 'selected_idx': selected_idx}
+        """get_local_dist(x) + multinomial + the flips.  Returns (ll_x [B], y, trajectory) with trajectory =
+        {'ll_x2y' [B], 'selected_idx': {'sites' int32 [B, kmax]: the chosen sites in order, -1 padded}}."""
+        x = x.contiguous()
+        b, ld = x.shape
+        lib = _lib.lib()
+        cut, cross, weighted, cross_ld = self._raw_fields(x)
+        t = self._temperature(temperature)
+        pl = path_length.to(device=self.device, dtype=th.int64).contiguous()
+        u = th.rand((b, ld), device=self.device)                   # the draw of gumbel() (util.py:4)
+        kmax = int(min(ld, max(1, int(pl.max().item())))) if b else 1
+        sel = th.empty((b, kmax), dtype=th.int32, device=self.device)
+        y = th.empty_like(x)
+        ll_x = th.empty((b,), dtype=th.float32, device=self.device)
+        ll_x2y = th.empty_like(ll_x)
+        with on_device(self.device):
+            _lib.check(lib.rlsb_isco_propose(_ptr(x), _ptr(y), int(x.dtype == th.float16), _ptr(cross), weighted, cross_ld,
+                                             _ptr(self._deg32()), _ptr(cut), int(self._pisco), _ptr(t), _ptr(pl), _ptr(u),
+                                             _ptr(sel), kmax, _ptr(ll_x), _ptr(ll_x2y), self.max_num_nodes, ld, b,
+                                             _stream_ptr(self.device)), "isco_propose")
+        return ll_x, y, {'ll_x2y': ll_x2y, 'selected_idx': {'sites': sel}, '_t': t}
 
-    def ll_y2x(self, forward_trajectory, y, temperature):
-        ll_y, log_prob = self.get_local_dist(y, temperature)
-        selected_mask = forward_trajectory['selected_idx']['selected_mask']
-        backwd_idx = th.argsort(forward_trajectory['selected_idx']['perturbed_ll'], dim=-1)
-        log_prob = th.where(selected_mask.bool(), log_prob, th.tensor(-1e18, device=log_prob.device))
-        backwd_ll = th.gather(log_prob, dim=-1, index=backwd_idx)
-        backwd_mask = th.gather(selected_mask, dim=-1, index=backwd_idx)
-        ll_backwd = noreplacement_sampling_renormalize(backwd_ll)
-        zero = th.tensor(0.0, device=log_prob.device)
-        return ll_y, th.sum(th.where(backwd_mask.bool(), ll_backwd, zero), dim=-1)
-
-    def select_sample(self, log_acc, x, y):
-        y, _ = mh_step(log_acc, x, y)
-        return y
+    def step(self, x, path_length, temperature):
+        x = x.contiguous()
+        ll_x, y, trajectory = self.proposal(x, path_length, temperature)
+        b, ld = x.shape
+        cut_y, cross_y, weighted, cross_ld = self._raw_fields(y)
+        u = th.rand((b,), device=self.device)                      # the draw of bernoulli_logp() (util.py:64)
+        sel = trajectory['selected_idx']['sites']
+        energy = th.empty((b,), dtype=th.float32, device=self.device)
+        acc = th.empty_like(energy)
+        with on_device(self.device):
+            _lib.check(_lib.lib().rlsb_isco_accept(_ptr(x), _ptr(y), int(x.dtype == th.float16), _ptr(cross_y), weighted,
+                                                   cross_ld, _ptr(self._deg32()), _ptr(cut_y), int(self._pisco),
+                                                   _ptr(trajectory['_t']), _ptr(u), _ptr(sel), sel.shape[1], _ptr(ll_x),
+                                                   _ptr(trajectory['ll_x2y']), _ptr(energy), _ptr(acc),
+                                                   self.max_num_nodes, ld, b, _stream_ptr(self.device)), "isco_accept")
+        return y, energy, acc
 
 
 class ISCO_maxcut(_PathAuxMaxcut):
@@ -109,6 +143,8 @@ class ISCO_maxcut(_PathAuxMaxcut):
 
 
 class PISCO_maxcut(_PathAuxMaxcut):
+    _pisco = True
+
     def __init__(self, params_dict):
         super().__init__(params_dict)
         self.adj_matrix = params_dict['adj_matrix']
@@ -126,6 +162,24 @@ class PISCO_maxcut(_PathAuxMaxcut):
             graph = th.stack([iu[:, 0], iu[:, 1], w], dim=1).cpu().numpy()
             self.store = GraphStore(graph, True, device=self.device, num_nodes=self.max_num_nodes)
             self._wdeg = a.sum(dim=1).long()[None, :]
+
+    def _raw_fields(self, sample: TEN):
+        if self._wdeg is None:
+            return super()._raw_fields(sample)
+        n = self.max_num_nodes
+        bits = (sample[:, :n] != 0).contiguous()
+        b = bits.shape[0]
+        packed = self.store.pack(bits)
+        return (self.store.cut_eval_weighted(packed=packed, num_envs=b), self.store.node_fields_weighted(packed, b), 1,
+                self.store.padded_nodes)
+
+    def _deg32(self) -> TEN:
+        if self._wdeg is None:
+            return super()._deg32()
+        d = getattr(self, "_deg_i32", None)
+        if d is None:
+            d = self._deg_i32 = self._wdeg.reshape(-1).to(th.int32).contiguous()
+        return d
 
     def _int_fields(self, sample: TEN):
         if self._wdeg is None:

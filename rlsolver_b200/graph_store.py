@@ -410,9 +410,12 @@ class GraphStore:
                                                    int(finish), _ptr(xs_out), _ptr(workspace),
                                                    _stream_ptr(self.device)), "ls_run_masks")
 
-    # overlap=True: the mask generator runs next to the tile kernel (rlsb_ls_fused_search); False: one after the
-    # other (rlsb_ls_noise_masks, then rlsb_ls_run_masks) -- same results, kept as the cross-check
-    overlap_generator = True
+    # True: the mask generator runs next to the tile kernel (rlsb_ls_fused_search); False (default): one after the
+    # other (rlsb_ls_noise_masks, then rlsb_ls_run_masks).  Same results.  Measured on B200 (profiles/r02_fused_*):
+    # beside a tile CTA the generator gets a quarter of the register file (8 warps per SM) and runs > 2x slower than
+    # alone, which costs more than the overlap hides -- 395 vs 372 us per eager G22 x 4096 step, 4.67 vs 3.76 ms
+    # at G70 x 16384 -- so the sequential form stays the default; DESIGN.md section 5 has the analysis.
+    overlap_generator = False
 
     def _mask_scratch(self, num_draws: int, words: int) -> TEN:
         m = getattr(self, "_masks", None)
@@ -434,6 +437,13 @@ class GraphStore:
                                                       _ptr(cursor), int(threads), int(iters), int(num_iters),
                                                       int(finish), _ptr(xs_out), _ptr(masks), _ptr(workspace),
                                                       _stream_ptr(self.device)), "ls_fused_search")
+
+    def ls_fused_status(self, num_envs: int, workspace: TEN):
+        """(generator blocks started, stalled tile CTAs, units of group 0 finished) of the last fused search."""
+        out = (C.c_uint32 * 3)()
+        _lib.check(self._lib.rlsb_ls_fused_status(self._h, num_envs, _ptr(workspace), out, _stream_ptr(self.device)),
+                   "ls_fused_status")
+        return int(out[0]), int(out[1]), int(out[2])
 
     def ls_begin_packed(self, packed: TEN, num_envs: int, vs: Optional[TEN], ws_mult: int, noise_std: float,
                         workspace: TEN) -> TEN:

@@ -31,7 +31,6 @@ class Replay:
 def test_isco_step_matches_reference(path, cuda_device, monkeypatch):
     from rlsolver_b200.envs import env_ISCO
     from rlsolver_b200.methods.ISCO import config_maxcut as cfg
-    from rlsolver_b200.methods.ISCO import util as isco_util
     z = np.load(path)
     pisco = os.path.basename(path).startswith("pisco")
     n = int(z["num_nodes"])
@@ -51,7 +50,7 @@ def test_isco_step_matches_reference(path, cuda_device, monkeypatch):
     else:
         sampler = env_ISCO.ISCO_maxcut(params)
     replay = Replay(z["draws"], z["draw_sizes"], cuda_device)
-    monkeypatch.setattr(isco_util.th, "rand", replay)
+    monkeypatch.setattr(env_ISCO.th, "rand", replay)
     x = th.from_numpy(z["xs"][0]).to(cuda_device)
     x = x.to(th.float16) if pisco else x
     steps = z["energies"].shape[0]
@@ -70,3 +69,53 @@ def test_isco_step_matches_reference(path, cuda_device, monkeypatch):
         np.testing.assert_allclose(energy.float().cpu().numpy(), z["energies"][k], rtol=1e-5, atol=1e-5)
         np.testing.assert_allclose(acc.float().cpu().numpy(), z["accs"][k], rtol=2e-4, atol=1e-30)
     assert replay.k == len(z["draw_sizes"])
+
+
+@pytest.mark.parametrize("kind,nodes,edges_n,batch", [("isco", 2000, 19990, 64), ("pisco", 800, 4694, 33), ("pisco_w", 300, 1500, 17),
+                                                      ("isco", 37, 90, 5)])
+def test_step_kernels_vs_torch_restatement(kind, nodes, edges_n, batch, cuda_device, monkeypatch):
+    """csrc/isco.cu (rlsb_isco_propose / rlsb_isco_accept) against the torch restatement of the reference's helper
+    functions (oracle/isco.py: two sorts, gather / scatter / cumsum) at Gset-like sizes, fed the same uniform draws:
+    same chosen sites, same accepts -> same next states; log-probabilities to 1e-5."""
+    from oracle import isco as oi
+    from synth import random_graph
+    from rlsolver_b200.envs import env_ISCO
+    from rlsolver_b200.methods.ISCO import config_maxcut as cfg
+    dev = cuda_device
+    monkeypatch.setattr(cfg, "BATCH_SIZE", batch)
+    monkeypatch.setattr(cfg, "DEVICE", dev)
+    edges = random_graph(nodes, edges_n, seed=12)
+    rng = np.random.default_rng(1)
+    ef = th.tensor([a for a, _, _ in edges], device=dev)
+    et = th.tensor([b for _, b, _ in edges], device=dev)
+    params = {"num_nodes": nodes, "num_edges": len(edges), "edge_from": ef, "edge_to": et}
+    if kind.startswith("pisco"):
+        npad = (nodes + 7) // 8 * 8
+        A = th.zeros((npad, npad), dtype=th.float16, device=dev)
+        w = th.from_numpy(rng.choice([-2, -1, 1, 3], size=len(edges))).to(dev).to(th.float16) if kind == "pisco_w" else 1
+        A[ef, et] = w
+        A[et, ef] = w
+        params["adj_matrix"] = A
+        sampler = env_ISCO.PISCO_maxcut(params)
+        x = sampler.random_gen_init_sample()
+        x = th.nn.functional.pad(x, (0, npad - nodes))
+    else:
+        sampler = env_ISCO.ISCO_maxcut(params)
+        x = sampler.random_gen_init_sample()
+    th.manual_seed(3)
+    for step in range(6):
+        temperature = th.tensor(1.0 - 0.15 * step, device=dev)
+        path_length = th.randint(1, 9, (batch,), device=dev)
+        u1 = th.rand(x.shape, device=dev)
+        u2 = th.rand((batch,), device=dev)
+        want = oi.step(lambda s: sampler.get_local_dist(s, temperature), x, path_length, u1, u2)
+        draws = iter([u1, u2])
+        monkeypatch.setattr(env_ISCO.th, "rand", lambda *a, **k: next(draws))
+        got_x, got_e, got_acc = sampler.step(x, path_length, temperature)
+        monkeypatch.undo()
+        monkeypatch.setattr(cfg, "BATCH_SIZE", batch)
+        monkeypatch.setattr(cfg, "DEVICE", dev)
+        assert th.equal(got_x.float(), want[0].float()), step
+        np.testing.assert_allclose(got_e.cpu().numpy(), (want[1] * temperature).cpu().numpy(), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(got_acc.cpu().numpy(), want[2].exp().cpu().numpy(), rtol=2e-4, atol=1e-30)
+        x = got_x

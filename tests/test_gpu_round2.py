@@ -69,6 +69,7 @@ def test_overlapped_generator_many_calls_and_graph_replay(cuda_device):
     edges = gset_like("G22")
     sims = [EnvMaxcut(mygraph=edges, device=cuda_device, if_bidirectional=True) for _ in range(2)]
     sims[0].store.overlap_generator = False
+    sims[1].store.overlap_generator = True
     envs = 1024
     th.manual_seed(11)
     x0 = sims[0].generate_xs_randomly(envs)

@@ -17,7 +17,7 @@ def test_load_data_matches_params(tmp_path):
 
 def test_path_helpers_shapes_and_mask_counts():
     """multinomial picks exactly path_length[b] sites per chain and scores only those."""
-    from rlsolver_b200.methods.ISCO.util import mh_step, multinomial
+    from oracle.isco import mh_step, multinomial
     th.manual_seed(3)
     lp = th.log_softmax(th.randn(6, 23), dim=-1)
     pl = th.tensor([1, 2, 5, 23 - 1, 7, 3])
