@@ -444,9 +444,38 @@ def config4(ctx, total_envs):
                                       algorithmic_bytes_per_launch=alg, bytes_per_env_step=alg / envs,
                                       traffic=dram_traffic().get("config4_peco_step_" + kind)),
                      "clocks": ctx.window_clocks(t0, t1)}
+        if ctx.world == 1 and ctx.rank == 0 and not ctx.args.no_cpu_baseline and kind == "ER":
+            out["cpu_baseline"] = peco_cpu_baseline(env, n)
         del env, gg, acts
         th.cuda.empty_cache()
     return out
+
+
+def peco_cpu_baseline(env, n, sample_envs=4096, steps=10):
+    """Pattern-I CPU baseline: the NumPy restatement of the reference's SpinSystemUnbiased.step
+    (oracle/peco.py: every local field recomputed with a batched matmul, the state cloned, like the reference) on a
+    sample of the same graphs, host cores."""
+    import numpy as np
+    from oracle import peco as op
+    eco = [op.SPIN, op.IMM, op.TSF, op.DSCORE, op.DSTATE, op.GREEDY, op.TERM]
+    from rlsolver_b200.envs.env_PECO import CompactGraphs
+    c = env._compact
+    sub = CompactGraphs(c.adj[:sample_envs].contiguous(),
+                        None if c.sgn is None else (c.sgn if c.sgn.dim() == 2 else c.sgn[:sample_envs].contiguous()), n)
+    matrix = sub.dense().cpu().numpy()
+    spins = env.state[:sample_envs, 0, :].cpu().numpy() if env.num_envs <= (1 << 17) else \
+        (2.0 * np.random.default_rng(0).integers(0, 2, (sample_envs, n)) - 1.0).astype(np.float32)
+    ref = op.SpinSystem(matrix, spins, eco, 2 * n, op.BLS, True, scalar_div_as_cuda=True)
+    rng = np.random.default_rng(1)
+    acts = [rng.integers(0, n, sample_envs) for _ in range(steps + 1)]
+    ref.step(acts[0])
+    t = time.perf_counter()
+    for k in range(steps):
+        ref.step(acts[1 + k])
+    dt = time.perf_counter() - t
+    return {"value": sample_envs * steps / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{sample_envs} of the envs x {steps} steps, oracle/peco.py (NumPy float32, batched matmul per step "
+                      f"like spinsystem_PECO.py:306-486)"}
 
 
 # ----------------------------------------------------------------------------- config 5: dense QUBO

@@ -738,8 +738,9 @@ struct MaskChunk {
   uint32_t lo[4], hi[4];
 };
 
+// coherent: the words were written by a kernel that is still running (fused search): read them through L2
 __device__ __forceinline__ MaskChunk mask_chunk_load(const uint32_t* __restrict__ mask, uint64_t row, int b0, int blocks,
-                                                     bool live) {
+                                                     bool live, bool coherent = false) {
   MaskChunk c;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
@@ -747,7 +748,8 @@ __device__ __forceinline__ MaskChunk mask_chunk_load(const uint32_t* __restrict_
     c.lo[u] = c.hi[u] = 0;
     if (live && b < blocks) {
       const uint64_t o = row + 32u * (uint32_t)b;
-      c.lo[u] = __ldcg(mask + (o >> 5)), c.hi[u] = __ldcg(mask + (o >> 5) + 1);   // L2: written by another kernel
+      if (coherent) c.lo[u] = __ldcg(mask + (o >> 5)), c.hi[u] = __ldcg(mask + (o >> 5) + 1);
+      else c.lo[u] = __ldg(mask + (o >> 5)), c.hi[u] = __ldg(mask + (o >> 5) + 1);
     }
   }
   return c;
@@ -879,12 +881,17 @@ __device__ __forceinline__ void gen_group_wait(const uint32_t* ctl, int group, u
   }
 }
 
-// 96 registers: a CTA (512 threads) leaves a quarter of the register file to the generator block that runs
-// on the same SM (rlsb_ls_fused_search); the kernel needs ~100 without spilling anything that matters.
-template <int P>
-__global__ void __maxnreg__(96) ls_bits_kernel(GraphDev g, LsArgs a, const uint32_t* __restrict__ masks,
-                                               int64_t mask_words, int use_delta, const uint32_t* __restrict__ ctl,
-                                               uint32_t units) {
+// The body of the bit-mask tile kernel, shared by its two entry points: ls_bits_kernel (alone on the SM: the
+// compiler may use 128 registers) and ls_bits_fused_kernel (96 registers: a CTA of 512 threads leaves a quarter
+// of the register file to the generator block that runs on the same SM, rlsb_ls_fused_search).
+// FUSED: persistent over tiles (grid <= one CTA per SM, so that every CTA of this kernel and every block of the
+// generator is resident at the same time whatever order the two grids are dispatched in -- a CTA that waits for a
+// group of draws can never keep the generator's blocks from being scheduled), waits on the generator's counters,
+// L2-coherent mask loads.  Not FUSED: one tile per CTA, masks complete before the launch.
+template <int P, bool FUSED>
+__device__ __forceinline__ void ls_bits_body(const GraphDev& g, const LsArgs& a, const uint32_t* __restrict__ masks,
+                                             int64_t mask_words, int use_delta, const uint32_t* __restrict__ ctl,
+                                             uint32_t units) {
   extern __shared__ __align__(1024) uint32_t smem[];
   uint32_t* sP = smem;
   uint32_t* sX = smem + g.np;
@@ -914,10 +921,7 @@ __global__ void __maxnreg__(96) ls_bits_kernel(GraphDev g, LsArgs a, const uint3
   const int blocks = (g.n + 31) >> 5;
   uint16_t* flist = use_delta ? sF : nullptr;
   int tk = 0;
-  // PERSISTENT over tiles: the grid never exceeds one CTA per SM, so every CTA of this kernel and every block of
-  // the generator is resident at the same time whatever order the two grids are dispatched in -- a CTA that
-  // waits for a group of draws can never keep the generator's blocks from being scheduled.
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  auto process = [&](const int64_t tile) {
     const int64_t env0 = tile * kTileEnvs;
     const int valid = (int)min((int64_t)kTileEnvs, a.num_envs - env0);
     for (int i = threadIdx.x; i < g.np; i += kLSThreads) {
@@ -927,34 +931,43 @@ __global__ void __maxnreg__(96) ls_bits_kernel(GraphDev g, LsArgs a, const uint3
     if (threadIdx.x < kTileEnvs) sCnt[threadIdx.x] = 0;
     int64_t my_vs = 0;
     if (warp == 0 && lane < valid) my_vs = a.vs[env0 + lane];
-    if (ctl && a.num_iters > 0 && threadIdx.x == 0) gen_group_wait(ctl, 0, units);     // the first group of draws
+    if constexpr (FUSED)
+      if (a.num_iters > 0 && threadIdx.x == 0) gen_group_wait(ctl, 0, units);     // the first group of draws
     ls_sync();
     const uint64_t row = (uint64_t)(env0 + lane) * (uint64_t)g.n;     // first bit of the lane's env row
     const bool live = lane < valid;
     stamp(a, tk);
-    MaskChunk pre = mask_chunk_load(masks, row, warp, a.num_iters > 0 ? blocks : 0, live);
+    constexpr bool coh = FUSED;
+    MaskChunk pre = mask_chunk_load(masks, row, warp, a.num_iters > 0 ? blocks : 0, live, coh);
     bool have_pre = true;
     if (use_delta && a.stage_sweep && a.num_iters > 0) mbar_wait(&sBar, 0);   // the neighbour lists have landed
     stamp(a, tk);
     for (int it = 0; it < a.num_iters; ++it) {
       const uint32_t* mask = masks + it * mask_words;
-      if (!have_pre) {      // the draw was not complete when the previous iteration could have fetched ahead
-        if (threadIdx.x == 0) gen_group_wait(ctl, it / kGenGroup, units);
-        ls_sync();
-        pre = mask_chunk_load(mask, row, warp, blocks, live);
+      if constexpr (FUSED) {
+        if (!have_pre) {      // the draw was not complete when the previous iteration could have fetched ahead
+          if (threadIdx.x == 0) gen_group_wait(ctl, it / kGenGroup, units);
+          ls_sync();
+          pre = mask_chunk_load(mask, row, warp, blocks, live, coh);
+        }
       }
       mask_chunk_apply(pre, row, warp, g.n, sP, sX, flist, &sNF);
       for (int b0 = warp + 4 * kLSWarps; b0 < blocks; b0 += 4 * kLSWarps)
-        mask_chunk_apply(mask_chunk_load(mask, row, b0, blocks, live), row, b0, g.n, sP, sX, flist, &sNF);
+        mask_chunk_apply(mask_chunk_load(mask, row, b0, blocks, live, coh), row, b0, g.n, sP, sX, flist, &sNF);
       // fetch ahead only when the next draw's group is known to be complete (same group: it is; next group: one
       // poll, published by the barrier below)
       const bool more = it + 1 < a.num_iters;
-      const bool same_group = !ctl || (it + 1) / kGenGroup == it / kGenGroup;
-      if (more && !same_group && threadIdx.x == 0)
-        sNextReady = gen_group_ready(ctl, (it + 1) / kGenGroup, units) ? 1 : 0;
-      ls_sync();
-      have_pre = !more || same_group || sNextReady != 0;
-      if (have_pre) pre = mask_chunk_load(mask + mask_words, row, warp, more ? blocks : 0, live);
+      if constexpr (FUSED) {
+        const bool same_group = (it + 1) / kGenGroup == it / kGenGroup;
+        if (more && !same_group && threadIdx.x == 0)
+          sNextReady = gen_group_ready(ctl, (it + 1) / kGenGroup, units) ? 1 : 0;
+        ls_sync();
+        have_pre = !more || same_group || sNextReady != 0;
+        if (have_pre) pre = mask_chunk_load(mask + mask_words, row, warp, more ? blocks : 0, live, coh);
+      } else {
+        ls_sync();
+        pre = mask_chunk_load(mask + mask_words, row, warp, more ? blocks : 0, live, coh);
+      }
       stamp(a, tk);
       if (use_delta)
         evaluate_delta_and_accept<P>(g, a, sSweep, sInv, sF, &sNF, sP, sX, sCnt, &sAccept, valid, my_vs);
@@ -970,8 +983,27 @@ __global__ void __maxnreg__(96) ls_bits_kernel(GraphDev g, LsArgs a, const uint3
     }
     stamp(a, tk);
     for (int i = threadIdx.x; i < g.np; i += kLSThreads) a.packed[tile * g.np + i] = sP[i] & vmask;
-    ls_sync();          // the tile copies are free for the next tile
+  };
+  if constexpr (FUSED) {
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      process(tile);
+      ls_sync();          // the tile copies are free for the next tile
+    }
+  } else {
+    process(blockIdx.x);
   }
+}
+
+template <int P>
+__global__ void __launch_bounds__(kLSThreads) ls_bits_kernel(GraphDev g, LsArgs a, const uint32_t* __restrict__ masks,
+                                                             int64_t mask_words, int use_delta) {
+  ls_bits_body<P, false>(g, a, masks, mask_words, use_delta, nullptr, 0u);
+}
+template <int P>
+__global__ void __maxnreg__(96) ls_bits_fused_kernel(GraphDev g, LsArgs a, const uint32_t* __restrict__ masks,
+                                                     int64_t mask_words, int use_delta, const uint32_t* __restrict__ ctl,
+                                                     uint32_t units) {
+  ls_bits_body<P, true>(g, a, masks, mask_words, use_delta, ctl, units);
 }
 
 // single-flip pass on packed tiles only (rlsb_flip_sweep)
@@ -1137,13 +1169,18 @@ static int launch_bits(const GraphDev& g, LsArgs a, const uint32_t* masks, cudaS
   const int64_t tiles = (a.num_envs + kTileEnvs - 1) / kTileEnvs;
   // slots of the sweep structure are addressed with 16 bits; RLSB_DEBUG_FULL_CUT keeps the full re-count (cross-check)
   const int use_delta = (g.num_sweep_slices * 32 <= 65536 && !(debug_flags() & RLSB_DEBUG_FULL_CUT)) ? 1 : 0;
-  if (int rc = allow_smem(ls_bits_kernel<P>, smem)) return rc;
-  if (ctl && !(debug_flags() & RLSB_DEBUG_CARVEOUT_DEFAULT))      // fused search: same carve-out as the generator (see there)
-    RLSB_CUDA_OK(cudaFuncSetAttribute(ls_bits_kernel<P>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
-  // persistent: at most one CTA per SM (96 registers x 512 threads: a second one would not fit anyway)
-  const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  ls_bits_kernel<P><<<grid, kLSThreads, smem, st>>>(g, a, masks, ls_mask_words(a.num_envs, g.n), use_delta, ctl, units);
+  const int64_t words = ls_mask_words(a.num_envs, g.n);
+  if (ctl) {
+    const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);      // persistent: at most one CTA per SM
+    if (int rc = allow_smem(ls_bits_fused_kernel<P>, smem)) return rc;
+    if (!(debug_flags() & RLSB_DEBUG_CARVEOUT_DEFAULT))      // same carve-out as the generator (see noise_masks.cu)
+      RLSB_CUDA_OK(cudaFuncSetAttribute(ls_bits_fused_kernel<P>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
+    ls_bits_fused_kernel<P><<<grid, kLSThreads, smem, st>>>(g, a, masks, words, use_delta, ctl, units);
+  } else {
+    if (int rc = allow_smem(ls_bits_kernel<P>, smem)) return rc;
+    ls_bits_kernel<P><<<(unsigned)tiles, kLSThreads, smem, st>>>(g, a, masks, words, use_delta);
+  }
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }

@@ -59,33 +59,47 @@ struct PecoC {
 
 __device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(kFull, v); }
 
-// one warp per env
+// One warp per env.  Everything that does not depend on the action -- the spin words, the env's fields, its best
+// spins and scalars -- is requested BEFORE the action is looked at, so that a step is two dependent trips to
+// HBM (action -> matrix row) instead of four: the kernel is bound by that latency chain, not by bandwidth.
+// KW: words per spin vector held in registers (N <= 32 KW); 0 = generic loop for larger N.
+template <int KW>
 __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step_kernel(PecoC p) {
   const int lane = threadIdx.x & 31;
   const int64_t env = (int64_t)blockIdx.x * kPcWarps + (threadIdx.x >> 5);
   if (env >= p.num_envs) return;
   const int n = p.n, W = p.words;
+  int16_t* fl = p.fields + env * (int64_t)p.np;
   const int64_t a = p.action[env];
+  uint32_t sp = lane < W ? p.spins[env * W + lane] : 0u;           // lane w holds word w
+  int pre[KW > 0 ? KW : 1];
+  if (KW > 0) {
+#pragma unroll
+    for (int k = 0; k < KW; ++k) pre[k] = (k < W && 32 * k + lane < n) ? (int)fl[32 * k + lane] : 0;
+  }
+  const uint32_t bs = lane < W ? p.best_spins[env * W + lane] : 0u;
+  const float score0 = p.score[env], best_obs = p.best_score[env];
+  unsigned long long key0 = 0ull;
+  if (p.hset) key0 = p.hkey[env];
+  (void)bs;
   if (a < 0 || a >= n) {                               // IndexError in the reference
     if (lane == 0) p.reward[env] = 0.f, atomicAdd(p.bad_actions, 1);
     return;
   }
   const int wa = (int)a >> 5, ba = (int)a & 31;
-  uint32_t sp = lane < W ? p.spins[env * W + lane] : 0u;           // lane w holds word w
+  const uint32_t arow = lane < W ? __ldg(p.adj + (env * n + a) * W + lane) : 0u;
+  const uint32_t srow = (p.sgn && lane < W) ? __ldg(p.sgn + env * p.sgn_stride + a * W + lane) : 0u;
   const int s_old = ((__shfl_sync(kFull, sp, wa) >> ba) & 1u) ? 1 : -1;
   if (lane == wa) {
     sp ^= 1u << ba;
     p.spins[env * W + lane] = sp;
   }
-  const uint32_t arow = lane < W ? __ldg(p.adj + (env * n + a) * W + lane) : 0u;
-  const uint32_t srow = (p.sgn && lane < W) ? __ldg(p.sgn + env * p.sgn_stride + a * W + lane) : 0u;
-  int16_t* fl = p.fields + env * (int64_t)p.np;
   int nonpos = 0, delta = 0;
-  for (int k = 0; k < W; ++k) {
+  auto node = [&](int k, int v0) {
     const uint32_t aw = __shfl_sync(kFull, arow, k), sw = __shfl_sync(kFull, srow, k), spw = __shfl_sync(kFull, sp, k);
     const int j = 32 * k + lane;
     if (j < n) {
-      int v = fl[j];
+      int v = v0;
       if ((aw >> lane) & 1u) {                         // (A s)_j -= 2 A[a][j] s_old
         v -= ((sw >> lane) & 1u) ? -2 * s_old : 2 * s_old;
         fl[j] = (int16_t)v;
@@ -94,12 +108,18 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step_kernel(PecoC 
       nonpos += (int)(f <= 0);
       if (j == (int)a) delta = -f;
     }
+  };
+  if (KW > 0) {
+#pragma unroll
+    for (int k = 0; k < KW; ++k)
+      if (k < W) node(k, pre[k]);
+  } else {
+    for (int k = 0; k < W; ++k) node(k, 32 * k + lane < n ? (int)fl[32 * k + lane] : 0);
   }
   nonpos = warp_sum_i(nonpos);
   delta = warp_sum_i(delta);
   if (lane == 0) p.last_flip[env * (int64_t)p.np + a] = (uint16_t)p.step;
-  const float score = __fadd_rn(p.score[env], (float)delta);
-  const float best_obs = p.best_score[env];
+  const float score = __fadd_rn(score0, (float)delta);
   const float improvement = __fsub_rn(score, best_obs);
   float rew = 0.f;
   if (p.reward_signal == 2) rew = improvement > 0.f ? improvement : 0.f;
@@ -109,8 +129,7 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step_kernel(PecoC 
   if (p.hset) {
     // the state's key moves by one table entry; look it up / insert it in the env's table (linear probing, a
     // window of 32 slots per round trip)
-    unsigned long long key = p.hkey[env] ^ __ldg(p.zobrist + a);
-    __syncwarp();
+    unsigned long long key = key0 ^ __ldg(p.zobrist + a);
     if (lane == 0) p.hkey[env] = key;
     if (key == 0ull) key = 1ull;                       // 0 marks an empty slot
     unsigned long long* tab = p.hset + env * (int64_t)p.hcap;
@@ -428,8 +447,11 @@ int rlsb_peco_compact_step(const uint32_t* adj, const uint32_t* sgn, int64_t sgn
   p.words = (num_spins + 31) / 32, p.step = step, p.reward_signal = reward_signal, p.norm_rewards = norm_rewards;
   p.use_stag = use_stag, p.use_basin = use_basin, p.stag = stag, p.basin = basin;
   p.recip_div = scalar_div_as_cuda, p.inv_n = 1.0f / (float)num_spins;
-  peco_compact_step_kernel<<<(unsigned)((num_envs + kPcWarps - 1) / kPcWarps), kPcWarps * 32, 0,
-                             static_cast<cudaStream_t>(stream)>>>(p);
+  const unsigned grid = (unsigned)((num_envs + kPcWarps - 1) / kPcWarps);
+  auto st = static_cast<cudaStream_t>(stream);
+  if (p.words <= 4) peco_compact_step_kernel<4><<<grid, kPcWarps * 32, 0, st>>>(p);
+  else if (p.words <= 8) peco_compact_step_kernel<8><<<grid, kPcWarps * 32, 0, st>>>(p);
+  else peco_compact_step_kernel<0><<<grid, kPcWarps * 32, 0, st>>>(p);
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }

@@ -322,7 +322,7 @@ class SpinSystemUnbiased:
         self._zobrist = th.from_numpy(zr.integers(1, 2 ** 63 - 1, size=self.n_spins, dtype=np.int64)).to(self.device)
         self._compact: Optional[CompactGraphs] = None
         self._draw_graphs()                  # the reference draws one graph batch in __init__ and another in reset()
-        self.reset()
+        self.reset(return_observation=False)
         self.best_score = self.score.clone()
 
     # ------------------------------------------------------------------ layout plumbing
@@ -397,7 +397,8 @@ class SpinSystemUnbiased:
         return fields[:, :self.n_spins].float() * spins
 
     # ------------------------------------------------------------------ reset (spinsystem_PECO.py:151-193)
-    def reset(self, spins=None):
+    def reset(self, spins=None, return_observation: bool = True):
+        """`return_observation=False` skips materialising the [E, obs + N, N] observation (43 GB at 10^6 envs)."""
         self.current_step = 0
         e, n, dev = self.num_envs, self.n_spins, self.device
         w = _words(n)
@@ -449,8 +450,8 @@ class SpinSystemUnbiased:
                 self._history = th.empty((self.max_steps + 1, e, w), dtype=th.int32, device=dev)
         self.best_score = self.score.clone()
         self.best_obs_score = self.score.clone()
-        self.best_obs_spins = self.best_spins
-        return self.get_observation()
+        self.best_obs_spins = None                      # == best_spins (materialised on request)
+        return self.get_observation() if return_observation else None
 
     def _reset_state(self, spins_f: TEN):
         """Dense layout: the reference's state tensor after reset (spinsystem_PECO.py:173-193)."""

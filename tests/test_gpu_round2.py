@@ -182,11 +182,13 @@ def test_local_search_packed_equals_bool_rows(name, envs, cuda_device):
     pk, vb = sim.local_search_packed(sim.store.pack(x0), num_sims=envs)
     assert th.equal(th.cuda.get_rng_state(cuda_device), state)
     assert th.equal(va, vb) and th.equal(sim.store.unpack(pk.contiguous(), envs), xa)
-    # second call starting from the packed result with the values handed in
+    # second call starting from the packed result with the values handed in (`pk` is a view of the simulator's
+    # workspace: copy it before the next local-search call overwrites it)
+    pk_copy = pk.clone()
     th.manual_seed(10)
     xa2, va2 = sim.local_search_inplace(xa.clone(), va.clone(), num_iters=3, num_spin=5)
     th.manual_seed(10)
-    pk2, vb2 = sim.local_search_packed(pk.clone(), 3, 5, num_sims=envs, good_vs=vb)
+    pk2, vb2 = sim.local_search_packed(pk_copy, 3, 5, num_sims=envs, good_vs=vb)
     assert th.equal(va2, vb2) and th.equal(sim.store.unpack(pk2.contiguous(), envs), xa2)
 
 
