@@ -233,6 +233,15 @@ class Ctx:
         return self.clocks.window(t0, t1) if self.clocks else None
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    """Progress marker on stderr (stdout carries the one JSON line): tells where a run that timed out was."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def roof(bound, achieved, peak, unit, kernel, traffic=None, **extra):
     d = {"kernel": kernel, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
          "frac": achieved / peak if peak else None, "traffic": traffic}
@@ -564,6 +573,7 @@ def run_b200(args):
     from rlsolver_b200.envs.env_L2A import EnvMaxcut
 
     rlsolver_b200.build()
+    log(f"world {world}: library ready")
 
     envs = args.envs
     edges = gset_like(GRAPH)
@@ -581,19 +591,24 @@ def run_b200(args):
         return sim.local_search_inplace(xs, sentinel, NUM_ITERS, NUM_SPIN, NOISE_STD)
 
     def step_body():
-        """One step: the local search and -- with several ranks -- the path's only exchange (best cut, its argmax,
-        the winner's spins), issued right behind it on the same stream."""
+        """The local part of a step: fixed launch sequence, captured into a CUDA graph below."""
         gx, gv = local_part()
-        best = exchange(gv, gx) if exchange is not None else None
-        return gx, gv, best
+        return gx, gv, None
 
     state = {"graph": None, "out": None}
 
     def one_step():
+        """One step: the local search (graph replay) and -- with several ranks -- the path's only exchange (best cut,
+        its argmax, the winner's spins), issued right behind it on the same stream.  The exchange stays OUTSIDE the
+        graph: capturing the NCCL all-gather hung both ranks on this torch / NCCL build (round 2, N = 2), so it is
+        three eager launches on preallocated buffers (record kernel, ncclAllGather, pick kernel), no host sync."""
         if state["graph"] is not None:
             state["graph"].replay()
-            return state["out"]
-        return step_body()
+            gx, gv, _ = state["out"]
+        else:
+            gx, gv, _ = step_body()
+        best = exchange(gv, gx) if exchange is not None else None
+        return gx, gv, best
 
     def timed_steps(k):
         evs = []
@@ -609,9 +624,9 @@ def run_b200(args):
         return [a.elapsed_time(b) for a, b in evs]
 
     def try_capture():
-        """The step is a fixed sequence of launches (this library's kernels, and with several ranks the NCCL
-        all-gather of the exchange): capture it once into a CUDA graph so its host cost is one replay.  The
-        device-resident generator cursor keeps the random stream identical to eager execution."""
+        """The local part of the step is a fixed sequence of launches of this library's kernels: capture it once into
+        a CUDA graph so its host cost is one replay.  The device-resident generator cursor keeps the random stream
+        identical to eager execution."""
         if args.no_graph:
             return "disabled (--no-graph)"
         try:
@@ -628,7 +643,7 @@ def run_b200(args):
                 out = step_body()
             th.cuda.synchronize()
             state["graph"], state["out"] = g, out
-            return "captured (local search" + (" + best-cut exchange incl. ncclAllGather)" if world > 1 else ")")
+            return "captured (local search)" + ("; best-cut exchange eager behind the replay" if world > 1 else "")
         except Exception as exc:                                   # noqa: BLE001 - eager remains correct
             state["graph"] = None
             th.cuda.synchronize()
@@ -640,7 +655,9 @@ def run_b200(args):
     launches_before = sim.store.launch_count
     timed_steps(1)
     launches_per_step = sim.store.launch_count - launches_before + (2 if world > 1 else 0)
+    log("first eager step done")
     graph_status = try_capture()
+    log(f"graph: {graph_status}")
     if world > 1:       # all ranks must agree on the mode (the collective sequence is part of it)
         flag = th.tensor([1 if state["graph"] is not None else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
@@ -653,6 +670,7 @@ def run_b200(args):
     ms = timed_steps(args.steps)
     barrier()
     t1 = time.time()
+    log("timed steps done")
     launches = launches_per_step * args.steps          # kernels of this library per step (counted on an eager step)
     total_ms = ctx.max_over_ranks(sum(ms))
     per_call = env_steps_per_call(envs, n, NUM_ITERS, n)
@@ -774,7 +792,9 @@ def run_b200(args):
                 "d2h_bytes_per_step": nbytes + 8 * envs}
 
     e2e_bool = e2e_measure("bool")
+    log("e2e (bool rows) done")
     e2e_packed = e2e_measure("packed")
+    log("e2e (packed) done")
     t_headline_end = time.time()
 
     # ---- per-kernel pass (CUDA events around every launch of this library) for the roofline
@@ -801,6 +821,7 @@ def run_b200(args):
                 "whole_step_noise_equivalent_frac": ((1 + NUM_ITERS) * 4 * envs * n / (total_ms / args.steps * 1e-3)
                                                      / 1e9 / peak)}
 
+    log("per-kernel pass done")
     cpu = gpu_ref = None
     if world == 1 and not args.no_cpu_baseline:
         if rank == 0:
@@ -821,6 +842,7 @@ def run_b200(args):
     def attempt(name, fn):
         try:
             barrier()
+            log(f"{name} ...")
             configs[name] = fn()
         except Exception as exc:                                   # noqa: BLE001 - one config must not sink the line
             configs[name] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
@@ -846,9 +868,9 @@ def run_b200(args):
                            "env_steps_per_step_per_gpu": per_call, "l2": "flushed between steps (256 MiB write)", "cuda_graph": graph_status,
                            "rng": "torch's CUDA Philox stream, 1+8 draws of randn [E,N] f32 per step inside the timed region, "
                                   "recomputed in place (only thresholds / flip bits leave the kernels)",
-                           "multi_gpu": ("env batch sharded, graph replicated, one best-cut exchange per step inside the "
-                                         "captured graph: best_record kernel + ncclAllGather of world x (8+N) B + "
-                                         "best_pick kernel, no host sync"),
+                           "multi_gpu": ("env batch sharded, graph replicated, one best-cut exchange per step behind the "
+                                         "graph replay: best_record kernel + ncclAllGather of world x (8+N) B + "
+                                         "best_pick kernel on preallocated buffers, no host sync"),
                            "exchange_us": exch_us},
                 "e2e": {"value": e2e_bool["value"], "unit": UNIT, "h2d_bytes_per_step": e2e_bool["h2d_bytes_per_step"],
                         "d2h_bytes_per_step": e2e_bool["d2h_bytes_per_step"], "ms_per_step": e2e_bool["ms_per_step"],

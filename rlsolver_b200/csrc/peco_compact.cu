@@ -164,6 +164,108 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step_kernel(PecoC 
   }
 }
 
+// Eight lanes per env (N <= 128): four envs share a warp, so four times as many dependent load chains are in flight
+// per resident warp -- the step is bound by the latency of its two dependent HBM trips, and at 10^6 envs of N = 100 a
+// warp per env leaves the memory system idle most of the time.  Lane `sub` of a group owns nodes sub, sub + 8, ...;
+// lanes 0..W-1 of the group hold the spin / adjacency / sign words.
+constexpr int kPcLpe = 8, kPcMaxT = 16;      // lanes per env, nodes per lane (N <= 128)
+__global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step8_kernel(PecoC p) {
+  const int lane = threadIdx.x & 31, sub = lane & (kPcLpe - 1), grp = lane / kPcLpe, base = grp * kPcLpe;
+  const int64_t env = ((int64_t)blockIdx.x * kPcWarps + (threadIdx.x >> 5)) * (32 / kPcLpe) + grp;
+  const bool live = env < p.num_envs;
+  const int64_t ev = live ? env : 0;             // dead groups shadow env 0 read-only (all lanes stay in the shuffles)
+  const int n = p.n, W = p.words, T = (n + kPcLpe - 1) / kPcLpe;
+  int16_t* fl = p.fields + ev * (int64_t)p.np;
+  const int64_t a_raw = p.action[ev];
+  uint32_t sp = sub < W ? p.spins[ev * W + sub] : 0u;
+  int pre[kPcMaxT];
+#pragma unroll
+  for (int t = 0; t < kPcMaxT; ++t) pre[t] = (t < T && sub + kPcLpe * t < n) ? (int)fl[sub + kPcLpe * t] : 0;
+  const float score0 = p.score[ev], best_obs = p.best_score[ev];
+  unsigned long long key0 = 0ull;
+  if (p.hset) key0 = p.hkey[ev];
+  const bool valid = live && a_raw >= 0 && a_raw < n;
+  if (live && !valid && sub == 0) p.reward[env] = 0.f, atomicAdd(p.bad_actions, 1);     // IndexError in the reference
+  const int a = valid ? (int)a_raw : 0;
+  const int wa = a >> 5, ba = a & 31;
+  const uint32_t arow = sub < W ? __ldg(p.adj + (ev * n + a) * W + sub) : 0u;
+  const uint32_t srow = (p.sgn && sub < W) ? __ldg(p.sgn + ev * p.sgn_stride + (int64_t)a * W + sub) : 0u;
+  const int s_old = ((__shfl_sync(kFull, sp, base + wa) >> ba) & 1u) ? 1 : -1;
+  if (valid && sub == wa) {
+    sp ^= 1u << ba;
+    p.spins[env * W + sub] = sp;
+  } else if (sub == wa) {
+    sp ^= 0u;
+  }
+  int nonpos = 0, delta = 0;
+#pragma unroll
+  for (int t = 0; t < kPcMaxT; ++t) {
+    if (t < T) {                                    // warp-uniform
+      const int j = sub + kPcLpe * t;
+      const int wj = min(j >> 5, W - 1);
+      const uint32_t aw = __shfl_sync(kFull, arow, base + wj), sw = __shfl_sync(kFull, srow, base + wj),
+                     spw = __shfl_sync(kFull, sp, base + wj);
+      if (j < n) {
+        int v = pre[t];
+        if ((aw >> (j & 31)) & 1u) {                 // (A s)_j -= 2 A[a][j] s_old
+          v -= ((sw >> (j & 31)) & 1u) ? -2 * s_old : 2 * s_old;
+          if (valid) fl[j] = (int16_t)v;
+        }
+        const int f = ((spw >> (j & 31)) & 1u) ? v : -v;
+        nonpos += (int)(f <= 0);
+        if (j == a) delta = -f;
+      }
+    }
+  }
+#pragma unroll
+  for (int off = kPcLpe / 2; off >= 1; off >>= 1) {
+    nonpos += __shfl_xor_sync(kFull, nonpos, off);
+    delta += __shfl_xor_sync(kFull, delta, off);
+  }
+  if (valid && sub == 0) p.last_flip[env * (int64_t)p.np + a] = (uint16_t)p.step;
+  const float score = __fadd_rn(score0, (float)delta);
+  const float improvement = __fsub_rn(score, best_obs);
+  float rew = 0.f;
+  if (p.reward_signal == 2) rew = improvement > 0.f ? improvement : 0.f;
+  else if (p.reward_signal == 4) rew = improvement > 0.f ? __fdiv_rn(improvement, __fadd_rn(improvement, 0.1f)) : 0.f;
+  else if (p.reward_signal == 1) rew = (float)delta;
+  if (p.norm_rewards) rew = p.recip_div ? __fmul_rn(rew, p.inv_n) : __fdiv_rn(rew, (float)n);
+  if (p.hset) {
+    unsigned long long key = key0 ^ __ldg(p.zobrist + a);
+    if (valid && sub == 0) p.hkey[env] = key;
+    if (key == 0ull) key = 1ull;
+    unsigned long long* tab = p.hset + ev * (int64_t)p.hcap;
+    const uint32_t mask = (uint32_t)p.hcap - 1u;
+    const uint32_t h = (uint32_t)(key >> 17) & mask;
+    bool fresh = true, done = !valid;
+    for (int probe = 0; probe < p.hcap; probe += kPcLpe) {      // windows of 8 slots per group; groups finish on their own
+      const uint32_t slot = (h + probe + sub) & mask;
+      const unsigned long long v = done ? ~0ull : tab[slot];
+      const uint32_t hit = (__ballot_sync(kFull, !done && v == key) >> base) & 0xFFu;
+      const uint32_t empty = (__ballot_sync(kFull, !done && v == 0ull) >> base) & 0xFFu;
+      const int first_empty = empty ? __ffs(empty) - 1 : kPcLpe;
+      if (!done) {
+        if (hit && (__ffs(hit) - 1) < first_empty) fresh = false, done = true;
+        else if (empty) {
+          if (sub == first_empty) tab[slot] = key;
+          done = true;
+        }
+      }
+      if (__all_sync(kFull, done)) break;
+    }
+    if (p.use_stag && !fresh) rew = __fsub_rn(rew, p.stag);
+    if (p.use_basin && nonpos == n && fresh) rew = __fadd_rn(rew, p.basin);
+  }
+  if (!valid) return;
+  const bool better = score > best_obs;
+  if (better && sub < W) p.best_spins[env * W + sub] = sp;
+  if (sub == 0) {
+    p.score[env] = score;
+    p.best_score[env] = better ? score : best_obs;
+    p.reward[env] = rew;
+  }
+}
+
 // ---- reset pieces ----------------------------------------------------------------------------------------------
 // fields = A s for the given spins, the cut (spinsystem_PECO.py:601-607: 1/4 sum(-s A s) + 1/4 sum(A)), the largest
 // field of the all-ones state (max_local_reward_available, :163-171) and a flag for envs whose graph is empty
@@ -449,7 +551,10 @@ int rlsb_peco_compact_step(const uint32_t* adj, const uint32_t* sgn, int64_t sgn
   p.recip_div = scalar_div_as_cuda, p.inv_n = 1.0f / (float)num_spins;
   const unsigned grid = (unsigned)((num_envs + kPcWarps - 1) / kPcWarps);
   auto st = static_cast<cudaStream_t>(stream);
-  if (p.words <= 4) peco_compact_step_kernel<4><<<grid, kPcWarps * 32, 0, st>>>(p);
+  if (p.n <= kPcLpe * kPcMaxT && p.words <= kPcLpe && p.hcap % kPcLpe == 0 && !(debug_flags() & RLSB_DEBUG_PECO_WARP_PER_ENV)) {
+    const int64_t per_block = (int64_t)kPcWarps * (32 / kPcLpe);
+    peco_compact_step8_kernel<<<(unsigned)((num_envs + per_block - 1) / per_block), kPcWarps * 32, 0, st>>>(p);
+  } else if (p.words <= 4) peco_compact_step_kernel<4><<<grid, kPcWarps * 32, 0, st>>>(p);
   else if (p.words <= 8) peco_compact_step_kernel<8><<<grid, kPcWarps * 32, 0, st>>>(p);
   else peco_compact_step_kernel<0><<<grid, kPcWarps * 32, 0, st>>>(p);
   RLSB_LAUNCH_OK();

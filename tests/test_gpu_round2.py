@@ -254,23 +254,22 @@ def _nccl_worker(rank, world, port, envs, out):
     cut, gid, row = best_allreduce(vs, xs, rank, world, envs)
     ex = BestExchange(sim.num_nodes, rank, world, envs, dev)
     cut2, gid2, row2 = ex(vs, xs)
-    # the exchange captured in a CUDA graph with the local search (what bench.py replays)
+    cut2, gid2, row2 = int(cut2), int(gid2), row2.clone()      # views of the exchange's buffers: keep the values
+    # what bench.py does per step: the local search replayed from a CUDA graph, the exchange eager behind it
     sim.store.rng_cursor_sync()
     side = th.cuda.Stream(device=dev)
     side.wait_stream(th.cuda.current_stream(dev))
     g = th.cuda.CUDAGraph()
     xg = xs.clone()
     with th.cuda.stream(side):
-        for _ in range(2):
-            ex(vs, xs)
         with th.cuda.graph(g, stream=side):
             gx, gv = sim.local_search_inplace(xg, th.empty(()))
-            best = ex(gv, gx)
     th.cuda.current_stream(dev).wait_stream(side)
     g.replay()
+    best = ex(gv, gx)
     th.cuda.synchronize()
     out[rank] = {"xs": xs.cpu(), "vs": vs.cpu(), "cut": int(cut), "gid": int(gid), "row": row.cpu(),
-                 "cut2": int(cut2), "gid2": int(gid2), "row2": row2.cpu(),
+                 "cut2": cut2, "gid2": gid2, "row2": row2.cpu(),
                  "g_vs": gv.cpu(), "g_xs": gx.cpu(), "g_cut": int(best[0]), "g_gid": int(best[1]), "g_row": best[2].cpu()}
     dist.destroy_process_group()
 
@@ -278,8 +277,8 @@ def _nccl_worker(rank, world, port, envs, out):
 @pytest.mark.skipif(th.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
 def test_two_rank_nccl_shards_equal_single_gpu_runs():
     """Rank r's (xs, vs) equal the single-GPU run of shard r with seed 74 + r (bit-exactness is per shard,
-    SURVEY.md 8e) and best_allreduce / BestExchange return the global argmax on both ranks, eagerly and when the
-    step (local search + exchange) is replayed from a CUDA graph."""
+    SURVEY.md 8e) and best_allreduce / BestExchange return the global argmax on both ranks, also behind a CUDA-graph
+    replay of the local search."""
     import torch.multiprocessing as mp
     from rlsolver_b200.envs.env_L2A import EnvMaxcut
     world, envs = 2, 1024
