@@ -116,13 +116,22 @@ class BestExchange:
                                                          th.cuda.current_stream(self.device).cuda_stream), "best_pick")
         return self.out2[0], self.out2[1], self.row
 
-    def __call__(self, vs: TEN, xs: TEN):
+    def post(self, vs: TEN, xs: TEN) -> None:
+        """First half: the record kernel (reads vs / xs).  Once it has run, vs / xs may be overwritten: a caller that
+        pipelines the exchange behind its next step only has to order that step after this launch."""
         from . import _lib
         assert vs.dtype == th.int64 and xs.dtype == th.bool and vs.is_contiguous() and xs.is_contiguous()
         with on_device(self.device):
             _lib.check(_lib.lib().rlsb_best_record(vs.data_ptr(), xs.data_ptr(), vs.shape[0], self.n,
                                                    self.rank * self.envs, self.record.data_ptr(),
                                                    th.cuda.current_stream(self.device).cuda_stream), "best_record")
+
+    def finish(self):
+        """Second half: all-gather of the records + pick kernel (touches only this object's buffers)."""
+        return self._finish()
+
+    def __call__(self, vs: TEN, xs: TEN):
+        self.post(vs, xs)
         return self._finish()
 
     def packed(self, vs: TEN, packed: TEN, store):
