@@ -166,21 +166,27 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step_kernel(PecoC 
 
 // Eight lanes per env (N <= 128): four envs share a warp, so four times as many dependent load chains are in flight
 // per resident warp -- the step is bound by the latency of its two dependent HBM trips, and at 10^6 envs of N = 100 a
-// warp per env leaves the memory system idle most of the time.  Lane `sub` of a group owns nodes sub, sub + 8, ...;
-// lanes 0..W-1 of the group hold the spin / adjacency / sign words.
-constexpr int kPcLpe = 8, kPcMaxT = 16;      // lanes per env, nodes per lane (N <= 128)
+// warp per env leaves the memory system idle most of the time.  Lane `sub` of a group owns the 16 nodes
+// 16 sub .. 16 sub + 15: they sit in ONE word of the spin / adjacency / sign rows (word sub / 2), which the lane loads
+// itself, and their 16 int16 fields are two 16-byte loads -- no shuffles in the node loop (the first version spent
+// 700 instructions per warp, 70 % issue-active, on 13 rounds of three shuffles).
+constexpr int kPcLpe = 8, kPcNpl = 16;       // lanes per env, nodes per lane (N <= 128)
 __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step8_kernel(PecoC p) {
   const int lane = threadIdx.x & 31, sub = lane & (kPcLpe - 1), grp = lane / kPcLpe, base = grp * kPcLpe;
   const int64_t env = ((int64_t)blockIdx.x * kPcWarps + (threadIdx.x >> 5)) * (32 / kPcLpe) + grp;
   const bool live = env < p.num_envs;
   const int64_t ev = live ? env : 0;             // dead groups shadow env 0 read-only (all lanes stay in the shuffles)
-  const int n = p.n, W = p.words, T = (n + kPcLpe - 1) / kPcLpe;
+  const int n = p.n, W = p.words;
+  const int myw = sub >> 1, j0 = kPcNpl * sub;   // my word, my first node
+  const bool has = myw < W;                      // the lane owns nodes of this graph (np >= 32 W covers them)
   int16_t* fl = p.fields + ev * (int64_t)p.np;
   const int64_t a_raw = p.action[ev];
-  uint32_t sp = sub < W ? p.spins[ev * W + sub] : 0u;
-  int pre[kPcMaxT];
-#pragma unroll
-  for (int t = 0; t < kPcMaxT; ++t) pre[t] = (t < T && sub + kPcLpe * t < n) ? (int)fl[sub + kPcLpe * t] : 0;
+  const uint32_t sp0 = has ? p.spins[ev * W + myw] : 0u;
+  uint4 fa = make_uint4(0, 0, 0, 0), fb = fa;
+  if (has) {
+    fa = *reinterpret_cast<const uint4*>(fl + j0);
+    fb = *reinterpret_cast<const uint4*>(fl + j0 + 8);
+  }
   const float score0 = p.score[ev], best_obs = p.best_score[ev];
   unsigned long long key0 = 0ull;
   if (p.hset) key0 = p.hkey[ev];
@@ -188,33 +194,27 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step8_kernel(PecoC
   if (live && !valid && sub == 0) p.reward[env] = 0.f, atomicAdd(p.bad_actions, 1);     // IndexError in the reference
   const int a = valid ? (int)a_raw : 0;
   const int wa = a >> 5, ba = a & 31;
-  const uint32_t arow = sub < W ? __ldg(p.adj + (ev * n + a) * W + sub) : 0u;
-  const uint32_t srow = (p.sgn && sub < W) ? __ldg(p.sgn + ev * p.sgn_stride + (int64_t)a * W + sub) : 0u;
-  const int s_old = ((__shfl_sync(kFull, sp, base + wa) >> ba) & 1u) ? 1 : -1;
-  if (valid && sub == wa) {
-    sp ^= 1u << ba;
-    p.spins[env * W + sub] = sp;
-  } else if (sub == wa) {
-    sp ^= 0u;
-  }
+  const uint32_t arow = has ? __ldg(p.adj + (ev * n + a) * W + myw) : 0u;
+  const uint32_t srow = (p.sgn && has) ? __ldg(p.sgn + ev * p.sgn_stride + (int64_t)a * W + myw) : 0u;
+  const int s_old = ((__shfl_sync(kFull, sp0, base + 2 * wa) >> ba) & 1u) ? 1 : -1;
+  const uint32_t sp = (myw == wa) ? sp0 ^ (1u << ba) : sp0;      // both lanes of the word see the flipped spin
+  if (valid && sub == 2 * wa) p.spins[env * W + wa] = sp;
+  const uint32_t fw[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
+  const int sh = (sub & 1) * kPcNpl;             // my 16 bits inside the word
+  const uint32_t abits = (arow >> sh) & 0xFFFFu, sbits = (srow >> sh) & 0xFFFFu, pbits = (sp >> sh) & 0xFFFFu;
   int nonpos = 0, delta = 0;
 #pragma unroll
-  for (int t = 0; t < kPcMaxT; ++t) {
-    if (t < T) {                                    // warp-uniform
-      const int j = sub + kPcLpe * t;
-      const int wj = min(j >> 5, W - 1);
-      const uint32_t aw = __shfl_sync(kFull, arow, base + wj), sw = __shfl_sync(kFull, srow, base + wj),
-                     spw = __shfl_sync(kFull, sp, base + wj);
-      if (j < n) {
-        int v = pre[t];
-        if ((aw >> (j & 31)) & 1u) {                 // (A s)_j -= 2 A[a][j] s_old
-          v -= ((sw >> (j & 31)) & 1u) ? -2 * s_old : 2 * s_old;
-          if (valid) fl[j] = (int16_t)v;
-        }
-        const int f = ((spw >> (j & 31)) & 1u) ? v : -v;
-        nonpos += (int)(f <= 0);
-        if (j == a) delta = -f;
-      }
+  for (int t = 0; t < kPcNpl; ++t) {
+    const int j = j0 + t;
+    int v = (int)(int16_t)((fw[t >> 1] >> (16 * (t & 1))) & 0xFFFFu);
+    if ((abits >> t) & 1u) {                       // (A s)_j -= 2 A[a][j] s_old
+      v -= ((sbits >> t) & 1u) ? -2 * s_old : 2 * s_old;
+      if (valid) fl[j] = (int16_t)v;
+    }
+    if (j < n) {
+      const int f = ((pbits >> t) & 1u) ? v : -v;   // fields_j = s_j (A s)_j with the flipped spin
+      nonpos += (int)(f <= 0);
+      if (j == a) delta = -f;
     }
   }
 #pragma unroll
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step8_kernel(PecoC
   }
   if (!valid) return;
   const bool better = score > best_obs;
-  if (better && sub < W) p.best_spins[env * W + sub] = sp;
+  if (better && has && !(sub & 1)) p.best_spins[env * W + myw] = sp;
   if (sub == 0) {
     p.score[env] = score;
     p.best_score[env] = better ? score : best_obs;
@@ -551,7 +551,7 @@ int rlsb_peco_compact_step(const uint32_t* adj, const uint32_t* sgn, int64_t sgn
   p.recip_div = scalar_div_as_cuda, p.inv_n = 1.0f / (float)num_spins;
   const unsigned grid = (unsigned)((num_envs + kPcWarps - 1) / kPcWarps);
   auto st = static_cast<cudaStream_t>(stream);
-  if (p.n <= kPcLpe * kPcMaxT && p.words <= kPcLpe && p.hcap % kPcLpe == 0 && !(debug_flags() & RLSB_DEBUG_PECO_WARP_PER_ENV)) {
+  if (p.n <= kPcLpe * kPcNpl && p.hcap % kPcLpe == 0 && !(debug_flags() & RLSB_DEBUG_PECO_WARP_PER_ENV)) {
     const int64_t per_block = (int64_t)kPcWarps * (32 / kPcLpe);
     peco_compact_step8_kernel<<<(unsigned)((num_envs + per_block - 1) / per_block), kPcWarps * 32, 0, st>>>(p);
   } else if (p.words <= 4) peco_compact_step_kernel<4><<<grid, kPcWarps * 32, 0, st>>>(p);

@@ -233,6 +233,7 @@ qubo_energy_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 constexpr int kSM = 128;                              // chains per CTA (MMA M)
 constexpr int kSB = 64;                               // rows of Q per block (MMA N)
 constexpr int kSStages = 3;
+constexpr int kSplitMaxOwn = 16;                      // split-K: chains a CTA decides (128 / ks), ks in {8, 16, 32}
 constexpr uint32_t kSTileX = kSM * kQK * 2;           // 16 KB
 constexpr uint32_t kSTileQ = kSB * kQK * 2;           // 8 KB
 constexpr uint32_t kSStageBytes = kSTileX + kQLimbs * kSTileQ;   // 40 KB
@@ -240,19 +241,70 @@ constexpr uint32_t kSStageBytes = kSTileX + kQLimbs * kSTileQ;   // 40 KB
 struct SweepSmem {
   uint8_t tiles[kSStages][kSStageBytes];              // [X | Q_hi | Q_mid | Q_lo]
   float qd[kSB][kSB];                                 // qd[j][i] = Q[m0 + j][m0 + i]
+  float sf[kSplitMaxOwn][kSB];                        // split-K: the summed F of the chains this CTA decides
   uint64_t full_bar[kSStages], empty_bar[kSStages], tmem_full_bar[2], tmem_empty_bar[2];
   uint32_t tmem_base;
 };
 
+// The 64 in-order decisions of a row block for ONE chain (f = F of the block, xv = its current x values) and the
+// write-back of the new x: the bf16 chain-major copy the next block's GEMM reads, and float32 [N][C].
+__device__ __forceinline__ void sweep_decide_block(const float (&qd)[kSB][kSB], float (&f)[kSB], float (&xv)[kSB], int m0, int n,
+                                                   int np, int binary, int64_t chain, int64_t num_chains,
+                                                   __nv_bfloat16* __restrict__ xt, float* __restrict__ x) {
+  const float lo = binary ? 0.f : -1.f;
+#pragma unroll
+  for (int i = 0; i < kSB; ++i) {
+    const float qii = qd[i][i];
+    const float res = f[i] - qii * xv[i];                // Q[i] . x with x_i zeroed
+    const float xn = res > (binary ? -qii * 0.5f : 0.f) ? 1.f : lo;
+    const float d = (m0 + i < n) ? xn - xv[i] : 0.f;     // padding rows never move
+    xv[i] += d;
+#pragma unroll
+    for (int j = i + 1; j < kSB; ++j) f[j] = fmaf(qd[j][i], d, f[j]);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(xt + (size_t)chain * np + m0);
+#pragma unroll
+  for (int v8 = 0; v8 < kSB / 8; ++v8) {
+    uint32_t ws[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)       // values are -1, 0, +1: exact in bf16 (upper half of the f32 pattern)
+      ws[k] = (__float_as_uint(xv[v8 * 8 + 2 * k]) >> 16) | (__float_as_uint(xv[v8 * 8 + 2 * k + 1]) & 0xffff0000u);
+    dst[v8] = make_uint4(ws[0], ws[1], ws[2], ws[3]);
+  }
+  if (chain < num_chains) {
+#pragma unroll
+    for (int i = 0; i < kSB; ++i)
+      if (m0 + i < n) x[(int64_t)(m0 + i) * num_chains + chain] = xv[i];
+  }
+}
+// current x of the block for one chain from the bf16 chain-major copy (128 contiguous bytes)
+__device__ __forceinline__ void sweep_load_x(const __nv_bfloat16* __restrict__ xt, int64_t chain, int np, int m0, float (&xv)[kSB]) {
+  const uint4* src = reinterpret_cast<const uint4*>(xt + (size_t)chain * np + m0);
+#pragma unroll
+  for (int v8 = 0; v8 < kSB / 8; ++v8) {
+    const uint4 w = src[v8];
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      xv[v8 * 8 + 2 * k] = __uint_as_float(ws[k] << 16);              // bf16 -> f32
+      xv[v8 * 8 + 2 * k + 1] = __uint_as_float(ws[k] & 0xffff0000u);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kQThreads, 1)
 qubo_sweep_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQ,
                   const float* __restrict__ q, int n, int np, int m0, int64_t num_chains, int binary,
-                  __nv_bfloat16* __restrict__ xt, float* __restrict__ x) {
+                  __nv_bfloat16* __restrict__ xt, float* __restrict__ x, int ks, float* __restrict__ part,
+                  unsigned* __restrict__ counter, unsigned target) {
   extern __shared__ uint8_t smem_raw[];
   SweepSmem& S = *reinterpret_cast<SweepSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * kSM;                        // first chain of this CTA
-  const int kblocks = np / kQK;
+  // split-K (ks > 1, few chains): blockIdx.y owns the k-blocks [kb0, kb0 + kblocks) of the row block's dot products;
+  // the ks CTAs of a chain group add their partial F through global memory, then each decides 128 / ks chains
+  const int kblocks = np / kQK / ks;
+  const int kb0 = (int)blockIdx.y * kblocks;
   const int chunks = (kblocks + kQChunk - 1) / kQChunk;
 
   if (threadIdx.x == 0) {
@@ -277,9 +329,9 @@ qubo_sweep_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int s = kb % kSStages, ph = (kb / kSStages) & 1;
         mbar_wait(&S.empty_bar[s], ph ^ 1);
         mbar_arrive_expect_tx(&S.full_bar[s], kSStageBytes);
-        tma_load_2d(S.tiles[s], &tmX, &S.full_bar[s], kb * kQK, n0);
+        tma_load_2d(S.tiles[s], &tmX, &S.full_bar[s], (kb0 + kb) * kQK, n0);
         for (int l = 0; l < kQLimbs; ++l)
-          tma_load_2d(S.tiles[s] + kSTileX + l * kSTileQ, &tmQ, &S.full_bar[s], kb * kQK, l * np + m0);
+          tma_load_2d(S.tiles[s] + kSTileX + l * kSTileQ, &tmQ, &S.full_bar[s], (kb0 + kb) * kQK, l * np + m0);
       }
     }
   } else if (warp == 1) {
@@ -317,19 +369,7 @@ qubo_sweep_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       S.qd[j][i] = (m0 + j < n && m0 + i < n) ? __ldg(q + (int64_t)(m0 + j) * n + m0 + i) : 0.f;
     }
     float xv[kSB], f[kSB];
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(xt + (size_t)chain * np + m0);     // 128 contiguous bytes
-#pragma unroll
-      for (int v8 = 0; v8 < kSB / 8; ++v8) {
-        const uint4 w = src[v8];
-        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          xv[v8 * 8 + 2 * k] = __uint_as_float(ws[k] << 16);              // bf16 -> f32
-          xv[v8 * 8 + 2 * k + 1] = __uint_as_float(ws[k] & 0xffff0000u);
-        }
-      }
-    }
+    sweep_load_x(xt, chain, np, m0, xv);
 #pragma unroll
     for (int c = 0; c < kSB; ++c) f[c] = 0.f;
     for (int ch = 0; ch < chunks; ++ch) {
@@ -357,33 +397,44 @@ qubo_sweep_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (lane == 0) mbar_arrive(&S.tmem_empty_bar[buf]);
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");        // qd complete
-    const float lo = binary ? 0.f : -1.f;
+    if (ks == 1) {
+      sweep_decide_block(S.qd, f, xv, m0, n, np, binary, chain, num_chains, xt, x);
+    } else {
+      // partial F of this K slice -> global; barrier over the ks CTAs of the chain group (all resident: the host keeps
+      // groups * ks <= SMs, and the counter only grows: `target` = ks * launches so far); then every CTA adds the
+      // ks partials of ITS 128 / ks chains in slice order (deterministic) and decides them
+      const int own = kSM / ks;
+      float4* dst = reinterpret_cast<float4*>(part + (((size_t)blockIdx.x * ks + blockIdx.y) * kSM + (32 * qw + lane)) * kSB);
 #pragma unroll
-    for (int i = 0; i < kSB; ++i) {
-      const float qii = S.qd[i][i];
-      const float res = f[i] - qii * xv[i];                // Q[i] . x with x_i zeroed
-      const float xn = res > (binary ? -qii * 0.5f : 0.f) ? 1.f : lo;
-      const float d = (m0 + i < n) ? xn - xv[i] : 0.f;     // padding rows never move
-      xv[i] += d;
-#pragma unroll
-      for (int j = i + 1; j < kSB; ++j) f[j] = fmaf(S.qd[j][i], d, f[j]);
-    }
-    // new x of the block: the bf16 chain-major copy the next block's GEMM reads, and float32 [N][C]
-    {
-      uint4* dst = reinterpret_cast<uint4*>(xt + (size_t)chain * np + m0);
-#pragma unroll
-      for (int v8 = 0; v8 < kSB / 8; ++v8) {
-        uint32_t ws[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)       // values are -1, 0, +1: exact in bf16 (upper half of the f32 pattern)
-          ws[k] = (__float_as_uint(xv[v8 * 8 + 2 * k]) >> 16) | (__float_as_uint(xv[v8 * 8 + 2 * k + 1]) & 0xffff0000u);
-        dst[v8] = make_uint4(ws[0], ws[1], ws[2], ws[3]);
+      for (int v4 = 0; v4 < kSB / 4; ++v4) dst[v4] = make_float4(f[4 * v4], f[4 * v4 + 1], f[4 * v4 + 2], f[4 * v4 + 3]);
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        atomicAdd(counter + blockIdx.x, 1u);
+        unsigned v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter + blockIdx.x) : "memory");
+        } while (v < target);
       }
-    }
-    if (chain < num_chains) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int item = et; item < own * (kSB / 4); item += 128) {
+        const int c = item / (kSB / 4), v4 = item % (kSB / 4);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sl = 0; sl < ks; ++sl) {
+          const float4 p4 = __ldcg(reinterpret_cast<const float4*>(
+              part + (((size_t)blockIdx.x * ks + sl) * kSM + (blockIdx.y * own + c)) * kSB) + v4);
+          acc.x += p4.x, acc.y += p4.y, acc.z += p4.z, acc.w += p4.w;
+        }
+        S.sf[c][4 * v4] = acc.x, S.sf[c][4 * v4 + 1] = acc.y, S.sf[c][4 * v4 + 2] = acc.z, S.sf[c][4 * v4 + 3] = acc.w;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et < own) {
+        const int64_t mine = n0 + blockIdx.y * own + et;
+        sweep_load_x(xt, mine, np, m0, xv);
 #pragma unroll
-      for (int i = 0; i < kSB; ++i)
-        if (m0 + i < n) x[(int64_t)(m0 + i) * num_chains + chain] = xv[i];
+        for (int c = 0; c < kSB; ++c) f[c] = S.sf[et][c];
+        sweep_decide_block(S.qd, f, xv, m0, n, np, binary, mine, num_chains, xt, x);
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -518,7 +569,8 @@ int64_t rlsb_qubo_workspace_bytes(const rlsb_qubo_t* h, int64_t num_chains) {
   using namespace rlsb;
   if (!h || num_chains < 0) return -1;
   const int64_t cp = (num_chains + kQN - 1) / kQN * kQN;
-  return cp * h->np * 2 + (int64_t)(h->np / kQM) * cp * 4 + 512;
+  // bf16 chain-major X, energy partials, split-K partials of the sweeps (<= one CTA per SM) + group counters
+  return cp * h->np * 2 + (int64_t)(h->np / kQM) * cp * 4 + (int64_t)kNumSMs * kSM * kSB * 4 + 1024 + 512;
 }
 
 int rlsb_qubo_energy(const rlsb_qubo_t* h, const float* x, int64_t num_chains, float* energy, void* workspace,
@@ -569,11 +621,28 @@ int rlsb_qubo_sweeps(const rlsb_qubo_t* h, const float* q, float* x, int64_t num
   if (int rc = make_map(&map_q, h->limbs, (uint64_t)3 * h->np, (uint64_t)h->np, kSB)) return rc;
   const size_t smem = sizeof(SweepSmem) + 1024;
   RLSB_CUDA_OK(cudaFuncSetAttribute(qubo_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const unsigned grid = (unsigned)((num_chains + kSM - 1) / kSM);
+  const unsigned groups = (unsigned)((num_chains + kSM - 1) / kSM);
+  // Few chains (config 5 hands each GPU 1024): one CTA per 128 chains would leave most SMs idle, so the K range of
+  // every row block is split over ks CTAs per chain group, groups * ks <= SMs (they synchronise inside the launch)
+  int ks = 1;
+  if (!(debug_flags() & RLSB_DEBUG_QUBO_NO_SPLITK))
+    for (int cand : {32, 16, 8})
+      if ((int64_t)groups * cand <= kNumSMs && (h->np / kQK) % cand == 0 && (h->np / kQK) / cand >= 2) {
+        ks = cand;
+        break;
+      }
+  char* tail = static_cast<char*>(workspace) + cp * h->np * 2 + (int64_t)(h->np / kQM) * cp * 4;
+  tail = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tail) + 255) & ~uintptr_t(255));
+  float* part = reinterpret_cast<float*>(tail);
+  unsigned* counter = reinterpret_cast<unsigned*>(tail + (size_t)kNumSMs * kSM * kSB * 4);
+  if (ks > 1) RLSB_CUDA_OK(cudaMemsetAsync(counter, 0, 1024, st));
+  unsigned launches = 0;
   for (int sweep = 0; sweep < num_sweeps; ++sweep)
     for (int m0 = 0; m0 < h->n; m0 += kSB) {
-      qubo_sweep_kernel<<<grid, kQThreads, smem, st>>>(map_x, map_q, q, h->n, h->np, m0, num_chains, binary ? 1 : 0,
-                                                       xt, x);
+      ++launches;
+      qubo_sweep_kernel<<<dim3(groups, (unsigned)ks), kQThreads, smem, st>>>(map_x, map_q, q, h->n, h->np, m0, num_chains,
+                                                                            binary ? 1 : 0, xt, x, ks, part, counter,
+                                                                            (unsigned)ks * launches);
       RLSB_LAUNCH_OK();
     }
   return RLSB_OK;

@@ -100,3 +100,66 @@ def test_qubo_sweeps_vs_oracle(n, c, binary, integer, cuda_device):
     e0 = oq.energy(q, x0)
     e1 = oq.energy(q, _np(x))
     assert (e1 >= e0 - 1e-6 * oq.scale(q)).all()
+
+
+def _small_int_q(n, seed):
+    rng = np.random.default_rng(seed)
+    u = rng.integers(-3, 4, (n, n)).astype(np.float32)
+    return (np.triu(u) + np.triu(u, 1).T).astype(np.float32), rng
+
+
+@pytest.mark.parametrize("c", [1024, 8192])
+def test_qubo_config5_integer_q_exact(c, cuda_device):
+    """BASELINE config 5 shape (N = 4096; 8192 chains in total, 1024 per GPU on 8 GPUs) with a small-integer Q: every
+    product and partial sum is exact in fp32, so energies equal the float64 oracle exactly and the sweeps -- split
+    over K for the few-chain case, one CTA per 128 chains otherwise -- equal the oracle on sampled chains and each
+    other on all of them."""
+    from rlsolver_b200 import _lib
+    from rlsolver_b200.qubo import QuboModel
+    n = 4096
+    q, rng = _small_int_q(n, 5)
+    x0 = (2 * rng.integers(0, 2, (n, c)) - 1).astype(np.float32)
+    model = QuboModel(th.from_numpy(q).to(cuda_device))
+    x = th.from_numpy(x0).to(cuda_device)
+    sample = np.arange(3, c, c // 24)
+    assert np.array_equal(_np(model.energy(x))[sample].astype(np.float64), oq.energy(q, x0[:, sample]))
+    xa = x.clone()
+    model.sweeps(xa, 1)
+    _lib.debug_flags(_lib.DEBUG_QUBO_NO_SPLITK, 0)
+    try:
+        xb = x.clone()
+        model.sweeps(xb, 1)
+    finally:
+        _lib.debug_flags(0, _lib.DEBUG_QUBO_NO_SPLITK)
+    assert th.equal(xa, xb)
+    want = oq.sweeps(q, x0[:, sample], 1, False)
+    assert np.array_equal(_np(xa)[:, sample], want)
+    e0, e1 = oq.energy(q, x0[:, sample]), oq.energy(q, _np(xa)[:, sample])
+    assert (e1 >= e0).all()
+
+
+@pytest.mark.parametrize("n,c,binary", [(1024, 256, False), (2048, 300, True), (4096, 128, False)])
+def test_qubo_sweeps_split_k_equals_single_cta(n, c, binary, cuda_device):
+    """Float Q, few chains: the K-split sweep adds its partial dot products in another order than the single-CTA form,
+    so chains may differ only where a decision sat within fp32 rounding of its threshold."""
+    from rlsolver_b200 import _lib
+    from rlsolver_b200.qubo import QuboModel
+    rng = np.random.default_rng(n + c)
+    u = rng.standard_normal((n, n)).astype(np.float32)
+    q = (np.triu(u) + np.triu(u, 1).T).astype(np.float32)
+    x0 = rng.integers(0, 2, (n, c)).astype(np.float32)
+    if not binary:
+        x0 = 2 * x0 - 1
+    model = QuboModel(th.from_numpy(q).to(cuda_device))
+    xa = th.from_numpy(x0.copy()).to(cuda_device)
+    model.sweeps(xa, 2, binary=binary)
+    _lib.debug_flags(_lib.DEBUG_QUBO_NO_SPLITK, 0)
+    try:
+        xb = th.from_numpy(x0.copy()).to(cuda_device)
+        model.sweeps(xb, 2, binary=binary)
+    finally:
+        _lib.debug_flags(0, _lib.DEBUG_QUBO_NO_SPLITK)
+    same = (_np(xa) == _np(xb)).all(axis=0)
+    margin = oq.sweep_margin(q, x0, 2, binary)
+    safe = margin > 2e-5 * np.sqrt(n) * np.abs(q).max()
+    assert same[safe].all() and same.mean() > 0.95, (float(safe.mean()), float(same.mean()))
