@@ -436,13 +436,14 @@ __global__ void __launch_bounds__(256) peco_gen_er_kernel(uint32_t* __restrict__
 // topk(prob / q, m) with q ~ Exp(1) drawn by ONE exponential_ call over [E, n] (ATen Distributions.cpp,
 // multinomial fast path): element (e, j) of call number t - m - 1.  exponential_ on CUDA = -log(curand_uniform)
 // with log replaced by -eps/2 at 1 (TransformationHelper.h); the division is IEEE.
+// kMaxSlots: candidate nodes per lane held in registers (N <= 32 kMaxSlots)
+template <int kMaxSlots>
 __global__ void __launch_bounds__(kPcWarps * 32) peco_gen_ba_kernel(uint32_t* __restrict__ adj, int64_t num_envs, int n,
                                                                     int W, int m, TorchRng r) {
   const int lane = threadIdx.x & 31;
   const int64_t env = (int64_t)blockIdx.x * kPcWarps + (threadIdx.x >> 5);
   if (env >= num_envs) return;
   uint32_t* rows = adj + env * n * W;
-  constexpr int kMaxSlots = 32;                            // n <= 1024
   int deg[kMaxSlots];
   const int slots = (n + 31) >> 5;
 #pragma unroll
@@ -668,8 +669,10 @@ int rlsb_peco_gen_ba(uint32_t* adj, int64_t num_envs, int32_t num_spins, int32_t
   auto st = static_cast<cudaStream_t>(stream);
   RLSB_CUDA_OK(cudaMemsetAsync(adj, 0, (size_t)num_envs * num_spins * W * sizeof(uint32_t), st));
   TorchRng r{seed, offset / 4, rng_threads, rng_iters, nullptr};
-  peco_gen_ba_kernel<<<(unsigned)((num_envs + kPcWarps - 1) / kPcWarps), kPcWarps * 32, 0, st>>>(adj, num_envs, num_spins,
-                                                                                                 W, m_insertion_edges, r);
+  const unsigned grid = (unsigned)((num_envs + kPcWarps - 1) / kPcWarps);
+  if (num_spins <= 128) peco_gen_ba_kernel<4><<<grid, kPcWarps * 32, 0, st>>>(adj, num_envs, num_spins, W, m_insertion_edges, r);
+  else if (num_spins <= 256) peco_gen_ba_kernel<8><<<grid, kPcWarps * 32, 0, st>>>(adj, num_envs, num_spins, W, m_insertion_edges, r);
+  else peco_gen_ba_kernel<32><<<grid, kPcWarps * 32, 0, st>>>(adj, num_envs, num_spins, W, m_insertion_edges, r);
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }

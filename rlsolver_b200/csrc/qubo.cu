@@ -233,7 +233,7 @@ qubo_energy_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 constexpr int kSM = 128;                              // chains per CTA (MMA M)
 constexpr int kSB = 64;                               // rows of Q per block (MMA N)
 constexpr int kSStages = 3;
-constexpr int kSplitMaxOwn = 16;                      // split-K: chains a CTA decides (128 / ks), ks in {8, 16, 32}
+constexpr int kSplitMaxOwn = 32;                      // split-K: chains a CTA decides (128 / ks), ks in {4, 8, 16, 32}
 constexpr uint32_t kSTileX = kSM * kQK * 2;           // 16 KB
 constexpr uint32_t kSTileQ = kSB * kQK * 2;           // 8 KB
 constexpr uint32_t kSStageBytes = kSTileX + kQLimbs * kSTileQ;   // 40 KB
@@ -364,9 +364,23 @@ qubo_sweep_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int qw = warp & 3;                               // TMEM lane quarter this warp may read
     const int64_t chain = n0 + 32 * qw + lane;             // < cp (padded chains carry zeros)
     const int et = threadIdx.x - 64;
-    for (int idx = et; idx < kSB * kSB; idx += 128) {      // diagonal block of Q in full precision
-      const int j = idx / kSB, i = idx % kSB;
-      S.qd[j][i] = (m0 + j < n && m0 + i < n) ? __ldg(q + (int64_t)(m0 + j) * n + m0 + i) : 0.f;
+    // diagonal block of Q in full precision: half a row (128 B) per thread as eight independent 16-byte loads -- one
+    // trip to L2 (a scalar loop serialised 32 of them: ~10 us per launch, visible once the GEMM is split over K)
+    if (n % 4 == 0 && m0 + kSB <= n) {
+      const int j = et >> 1, i0 = (et & 1) * (kSB / 2);
+      const float4* src = reinterpret_cast<const float4*>(q + (int64_t)(m0 + j) * n + m0 + i0);
+      float4 v[kSB / 8];
+#pragma unroll
+      for (int k = 0; k < kSB / 8; ++k) v[k] = __ldg(src + k);
+#pragma unroll
+      for (int k = 0; k < kSB / 8; ++k)
+        S.qd[j][i0 + 4 * k] = v[k].x, S.qd[j][i0 + 4 * k + 1] = v[k].y, S.qd[j][i0 + 4 * k + 2] = v[k].z,
+        S.qd[j][i0 + 4 * k + 3] = v[k].w;
+    } else {
+      for (int idx = et; idx < kSB * kSB; idx += 128) {
+        const int j = idx / kSB, i = idx % kSB;
+        S.qd[j][i] = (m0 + j < n && m0 + i < n) ? __ldg(q + (int64_t)(m0 + j) * n + m0 + i) : 0.f;
+      }
     }
     float xv[kSB], f[kSB];
     sweep_load_x(xt, chain, np, m0, xv);
@@ -626,7 +640,7 @@ int rlsb_qubo_sweeps(const rlsb_qubo_t* h, const float* q, float* x, int64_t num
   // every row block is split over ks CTAs per chain group, groups * ks <= SMs (they synchronise inside the launch)
   int ks = 1;
   if (!(debug_flags() & RLSB_DEBUG_QUBO_NO_SPLITK))
-    for (int cand : {32, 16, 8})
+    for (int cand : {32, 16, 8, 4})
       if ((int64_t)groups * cand <= kNumSMs && (h->np / kQK) % cand == 0 && (h->np / kQK) / cand >= 2) {
         ks = cand;
         break;
