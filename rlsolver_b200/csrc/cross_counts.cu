@@ -139,6 +139,7 @@ static int launch_prepare(const GraphDev& g, const uint8_t* xs, const uint32_t* 
                           int32_t* col_max, int64_t* vs, cudaStream_t st) {
   const size_t smem = (size_t)g.np * sizeof(uint32_t);
   auto kernel = prepare_kernel<P, CrossT, VEC>;
+  RLSB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   if (smem > 48 * 1024)
     RLSB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;

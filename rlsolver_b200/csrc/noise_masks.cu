@@ -480,6 +480,14 @@ int rlsb_torch_randn(float* out, int64_t numel, uint64_t seed, uint64_t offset, 
   RLSB_REQUIRE(out, RLSB_ERR_INVALID, "torch_randn: null pointer");
   TorchRng r{seed, offset / 4, (uint32_t)rng_threads, (uint32_t)rng_iters, rng_dev};
   const dim3 grid((unsigned)(rng_threads / 256), (unsigned)rng_iters, (unsigned)num_draws);
+  // same carve-out as the tile "prepare" kernel, so that the two can share SMs when a caller runs the threshold
+  // draw on a second stream next to rlsb_ls_begin (GraphStore.ls_fused under graph capture)
+  static bool carve_set = false;
+  if (!carve_set) {
+    RLSB_CUDA_OK(cudaFuncSetAttribute(noise_values_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+    carve_set = true;
+  }
   noise_values_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, (uint32_t)numel, r);
   RLSB_LAUNCH_OK();
   return RLSB_OK;

@@ -31,6 +31,9 @@ class EnvMaxcut:
     # torch.randn tensor streamed through rlsb_ls_run -- the form to use when the noise itself must be
     # supplied (tests replaying recorded draws) and the one taken when the mask path does not apply.
     fused_rng = True
+    # under CUDA-graph capture the threshold draw is issued on a second stream next to ls_begin (it does not depend
+    # on the state); False keeps the single-stream order
+    overlap_threshold_draw = True
 
     def __init__(self, sim_name: str = 'max_cut', mygraph: MyGraph = (),
                  device=th.device('cpu'), if_bidirectional: bool = False):
@@ -112,8 +115,11 @@ class EnvMaxcut:
             if not vs_in.is_contiguous():
                 vs_in = vs_in.contiguous()
         ws = st.ls_workspace(num_sims)
+        fused = self.fused_rng and num_sims > 0 and st.ls_mask_words(num_sims) >= 0
+        if fused and self.overlap_threshold_draw:
+            st.ls_prefetch_threshold_draw(num_sims)      # graph capture only: the draw runs next to ls_begin
         good_vs = st.ls_begin(good_xs, vs_in, 1, noise_std, ws)
-        if self.fused_rng and num_sims > 0 and st.ls_mask_words(num_sims) >= 0:
+        if fused:
             st.ls_fused(good_vs, 1, num_spin, num_iters, False, good_xs, ws)
             return good_xs, good_vs
         shape = (num_sims, self.num_nodes)

@@ -377,10 +377,11 @@ class GraphStore:
                                                          _stream_ptr(self.device)), "rng_cursor_advance")
 
     def torch_randn(self, numel: int, num_draws: int, seed: int, offset: int, threads: int, iters: int,
-                    cursor: Optional[TEN] = None) -> TEN:
+                    cursor: Optional[TEN] = None, out: Optional[TEN] = None) -> TEN:
         """float32 [num_draws, numel]: the values `num_draws` consecutive torch.randn(numel) calls would
         return from generator state (seed, offset) -- or from the device cursor + offset."""
-        out = th.empty((num_draws, numel), dtype=th.float32, device=self.device)
+        if out is None:
+            out = th.empty((num_draws, numel), dtype=th.float32, device=self.device)
         with self._op("torch_randn"):
             _lib.check(self._lib.rlsb_torch_randn(_ptr(out), int(numel), int(seed), int(offset), _ptr(cursor),
                                                   int(threads), int(iters), int(num_draws),
@@ -461,6 +462,26 @@ class GraphStore:
                                                       _stream_ptr(self.device)), "ls_begin_packed")
         return vs
 
+    def ls_prefetch_threshold_draw(self, num_envs: int) -> None:
+        """Under CUDA-graph capture: issue the threshold draw of the coming ls_fused call NOW, on a second stream, so
+        that it runs next to rlsb_ls_begin (the draw does not depend on the state).  The next ls_fused joins the
+        stream and uses the tensor.  Outside capture this does nothing (torch's own randn call is kept there)."""
+        if not th.cuda.is_current_stream_capturing():
+            return
+        n = self.num_nodes
+        numel = num_envs * n
+        threads, iters = rng.torch_call_geometry(self.device, numel)
+        buf = getattr(self, "_noise0", None)
+        if buf is None or buf.numel() != numel:
+            raise RuntimeError("ls_prefetch_threshold_draw: run one eager local search of this batch size before capturing "
+                               "(the noise buffer and the side stream are created there)")
+        cur = th.cuda.current_stream(self.device)
+        side = self._side_stream
+        side.wait_stream(cur)
+        with th.cuda.stream(side):
+            self.torch_randn(numel, 1, 0, 0, threads, iters, cursor=self.rng_cursor(), out=buf.view(1, numel))
+        self._noise0_pending = True
+
     def ls_fused(self, vs: TEN, ws_mult: int, num_spin: int, num_iters: int, first_draw_is_iter: bool,
                  xs_out: Optional[TEN], workspace: TEN) -> None:
         """Threshold + noisy iterations + single-flip pass with the generator consumed in place.
@@ -481,11 +502,20 @@ class GraphStore:
         capturing = th.cuda.is_current_stream_capturing()
         if capturing:
             cur, seed, base = self.rng_cursor(), 0, 0
-            noise0 = self.torch_randn(numel, 1, 0, 0, threads, iters, cursor=cur).view(e, n)
+            if getattr(self, "_noise0_pending", False):       # drawn on the side stream next to ls_begin
+                th.cuda.current_stream(self.device).wait_stream(self._side_stream)
+                noise0 = self._noise0.view(e, n)
+                self._noise0_pending = False
+            else:
+                noise0 = self.torch_randn(numel, 1, 0, 0, threads, iters, cursor=cur).view(e, n)
         else:
             cur = None
             seed, base, _, _ = rng.peek(self.device, numel)
             noise0 = th.randn((e, n), dtype=th.float32, device=self.device)
+            if getattr(self, "_noise0", None) is None or self._noise0.numel() != numel:
+                # what a later captured call of this batch size needs: a persistent buffer and a second stream
+                self._noise0 = th.empty((numel,), dtype=th.float32, device=self.device)
+                self._side_stream = th.cuda.Stream(device=self.device)
         self.ls_run(vs, ws_mult, noise0, num_spin, [], False, None, workspace)
         done = 0
         chunk = 1024 if self.overlap_generator else 16384           # kLsMaxFusedDraws per fused launch
