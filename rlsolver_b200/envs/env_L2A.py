@@ -31,9 +31,12 @@ class EnvMaxcut:
     # torch.randn tensor streamed through rlsb_ls_run -- the form to use when the noise itself must be
     # supplied (tests replaying recorded draws) and the one taken when the mask path does not apply.
     fused_rng = True
-    # under CUDA-graph capture the threshold draw is issued on a second stream next to ls_begin (it does not depend
-    # on the state); False keeps the single-stream order
-    overlap_threshold_draw = True
+    # True: under CUDA-graph capture the threshold draw is issued on a second stream next to ls_begin (it does not
+    # depend on the state).  Same results, but measured on B200 it buys nothing (235.6 us in line vs 237.8 / 239.6 us per G22 x
+    # 4096 step, profiles/r02_threshold_draw_second_stream.log): the draw's 8288 short blocks are dispatched first and
+    # fill every SM, the begin kernel's 128 CTAs of 512 threads x 104 registers only find room when the draw is
+    # nearly over -- a launch priority on the begin kernel does not change that -- so the default keeps one stream.
+    overlap_threshold_draw = False
 
     def __init__(self, sim_name: str = 'max_cut', mygraph: MyGraph = (),
                  device=th.device('cpu'), if_bidirectional: bool = False):
