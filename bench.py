@@ -569,7 +569,7 @@ def run_b200(args):
     from synth import gset_like
 
     import rlsolver_b200
-    from rlsolver_b200.dist import BestExchange
+    from rlsolver_b200.dist import BestExchange, PeerBestExchange
     from rlsolver_b200.envs.env_L2A import EnvMaxcut
 
     rlsolver_b200.build()
@@ -586,7 +586,18 @@ def run_b200(args):
     flush = ctx.flush
     small_flush_steps = flush[:160 << 20]                          # > 126 MB L2 (timed when the exchange is pipelined)
     barrier = ctx.barrier
-    exchange = BestExchange(n, rank, world, envs, dev) if world > 1 else None
+    # the path's only exchange: one kernel over NVLink peer memory (PeerBestExchange); NCCL all-gather form on request
+    # (--exchange nccl, --pipelined-exchange) or when CUDA IPC between the ranks is not available on the box
+    exchange, exchange_kind = None, None
+    if world > 1:
+        if args.exchange == "peer" and not args.pipelined_exchange:
+            try:
+                exchange, exchange_kind = PeerBestExchange(n, rank, world, envs, dev), "peer"
+            except RuntimeError as exc:      # raised on every rank alike (the constructor agrees on the outcome)
+                log(f"peer exchange not available: {str(exc)[:200]}")
+        if exchange is None:
+            exchange, exchange_kind = BestExchange(n, rank, world, envs, dev), "nccl"
+    in_graph = exchange_kind == "peer"       # a plain kernel launch: it is captured with the local search
     ex_stream = th.cuda.Stream(device=dev) if world > 1 else None
     posted = th.cuda.Event() if world > 1 else None
 
@@ -596,22 +607,22 @@ def run_b200(args):
     def step_body():
         """The local part of a step: fixed launch sequence, captured into a CUDA graph below."""
         gx, gv = local_part()
-        return gx, gv, None
+        return gx, gv, (exchange(gv, gx) if in_graph else None)
 
     state = {"graph": None, "out": None}
 
     def one_step():
-        """One step: the local search (graph replay) and -- with several ranks -- the path's only exchange (best cut,
-        its argmax, the winner's spins), issued right behind it on the same stream.  The exchange stays OUTSIDE the
-        graph: capturing the NCCL all-gather hung both ranks on this torch / NCCL build (round 2, N = 2), so it is
-        three eager launches on preallocated buffers (record kernel, ncclAllGather, pick kernel), no host sync."""
+        """One step: the local search and -- with several ranks -- the path's only exchange (best cut, its argmax, the
+        winner's spins) right behind it on the same stream.  The peer-memory exchange is one kernel and part of the
+        captured graph.  The NCCL form stays OUTSIDE the graph: capturing the all-gather hung both ranks on this
+        torch / NCCL build (round 2, N = 2), so it is three eager launches on preallocated buffers (record kernel,
+        ncclAllGather, pick kernel), no host sync."""
         if state["graph"] is not None:
             state["graph"].replay()
-            gx, gv, _ = state["out"]
+            gx, gv, best = state["out"]
         else:
-            gx, gv, _ = step_body()
-        best = None
-        if exchange is not None:
+            gx, gv, best = step_body()
+        if exchange is not None and not in_graph:
             if not args.pipelined_exchange:
                 best = exchange(gv, gx)
             else:
@@ -677,7 +688,8 @@ def run_b200(args):
                 out = step_body()
             th.cuda.synchronize()
             state["graph"], state["out"] = g, out
-            return "captured (local search)" + ("; best-cut exchange eager behind the replay" if world > 1 else "")
+            return "captured (local search" + (")" if world == 1 else " + peer-memory best-cut exchange)" if in_graph else
+                                               "); best-cut exchange eager behind the replay")
         except Exception as exc:                                   # noqa: BLE001 - eager remains correct
             state["graph"] = None
             th.cuda.synchronize()
@@ -688,7 +700,7 @@ def run_b200(args):
     t_w = time.time()
     launches_before = sim.store.launch_count
     timed_steps(1)
-    launches_per_step = sim.store.launch_count - launches_before + (2 if world > 1 else 0)
+    launches_per_step = sim.store.launch_count - launches_before + (0 if world == 1 else 1 if in_graph else 2)
     log("first eager step done")
     graph_status = try_capture()
     log(f"graph: {graph_status}")
@@ -710,12 +722,17 @@ def run_b200(args):
     per_call = env_steps_per_call(envs, n, NUM_ITERS, n)
     value = per_call * world * args.steps / (total_ms * 1e-3)
 
-    # exchange cost alone (multi-GPU): record kernel + all-gather + pick kernel, eager, CUDA events
+    # exchange cost alone (multi-GPU), eager, CUDA events
     exch_us = None
     if world > 1:
         gx, gv = xs, sim.calculate_obj_values(xs)
         ex_ms = ctx.timed(lambda: exchange(gv, gx), reps=50, warm=5, flush=False)
         exch_us = 1e3 * ctx.job_ms(ex_ms)
+        if exchange_kind == "peer":
+            calls, timeouts = exchange.status()
+            if timeouts:
+                raise RuntimeError(f"peer exchange: {timeouts} polls timed out in {calls} calls -- the ranks did not make "
+                                   f"the same sequence of calls")
 
     # ---- end to end from pinned host buffers through the public API.  Every step copies its spins from pinned host
     # memory to the device, runs the step, and copies spins + values back.  Two host layouts: `bool` = the
@@ -902,14 +919,18 @@ def run_b200(args):
                            "env_steps_per_step_per_gpu": per_call, "l2": "flushed between steps (256 MiB write)", "cuda_graph": graph_status,
                            "rng": "torch's CUDA Philox stream, 1+8 draws of randn [E,N] f32 per step inside the timed region, "
                                   "recomputed in place (only thresholds / flip bits leave the kernels)",
-                           "multi_gpu": ("env batch sharded, graph replicated, one best-cut exchange per step behind the "
+                           "multi_gpu": ("env batch sharded, graph replicated, one best-cut exchange per step: ONE kernel over "
+                                         "NVLink peer memory (every rank stores its 8+N B record into each peer's mailbox, "
+                                         "raises an arrival word, polls its own, picks the winner), captured in the step's "
+                                         "CUDA graph, no NCCL call, no host sync" if exchange_kind == "peer" else
+                                         "env batch sharded, graph replicated, one best-cut exchange per step behind the "
                                          "graph replay: best_record kernel + ncclAllGather of world x (8+N) B + "
                                          "best_pick kernel on preallocated buffers, no host sync; "
                                          + ("serial behind every step" if not args.pipelined_exchange else
                                             "pipelined: only the record kernel is ordered before the next step, all-gather "
                                             "+ pick run on a second stream under it; K steps timed as one region that "
                                             "ends after the last exchange, the 160 MiB L2-evicting write per step included")),
-                           "exchange_us": exch_us},
+                           "exchange": exchange_kind, "exchange_us": exch_us},
                 "e2e": {"value": e2e_bool["value"], "unit": UNIT, "h2d_bytes_per_step": e2e_bool["h2d_bytes_per_step"],
                         "d2h_bytes_per_step": e2e_bool["d2h_bytes_per_step"], "ms_per_step": e2e_bool["ms_per_step"],
                         "layout": "bool [E, N] rows (the reference's layout), EnvMaxcut.local_search_inplace",
@@ -962,6 +983,9 @@ def main():
     ap.add_argument("--pipelined-exchange", action="store_true",
                     help="N > 1: order only the record kernel before the next step and run all-gather + pick under it "
                          "(K steps timed as one region, L2-evicting writes inside); default: serial behind every step")
+    ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
+                    help="N > 1: the best-cut exchange as one kernel over NVLink peer memory (default) or as record kernel + "
+                         "ncclAllGather + pick kernel")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     with _QuietStdout():

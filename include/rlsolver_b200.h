@@ -405,6 +405,30 @@ int rlsb_best_pick(const uint8_t* gathered, int32_t world, int32_t num_nodes, in
 int rlsb_best_pick_strided(const uint8_t* gathered, int32_t world, int32_t num_nodes, int64_t stride, int64_t* out2,
                            uint8_t* row, void* stream);
 
+/* ---- the same exchange as ONE kernel over NVLink peer memory (csrc/peer_exchange.cu), one process per GPU of one box.
+ * Replaces record kernel + ncclAllGather + pick kernel of the sharded best-cut exchange (the reference has no
+ * multi-GPU form of this path: rlsolver/envs/env_L2A.py:118-165 runs one device).  Every rank owns a
+ * mailbox in its HBM which the other ranks map through CUDA IPC; a call stores the rank's record into every mailbox,
+ * raises an arrival word, polls its own arrival words and picks the winner.  Collective: every rank must make the same
+ * sequence of calls.  The poll is bounded (20 s, RLSB_PEER_TIMEOUT_MS overrides): time-outs are counted, never hang.
+ * The launch has no per-call arguments (the call counter lives in the mailbox), so it may be captured in a CUDA graph.
+ *   create : allocates the mailbox on the current device, handle_out receives rlsb_peer_exchange_handle_bytes() bytes
+ *   connect: handles = the world handles, rank-major (all-gathered by the host side) */
+typedef struct rlsb_peer_exchange rlsb_peer_exchange_t;
+int64_t rlsb_peer_exchange_handle_bytes(void);
+int rlsb_peer_exchange_create(int32_t rank, int32_t world, int32_t num_nodes, rlsb_peer_exchange_t** out, uint8_t* handle_out);
+int rlsb_peer_exchange_connect(rlsb_peer_exchange_t* ex, const uint8_t* handles);
+/* vs int64 [E], xs bool [E][N]; env_offset = global id of local env 0; out2[0] = best cut, out2[1] = its global env id,
+ * row = the winner's N spin bytes -- identical on every rank */
+int rlsb_peer_exchange_best(rlsb_peer_exchange_t* ex, const int64_t* vs, const uint8_t* xs, int64_t num_envs, int64_t env_offset,
+                            int64_t* out2, uint8_t* row, void* stream);
+/* the same for a batch kept as packed tiles (uint32 [ceil(E/32)][Np]) */
+int rlsb_peer_exchange_best_packed(rlsb_peer_exchange_t* ex, const int64_t* vs, const uint32_t* packed, int64_t num_envs,
+                                   int32_t padded_nodes, int64_t env_offset, int64_t* out2, uint8_t* row, void* stream);
+/* out[0] = calls completed, out[1] = polls that ran into the time-out; synchronises `stream` */
+int rlsb_peer_exchange_status(rlsb_peer_exchange_t* ex, uint32_t* out, void* stream);
+int rlsb_peer_exchange_destroy(rlsb_peer_exchange_t* ex);
+
 /* ---- weighted max-cut sampler of MCPG: the local-search sweeps + expected cut of mcpg_sampling_maxcut
  * (rlsolver/methods/MCPG/sampling.py:101-121) for float edge weights (MCPG/dataloader.py:53-103).
  * xs float32 [N][C] node-major, in: the 0/1 output of metro_sampling, out: the states after the sweeps (0/1).

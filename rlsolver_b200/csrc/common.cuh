@@ -151,6 +151,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// key of the multi-GPU best-cut exchange (select.cu, peer_exchange.cu): (value + 2^31) << 32 | (0xFFFFFFFF - global env
+// id), compared unsigned; values saturate to the int32 range
+__device__ __forceinline__ unsigned long long best_key(int64_t v, unsigned long long gid) {
+  v = v > 2147483647ll ? 2147483647ll : (v < -2147483648ll ? -2147483648ll : v);
+  return ((unsigned long long)(v + 2147483648ll) << 32) | (0xFFFFFFFFull - gid);
+}
+__device__ __forceinline__ int64_t best_key_value(unsigned long long key) {
+  return (int64_t)(key >> 32) - 2147483648ll;
+}
+
 __device__ __forceinline__ int warp_sum(int v) {
   return __reduce_add_sync(kFull, v);
 }

@@ -70,13 +70,7 @@ __global__ void __launch_bounds__(128) pick_best_kernel(const uint8_t* __restric
 // row.  key = (value + 2^31) << 32 | (0xFFFFFFFF - global env id), compared UNSIGNED: the bias makes negative
 // values (weighted cuts, QUBO energies) order below positive ones, ties go to the lowest env id.  Values are
 // saturated to the int32 range (the Python mirror applies the same rule).  One CTA: block-wide max, row copy.
-__device__ __forceinline__ unsigned long long best_key(int64_t v, unsigned long long gid) {
-  v = v > 2147483647ll ? 2147483647ll : (v < -2147483648ll ? -2147483648ll : v);
-  return ((unsigned long long)(v + 2147483648ll) << 32) | (0xFFFFFFFFull - gid);
-}
-__device__ __forceinline__ int64_t best_key_value(unsigned long long key) {
-  return (int64_t)(key >> 32) - 2147483648ll;
-}
+// (best_key / best_key_value: common.cuh)
 __global__ void __launch_bounds__(1024) best_record_kernel(const int64_t* __restrict__ vs, const uint8_t* __restrict__ xs,
                                                            int64_t num_envs, int n, int64_t env_offset,
                                                            uint8_t* __restrict__ record) {

@@ -144,3 +144,103 @@ class BestExchange:
                                                           th.cuda.current_stream(self.device).cuda_stream),
                        "best_record_packed")
         return self._finish()
+
+
+class PeerBestExchange:
+    """The same exchange as ONE kernel over NVLink peer memory (csrc/peer_exchange.cu): every rank stores its record
+    straight into a mailbox in each peer's HBM (mapped through CUDA IPC), raises an arrival word and polls its own --
+    no NCCL call, one launch, and because the launch carries no per-call arguments it can be captured into the CUDA
+    graph of the step.  Same interface and the same results as BestExchange.  One process per GPU of one box; the
+    constructor is collective (the IPC handles travel through one all-gather of `group`)."""
+
+    def __init__(self, num_nodes: int, rank: int, world: int, envs_per_rank: int, device, group=None):
+        import ctypes as C
+        from . import _lib
+        self.n, self.rank, self.world, self.envs, self.group = int(num_nodes), rank, world, envs_per_rank, group
+        self.device = th.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("PeerBestExchange needs CUDA devices (use BestExchange / best_allreduce elsewhere)")
+        lib = _lib.lib()
+        hb = int(lib.rlsb_peer_exchange_handle_bytes())
+        handle = (C.c_uint8 * hb)()
+        self._h = C.c_void_p()
+        # Every rank walks through the same collectives whatever fails locally (a rank that raised early would leave
+        # the others waiting in the all-gather); the outcome is agreed on at the end and raised everywhere.
+        error = None
+        try:
+            with on_device(self.device):
+                _lib.check(lib.rlsb_peer_exchange_create(rank, world, self.n, C.byref(self._h), handle),
+                           "peer_exchange_create")
+        except Exception as exc:        # noqa: BLE001 - reported after the collectives
+            error, self._h = exc, None
+        mine = th.frombuffer(bytearray(handle), dtype=th.uint8).to(self.device)
+        if world > 1:
+            every = th.empty((world, hb), dtype=th.uint8, device=self.device)
+            dist.all_gather_into_tensor(every, mine.unsqueeze(0), group=group)
+        else:
+            every = mine.unsqueeze(0)
+        if error is None:
+            try:
+                with on_device(self.device):
+                    _lib.check(lib.rlsb_peer_exchange_connect(self._h, every.cpu().contiguous().numpy().tobytes()),
+                               "peer_exchange_connect")
+            except Exception as exc:    # noqa: BLE001
+                error = exc
+        if world > 1:
+            # also the barrier: nobody stores into a mailbox that is not mapped everywhere yet
+            ok = th.tensor([0 if error is not None else 1], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0 and error is None:
+                error = RuntimeError("another rank could not set up its mailbox")
+        if error is not None:
+            self.close()
+            raise RuntimeError(f"PeerBestExchange: CUDA IPC / peer access between the ranks is not available "
+                               f"({error}); use BestExchange (NCCL all-gather)") from error
+        self.out2 = th.zeros((2,), dtype=th.int64, device=self.device)
+        self.row = th.zeros((self.n,), dtype=th.bool, device=self.device)
+
+    def __call__(self, vs: TEN, xs: TEN):
+        from . import _lib
+        assert vs.dtype == th.int64 and xs.dtype == th.bool and vs.is_contiguous() and xs.is_contiguous()
+        assert xs.shape[1] == self.n
+        with on_device(self.device):
+            _lib.check(_lib.lib().rlsb_peer_exchange_best(self._h, vs.data_ptr(), xs.data_ptr(), vs.shape[0],
+                                                          self.rank * self.envs, self.out2.data_ptr(), self.row.data_ptr(),
+                                                          th.cuda.current_stream(self.device).cuda_stream),
+                       "peer_exchange_best")
+        return self.out2[0], self.out2[1], self.row
+
+    def packed(self, vs: TEN, packed: TEN, store):
+        from . import _lib
+        assert vs.dtype == th.int64 and packed.dtype == th.int32 and packed.is_contiguous()
+        with on_device(self.device):
+            _lib.check(_lib.lib().rlsb_peer_exchange_best_packed(self._h, vs.data_ptr(), packed.data_ptr(), vs.shape[0],
+                                                                 store.padded_nodes, self.rank * self.envs,
+                                                                 self.out2.data_ptr(), self.row.data_ptr(),
+                                                                 th.cuda.current_stream(self.device).cuda_stream),
+                       "peer_exchange_best_packed")
+        return self.out2[0], self.out2[1], self.row
+
+    def status(self) -> Tuple[int, int]:
+        """(calls completed, polls that timed out) -- synchronises the current stream.  A non-zero second number
+        means a peer did not make the matching call within the bound and the results since then are not valid."""
+        import ctypes as C
+        from . import _lib
+        out = (C.c_uint32 * 2)()
+        with on_device(self.device):
+            _lib.check(_lib.lib().rlsb_peer_exchange_status(self._h, out, th.cuda.current_stream(self.device).cuda_stream),
+                       "peer_exchange_status")
+        return int(out[0]), int(out[1])
+
+    def close(self) -> None:
+        from . import _lib
+        if getattr(self, "_h", None):
+            with on_device(self.device):
+                _lib.lib().rlsb_peer_exchange_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # noqa: BLE001 - interpreter shutdown
+            pass

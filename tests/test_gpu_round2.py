@@ -311,6 +311,104 @@ def test_two_rank_nccl_shards_equal_single_gpu_runs():
     assert th.equal(res[0]["g_row"], res[owner]["g_xs"][res[0]["g_gid"] % envs])
 
 
+# ------------------------------------------------------------------ the exchange as one kernel over peer memory
+def test_peer_exchange_single_rank_equals_best_allreduce(cuda_device):
+    """world = 1: the mailbox kernel alone (record, arrival word, pick) against the torch formulation, bool rows and
+    packed tiles, negative values and ties (lowest env id wins), many calls (both banks), inside a CUDA graph."""
+    from rlsolver_b200.dist import PeerBestExchange, best_allreduce
+    from rlsolver_b200.graph_store import GraphStore
+    st = GraphStore(gset_like("G14"), True, device=cuda_device)
+    n, envs = st.num_nodes, 300
+    ex = PeerBestExchange(n, 0, 1, envs, cuda_device)
+    gen = th.Generator(device="cpu").manual_seed(5)
+    vs_buf = th.zeros((envs,), dtype=th.int64, device=cuda_device)
+    xs_buf = th.zeros((envs, n), dtype=th.bool, device=cuda_device)
+    graph = None
+    for it in range(7):
+        vs = th.randint(-50, 50, (envs,), generator=gen).to(cuda_device)
+        if it == 3:
+            vs[:] = 7                                   # all tied: env 0 wins
+        xs = (th.rand((envs, n), generator=gen) < 0.5).to(cuda_device)
+        want = best_allreduce(vs, xs, 0, 1, envs)
+        got = ex(vs, xs)
+        assert int(got[0]) == int(want[0]) and int(got[1]) == int(want[1]) and th.equal(got[2], want[2])
+        got = ex.packed(vs, st.pack(xs), st)
+        assert int(got[0]) == int(want[0]) and int(got[1]) == int(want[1]) and th.equal(got[2], want[2])
+        vs_buf.copy_(vs), xs_buf.copy_(xs)
+        if graph is None:
+            th.cuda.synchronize()
+            graph = th.cuda.CUDAGraph()
+            with th.cuda.graph(graph):
+                g_out = ex(vs_buf, xs_buf)
+        graph.replay()
+        assert int(g_out[0]) == int(want[0]) and int(g_out[1]) == int(want[1]) and th.equal(g_out[2], want[2])
+    calls, timeouts = ex.status()
+    assert calls == 7 * 3 and timeouts == 0
+    ex.close()
+
+
+def _peer_worker(rank, world, port, envs, out):
+    import time
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RLSB_PEER_TIMEOUT_MS="8000")
+    from rlsolver_b200.dist import BestExchange, PeerBestExchange
+    from rlsolver_b200.graph_store import GraphStore
+    th.cuda.set_device(rank)
+    dev = th.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    st = GraphStore(gset_like("G22"), True, device=dev)
+    n = st.num_nodes
+    ref = BestExchange(n, rank, world, envs, dev)
+    ex = PeerBestExchange(n, rank, world, envs, dev)
+    vs_buf = th.zeros((envs,), dtype=th.int64, device=dev)
+    xs_buf = th.zeros((envs, n), dtype=th.bool, device=dev)
+    graph, rows, ok = None, [], True
+    for it in range(12):
+        gen = th.Generator(device="cpu").manual_seed(1000 * it + rank)
+        vs = th.randint(-1000, 1000, (envs,), generator=gen).to(dev)
+        if it == 4:
+            vs[:] = 3                                   # every env of every rank tied: global env 0 wins
+        xs = (th.rand((envs, n), generator=gen) < 0.5).to(dev)
+        if it == 6 and rank == 1:
+            th.cuda.synchronize()
+            time.sleep(0.5)                             # a late rank: the others poll
+        want = tuple(t.clone() for t in ref(vs, xs))
+        got = tuple(t.clone() for t in ex(vs, xs))
+        got_p = tuple(t.clone() for t in ex.packed(vs, st.pack(xs), st))
+        vs_buf.copy_(vs), xs_buf.copy_(xs)
+        if graph is None:
+            th.cuda.synchronize()
+            graph = th.cuda.CUDAGraph()
+            with th.cuda.graph(graph):
+                g_out = ex(vs_buf, xs_buf)
+        graph.replay()
+        got_g = tuple(t.clone() for t in g_out)
+        for g in (got, got_p, got_g):
+            ok = ok and int(g[0]) == int(want[0]) and int(g[1]) == int(want[1]) and bool(th.equal(g[2], want[2]))
+        rows.append((int(want[0]), int(want[1])))
+    calls, timeouts = ex.status()
+    out[rank] = {"ok": ok, "rows": rows, "calls": calls, "timeouts": timeouts}
+    ex.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(th.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_rank_peer_exchange_equals_all_gather_exchange():
+    """PeerBestExchange (one kernel, mailboxes in peer memory) against BestExchange (NCCL all-gather) on the same
+    data: bool rows, packed tiles, a captured replay, a tie across ranks, a rank that arrives half a second late."""
+    import torch.multiprocessing as mp
+    world, envs = 2, 512
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_peer_worker, args=(world, _free_port(), envs, out), nprocs=world, join=True)
+        res = [out[r] for r in range(world)]
+    for r in range(world):
+        assert res[r]["ok"] and res[r]["timeouts"] == 0 and res[r]["calls"] == 12 * 3
+        assert res[r]["rows"] == res[0]["rows"]
+    assert res[0]["rows"][4] == (3, 0)
+    assert len({gid // envs for _, gid in res[0]["rows"]}) == 2        # both ranks won at least once
+
+
 # ------------------------------------------------------------------ integer-weighted objective (row W)
 from conftest import golden_files  # noqa: E402
 
