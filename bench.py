@@ -571,6 +571,7 @@ def run_b200(args):
     import rlsolver_b200
     from rlsolver_b200.dist import BestExchange, PeerBestExchange
     from rlsolver_b200.envs.env_L2A import EnvMaxcut
+    from rlsolver_b200.host_pipeline import HostPipeline
 
     rlsolver_b200.build()
     log(f"world {world}: library ready")
@@ -739,19 +740,18 @@ def run_b200(args):
     # reference's bool [E, N] rows (one byte per spin, what EnvMaxcut.local_search_inplace takes), and `packed` =
     # the library's packed tiles (uint32 [E/32, Np], one bit per spin: rlsb_ls_begin_packed in, the workspace's
     # packed section out), through EnvMaxcut.local_search_packed.  For each: `serial` (copy in, compute, copy out,
-    # one event pair per step) and `pipelined` (three streams, double buffered: H2D(i+1) | step(i) | D2H(i-1), one
-    # event pair around all K steps, fill and drain included).  The headline e2e is pipelined / bool (the
+    # one event pair per step) and `pipelined` (rlsolver_b200.host_pipeline.HostPipeline: three streams, three device
+    # buffers, one captured graph of the step per buffer, H2D(i+1) | step(i) | D2H(i-1); one event pair around all K
+    # steps, fill and drain included).  The headline e2e is pipelined / bool (the
     # reference-facing call); the packed figures are reported next to it.
     cur = th.cuda.current_stream(dev)
-    s_in, s_out = th.cuda.Stream(device=dev), th.cuda.Stream(device=dev)
     small_flush = flush[:160 << 20]                                # > 126 MB L2, inside the timed region
     pk0 = sim.store.pack(xs0)
 
     def make_layout(kind):
         if kind == "bool":
             h_in = xs0.cpu().pin_memory()
-            d_in = [th.empty_like(xs0) for _ in range(2)]
-            d_out = [th.empty_like(xs0) for _ in range(2)]
+            d_in = th.empty_like(xs0)
 
             def run(src):
                 xs.copy_(src)
@@ -759,8 +759,7 @@ def run_b200(args):
                 return gx, gv
         else:
             h_in = pk0.cpu().pin_memory()
-            d_in = [th.empty_like(pk0) for _ in range(2)]
-            d_out = [th.empty_like(pk0) for _ in range(2)]
+            d_in = th.empty_like(pk0)
 
             def run(src):
                 pk, gv = sim.local_search_packed(src, NUM_ITERS, NUM_SPIN, NOISE_STD)
@@ -769,15 +768,14 @@ def run_b200(args):
                 return pk, gv
         h_out = th.empty_like(h_in).pin_memory()
         h_vs = th.empty((envs,), dtype=th.int64).pin_memory()
-        d_vs = [th.empty((envs,), dtype=th.int64, device=dev) for _ in range(2)]
-        return h_in, h_out, h_vs, d_in, d_out, d_vs, run
+        return h_in, h_out, h_vs, d_in, run
 
     def e2e_measure(kind):
-        h_in, h_out, h_vs, d_in, d_out, d_vs, run = make_layout(kind)
+        h_in, h_out, h_vs, d_in, run = make_layout(kind)
 
         def serial_step():
-            d_in[0].copy_(h_in, non_blocking=True)
-            gx, gv = run(d_in[0])
+            d_in.copy_(h_in, non_blocking=True)
+            gx, gv = run(d_in)
             h_out.copy_(gx, non_blocking=True)
             h_vs.copy_(gv, non_blocking=True)
 
@@ -796,39 +794,23 @@ def run_b200(args):
         barrier()
         serial_ms = ctx.max_over_ranks(sum(ser)) / args.steps
 
+        # the pipelined form is the package's HostPipeline: three device buffers, one captured graph of the step per
+        # buffer (L2-evicting write + local search in place + the peer-memory exchange), H2D / step / D2H on three streams
+        if kind == "bool":
+            in_post = (lambda res, vs: exchange(vs, res)) if in_graph else None
+            eager_post = (lambda res, vs: exchange(vs, res)) if exchange is not None and not in_graph else None
+        else:
+            in_post = (lambda res, vs: exchange.packed(vs, res, sim.store)) if in_graph else None
+            eager_post = (lambda res, vs: exchange.packed(vs, res, sim.store)) if exchange is not None and not in_graph else None
+        pipe = HostPipeline(sim, envs, layout=kind, num_iters=NUM_ITERS, num_spin=NUM_SPIN, noise_std=NOISE_STD,
+                            pre_step=small_flush.zero_, in_graph_post=in_post, eager_post=eager_post)
+
         def pipelined(k):
-            in_ready = [th.cuda.Event() for _ in range(2)]
-            in_free = [th.cuda.Event() for _ in range(2)]
-            out_ready = [th.cuda.Event() for _ in range(2)]
-            out_free = [th.cuda.Event() for _ in range(2)]
-            for e in in_free + out_free:
-                e.record(cur)
-            s_in.wait_stream(cur)
-            s_out.wait_stream(cur)
             ta, tb = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
             ta.record(cur)
-            s_in.wait_event(ta)
-            for i in range(k):
-                b = i & 1
-                with th.cuda.stream(s_in):
-                    s_in.wait_event(in_free[b])
-                    d_in[b].copy_(h_in, non_blocking=True)             # H2D of step i
-                    in_ready[b].record(s_in)
-                cur.wait_event(in_ready[b])
-                small_flush.zero_()                                    # evict L2 between steps (timed)
-                gx, gv = run(d_in[b])
-                in_free[b].record(cur)
-                cur.wait_event(out_free[b])
-                d_out[b].copy_(gx)
-                d_vs[b].copy_(gv)
-                out_ready[b].record(cur)
-                with th.cuda.stream(s_out):
-                    s_out.wait_event(out_ready[b])
-                    h_out.copy_(d_out[b], non_blocking=True)           # D2H of step i
-                    h_vs.copy_(d_vs[b], non_blocking=True)
-                    out_free[b].record(s_out)
-            cur.wait_stream(s_out)
-            cur.wait_stream(s_in)
+            for _ in range(k):
+                pipe.submit(h_in, h_out, h_vs)
+            pipe.join()
             tb.record(cur)
             th.cuda.synchronize()
             return ta.elapsed_time(tb)
@@ -934,8 +916,10 @@ def run_b200(args):
                 "e2e": {"value": e2e_bool["value"], "unit": UNIT, "h2d_bytes_per_step": e2e_bool["h2d_bytes_per_step"],
                         "d2h_bytes_per_step": e2e_bool["d2h_bytes_per_step"], "ms_per_step": e2e_bool["ms_per_step"],
                         "layout": "bool [E, N] rows (the reference's layout), EnvMaxcut.local_search_inplace",
-                        "mode": ("pipelined: H2D(i+1) | step(i) | D2H(i-1) on three streams, double buffered, one event "
-                                 "pair around all K steps (fill + drain and a 160 MiB L2-evicting write per step included)"),
+                        "mode": ("pipelined (rlsolver_b200.host_pipeline.HostPipeline): H2D(i+1) | step(i) | D2H(i-1) on three "
+                                 "streams, three device buffers, the step a captured CUDA graph per buffer that runs in "
+                                 "place on it; one event pair around all K steps (fill + drain and a 160 MiB L2-evicting "
+                                 "write per step included)"),
                         "serial_ms_per_step": e2e_bool["serial_ms_per_step"], "serial_value": e2e_bool["serial_value"],
                         "packed": dict(e2e_packed, layout="packed tiles uint32 [E/32, Np] (one bit per spin), "
                                                           "EnvMaxcut.local_search_packed / rlsb_ls_begin_packed")},

@@ -505,3 +505,41 @@ def test_weighted_mcpg_sampler_same_seed_vs_oracle(cuda_device):
     assert th.equal(th.cuda.get_rng_state(cuda_device), after)
     want = oq.weighted_sampler(n, edges, weights, data.sorted_degree_nodes.numpy(), _np(metro_out), num_ls, t, draws)
     assert np.array_equal(_np(xs_good), want[1]) and np.array_equal(_np(vs_good), want[0])
+
+
+# ------------------------------------------------------------------ host-resident batches (HostPipeline)
+@pytest.mark.parametrize("layout", ["bool", "packed"])
+def test_host_pipeline_equals_eager_calls(layout, cuda_device):
+    """Seven host batches through HostPipeline (3 buffers, one graph per buffer, three streams) == seven eager
+    local_search calls from the same seed, batch for batch; torch's generator ends where the eager calls leave it."""
+    from rlsolver_b200.envs.env_L2A import EnvMaxcut
+    from rlsolver_b200.host_pipeline import HostPipeline
+    sim = EnvMaxcut(mygraph=gset_like("G14"), device=cuda_device, if_bidirectional=True)
+    st, envs, k = sim.store, 512, 7
+    gen = th.Generator().manual_seed(11)
+    batches = [(th.rand((envs, sim.num_nodes), generator=gen) < 0.5) for _ in range(k)]
+    th.manual_seed(901)
+    want = []
+    for xb in batches:
+        xs, vs = sim.local_search_inplace(xb.to(cuda_device), th.empty(()))
+        want.append((xs.cpu(), vs.cpu()))
+    end_state = th.cuda.get_rng_state(cuda_device)
+
+    pipe = HostPipeline(sim, envs, layout=layout)
+    th.manual_seed(901)
+    pipe.sync_rng()
+    if layout == "bool":
+        h_in = [xb.pin_memory() for xb in batches]
+    else:
+        h_in = [st.pack(xb.to(cuda_device)).cpu().pin_memory() for xb in batches]
+    h_out = [th.empty_like(t).pin_memory() for t in h_in]
+    h_vs = [th.empty((envs,), dtype=th.int64).pin_memory() for _ in range(k)]
+    for i in range(k):
+        pipe.submit(h_in[i], h_out[i], h_vs[i])
+    pipe.drain()
+    pipe.commit_rng()
+    for i in range(k):
+        got_xs = h_out[i] if layout == "bool" else st.unpack(h_out[i].to(cuda_device), envs).cpu()
+        assert th.equal(got_xs, want[i][0]), f"batch {i}"
+        assert th.equal(h_vs[i], want[i][1]), f"batch {i}"
+    assert th.equal(th.cuda.get_rng_state(cuda_device), end_state)
