@@ -6,18 +6,20 @@
 // every peer's mailbox and then polls its own mailbox needs one launch and one NVLink round trip.
 //
 // Every rank owns a mailbox in its own HBM (cudaMalloc; the other ranks map it through CUDA IPC, which also enables
-// peer access): two banks (call parity) of `world` record slots, one arrival word per slot, the call counter and
-// a time-out counter.  One call, one CTA:
-//   1. block-wide max of the 64-bit keys (select.cu: best_key) -> the local record {key, winner's spins};
-//   2. the record is stored into slot [bank][rank] of EVERY mailbox (peer stores travel over NVLink / NVSwitch),
-//      system-scope fence, then the arrival word of that slot is set to the call number (release);
-//   3. thread r polls arrival word [bank][r] of the OWN mailbox (acquire) until it shows this call;
-//   4. the winner among the world records is copied out.
-// Two banks suffice: a rank can only enter call s + 2 after it saw every peer arrive at s + 1, and a peer arrives at
-// s + 1 only after its kernel of call s -- the last reader of bank s % 2 -- has finished.  The call counter lives
+// peer access): two banks (call parity) of `world` record slots, the call counter and a time-out counter.  A record
+// is 2 + ceil(N / 4) words -- the 64-bit key (common.cuh: best_key), then four spins per word -- and every word
+// travels as ONE 8-byte store {word, call number}: 8-byte stores are single-copy atomic over NVLink, so a reader that
+// sees the call number in the upper half has the data in the lower half, and the exchange needs no fence and no
+// separate flag -- one NVLink traversal (the "LL" scheme of NCCL's latency-bound protocols).  One call, one CTA:
+//   1. block-wide max of the keys -> the local record;
+//   2. the record is stored into slot [bank][rank] of EVERY mailbox (peer stores over NVLink / NVSwitch);
+//   3. two threads per rank poll the key words of slot [bank][r] of the OWN mailbox until they carry this call's number;
+//   4. the winner is picked, and only ITS spin words are polled and copied out.
+// Two banks suffice: a rank can only enter call s + 2 after it saw every peer's record of call s + 1, and a peer sends
+// that only after its kernel of call s -- the last reader of bank s % 2 -- has finished.  The call counter lives
 // in the mailbox, so the launch has no per-call arguments and can sit inside a captured CUDA graph.
 //
-// Like every collective it needs all ranks to make the same sequence of calls.  The poll is bounded (default 20 s,
+// Like every collective it needs all ranks to make the same sequence of calls.  The polls are bounded (default 20 s,
 // RLSB_PEER_TIMEOUT_MS): a peer that never arrives costs a counted time-out (rlsb_peer_exchange_status) and a result
 // made of whatever the slots held, never a hung GPU.
 #include <stdlib.h>
@@ -28,30 +30,41 @@
 namespace rlsb {
 
 constexpr int kPeerMaxWorld = 64;
-constexpr int kPeerHeaderBytes = 1024;     // {calls, time-outs, pad}, then arrival words [2][kPeerMaxWorld]
+constexpr int kPeerHeaderBytes = 128;      // {calls, time-outs, pad}
 
 struct PeerBoxes {
   uint8_t* box[kPeerMaxWorld];             // box[rank] = the own mailbox
 };
 
-__device__ __forceinline__ uint32_t* box_arrival(uint8_t* box, int bank, int r) {
-  return reinterpret_cast<uint32_t*>(box + 64) + bank * kPeerMaxWorld + r;
+__device__ __forceinline__ uint2* box_slot(uint8_t* box, int bank, int r, int world, int64_t stride) {
+  return reinterpret_cast<uint2*>(box + kPeerHeaderBytes + ((int64_t)bank * world + r) * stride);
 }
-__device__ __forceinline__ uint8_t* box_slot(uint8_t* box, int bank, int r, int world, int64_t stride) {
-  return box + kPeerHeaderBytes + ((int64_t)bank * world + r) * stride;
+__device__ __forceinline__ void st_pair_sys(uint2* p, uint32_t data, uint32_t flag) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(flag) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint2 ld_pair_sys(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
-}
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint64_t global_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+}
+// the data half of *p once its flag half shows `call` (bounded: counts a time-out and returns what is there)
+__device__ __forceinline__ uint32_t poll_word(const uint2* p, uint32_t call, uint64_t timeout_ns, uint32_t* timeouts) {
+  uint2 v = ld_pair_sys(p);
+  if (v.y == call) return v.x;
+  const uint64_t t0 = global_ns();
+  for (int spin = 0;; ++spin) {
+    v = ld_pair_sys(p);
+    if (v.y == call) return v.x;
+    if ((spin & 63) == 63 && global_ns() - t0 > timeout_ns) {
+      atomicAdd(timeouts, 1u);
+      return v.x;
+    }
+  }
 }
 
 // xs: bool rows [E][n] or null; packed: tiles uint32 [ceil(E/32)][np] (used when xs is null)
@@ -61,10 +74,11 @@ __global__ void __launch_bounds__(1024) peer_best_kernel(PeerBoxes boxes, int ra
                                                          uint64_t timeout_ns, int64_t* __restrict__ out,
                                                          uint8_t* __restrict__ row_out) {
   __shared__ unsigned long long sBest[32];
+  __shared__ uint32_t sKey[kPeerMaxWorld][2];
   __shared__ int sWin;
   uint8_t* own = boxes.box[rank];
   uint32_t* header = reinterpret_cast<uint32_t*>(own);
-  const uint32_t call = header[0] + 1u;            // written back by thread 0 after the last barrier
+  const uint32_t call = header[0] + 1u;            // written back by thread 0 behind a barrier
   const int bank = (int)(call & 1u);
 
   unsigned long long best = 0;
@@ -83,7 +97,7 @@ __global__ void __launch_bounds__(1024) peer_best_kernel(PeerBoxes boxes, int ra
   for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = sBest[w] > best ? sBest[w] : best;
   const int64_t local = (int64_t)(0xFFFFFFFFull - (best & 0xFFFFFFFFull)) - env_offset;
 
-  // the record, one 32-bit word per store: word 0..1 = key, then four spins per word
+  // the record: word 0..1 = key, then four spins per word; every word goes out as {word, call}
   const int words = 2 + (n + 3) / 4;
   const uint8_t* row = xs ? xs + local * (int64_t)n : nullptr;
   const uint32_t* tile = xs ? nullptr : packed + (local >> 5) * (int64_t)np;
@@ -102,30 +116,20 @@ __global__ void __launch_bounds__(1024) peer_best_kernel(PeerBoxes boxes, int ra
         if (node < n) w |= (uint32_t)(row ? (row[node] != 0) : ((tile[node] >> bit) & 1u)) << (8 * b);
       }
     }
-    for (int p = 0; p < world; ++p) reinterpret_cast<uint32_t*>(box_slot(boxes.box[p], bank, rank, world, stride))[i] = w;
+    for (int p = 0; p < world; ++p) st_pair_sys(box_slot(boxes.box[p], bank, rank, world, stride) + i, w, call);
   }
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < world) st_release_sys(box_arrival(boxes.box[threadIdx.x], bank, rank), call);
 
-  if ((int)threadIdx.x < world) {
-    const uint32_t* flag = box_arrival(own, bank, threadIdx.x);
-    const uint64_t t0 = global_ns();
-    while (ld_acquire_sys(flag) != call) {
-      if (global_ns() - t0 > timeout_ns) {
-        atomicAdd(header + 1, 1u);
-        break;
-      }
-      __nanosleep(64);
-    }
+  // every rank's key (two threads per rank), then the winner
+  if ((int)threadIdx.x < 2 * world) {
+    const int r = threadIdx.x >> 1, w = threadIdx.x & 1;
+    sKey[r][w] = poll_word(box_slot(own, bank, r, world, stride) + w, call, timeout_ns, header + 1);
   }
   __syncthreads();
-
   if (threadIdx.x < 32) {
     unsigned long long key = 0;
     int win = 0;
     for (int r = threadIdx.x; r < world; r += 32) {
-      const unsigned long long k = __ldcg(reinterpret_cast<const unsigned long long*>(box_slot(own, bank, r, world, stride)));
+      const unsigned long long k = ((unsigned long long)sKey[r][1] << 32) | sKey[r][0];
       if (k > key) key = k, win = r;           // keys are distinct across ranks (they embed the global env id)
     }
 #pragma unroll
@@ -142,9 +146,9 @@ __global__ void __launch_bounds__(1024) peer_best_kernel(PeerBoxes boxes, int ra
     }
   }
   __syncthreads();
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(box_slot(own, bank, sWin, world, stride)) + 2;
+  const uint2* src = box_slot(own, bank, sWin, world, stride) + 2;
   for (int i = threadIdx.x; i < (n + 3) / 4; i += blockDim.x) {
-    const uint32_t w = __ldcg(src + i);
+    const uint32_t w = poll_word(src + i, call, timeout_ns, header + 1);
 #pragma unroll
     for (int b = 0; b < 4; ++b)
       if (4 * i + b < n) row_out[4 * i + b] = (uint8_t)((w >> (8 * b)) & 0xffu);
@@ -174,7 +178,7 @@ int rlsb_peer_exchange_create(int32_t rank, int32_t world, int32_t num_nodes, rl
   auto* ex = new rlsb_peer_exchange();
   memset(ex, 0, sizeof(*ex));
   ex->rank = rank, ex->world = world, ex->n = num_nodes;
-  ex->stride = (8 + ((int64_t)num_nodes + 3) / 4 * 4 + 15) / 16 * 16;
+  ex->stride = (2 + ((int64_t)num_nodes + 3) / 4) * 8;       // 8 bytes per record word: {word, call number}
   ex->bytes = kPeerHeaderBytes + 2 * (int64_t)world * ex->stride;
   const char* ms = getenv("RLSB_PEER_TIMEOUT_MS");
   const long long t = ms ? atoll(ms) : 0;
