@@ -405,58 +405,75 @@ def config3(ctx, inner=4, outer=2):
 
 # ----------------------------------------------------------------------------- config 4: 10^6 BA / ER instances
 def config4(ctx, total_envs):
-    """Distribution-wise pattern-I step: one graph per env (BA m=4 and ER p=0.15, N=100, +-1 weights),
-    SpinSystemUnbiased.step with uniformly random actions, BLS reward (spinsystem_PECO.py:306-486)."""
+    """Distribution-wise pattern-I step: one graph per env (BA m=4 and ER p=0.15, N=100, +-1 weights), uniformly random
+    actions.  Two step/reward patterns on the same graphs:
+      * "s2v" -- what the config names (train_S2V.py:37-47, ECO_S2V/src/envs/spinsystem.py): irreversible spins from all
+        +1, the single SPIN_STATE observable, DENSE reward = delta cut / N; every env flips its spins in a random order;
+      * "eco" -- the batched PECO environment's training configuration (train_PECO.py:34-44, spinsystem_PECO.py:306-486):
+        reversible spins, seven observables, BLS reward."""
     th = ctx.th
     from rlsolver_b200.envs import env_PECO as P
     n = 100
     envs = total_envs // ctx.world
     out = {}
     for kind in ("BA", "ER"):
-        t_gen = time.time()
-        if kind == "BA":
-            gg = P.RandomBAGraphGenerator(n_spins=n, m_insertion_edges=4, edge_type=P.EdgeType.DISCRETE, num_envs=envs,
-                                          device=ctx.dev)
-        else:
-            gg = P.RandomERGraphGenerator(n_spins=n, p_connection=0.15, edge_type=P.EdgeType.DISCRETE, num_envs=envs,
-                                          device=ctx.dev)
-        th.manual_seed(74 + ctx.rank)
-        env = P.SpinSystemFactory.get(gg, 2 * n, observables=P.ECO_PECO_OBSERVABLES, reward_signal=P.RewardSignal.BLS,
-                                      extra_action=P.ExtraAction.NONE, optimisation_target=P.OptimisationTarget.CUT,
-                                      spin_basis=P.SpinBasis.BINARY, norm_rewards=True, memory_length=None,
-                                      horizon_length=None, stag_punishment=None, basin_reward=None,
-                                      reversible_spins=True, device=ctx.dev, num_envs=envs)
-        th.cuda.synchronize()
-        gen_s = time.time() - t_gen
-        acts = [th.randint(0, n, (envs,), device=ctx.dev) for _ in range(8)]
-        k = [0]
+        for style in ("s2v", "eco"):
+            t_gen = time.time()
+            if kind == "BA":
+                gg = P.RandomBAGraphGenerator(n_spins=n, m_insertion_edges=4, edge_type=P.EdgeType.DISCRETE, num_envs=envs,
+                                              device=ctx.dev)
+            else:
+                gg = P.RandomERGraphGenerator(n_spins=n, p_connection=0.15, edge_type=P.EdgeType.DISCRETE, num_envs=envs,
+                                              device=ctx.dev)
+            th.manual_seed(74 + ctx.rank)
+            s2v = style == "s2v"
+            env = P.SpinSystemFactory.get(gg, n if s2v else 2 * n,
+                                          observables=P.S2V_OBSERVABLES if s2v else P.ECO_PECO_OBSERVABLES,
+                                          reward_signal=P.RewardSignal.DENSE if s2v else P.RewardSignal.BLS,
+                                          extra_action=P.ExtraAction.NONE, optimisation_target=P.OptimisationTarget.CUT,
+                                          spin_basis=P.SpinBasis.BINARY, norm_rewards=True, memory_length=None,
+                                          horizon_length=None, stag_punishment=None, basin_reward=None,
+                                          reversible_spins=not s2v, device=ctx.dev, num_envs=envs)
+            th.cuda.synchronize()
+            gen_s = time.time() - t_gen
+            if s2v:         # a random order of every env's spins: no spin is flipped twice (what the agent's mask enforces)
+                order = th.rand((envs, n), device=ctx.dev).argsort(dim=1)[:, :32].t().contiguous()
+                acts = [order[i] for i in range(32)]
+                del order
+            else:
+                acts = [th.randint(0, n, (envs,), device=ctx.dev) for _ in range(8)]
+            k = [0]
 
-        def step():
-            env.step(acts[k[0] % 8], return_observation=False)
-            k[0] += 1
+            def step():
+                env.step(acts[k[0] % len(acts)], return_observation=False)
+                k[0] += 1
 
-        t0 = time.time()
-        ms = ctx.timed(step, reps=20, warm=3, flush=False)         # state >> L2: every step streams from HBM
-        t1 = time.time()
-        ms_job = ctx.job_ms(ms)
-        alg = env.step_algorithmic_bytes() if hasattr(env, "step_algorithmic_bytes") else \
-            envs * (4 * n + 8 * n + 2 * 4 * n * 4 + 40)
-        gbs = alg / (ms_job * 1e-3) / 1e9
-        deg = float(env.mean_degree()) if hasattr(env, "mean_degree") else \
-            float((env.matrix[:1024] != 0).float().sum() / min(envs, 1024) / n)
-        out[kind] = {"workload": f"{kind}-100 per-env graphs (+-1 weights), {total_envs} envs over {ctx.world} GPU(s) "
-                                 f"({envs}/GPU), mean degree {deg:.1f}: SpinSystemUnbiased.step, random actions, BLS reward",
-                     "n_gpus": ctx.world, "scaling": "strong", "ms": ms_job, "env_steps": total_envs,
-                     "env_steps_per_s": total_envs / (ms_job * 1e-3), "graph_generation_s": round(gen_s, 2),
-                     "state_layout": getattr(env, "state_layout", "dense float32 matrix [E,N,N] + state [E,7,N]"),
-                     "roofline": roof("hbm", gbs, ctx.peaks["hbm"], "GB/s", "peco_step",
-                                      algorithmic_bytes_per_launch=alg, bytes_per_env_step=alg / envs,
-                                      traffic=dram_traffic().get("config4_peco_step_" + kind)),
-                     "clocks": ctx.window_clocks(t0, t1)}
-        if ctx.world == 1 and ctx.rank == 0 and not ctx.args.no_cpu_baseline and kind == "ER":
-            out["cpu_baseline"] = peco_cpu_baseline(env, n)
-        del env, gg, acts
-        th.cuda.empty_cache()
+            t0 = time.time()
+            ms = ctx.timed(step, reps=20, warm=3, flush=False)         # state >> L2: every step streams from HBM
+            t1 = time.time()
+            assert k[0] <= len(acts) or not s2v
+            ms_job = ctx.job_ms(ms)
+            alg = env.step_algorithmic_bytes() if hasattr(env, "step_algorithmic_bytes") else \
+                envs * (4 * n + 8 * n + 2 * 4 * n * 4 + 40)
+            gbs = alg / (ms_job * 1e-3) / 1e9
+            deg = float(env.mean_degree()) if hasattr(env, "mean_degree") else \
+                float((env.matrix[:1024] != 0).float().sum() / min(envs, 1024) / n)
+            what = ("S2V-DQN pattern: irreversible spins, SPIN_STATE observable, DENSE reward / N, random flip order" if s2v
+                    else "PECO pattern: reversible spins, 7 observables, BLS reward, random actions")
+            out[kind if not s2v else kind + "_s2v"] = {
+                "workload": f"{kind}-100 per-env graphs (+-1 weights), {total_envs} envs over {ctx.world} GPU(s) "
+                            f"({envs}/GPU), mean degree {deg:.1f}: SpinSystemUnbiased.step, {what}",
+                "n_gpus": ctx.world, "scaling": "strong", "ms": ms_job, "env_steps": total_envs,
+                "env_steps_per_s": total_envs / (ms_job * 1e-3), "graph_generation_s": round(gen_s, 2),
+                "state_layout": getattr(env, "state_layout", "dense float32 matrix [E,N,N] + state [E,7,N]"),
+                "roofline": roof("hbm", gbs, ctx.peaks["hbm"], "GB/s", "peco_step",
+                                 algorithmic_bytes_per_launch=alg, bytes_per_env_step=alg / envs,
+                                 traffic=dram_traffic().get("config4_peco_step_" + kind)),
+                "clocks": ctx.window_clocks(t0, t1)}
+            if ctx.world == 1 and ctx.rank == 0 and not ctx.args.no_cpu_baseline and kind == "ER" and not s2v:
+                out["cpu_baseline"] = peco_cpu_baseline(env, n)
+            del env, gg, acts
+            th.cuda.empty_cache()
     return out
 
 

@@ -1,8 +1,12 @@
 """NumPy (float32) restatement of the reference's PECO pattern-I environment.  TEST INFRASTRUCTURE ONLY.
 SpinSystemUnbiased of rlsolver/methods/ECO_S2V/src/envs/spinsystem_PECO.py: _reset_state (212-236),
 step (306-486), calculate_cut (601-607), _get_immeditate_cuts_avaialable (660-662); HistoryBuffer.update of
-util_envs_PECO.py:262-288.  Configuration subset: unbiased, ExtraAction.NONE, reversible spins, infinite
-memory, reward signals DENSE / BLS / CUSTOM_BLS.  Observables are named as in util_envs.py:40-51."""
+util_envs_PECO.py:262-288.  Configuration subset: unbiased, ExtraAction.NONE, infinite memory, reward signals
+DENSE / BLS / CUSTOM_BLS.  Observables are named as in util_envs.py:40-51.
+`reversible_spins=False` is the S2V-DQN pattern of the single-env NumPy environment
+(rlsolver/methods/ECO_S2V/src/envs/spinsystem.py: every spin starts at +1, :242-247; an episode also ends when no +1
+spin is left, :476-480; train_S2V.py:37-47 pairs it with the DENSE reward, norm_rewards and the single SPIN_STATE
+observable), applied per env of the batch; pinned by tests/golden/s2v_*.npz (tools/make_goldens_s2v.py)."""
 from __future__ import annotations
 
 from typing import List, Optional
@@ -28,7 +32,8 @@ def cut(matrix: np.ndarray, spins: np.ndarray) -> np.ndarray:
 class SpinSystem:
     def __init__(self, matrix, spins, observables: List[int], max_steps: int, reward_signal: int, norm_rewards: bool,
                  horizon_length: Optional[int] = None, stag_punishment=None, basin_reward=None,
-                 scalar_div_as_cuda: bool = False):
+                 scalar_div_as_cuda: bool = False, reversible_spins: bool = True):
+        self.reversible = reversible_spins
         self.m = matrix.astype(f32)
         self.e, self.n = spins.shape
         self.obs = list(enumerate(observables))
@@ -104,6 +109,8 @@ class SpinSystem:
             elif o == DSTATE:
                 st[:, idx, :] = np.count_nonzero(self.best_spins - spins, axis=-1).astype(f32)[:, None]
         done = np.full(self.e, self.current_step == self.max_steps)
+        if not self.reversible:
+            done = done | ~(spins > 0).any(axis=-1)              # no spin left to flip (spinsystem.py:476-480)
         return rew, done
 
     def observation(self, binary: bool) -> np.ndarray:

@@ -18,8 +18,12 @@ Two resident layouts behind the same attributes:
     updated in place.
 The ER / BA generators write the compact layout straight from torch's Philox stream (same seed, same graphs as the
 reference's torch ops; `get()` still returns the dense tensor for callers that want it).
-Supported configuration = what PECO trains with (train_PECO.py:34-44): unbiased graphs, ExtraAction.NONE,
-reversible spins, infinite memory.
+Supported configuration = what PECO trains with (train_PECO.py:34-44): unbiased graphs, ExtraAction.NONE, infinite
+memory, reversible spins -- plus the S2V-DQN pattern of the reference's single-env NumPy environment
+(ECO_S2V/src/envs/spinsystem.py:242-247, 476-480; train_S2V.py:37-47): `reversible_spins=False` starts every env at all
++1 and ends an env's episode when no +1 spin is left; with `S2V_OBSERVABLES`, `RewardSignal.DENSE` and `norm_rewards` a
+step is flip -> reward = delta cut / N.  (The batched reference's own irreversible / finite-memory / ExtraAction branches
+index the [E, obs, N] state as if it were one env's and are not reproduced.)
 """
 from __future__ import annotations
 
@@ -280,8 +284,9 @@ class SpinSystemUnbiased:
         assert observables[0] == Observable.SPIN_STATE, "First observable must be Observation.SPIN_STATE."
         if extra_action != ExtraAction.NONE:
             raise NotImplementedError("only ExtraAction.NONE (PECO's configuration, train_PECO.py:36)")
-        if not reversible_spins or memory_length is not None or init_snap is not None:
-            raise NotImplementedError("reversible spins with infinite memory only (train_PECO.py:40-44)")
+        if memory_length is not None or init_snap is not None:
+            raise NotImplementedError("infinite memory only (train_PECO.py:40-44; the reference's finite-memory branch "
+                                      "indexes the batched state as a single env's)")
         if reward_signal == RewardSignal.SINGLE:
             raise NotImplementedError("RewardSignal.SINGLE")
         if optimisation_target != OptimisationTarget.CUT:
@@ -420,7 +425,10 @@ class SpinSystemUnbiased:
                 break
         self.max_local_reward_available = self.max_local_reward_available_.unsqueeze(1).expand(-1, n)
         if spins is None:
-            spins_f = 2 * th.randint(0, 2, (e, n), device=dev, dtype=th.float) - 1
+            if self.reversible_spins:
+                spins_f = 2 * th.randint(0, 2, (e, n), device=dev, dtype=th.float) - 1
+            else:       # irreversible (S2V-DQN, ECO_S2V/src/envs/spinsystem.py:242-247): every spin may still be flipped
+                spins_f = th.ones((e, n), device=dev, dtype=th.float)
         else:
             spins_f = spins.to(dev).to(th.float32)
         self._state_cache = None
@@ -562,6 +570,10 @@ class SpinSystemUnbiased:
         self.best_obs_score = self.best_score           # infinite memory (spinsystem_PECO.py:427-429)
         self.best_obs_spins = None                      # == best_spins (materialised on request)
         done = th.full((self.num_envs,), self.current_step == self.max_steps, device=self.device, dtype=th.bool)
+        if not self.reversible_spins:       # "no more spins to flip" (spinsystem.py:476-480), per env of the batch
+            left = (self._spins != 0).any(dim=-1) if self._compact is not None else \
+                (self._dense_state[:, 0, :self.n_spins] > 0).any(dim=-1)
+            done = done | ~left
         obs = self.get_observation() if return_observation else None
         return obs, rew, done
 
