@@ -457,6 +457,8 @@ int rlsb_mcpg_weighted_sweeps(int32_t num_nodes, int64_t num_chains, const int32
  *                   util_envs_PECO.py:228-288) as a per-env open-addressing set of 64-bit Zobrist keys: hset uint64
  *                   [E][hcap] (hcap a power of two >= 2 * (max_steps + 1), zeroed at reset), hkey uint64 [E] (0 at
  *                   reset), zobrist uint64 [N] random constants; NULL when no stag / basin reward is used.
+ *                   done_out uint8 [E] (nullable) = last_step, or -- irreversible spins, the S2V-DQN pattern of
+ *                   ECO_S2V/src/envs/spinsystem.py:476-480 -- no +1 spin left in the env after this flip.
  * compact_fields  : fields, cut (:601-607) and max_local (:163-171, from the all-ones state) for given spins;
  *                   *empty_graphs counts envs whose all-ones fields are all zero or whose largest is zero (:166-171).
  * compact_from_dense / expand_matrix : dense float32 [E][N][N] <-> bit rows (*bad_entries counts entries not in
@@ -475,7 +477,8 @@ int rlsb_peco_compact_step(const uint32_t* adj, const uint32_t* sgn, int64_t sgn
                            int32_t hcap, uint64_t* hkey, const uint64_t* zobrist, int32_t* bad_actions,
                            int64_t num_envs, int32_t num_spins, int32_t step, int32_t reward_signal,
                            int32_t norm_rewards, int32_t use_stag, float stag, int32_t use_basin, float basin,
-                           int32_t scalar_div_as_cuda, void* stream);
+                           int32_t scalar_div_as_cuda, uint8_t* done_out, int32_t last_step, int32_t irreversible,
+                           void* stream);
 int rlsb_peco_compact_fields(const uint32_t* adj, const uint32_t* sgn, int64_t sgn_stride, const uint32_t* spins,
                              int64_t num_envs, int32_t num_spins, int16_t* fields, float* cut, float* max_local,
                              int32_t* empty_graphs, void* stream);

@@ -150,7 +150,8 @@ SIGNATURES = {
     "rlsb_peco_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _i32, _vp,
                                  _i32, _i32, _f32, _f32, _i32, _f32, _i32, _f32, _i32, _vp]),
     "rlsb_peco_compact_step": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp,
-                                         _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _i32, _vp]),
+                                         _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _i32, _vp, _i32, _i32,
+                                         _vp]),
     "rlsb_peco_compact_fields": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "rlsb_peco_compact_from_dense": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "rlsb_peco_compact_expand_matrix": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _i64, _vp]),

@@ -50,6 +50,8 @@ struct PecoC {
   unsigned long long* hkey;   // [E] Zobrist key of the current state
   const unsigned long long* zobrist;   // [N]
   int32_t* bad_actions;
+  uint8_t* done;              // [E] nullable: last_step, or (irreversible) no +1 spin left after this flip
+  int last_step, irreversible;
   int64_t num_envs;
   int n, np, words, hcap, step;
   int reward_signal;          // 1 DENSE, 2 BLS, 4 CUSTOM_BLS
@@ -83,7 +85,10 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step_kernel(PecoC 
   if (p.hset) key0 = p.hkey[env];
   (void)bs;
   if (a < 0 || a >= n) {                               // IndexError in the reference
-    if (lane == 0) p.reward[env] = 0.f, atomicAdd(p.bad_actions, 1);
+    if (lane == 0) {
+      p.reward[env] = 0.f, atomicAdd(p.bad_actions, 1);
+      if (p.done) p.done[env] = (uint8_t)p.last_step;
+    }
     return;
   }
   const int wa = (int)a >> 5, ba = (int)a & 31;
@@ -157,10 +162,12 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step_kernel(PecoC 
   }
   const bool better = score > best_obs;
   if (better && lane < W) p.best_spins[env * W + lane] = sp;
+  const bool none_left = __ballot_sync(kFull, sp != 0u) == 0u;        // padding bits are never set
   if (lane == 0) {
     p.score[env] = score;
     p.best_score[env] = better ? score : best_obs;
     p.reward[env] = rew;
+    if (p.done) p.done[env] = (uint8_t)(p.last_step || (p.irreversible && none_left));
   }
 }
 
@@ -256,6 +263,8 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step8_kernel(PecoC
     if (p.use_stag && !fresh) rew = __fsub_rn(rew, p.stag);
     if (p.use_basin && nonpos == n && fresh) rew = __fadd_rn(rew, p.basin);
   }
+  const bool none_left = ((__ballot_sync(kFull, has && sp != 0u) >> base) & 0xFFu) == 0u;
+  if (live && sub == 0 && p.done) p.done[env] = (uint8_t)(p.last_step || (valid && p.irreversible && none_left));
   if (!valid) return;
   const bool better = score > best_obs;
   if (better && has && !(sub & 1)) p.best_spins[env * W + myw] = sp;
@@ -529,7 +538,8 @@ int rlsb_peco_compact_step(const uint32_t* adj, const uint32_t* sgn, int64_t sgn
                            int32_t hcap, uint64_t* hkey, const uint64_t* zobrist, int32_t* bad_actions,
                            int64_t num_envs, int32_t num_spins, int32_t step, int32_t reward_signal,
                            int32_t norm_rewards, int32_t use_stag, float stag, int32_t use_basin, float basin,
-                           int32_t scalar_div_as_cuda, void* stream) {
+                           int32_t scalar_div_as_cuda, uint8_t* done_out, int32_t last_step, int32_t irreversible,
+                           void* stream) {
   using namespace rlsb;
   if (int rc = pc_shape_ok(num_envs, num_spins, "peco_compact_step")) return rc;
   if (num_envs == 0) return RLSB_OK;
@@ -550,6 +560,7 @@ int rlsb_peco_compact_step(const uint32_t* adj, const uint32_t* sgn, int64_t sgn
   p.words = (num_spins + 31) / 32, p.step = step, p.reward_signal = reward_signal, p.norm_rewards = norm_rewards;
   p.use_stag = use_stag, p.use_basin = use_basin, p.stag = stag, p.basin = basin;
   p.recip_div = scalar_div_as_cuda, p.inv_n = 1.0f / (float)num_spins;
+  p.done = done_out, p.last_step = last_step != 0, p.irreversible = irreversible != 0;
   const unsigned grid = (unsigned)((num_envs + kPcWarps - 1) / kPcWarps);
   auto st = static_cast<cudaStream_t>(stream);
   if (p.n <= kPcLpe * kPcNpl && p.hcap % kPcLpe == 0 && !(debug_flags() & RLSB_DEBUG_PECO_WARP_PER_ENV)) {

@@ -542,6 +542,7 @@ class SpinSystemUnbiased:
             action = action.to(device=self.device, dtype=th.int64)
         action = action.reshape(self.num_envs).contiguous()
         rew = th.empty((self.num_envs,), dtype=th.float32, device=self.device)
+        done = th.empty((self.num_envs,), dtype=th.bool, device=self.device)
         use_stag, use_basin = self.stag_punishment is not None, self.basin_reward is not None
         if self._compact is not None:
             c = self._compact
@@ -553,7 +554,8 @@ class SpinSystemUnbiased:
                     _ptr(self._hkey), _ptr(self._zobrist), _ptr(self._bad), self.num_envs, self.n_spins,
                     self.current_step, self.reward_signal.value, int(bool(self.norm_rewards)), int(use_stag),
                     float(self.stag_punishment or 0.0), int(use_basin), float(self.basin_reward or 0.0),
-                    int(bool(self.scalar_div_as_cuda)), _stream_ptr(self.device)), "peco_compact_step")
+                    int(bool(self.scalar_div_as_cuda)), _ptr(done), int(self.current_step == self.max_steps),
+                    int(not self.reversible_spins), _stream_ptr(self.device)), "peco_compact_step")
             self._state_cache = None
         else:
             with on_device(self.device):
@@ -569,11 +571,10 @@ class SpinSystemUnbiased:
                 self._hist_len += 1
         self.best_obs_score = self.best_score           # infinite memory (spinsystem_PECO.py:427-429)
         self.best_obs_spins = None                      # == best_spins (materialised on request)
-        done = th.full((self.num_envs,), self.current_step == self.max_steps, device=self.device, dtype=th.bool)
-        if not self.reversible_spins:       # "no more spins to flip" (spinsystem.py:476-480), per env of the batch
-            left = (self._spins != 0).any(dim=-1) if self._compact is not None else \
-                (self._dense_state[:, 0, :self.n_spins] > 0).any(dim=-1)
-            done = done | ~left
+        if self._compact is None:           # (the compact kernel wrote `done` itself)
+            done.fill_(self.current_step == self.max_steps)
+            if not self.reversible_spins:   # "no more spins to flip" (spinsystem.py:476-480), per env of the batch
+                done |= ~(self._dense_state[:, 0, :self.n_spins] > 0).any(dim=-1)
         obs = self.get_observation() if return_observation else None
         return obs, rew, done
 
