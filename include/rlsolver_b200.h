@@ -450,7 +450,7 @@ int rlsb_mcpg_weighted_sweeps(int32_t num_nodes, int64_t num_chains, const int32
  * state that lives in HBM reduced to bits and small integers:
  *   adj uint32 [E][N][W] adjacency bit rows (W = ceil(N/32), diagonal bit = self loop); sgn uint32 bit = weight -1,
  *   laid out [E][N][W] (sgn_stride = N*W), one shared [N][W] matrix (sgn_stride = 0) or NULL (all +1);
- *   spins / best_spins uint32 [E][W] (bit = spin +1); fields int16 [E][Np] = (A s)_j; last_flip uint16 [E][Np];
+ *   spins / best_spins uint32 [E][W] (bit = spin +1); fields [E][Np] = (A s)_j, int8 when N <= 128 (|field| <= N - 1) and int16 otherwise; last_flip uint16 [E][Np];
  *   score / best_score / max_local / reward float32 [E].
  * compact_step    : SpinSystemUnbiased.step (spinsystem_PECO.py:306-486) for ExtraAction.NONE, reversible spins,
  *                   infinite memory; `step` = 1-based index of this step.  Visited-state test (HistoryBuffer,
@@ -472,7 +472,7 @@ int rlsb_mcpg_weighted_sweeps(int32_t num_nodes, int64_t num_chains, const int32
  *                   the same seed.  The caller advances the generator (ER: 4 * rng_iters; BA: (N - m - 1) calls of
  *                   E * N elements).  E * N * N (ER) and E * N (BA) must stay below 2^31 per call. */
 int rlsb_peco_compact_step(const uint32_t* adj, const uint32_t* sgn, int64_t sgn_stride, uint32_t* spins,
-                           int16_t* fields, uint16_t* last_flip, uint32_t* best_spins, float* score, float* best_score,
+                           void* fields, uint16_t* last_flip, uint32_t* best_spins, float* score, float* best_score,
                            const float* max_local, float* reward, const int64_t* action, uint64_t* hset,
                            int32_t hcap, uint64_t* hkey, const uint64_t* zobrist, int32_t* bad_actions,
                            int64_t num_envs, int32_t num_spins, int32_t step, int32_t reward_signal,
@@ -480,13 +480,13 @@ int rlsb_peco_compact_step(const uint32_t* adj, const uint32_t* sgn, int64_t sgn
                            int32_t scalar_div_as_cuda, uint8_t* done_out, int32_t last_step, int32_t irreversible,
                            void* stream);
 int rlsb_peco_compact_fields(const uint32_t* adj, const uint32_t* sgn, int64_t sgn_stride, const uint32_t* spins,
-                             int64_t num_envs, int32_t num_spins, int16_t* fields, float* cut, float* max_local,
+                             int64_t num_envs, int32_t num_spins, void* fields, float* cut, float* max_local,
                              int32_t* empty_graphs, void* stream);
 int rlsb_peco_compact_from_dense(const float* matrix, int64_t num_envs, int32_t num_spins, uint32_t* adj, uint32_t* sgn,
                                  int32_t* bad_entries, void* stream);
 int rlsb_peco_compact_expand_matrix(const uint32_t* adj, const uint32_t* sgn, int64_t sgn_stride, int64_t num_envs,
                                     int32_t num_spins, float* out, int64_t out_env_stride, void* stream);
-int rlsb_peco_compact_expand_state(const uint32_t* spins, const uint32_t* best_spins, const int16_t* fields,
+int rlsb_peco_compact_expand_state(const uint32_t* spins, const uint32_t* best_spins, const void* fields,
                                    const uint16_t* last_flip, const float* score, const float* best_score,
                                    const float* max_local, const float* table, float* state, int64_t state_env_stride,
                                    int64_t num_envs, int32_t num_spins, int32_t num_obs, const int32_t* h_obs_rows,

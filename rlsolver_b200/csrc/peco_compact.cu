@@ -10,7 +10,7 @@
 //   sgn    uint32 [S][N][W]   bit = 1: weight -1.  S = E (per-env signs), 1 (one sign matrix shared by every env:
 //                             EdgeType.DISCRETE draws ONE [N, N] mask, util_envs_PECO.py:27-29) or absent (all +1)
 //   spins  uint32 [E][W]      bit = 1: s = +1
-//   fields int16  [E][Np]     (A s)_j
+//   fields int8 / int16 [E][Np]  (A s)_j -- one byte when N <= 128 (|(A s)_j| <= N - 1), two otherwise
 //   last_flip uint16 [E][Np]  step at which node j was flipped last (TIME_SINCE_FLIP is a function of the gap)
 //   best_spins uint32 [E][W], score / best_score / max_local float32 [E], the visited set (below)
 //
@@ -33,13 +33,14 @@
 namespace rlsb {
 
 constexpr int kPcWarps = 8;
+constexpr int kPcByteFields = 128;     // up to this many spins the fields are int8 (peco_field_bytes)
 
 struct PecoC {
   const uint32_t* adj;
   const uint32_t* sgn;        // null: every weight +1
   int64_t sgn_stride;         // words between the sign matrices of consecutive envs (0: shared)
   uint32_t* spins;
-  int16_t* fields;
+  void* fields;               // int8 [E][Np] when n <= kPcByteFields, int16 [E][Np] otherwise
   uint16_t* last_flip;
   uint32_t* best_spins;
   float *score, *best_score;
@@ -65,13 +66,13 @@ __device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(kFul
 // spins and scalars -- is requested BEFORE the action is looked at, so that a step is two dependent trips to
 // HBM (action -> matrix row) instead of four: the kernel is bound by that latency chain, not by bandwidth.
 // KW: words per spin vector held in registers (N <= 32 KW); 0 = generic loop for larger N.
-template <int KW>
+template <int KW, typename FT>
 __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step_kernel(PecoC p) {
   const int lane = threadIdx.x & 31;
   const int64_t env = (int64_t)blockIdx.x * kPcWarps + (threadIdx.x >> 5);
   if (env >= p.num_envs) return;
   const int n = p.n, W = p.words;
-  int16_t* fl = p.fields + env * (int64_t)p.np;
+  FT* fl = static_cast<FT*>(p.fields) + env * (int64_t)p.np;
   const int64_t a = p.action[env];
   uint32_t sp = lane < W ? p.spins[env * W + lane] : 0u;           // lane w holds word w
   int pre[KW > 0 ? KW : 1];
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step_kernel(PecoC 
       int v = v0;
       if ((aw >> lane) & 1u) {                         // (A s)_j -= 2 A[a][j] s_old
         v -= ((sw >> lane) & 1u) ? -2 * s_old : 2 * s_old;
-        fl[j] = (int16_t)v;
+        fl[j] = (FT)v;
       }
       const int f = ((spw >> lane) & 1u) ? v : -v;     // fields_j = s_j (A s)_j with the flipped spin
       nonpos += (int)(f <= 0);
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step_kernel(PecoC 
 // per resident warp -- the step is bound by the latency of its two dependent HBM trips, and at 10^6 envs of N = 100 a
 // warp per env leaves the memory system idle most of the time.  Lane `sub` of a group owns the 16 nodes
 // 16 sub .. 16 sub + 15: they sit in ONE word of the spin / adjacency / sign rows (word sub / 2), which the lane loads
-// itself, and their 16 int16 fields are two 16-byte loads -- no shuffles in the node loop (the first version spent
+// itself, and their 16 byte-sized fields are one 16-byte load -- no shuffles in the node loop (the first version spent
 // 700 instructions per warp, 70 % issue-active, on 13 rounds of three shuffles).
 constexpr int kPcLpe = 8, kPcNpl = 16;       // lanes per env, nodes per lane (N <= 128)
 __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step8_kernel(PecoC p) {
@@ -186,14 +187,11 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step8_kernel(PecoC
   const int n = p.n, W = p.words;
   const int myw = sub >> 1, j0 = kPcNpl * sub;   // my word, my first node
   const bool has = myw < W;                      // the lane owns nodes of this graph (np >= 32 W covers them)
-  int16_t* fl = p.fields + ev * (int64_t)p.np;
+  int8_t* fl = static_cast<int8_t*>(p.fields) + ev * (int64_t)p.np;        // N <= 128: byte fields
   const int64_t a_raw = p.action[ev];
   const uint32_t sp0 = has ? p.spins[ev * W + myw] : 0u;
-  uint4 fa = make_uint4(0, 0, 0, 0), fb = fa;
-  if (has) {
-    fa = *reinterpret_cast<const uint4*>(fl + j0);
-    fb = *reinterpret_cast<const uint4*>(fl + j0 + 8);
-  }
+  uint4 fa = make_uint4(0, 0, 0, 0);
+  if (has) fa = *reinterpret_cast<const uint4*>(fl + j0);
   const float score0 = p.score[ev], best_obs = p.best_score[ev];
   unsigned long long key0 = 0ull;
   if (p.hset) key0 = p.hkey[ev];
@@ -206,17 +204,17 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step8_kernel(PecoC
   const int s_old = ((__shfl_sync(kFull, sp0, base + 2 * wa) >> ba) & 1u) ? 1 : -1;
   const uint32_t sp = (myw == wa) ? sp0 ^ (1u << ba) : sp0;      // both lanes of the word see the flipped spin
   if (valid && sub == 2 * wa) p.spins[env * W + wa] = sp;
-  const uint32_t fw[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
+  uint32_t fw[4] = {fa.x, fa.y, fa.z, fa.w};
   const int sh = (sub & 1) * kPcNpl;             // my 16 bits inside the word
   const uint32_t abits = (arow >> sh) & 0xFFFFu, sbits = (srow >> sh) & 0xFFFFu, pbits = (sp >> sh) & 0xFFFFu;
   int nonpos = 0, delta = 0;
 #pragma unroll
   for (int t = 0; t < kPcNpl; ++t) {
     const int j = j0 + t;
-    int v = (int)(int16_t)((fw[t >> 1] >> (16 * (t & 1))) & 0xFFFFu);
+    int v = (int)(int8_t)((fw[t >> 2] >> (8 * (t & 3))) & 0xFFu);
     if ((abits >> t) & 1u) {                       // (A s)_j -= 2 A[a][j] s_old
       v -= ((sbits >> t) & 1u) ? -2 * s_old : 2 * s_old;
-      if (valid) fl[j] = (int16_t)v;
+      fw[t >> 2] = (fw[t >> 2] & ~(0xFFu << (8 * (t & 3)))) | (((uint32_t)v & 0xFFu) << (8 * (t & 3)));
     }
     if (j < n) {
       const int f = ((pbits >> t) & 1u) ? v : -v;   // fields_j = s_j (A s)_j with the flipped spin
@@ -224,6 +222,8 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step8_kernel(PecoC
       if (j == a) delta = -f;
     }
   }
+  // the lane's 16 fields go back as ONE 16-byte store (a group rewrites at most the env's 128 bytes, whole sectors)
+  if (valid && has && abits) *reinterpret_cast<uint4*>(fl + j0) = make_uint4(fw[0], fw[1], fw[2], fw[3]);
 #pragma unroll
   for (int off = kPcLpe / 2; off >= 1; off >>= 1) {
     nonpos += __shfl_xor_sync(kFull, nonpos, off);
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_fields_kernel(cons
                                                                             int64_t sgn_stride,
                                                                             const uint32_t* __restrict__ spins,
                                                                             int64_t num_envs, int n, int np, int W,
-                                                                            int16_t* __restrict__ fields,
+                                                                            void* __restrict__ fields,
                                                                             float* __restrict__ cut,
                                                                             float* __restrict__ max_local,
                                                                             int32_t* __restrict__ empty_graphs) {
@@ -304,7 +304,10 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_fields_kernel(cons
     int rs = __popc(pos) - __popc(neg);                // row sum = (A 1)_j
     as = warp_sum_i(as), rs = warp_sum_i(rs);
     const int sj = ((__shfl_sync(kFull, sp, j >> 5) >> (j & 31)) & 1u) ? 1 : -1;
-    if (lane == 0 && fields) fields[env * (int64_t)np + j] = (int16_t)as;
+    if (lane == 0 && fields) {
+      if (n <= kPcByteFields) static_cast<int8_t*>(fields)[env * (int64_t)np + j] = (int8_t)as;
+      else static_cast<int16_t*>(fields)[env * (int64_t)np + j] = (int16_t)as;
+    }
     sas += as * sj, suma += rs;
     best_one = max(best_one, rs), abs_one += abs(rs);
   }
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(256) peco_compact_expand_matrix_kernel(const u
 // compact state -> the reference's float32 state [E][num_obs][N] (rows by observable index, -1 = absent)
 struct PecoExpand {
   const uint32_t *spins, *best_spins;
-  const int16_t* fields;
+  const void* fields;
   const uint16_t* last_flip;
   const float *score, *best_score, *max_local;
   const float* table;        // table[k] = k-fold float32 accumulation of 1 / max_steps
@@ -380,7 +383,8 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_expand_state_kerne
   const uint32_t bs = lane < W ? p.best_spins[env * W + lane] : 0u;
   const int dist = warp_sum_i(__popc(sp ^ bs));
   const float maxl = p.max_local[env];
-  const int16_t* fl = p.fields + env * (int64_t)p.np;
+  const int8_t* fl8 = static_cast<const int8_t*>(p.fields) + env * (int64_t)p.np;
+  const int16_t* fl16 = static_cast<const int16_t*>(p.fields) + env * (int64_t)p.np;
   const uint16_t* lf = p.last_flip + env * (int64_t)p.np;
   float* st = p.state + env * p.state_env_stride;
   int nonpos = 0;
@@ -389,7 +393,8 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_expand_state_kerne
     const int j = 32 * k + lane;
     if (j < n) {
       const bool up = (spw >> lane) & 1u;
-      const int f = up ? fl[j] : -fl[j];
+      const int as = n <= kPcByteFields ? (int)fl8[j] : (int)fl16[j];
+      const int f = up ? as : -as;
       nonpos += (int)(f <= 0);
       st[j] = p.binary_spins ? (up ? 0.f : 1.f) : (up ? 1.f : -1.f);       // BINARY basis: (1 - s) / 2
       if (p.idx_imm >= 0) st[p.idx_imm * n + j] = __fdiv_rn((float)f, maxl);
@@ -533,7 +538,7 @@ static int pc_shape_ok(int64_t num_envs, int32_t n, const char* what) {
 }
 
 int rlsb_peco_compact_step(const uint32_t* adj, const uint32_t* sgn, int64_t sgn_stride, uint32_t* spins,
-                           int16_t* fields, uint16_t* last_flip, uint32_t* best_spins, float* score, float* best_score,
+                           void* fields, uint16_t* last_flip, uint32_t* best_spins, float* score, float* best_score,
                            const float* max_local, float* reward, const int64_t* action, uint64_t* hset,
                            int32_t hcap, uint64_t* hkey, const uint64_t* zobrist, int32_t* bad_actions,
                            int64_t num_envs, int32_t num_spins, int32_t step, int32_t reward_signal,
@@ -566,15 +571,15 @@ int rlsb_peco_compact_step(const uint32_t* adj, const uint32_t* sgn, int64_t sgn
   if (p.n <= kPcLpe * kPcNpl && p.hcap % kPcLpe == 0 && !(debug_flags() & RLSB_DEBUG_PECO_WARP_PER_ENV)) {
     const int64_t per_block = (int64_t)kPcWarps * (32 / kPcLpe);
     peco_compact_step8_kernel<<<(unsigned)((num_envs + per_block - 1) / per_block), kPcWarps * 32, 0, st>>>(p);
-  } else if (p.words <= 4) peco_compact_step_kernel<4><<<grid, kPcWarps * 32, 0, st>>>(p);
-  else if (p.words <= 8) peco_compact_step_kernel<8><<<grid, kPcWarps * 32, 0, st>>>(p);
-  else peco_compact_step_kernel<0><<<grid, kPcWarps * 32, 0, st>>>(p);
+  } else if (p.n <= kPcByteFields) peco_compact_step_kernel<4, int8_t><<<grid, kPcWarps * 32, 0, st>>>(p);
+  else if (p.words <= 8) peco_compact_step_kernel<8, int16_t><<<grid, kPcWarps * 32, 0, st>>>(p);
+  else peco_compact_step_kernel<0, int16_t><<<grid, kPcWarps * 32, 0, st>>>(p);
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }
 
 int rlsb_peco_compact_fields(const uint32_t* adj, const uint32_t* sgn, int64_t sgn_stride, const uint32_t* spins,
-                             int64_t num_envs, int32_t num_spins, int16_t* fields, float* cut, float* max_local,
+                             int64_t num_envs, int32_t num_spins, void* fields, float* cut, float* max_local,
                              int32_t* empty_graphs, void* stream) {
   using namespace rlsb;
   if (int rc = pc_shape_ok(num_envs, num_spins, "peco_compact_fields")) return rc;
@@ -615,7 +620,7 @@ int rlsb_peco_compact_expand_matrix(const uint32_t* adj, const uint32_t* sgn, in
   return RLSB_OK;
 }
 
-int rlsb_peco_compact_expand_state(const uint32_t* spins, const uint32_t* best_spins, const int16_t* fields,
+int rlsb_peco_compact_expand_state(const uint32_t* spins, const uint32_t* best_spins, const void* fields,
                                    const uint16_t* last_flip, const float* score, const float* best_score,
                                    const float* max_local, const float* table, float* state, int64_t state_env_stride,
                                    int64_t num_envs, int32_t num_spins, int32_t num_obs, const int32_t* h_obs_rows,

@@ -11,7 +11,7 @@ The reference recomputes all local fields with a batched matmul and clones the s
 
 Two resident layouts behind the same attributes:
   * COMPACT (csrc/peco_compact.cu) whenever every weight is -1, 0 or +1 -- all the reference's generators: adjacency
-    and sign bit rows, packed spins, int16 fields, a 64-bit hashed visited set.  `state`, `matrix`, `best_spins` and
+    and sign bit rows, packed spins, int8 / int16 fields, a 64-bit hashed visited set.  `state`, `matrix`, `best_spins` and
     the observation are materialised from it on request, with the reference's float32 values.  3.3 KB per env
     instead of 43 KB at N = 100; the step touches ~0.5 KB.
   * DENSE (csrc/peco.cu) for arbitrary float weights handed in through SetMatrixGenerator: the reference's tensors,
@@ -333,7 +333,8 @@ class SpinSystemUnbiased:
     # ------------------------------------------------------------------ layout plumbing
     @property
     def state_layout(self) -> str:
-        return ("compact: adjacency / sign bit rows, packed spins, int16 fields, hashed visited set"
+        return (f"compact: adjacency / sign bit rows, packed spins, {'int8' if self.n_spins <= 128 else 'int16'} fields, "
+                "hashed visited set"
                 if self._compact is not None else "dense float32 matrix [E,N,N] + state [E,obs,N]")
 
     def _draw_graphs(self) -> None:
@@ -355,6 +356,11 @@ class SpinSystemUnbiased:
     def matrix_obs(self) -> TEN:
         return self.matrix
 
+    @property
+    def _field_dtype(self):
+        """(A s)_j is bounded by the degree: one byte up to 128 spins (csrc/peco_compact.cu kPcByteFields)."""
+        return th.int8 if self.n_spins <= 128 else th.int16
+
     def mean_degree(self) -> float:
         if self._compact is not None:
             sample = self._compact.adj[:1024]
@@ -363,13 +369,14 @@ class SpinSystemUnbiased:
 
     def step_algorithmic_bytes(self) -> int:
         """HBM bytes one step has to move per launch: compact = action + one adjacency and one sign row +
-        the fields of the acted node's neighbours (read + write) + own field + spin words (r/w) + best spins (r) +
-        last_flip entry + score / best / max_local / reward scalars."""
+        the fields of the acted node's neighbours (read + write) + every field once (the greedy-actions count needs them
+        all) + spin words (r/w) + best spins (r) + last_flip entry + score / best / max_local / reward scalars."""
         n, w, e = self.n_spins, _words(self.n_spins), self.num_envs
         if self._compact is None:
             return e * (4 * n + 8 * n + 2 * 4 * n * 4 + 40)
         deg = self.mean_degree()
-        return int(e * (8 + 8 * w + 4 * deg + 2 * n + 8 * w + 4 * w + 2 + 24))
+        fb = 1 if n <= 128 else 2                    # bytes per field
+        return int(e * (8 + 8 * w + 2 * fb * deg + fb * n + 8 * w + 4 * w + 2 + 24))
 
     # ------------------------------------------------------------------ kernels
     def _fields(self, spins: TEN, want_as: bool = False, want_cut: bool = False):
@@ -397,7 +404,7 @@ class SpinSystemUnbiased:
         if self._compact is None:
             return self._fields(spins)[0]
         words = pack_rows(spins > 0)
-        fields = th.empty((self.num_envs, _words(self.n_spins) * 32), dtype=th.int16, device=self.device)
+        fields = th.empty((self.num_envs, _words(self.n_spins) * 32), dtype=self._field_dtype, device=self.device)
         self._compact_fields(words, fields, None, None, None)
         return fields[:, :self.n_spins].float() * spins
 
@@ -437,7 +444,7 @@ class SpinSystemUnbiased:
         use_hist = self.stag_punishment is not None or self.basin_reward is not None
         if self._compact is not None:
             self._spins = pack_rows(spins_f > 0)
-            self._cfields = th.empty((e, w * 32), dtype=th.int16, device=dev)
+            self._cfields = th.empty((e, w * 32), dtype=self._field_dtype, device=dev)
             self.score = th.empty((e,), dtype=th.float32, device=dev)
             self._compact_fields(self._spins, self._cfields, self.score, None, None)
             self._last_flip = th.zeros((e, w * 32), dtype=th.int16, device=dev)
