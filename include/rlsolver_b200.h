@@ -387,6 +387,11 @@ int rlsb_select_rows(uint8_t* xs0, int64_t* vs0, const uint8_t* xs1, const int64
                      int32_t num_nodes, int32_t maximize, void* stream);
 int rlsb_pick_best(const uint8_t* xs, const int64_t* vs, int32_t num_repeats, int64_t num_sims, int32_t num_nodes,
                    int32_t maximize, uint8_t* out_xs, int64_t* out_vs, void* stream);
+/* rows dst_ids[i] <- rows src_ids[i] (xs bool [E][N], vs int64 [E]) for disjoint index sets: the row copy of
+ * evolutionary_replacement (rlsolver/methods/util.py:87-94; its argsort and randperm stay torch calls so that ties and
+ * the random stream are the reference's).  *bad_ids counts pairs with an index outside [0, E). */
+int rlsb_copy_rows(uint8_t* xs, int64_t* vs, const int64_t* dst_ids, const int64_t* src_ids, int64_t count, int64_t num_envs,
+                   int32_t num_nodes, int32_t* bad_ids, void* stream);
 
 /* ---- multi-GPU best-cut exchange (new; the reference is single-process): the record a rank
  * contributes to the all-gather -- 64-bit key ((cut + 2^31) << 32) | (0xFFFFFFFF - global_env_id) of its best

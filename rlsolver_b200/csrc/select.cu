@@ -35,6 +35,23 @@ __global__ void __launch_bounds__(256) select_rows_kernel(uint8_t* __restrict__ 
   if (lane == 0) vs0[env] = b;
 }
 
+// rows dst[i] <- rows src[i] of the same batch (evolutionary_replacement, rlsolver/methods/util.py:87-94: the index
+// sets are disjoint -- the replaced rows come from the non-elite part of the argsort, the sources from the elite part)
+__global__ void __launch_bounds__(256) copy_rows_kernel(uint8_t* __restrict__ xs, int64_t* __restrict__ vs,
+                                                        const int64_t* __restrict__ dst, const int64_t* __restrict__ src,
+                                                        int64_t count, int64_t num_envs, int n, int32_t* __restrict__ bad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= count) return;
+  const int64_t d = dst[i], s = src[i];
+  if (d < 0 || d >= num_envs || s < 0 || s >= num_envs) {
+    if (lane == 0) atomicAdd(bad, 1);
+    return;
+  }
+  copy_row(xs + d * (int64_t)n, xs + s * (int64_t)n, n, lane, 32);
+  if (lane == 0) vs[d] = vs[s];
+}
+
 // one CTA per sim: warp 0 finds the best repeat (lowest index on ties), all threads copy the row
 __global__ void __launch_bounds__(128) pick_best_kernel(const uint8_t* __restrict__ xs, const int64_t* __restrict__ vs,
                                                         int num_repeats, int64_t num_sims, int n, int maximize,
@@ -201,6 +218,18 @@ int rlsb_select_rows(uint8_t* xs0, int64_t* vs0, const uint8_t* xs1, const int64
   RLSB_REQUIRE(xs0 && vs0 && xs1 && vs1, RLSB_ERR_INVALID, "select_rows: null pointer");
   select_rows_kernel<<<(unsigned)((num_envs + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       xs0, vs0, xs1, vs1, num_envs, num_nodes, maximize);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+int rlsb_copy_rows(uint8_t* xs, int64_t* vs, const int64_t* dst_ids, const int64_t* src_ids, int64_t count, int64_t num_envs,
+                   int32_t num_nodes, int32_t* bad_ids, void* stream) {
+  using namespace rlsb;
+  RLSB_REQUIRE(count >= 0 && num_envs >= 0 && num_nodes >= 0, RLSB_ERR_INVALID, "copy_rows: negative size");
+  if (count == 0) return RLSB_OK;
+  RLSB_REQUIRE(xs && vs && dst_ids && src_ids && bad_ids, RLSB_ERR_INVALID, "copy_rows: null pointer");
+  copy_rows_kernel<<<(unsigned)((count + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(xs, vs, dst_ids, src_ids, count,
+                                                                                              num_envs, num_nodes, bad_ids);
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }

@@ -31,10 +31,22 @@ def build_adjacency_bool(mygraph: MyGraph, num_nodes: int = 0, if_bidirectional:
 
 def evolutionary_replacement(xs: TEN, vs: TEN, low_k: int, if_maximize: bool):
     """Overwrite `low_k` random non-elite rows with the `low_k` best rows (in place).
-    Same RNG call as the reference: one randperm(E - low_k) on xs.device."""
+    The argsort (its order among equal values) and the one randperm(E - low_k) on xs.device are torch's, as in the
+    reference; the row copy is one kernel (rlsb_copy_rows) for bool CUDA rows."""
     num_sims = xs.shape[0]
     ids = vs.argsort()
     top_ids, low_ids = (ids[:-low_k], ids[-low_k:]) if if_maximize else (ids[:low_k], ids[low_k:])
     replace_ids = top_ids[th.randperm(num_sims - low_k, device=xs.device)[:low_k]]
-    xs[replace_ids] = xs[low_ids]
+    if (xs.is_cuda and xs.dtype == th.bool and xs.dim() == 2 and xs.is_contiguous() and vs.dtype == th.int64
+            and vs.is_contiguous() and replace_ids.numel() == low_ids.numel()):
+        from .. import _lib
+        from ..graph_store import on_device
+        bad = th.zeros((1,), dtype=th.int32, device=xs.device)
+        replace_ids, low_ids = replace_ids.contiguous(), low_ids.contiguous()
+        with on_device(xs.device):
+            _lib.check(_lib.lib().rlsb_copy_rows(xs.data_ptr(), vs.data_ptr(), replace_ids.data_ptr(), low_ids.data_ptr(),
+                                                 replace_ids.numel(), num_sims, xs.shape[1], bad.data_ptr(),
+                                                 th.cuda.current_stream(xs.device).cuda_stream), "copy_rows")
+        return
+    xs[replace_ids] = xs[low_ids]          # other layouts / devices: the reference's own indexing (and its errors)
     vs[replace_ids] = vs[low_ids]

@@ -543,3 +543,31 @@ def test_host_pipeline_equals_eager_calls(layout, cuda_device):
         assert th.equal(got_xs, want[i][0]), f"batch {i}"
         assert th.equal(h_vs[i], want[i][1]), f"batch {i}"
     assert th.equal(th.cuda.get_rng_state(cuda_device), end_state)
+
+
+# ------------------------------------------------------------------ evolutionary_replacement (row a8)
+@pytest.mark.parametrize("maximize", [True, False])
+def test_evolutionary_replacement_equals_reference_indexing(maximize, cuda_device):
+    """rlsb_copy_rows behind the mirror against the reference's two fancy-index assignments (util.py:87-94) from the
+    same generator state, G22 x 4096 with many tied values."""
+    from rlsolver_b200.methods.util import evolutionary_replacement
+    e, n, low_k = 4096, 2000, 512
+    g = th.Generator(device=cuda_device).manual_seed(3)
+    xs = th.rand((e, n), device=cuda_device, generator=g) < 0.5
+    vs = th.randint(13000, 13040, (e,), device=cuda_device, generator=g)
+    want_xs, want_vs = xs.clone(), vs.clone()
+    th.manual_seed(77)
+    ids = want_vs.argsort()
+    top_ids, low_ids = (ids[:-low_k], ids[-low_k:]) if maximize else (ids[:low_k], ids[low_k:])
+    replace_ids = top_ids[th.randperm(e - low_k, device=cuda_device)[:low_k]]
+    if replace_ids.numel() == low_ids.numel():
+        want_xs[replace_ids] = want_xs[low_ids]
+        want_vs[replace_ids] = want_vs[low_ids]
+        end = th.cuda.get_rng_state(cuda_device)
+        th.manual_seed(77)
+        evolutionary_replacement(xs, vs, low_k, maximize)
+        assert th.equal(xs, want_xs) and th.equal(vs, want_vs)
+        assert th.equal(th.cuda.get_rng_state(cuda_device), end)
+    else:       # minimise: ids[low_k:] has E - low_k rows, the reference's assignment raises on the shape mismatch
+        with pytest.raises((RuntimeError, IndexError)):
+            evolutionary_replacement(xs, vs, low_k, maximize)
