@@ -6,7 +6,9 @@ DENSE / BLS / CUSTOM_BLS.  Observables are named as in util_envs.py:40-51.
 `reversible_spins=False` is the S2V-DQN pattern of the single-env NumPy environment
 (rlsolver/methods/ECO_S2V/src/envs/spinsystem.py: every spin starts at +1, :242-247; an episode also ends when no +1
 spin is left, :476-480; train_S2V.py:37-47 pairs it with the DENSE reward, norm_rewards and the single SPIN_STATE
-observable), applied per env of the batch; pinned by tests/golden/s2v_*.npz (tools/make_goldens_s2v.py)."""
+observable), applied per env of the batch; pinned by tests/golden/s2v_*.npz (tools/make_goldens_s2v.py).
+`seed_best_from_batch=True` is the inference twin (inference_network_env.py: one graph for all envs, best_* seeded
+from the batch's best start, no reward); pinned by tests/golden/pecoinf_*.npz (tools/make_goldens_inference.py)."""
 from __future__ import annotations
 
 from typing import List, Optional
@@ -32,7 +34,7 @@ def cut(matrix: np.ndarray, spins: np.ndarray) -> np.ndarray:
 class SpinSystem:
     def __init__(self, matrix, spins, observables: List[int], max_steps: int, reward_signal: int, norm_rewards: bool,
                  horizon_length: Optional[int] = None, stag_punishment=None, basin_reward=None,
-                 scalar_div_as_cuda: bool = False, reversible_spins: bool = True):
+                 scalar_div_as_cuda: bool = False, reversible_spins: bool = True, seed_best_from_batch: bool = False):
         self.reversible = reversible_spins
         self.m = matrix.astype(f32)
         self.e, self.n = spins.shape
@@ -57,6 +59,12 @@ class SpinSystem:
         self.score = cut(self.m, spins)
         self.best_score = self.score.copy()
         self.best_spins = spins.astype(f32).copy()
+        if seed_best_from_batch:
+            # the inference env (inference_network_env.py:171-207): every env starts from the batch's best start state
+            # (torch.max(score, dim=0): the first index among equal maxima on the CPU and the CUDA kernel alike)
+            idx = int(np.argmax(self.score))
+            self.best_score = np.full(self.e, self.score[idx], f32)
+            self.best_spins = np.repeat(spins[idx:idx + 1].astype(f32), self.e, axis=0)
         self.history: List[np.ndarray] = []
 
     def step(self, action: np.ndarray):

@@ -328,7 +328,6 @@ class SpinSystemUnbiased:
         self._compact: Optional[CompactGraphs] = None
         self._draw_graphs()                  # the reference draws one graph batch in __init__ and another in reset()
         self.reset(return_observation=False)
-        self.best_score = self.score.clone()
 
     # ------------------------------------------------------------------ layout plumbing
     @property
@@ -466,7 +465,11 @@ class SpinSystemUnbiased:
         self.best_score = self.score.clone()
         self.best_obs_score = self.score.clone()
         self.best_obs_spins = None                      # == best_spins (materialised on request)
+        self._seed_best()
         return self.get_observation() if return_observation else None
+
+    def _seed_best(self) -> None:
+        """Hook: what best_score / best_spins start from (here: every env's own start, set by reset)."""
 
     def _reset_state(self, spins_f: TEN):
         """Dense layout: the reference's state tensor after reset (spinsystem_PECO.py:173-193)."""
