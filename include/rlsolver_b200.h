@@ -268,6 +268,16 @@ int rlsb_greedy_best_flip(const rlsb_graph_t* g, uint8_t* xs, int64_t num_envs, 
  * the generator offset by 4 * rng_iters per call the reference would have made.
  * rlsb_torch_rand / rlsb_torch_randint regenerate `calls` consecutive torch.rand(numel) /
  * torch.randint(0, range, [numel]) results (tests pin the stream identity with them). */
+/* One round of metropolis_hastings_sampling_TNCO (rlsolver/envs/env_L2A.py:233-276, the row-major variant of
+ * metro_sampling): xs bool [R*S][dim] in place, probs float32 [S][dim] (row r uses probs[r % S]), perm int64 [dim] =
+ * the round's torch.randperm(dim).  Position i proposes a flip of column perm[i] in every row, accepted when
+ * torch.rand(R*S) call number i (generator state (seed, offset), geometry of numel = R*S) is below (1 - q) / q;
+ * state[0] (int64, in/out) = accepts so far, state[1] (out) = positions visited = index of the first position at
+ * which the count reached `target`, plus one (dim when it never did).  counts: int32 [dim] scratch.  The caller
+ * advances the generator by state[1] calls. */
+int rlsb_mh_rows_round(const float* probs, uint8_t* xs, const int64_t* perm, int64_t num_rows, int64_t num_sims,
+                       int32_t dim, int64_t target, uint64_t seed, uint64_t offset, uint32_t rng_threads, uint32_t rng_iters,
+                       int64_t* state, int32_t* counts, void* stream);
 int rlsb_torch_rand(uint64_t seed, uint64_t offset, uint32_t rng_threads, uint32_t rng_iters, int64_t calls,
                     int64_t numel, float* out, void* stream);
 int rlsb_torch_randint(uint64_t seed, uint64_t offset, uint32_t rng_threads, uint32_t rng_iters, int64_t calls,

@@ -124,3 +124,30 @@ class TorchLocalSearch:
         sim.sweep(px, pv)
         n = sim.keep_not_worse(self.good_xs, self.good_vs, px, pv)
         return self.good_xs, self.good_vs, n
+
+
+def metropolis_hastings_sampling_tnco(probs, start_xs, num_repeats: int, num_iters: int = -1, accept_rate: float = 0.25):
+    """rlsolver/envs/env_L2A.py:233-276 op for op (row-major independent-site Metropolis; same torch calls in the same
+    order, so on one device and seed it consumes the generator exactly like the reference).  TEST INFRASTRUCTURE:
+    pinned on the CPU by tests/golden/mhrows_*.npz (tools/make_goldens_mhrows.py), compared with the kernels on CUDA."""
+    xs = start_xs.repeat(num_repeats, 1)
+    ps = probs.repeat(num_repeats, 1)
+    num, dim = xs.shape
+    device = xs.device
+    num_iters = int(dim * accept_rate) if num_iters == -1 else num_iters
+    count = 0
+    for _ in range(4):
+        ids = th.randperm(dim, device=device)
+        for i in range(dim):
+            idx = ids[i]
+            chosen_p0 = ps[:, idx]
+            chosen_xs = xs[:, idx]
+            chosen_ps = th.where(chosen_xs, chosen_p0, 1 - chosen_p0)
+            accept_masks = th.rand(num, device=device).lt((1 - chosen_ps) / chosen_ps)
+            xs[:, idx] = th.where(accept_masks, th.logical_not(chosen_xs), chosen_xs)
+            count += accept_masks.sum()
+            if count >= num * num_iters:
+                break
+        if count >= num * num_iters:
+            break
+    return xs

@@ -168,6 +168,7 @@ SIGNATURES = {
     "rlsb_best_record_packed": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i64, _vp, _vp]),
     "rlsb_best_pick_strided": (C.c_int, [_vp, _i32, _i32, _i64, _vp, _vp, _vp]),
     "rlsb_copy_rows": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp]),
+    "rlsb_mh_rows_round": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i64, _u64, _u64, _u32, _u32, _vp, _vp, _vp]),
     "rlsb_peer_exchange_handle_bytes": (_i64, []),
     "rlsb_peer_exchange_create": (C.c_int, [_i32, _i32, _i32, C.POINTER(_vp), _vp]),
     "rlsb_peer_exchange_connect": (C.c_int, [_vp, _vp]),

@@ -607,6 +607,93 @@ __global__ void torch_randint_kernel(TorchRng rng, int64_t calls, int64_t numel,
   out[i] = (int64_t)(torch_philox_u32(rng, (uint64_t)(i / numel), (uint32_t)(i % numel)) % range);
 }
 
+// ---- row-major independent-site Metropolis (metropolis_hastings_sampling_TNCO, rlsolver/envs/env_L2A.py:233-276).
+// One round of the reference: ids = randperm(dim); for i in range(dim): column ids[i] of EVERY row proposes a flip,
+// accepted when rand(num)[row] < (1 - q) / q with q = p if the bit is set else 1 - p; the accepted flips are counted and
+// the loop stops after the first column at which the running count reaches the target.  Within a round every column is
+// visited once and a decision reads nothing but its own bit, so all dim x num decisions are independent: (1) count the
+// accepts per position with the uniform of torch call number i, (2) one CTA scans the counts for the stop position,
+// (3) apply the flips of the positions up to it.  (1) and (3) recompute the same Philox numbers.
+__device__ __forceinline__ bool mh_accept(const TorchRng& rng, const float* __restrict__ probs, const uint8_t* __restrict__ xs,
+                                          int64_t row, int64_t src_row, int dim, int col, uint32_t call) {
+  const float p0 = __ldg(probs + src_row * dim + col);
+  const float q = xs[row * dim + col] ? p0 : __fsub_rn(1.f, p0);
+  const float rate = __fdiv_rn(__fsub_rn(1.f, q), q);
+  return torch_uniform_from_u32(torch_philox_u32(rng, call, (uint32_t)row)) < rate;
+}
+
+// grid = (row blocks, positions); counts[i] += accepts of position i
+__global__ void __launch_bounds__(256) mh_rows_count_kernel(TorchRng rng, const float* __restrict__ probs,
+                                                            const uint8_t* __restrict__ xs, const int64_t* __restrict__ perm,
+                                                            int64_t num, int64_t num_src, int dim, int32_t* __restrict__ counts) {
+  const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int i = blockIdx.y;
+  bool acc = false;
+  if (row < num) acc = mh_accept(rng, probs, xs, row, row % num_src, dim, (int)perm[i], (uint32_t)i);
+  const int c = __popc(__ballot_sync(kFull, acc));
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(counts + i, c);
+}
+
+// state[0] = running accept count (int64, in/out), state[1] = positions of this round that were visited (out)
+__global__ void __launch_bounds__(1024) mh_rows_stop_kernel(const int32_t* __restrict__ counts, int dim, int64_t target,
+                                                            int64_t* __restrict__ state) {
+  __shared__ int64_t sSum[32];
+  __shared__ int64_t sBase;
+  __shared__ int sStop;
+  if (threadIdx.x == 0) sBase = state[0], sStop = dim;      // dim = never reached: every position is visited
+  __syncthreads();
+  for (int base = 0; base < dim && sStop == dim; base += 1024) {
+    const int i = base + threadIdx.x;
+    int64_t v = i < dim ? counts[i] : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int64_t o = __shfl_up_sync(kFull, v, off);
+      if (lane >= off) v += o;
+    }
+    if (lane == 31) sSum[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      int64_t w = sSum[lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int64_t o = __shfl_up_sync(kFull, w, off);
+        if (lane >= off) w += o;
+      }
+      sSum[lane] = w;
+    }
+    __syncthreads();
+    const int64_t incl = sBase + v + (warp ? sSum[warp - 1] : 0);
+    if (i < dim && incl >= target) atomicMin(&sStop, i);
+    __syncthreads();
+    if (threadIdx.x == 1023) sBase = incl;                   // only used when no position of this chunk stopped
+    __syncthreads();
+  }
+  // the count after the last visited position
+  __shared__ int64_t sTotal;
+  if (threadIdx.x == 0) sTotal = 0;
+  __syncthreads();
+  const int last = sStop < dim ? sStop : dim - 1;
+  int64_t part = 0;
+  for (int i = threadIdx.x; i <= last; i += 1024) part += counts[i];
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) part += __shfl_xor_sync(kFull, part, off);
+  if ((threadIdx.x & 31) == 0 && part) atomicAdd(reinterpret_cast<unsigned long long*>(&sTotal), (unsigned long long)part);
+  __syncthreads();
+  if (threadIdx.x == 0) state[0] += sTotal, state[1] = last + 1;
+}
+
+__global__ void __launch_bounds__(256) mh_rows_apply_kernel(TorchRng rng, const float* __restrict__ probs,
+                                                            uint8_t* __restrict__ xs, const int64_t* __restrict__ perm,
+                                                            int64_t num, int64_t num_src, int dim,
+                                                            const int64_t* __restrict__ state) {
+  const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int i = blockIdx.y;
+  if (row >= num || i >= (int)state[1]) return;
+  const int col = (int)perm[i];
+  if (mh_accept(rng, probs, xs, row, row % num_src, dim, col, (uint32_t)i)) xs[row * dim + col] ^= 1;
+}
+
 static TorchRng make_rng(uint64_t seed, uint64_t offset, uint32_t threads, uint32_t iters) {
   TorchRng r;
   r.seed = seed, r.offset4 = offset / 4, r.threads = threads ? threads : 1, r.iters_per_call = iters ? iters : 1;
@@ -845,6 +932,29 @@ int rlsb_subset_sampling(uint8_t* xs, int64_t rows, int32_t num_nodes, int64_t n
   const int64_t tasks = rows * top_k;
   subset_kernel<<<(unsigned)((tasks + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       xs, rows, num_nodes, num_sims, top_k, ids, vals, explicit_u, make_rng(seed, offset, rng_threads, rng_iters));
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+int rlsb_mh_rows_round(const float* probs, uint8_t* xs, const int64_t* perm, int64_t num_rows, int64_t num_sims,
+                       int32_t dim, int64_t target, uint64_t seed, uint64_t offset, uint32_t rng_threads, uint32_t rng_iters,
+                       int64_t* state, int32_t* counts, void* stream) {
+  using namespace rlsb;
+  RLSB_REQUIRE(num_rows >= 0 && num_sims > 0 && dim > 0 && dim <= 65535 && num_rows % num_sims == 0, RLSB_ERR_INVALID,
+               "mh_rows_round: bad shape (rows must be num_repeats * num_sims, at most 65535 columns)");
+  RLSB_REQUIRE(num_rows < (int64_t(1) << 31), RLSB_ERR_UNSUPPORTED, "mh_rows_round: more than 2^31 rows");
+  if (num_rows == 0) return RLSB_OK;
+  RLSB_REQUIRE(probs && xs && perm && state && counts, RLSB_ERR_INVALID, "mh_rows_round: null pointer");
+  RLSB_REQUIRE(rng_threads > 0 && rng_iters > 0, RLSB_ERR_INVALID, "mh_rows_round: no random source");
+  auto st = static_cast<cudaStream_t>(stream);
+  const TorchRng rng = make_rng(seed, offset, rng_threads, rng_iters);
+  RLSB_CUDA_OK(cudaMemsetAsync(counts, 0, (size_t)dim * sizeof(int32_t), st));
+  const dim3 grid((unsigned)((num_rows + 255) / 256), (unsigned)dim);
+  mh_rows_count_kernel<<<grid, 256, 0, st>>>(rng, probs, xs, perm, num_rows, num_sims, dim, counts);
+  RLSB_LAUNCH_OK();
+  mh_rows_stop_kernel<<<1, 1024, 0, st>>>(counts, dim, target, state);
+  RLSB_LAUNCH_OK();
+  mh_rows_apply_kernel<<<grid, 256, 0, st>>>(rng, probs, xs, perm, num_rows, num_sims, dim, state);
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }

@@ -158,4 +158,43 @@ class EnvMaxcut:
         return st.ls_section(ws, num_sims, "packed").view(st.tiles(num_sims), st.padded_nodes), vs
 
 
-__all__ = ["EnvMaxcut", "update_xs_by_vs"]
+def metropolis_hastings_sampling_TNCO(probs: TEN, start_xs: TEN, num_repeats: int, num_iters: int = -1,
+                                      accept_rate: float = 0.25) -> TEN:
+    """env_L2A.py:233-276: row-major independent-site Metropolis toward product Bernoulli(probs) -- `num_repeats`
+    copies of every start row, up to 4 rounds over the columns in a random order, stopping after the column at which
+    the number of accepted flips reaches rows * num_iters (default: dim * accept_rate per row).
+    RNG == the reference's: one `th.randperm(dim)` per round (torch's own call) and one `th.rand(rows)` per visited
+    column, recomputed in the kernels from the generator state, which is advanced past exactly the calls the reference
+    would have made -- same seed, same samples, same generator state afterwards.  One host sync per round (the
+    reference has one per column)."""
+    from .. import _lib, rng
+    from ..graph_store import on_device
+    dev = require_cuda(start_xs.device)
+    if probs.shape != start_xs.shape or start_xs.dim() != 2 or start_xs.dtype != th.bool:
+        raise TypeError("probs float32 [S, dim] and start_xs bool [S, dim] are required")
+    xs = start_xs.repeat(num_repeats, 1).contiguous()
+    ps = probs.to(device=dev, dtype=th.float32).contiguous()
+    num, dim = xs.shape
+    num_sims = start_xs.shape[0]
+    num_iters = int(dim * accept_rate) if num_iters == -1 else num_iters
+    target = num * num_iters
+    if num == 0:
+        return xs
+    state = th.zeros((2,), dtype=th.int64, device=dev)
+    counts = th.empty((dim,), dtype=th.int32, device=dev)
+    lib = _lib.lib()
+    for _ in range(4):
+        ids = th.randperm(dim, device=dev)
+        seed, offset, threads, iters = rng.peek(dev, num)
+        with on_device(dev):
+            _lib.check(lib.rlsb_mh_rows_round(ps.data_ptr(), xs.data_ptr(), ids.data_ptr(), num, num_sims, dim, target, seed,
+                                              offset, threads, iters, state.data_ptr(), counts.data_ptr(),
+                                              th.cuda.current_stream(dev).cuda_stream), "mh_rows_round")
+        count, visited = (int(t) for t in state.tolist())
+        rng.advance(dev, num, visited)
+        if count >= target:
+            break
+    return xs
+
+
+__all__ = ["EnvMaxcut", "update_xs_by_vs", "metropolis_hastings_sampling_TNCO"]

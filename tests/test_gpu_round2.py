@@ -571,3 +571,29 @@ def test_evolutionary_replacement_equals_reference_indexing(maximize, cuda_devic
     else:       # minimise: ids[low_k:] has E - low_k rows, the reference's assignment raises on the shape mismatch
         with pytest.raises((RuntimeError, IndexError)):
             evolutionary_replacement(xs, vs, low_k, maximize)
+
+
+# ------------------------------------------------------------------ row-major Metropolis (a11, TNCO variant)
+@pytest.mark.parametrize("sims,dim,repeats,num_iters,sharp", [(6, 40, 3, -1, False), (5, 33, 2, 6, True), (3, 20, 4, 1, False),
+                                                              (64, 2000, 8, -1, False), (16, 1500, 4, 40, True),
+                                                              (7, 3000, 5, 0, False)])
+def test_row_major_metropolis_same_seed_same_samples(sims, dim, repeats, num_iters, sharp, cuda_device):
+    """metropolis_hastings_sampling_TNCO on the kernels == the torch restatement of env_L2A.py:233-276 on the same
+    device and seed: samples and the generator state afterwards (1 to 4 rounds, early stop inside a round, a stop
+    target of zero = exactly one column visited)."""
+    from oracle import torch_port as tp
+    from rlsolver_b200.envs.env_L2A import metropolis_hastings_sampling_TNCO
+    g = th.Generator(device=cuda_device).manual_seed(5)
+    probs = th.rand((sims, dim), device=cuda_device, generator=g)
+    if sharp:
+        probs = th.where(probs < 0.5, probs * 0.04 + 0.005, 1 - probs * 0.04)
+    start = th.rand((sims, dim), device=cuda_device, generator=g) < probs
+    start0 = start.clone()
+    th.manual_seed(99)
+    want = tp.metropolis_hastings_sampling_tnco(probs, start, repeats, num_iters)
+    end = th.cuda.get_rng_state(cuda_device)
+    th.manual_seed(99)
+    got = metropolis_hastings_sampling_TNCO(probs=probs, start_xs=start, num_repeats=repeats, num_iters=num_iters)
+    assert th.equal(got, want)
+    assert th.equal(th.cuda.get_rng_state(cuda_device), end)
+    assert th.equal(start, start0)            # the start rows are not modified
