@@ -36,6 +36,12 @@ def evolutionary_replacement(xs: TEN, vs: TEN, low_k: int, if_maximize: bool):
     num_sims = xs.shape[0]
     ids = vs.argsort()
     top_ids, low_ids = (ids[:-low_k], ids[-low_k:]) if if_maximize else (ids[:low_k], ids[low_k:])
+    if top_ids.shape[0] < num_sims - low_k:
+        # minimising, the reference indexes its low_k-row `top_ids` with a permutation of E - low_k > low_k numbers:
+        # IndexError on the CPU, a device-side assert (which poisons the CUDA context) on the GPU.  Same failure, raised
+        # on the host before anything is launched.
+        raise IndexError(f"index out of range: a permutation of {num_sims - low_k} indexes {top_ids.shape[0]} rows "
+                         f"(rlsolver/methods/util.py:91-92 with if_maximize=False)")
     replace_ids = top_ids[th.randperm(num_sims - low_k, device=xs.device)[:low_k]]
     if (xs.is_cuda and xs.dtype == th.bool and xs.dim() == 2 and xs.is_contiguous() and vs.dtype == th.int64
             and vs.is_contiguous() and replace_ids.numel() == low_ids.numel()):
