@@ -179,6 +179,8 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step_kernel(PecoC 
 // itself, and their 16 byte-sized fields are one 16-byte load -- no shuffles in the node loop (the first version spent
 // 700 instructions per warp, 70 % issue-active, on 13 rounds of three shuffles).
 constexpr int kPcLpe = 8, kPcNpl = 16;       // lanes per env, nodes per lane (N <= 128)
+// bits 0..3 -> 0x01 in bytes 0..3 (the partial products of the multiplier land on distinct bits: no carries)
+__device__ __forceinline__ uint32_t spread4(uint32_t nib) { return ((nib & 0xFu) * 0x00204081u) & 0x01010101u; }
 __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step8_kernel(PecoC p) {
   const int lane = threadIdx.x & 31, sub = lane & (kPcLpe - 1), grp = lane / kPcLpe, base = grp * kPcLpe;
   const int64_t env = ((int64_t)blockIdx.x * kPcWarps + (threadIdx.x >> 5)) * (32 / kPcLpe) + grp;
@@ -207,20 +209,30 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step8_kernel(PecoC
   uint32_t fw[4] = {fa.x, fa.y, fa.z, fa.w};
   const int sh = (sub & 1) * kPcNpl;             // my 16 bits inside the word
   const uint32_t abits = (arow >> sh) & 0xFFFFu, sbits = (srow >> sh) & 0xFFFFu, pbits = (sp >> sh) & 0xFFFFu;
-  int nonpos = 0, delta = 0;
+  // Four byte-sized fields per 32-bit word, handled together (the kernel is issue bound: 16 nodes x ~15 instructions per
+  // lane in the one-node-at-a-time form).  spread4 turns 4 bits into 0x01 flags of 4 bytes; the update adds +2 / -2 per
+  // flagged byte with a carry-free byte-wise add; "s_j (A s)_j <= 0" per byte is zero | (negative == spin up).
+  const uint32_t plus = s_old > 0 ? sbits : ~sbits;            // neighbours whose field moves by +2 (the others: -2)
+  const int rest = n - j0;                                      // my nodes below n
+  const uint32_t vbits = rest >= kPcNpl ? 0xFFFFu : (rest > 0 ? (1u << rest) - 1u : 0u);
+  int nonpos = 0;
 #pragma unroll
-  for (int t = 0; t < kPcNpl; ++t) {
-    const int j = j0 + t;
-    int v = (int)(int8_t)((fw[t >> 2] >> (8 * (t & 3))) & 0xFFu);
-    if ((abits >> t) & 1u) {                       // (A s)_j -= 2 A[a][j] s_old
-      v -= ((sbits >> t) & 1u) ? -2 * s_old : 2 * s_old;
-      fw[t >> 2] = (fw[t >> 2] & ~(0xFFu << (8 * (t & 3)))) | (((uint32_t)v & 0xFFu) << (8 * (t & 3)));
-    }
-    if (j < n) {
-      const int f = ((pbits >> t) & 1u) ? v : -v;   // fields_j = s_j (A s)_j with the flipped spin
-      nonpos += (int)(f <= 0);
-      if (j == a) delta = -f;
-    }
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t a4 = (abits >> (4 * q)) & 0xFu;
+    const uint32_t y = spread4(a4 & (plus >> (4 * q))) * 2u + spread4(a4 & ~(plus >> (4 * q))) * 0xFEu;
+    const uint32_t w = ((fw[q] & 0x7F7F7F7Fu) + (y & 0x7F7F7F7Fu)) ^ ((fw[q] ^ y) & 0x80808080u);
+    fw[q] = w;
+    const uint32_t neg = (w >> 7) & 0x01010101u;
+    const uint32_t zero = (~(((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) >> 7) & 0x01010101u;
+    const uint32_t up = spread4((pbits >> (4 * q)) & 0xFu);
+    nonpos += __popc((zero | (~(neg ^ up) & 0x01010101u)) & spread4((vbits >> (4 * q)) & 0xFu));
+  }
+  int delta = 0;
+  const int ta = a - j0;                                         // the acted node, if it is one of mine
+  if (ta >= 0 && ta < kPcNpl) {
+    const uint32_t wsel = (ta >> 2) == 0 ? fw[0] : (ta >> 2) == 1 ? fw[1] : (ta >> 2) == 2 ? fw[2] : fw[3];
+    const int v = (int)(int8_t)((wsel >> (8 * (ta & 3))) & 0xFFu);
+    delta = ((pbits >> ta) & 1u) ? -v : v;                       // -(s_a (A s)_a) with the flipped spin
   }
   // the lane's 16 fields go back as ONE 16-byte store (a group rewrites at most the env's 128 bytes, whole sectors)
   if (valid && has && abits) *reinterpret_cast<uint4*>(fl + j0) = make_uint4(fw[0], fw[1], fw[2], fw[3]);
