@@ -54,6 +54,7 @@ const char* rlsb_last_error(void);
 #define RLSB_DEBUG_GEN_PER_DRAW 32 /* RLSB_GEN_PER_DRAW=1: rlsb_ls_noise_masks uses the one-draw-per-thread generator (round-1 form) */
 #define RLSB_DEBUG_PECO_WARP_PER_ENV 64 /* RLSB_PECO_WARP_PER_ENV=1: rlsb_peco_compact_step uses one warp per env also for N <= 128 */
 #define RLSB_DEBUG_QUBO_NO_SPLITK 128 /* RLSB_QUBO_NO_SPLITK=1: rlsb_qubo_sweeps never splits the K range over several CTAs per chain group */
+#define RLSB_DEBUG_THRESH_PIPE 256 /* RLSB_LS_THRESH_PIPE=1: a threshold-only rlsb_ls_run keeps the pipelined tile kernel (round-2a form) instead of the warp-per-env kernel */
 int32_t rlsb_debug_flags(int32_t set_mask, int32_t clear_mask);
 
 /* ---- graph store: replaces EnvMaxcut.__init__ (rlsolver/envs/env_L2A.py:25-52),

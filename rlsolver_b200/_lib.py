@@ -183,6 +183,7 @@ SIGNATURES = {
 
 DEBUG_PLAIN_MASKS, DEBUG_FULL_CUT, DEBUG_LS_SKIP, DEBUG_LS_TIMES = 1, 2, 4, 8
 DEBUG_CARVEOUT_DEFAULT, DEBUG_GEN_PER_DRAW, DEBUG_PECO_WARP_PER_ENV, DEBUG_QUBO_NO_SPLITK = 16, 32, 64, 128
+DEBUG_THRESH_PIPE = 256
 
 
 def debug_flags(set_mask: int = 0, clear_mask: int = 0) -> int:

@@ -119,7 +119,8 @@ static int debug_flags_from_env() {
                                                         {"RLSB_CARVEOUT_DEFAULT", RLSB_DEBUG_CARVEOUT_DEFAULT},
                                                         {"RLSB_GEN_PER_DRAW", RLSB_DEBUG_GEN_PER_DRAW},
                                                         {"RLSB_PECO_WARP_PER_ENV", RLSB_DEBUG_PECO_WARP_PER_ENV},
-                                                        {"RLSB_QUBO_NO_SPLITK", RLSB_DEBUG_QUBO_NO_SPLITK}};
+                                                        {"RLSB_QUBO_NO_SPLITK", RLSB_DEBUG_QUBO_NO_SPLITK},
+                                                        {"RLSB_LS_THRESH_PIPE", RLSB_DEBUG_THRESH_PIPE}};
   for (const auto& v : vars) {
     const char* e = getenv(v.name);
     if (e && e[0] == '1') f |= v.bit;

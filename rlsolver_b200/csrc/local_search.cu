@@ -138,6 +138,52 @@ __global__ void __launch_bounds__(256) ls_thresh_kernel(GraphDev g, const CrossT
   if (lane == 0) thresh[env] = key_float(best);
 }
 
+// The threshold alone (the fused-RNG path: rlsb_ls_run with no noisy iteration and no finish).  One warp per
+// environment over the row-major uint8 copy of the cross counts: 4096 independent warps instead of the pipelined
+// kernel's 128 CTAs -- that kernel's strength is keeping a tile resident across several passes, which a lone threshold
+// pass has no use for (25.9 us at G22 x 4096 against the ~7 us its 41 MB take at HBM speed).  A lane takes four
+// consecutive nodes per trip: one 16-byte streaming load of noise, one word of counts, rd_std / degree words as
+// vectors (L1 resident: every warp reads the same 16 KB).
+template <int KMAX>
+__global__ void __launch_bounds__(256) ls_thresh_rows_kernel(int n, int np, const uint8_t* __restrict__ cross_rows,
+                                                             const float* __restrict__ rd_std,
+                                                             const int32_t* __restrict__ degm, int mult,
+                                                             const float* __restrict__ noise, int kth_big,
+                                                             int64_t num_envs, float* __restrict__ thresh) {
+  const int lane = threadIdx.x & 31;
+  const int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (env >= num_envs) return;
+  TopList<KMAX> tl;
+  tl.clear();
+  const uint32_t* crow = reinterpret_cast<const uint32_t*>(cross_rows + env * (int64_t)np);
+  const float* nrow = noise + env * (int64_t)n;
+  const int groups = n >> 2;
+  auto take = [&](int q, const float4& z, uint32_t c) {
+    const float4 rd = __ldg(reinterpret_cast<const float4*>(rd_std) + q);
+    const int4 dm = __ldg(reinterpret_cast<const int4*>(degm) + q);
+    tl.push(spin_rand(dm.x, -mult, (int)(c & 0xffu), z.x, rd.x));
+    tl.push(spin_rand(dm.y, -mult, (int)((c >> 8) & 0xffu), z.y, rd.y));
+    tl.push(spin_rand(dm.z, -mult, (int)((c >> 16) & 0xffu), z.z, rd.z));
+    tl.push(spin_rand(dm.w, -mult, (int)(c >> 24), z.w, rd.w));
+  };
+  int q = lane;
+  for (; q + 96 < groups; q += 128) {                 // four trips in flight per lane
+    const float4 z0 = ldg_stream4(nrow + 4 * q), z1 = ldg_stream4(nrow + 4 * (q + 32));
+    const float4 z2 = ldg_stream4(nrow + 4 * (q + 64)), z3 = ldg_stream4(nrow + 4 * (q + 96));
+    const uint32_t c0 = __ldg(crow + q), c1 = __ldg(crow + q + 32), c2 = __ldg(crow + q + 64), c3 = __ldg(crow + q + 96);
+    take(q, z0, c0), take(q + 32, z1, c1), take(q + 64, z2, c2), take(q + 96, z3, c3);
+  }
+  for (; q < groups; q += 32) take(q, ldg_stream4(nrow + 4 * q), __ldg(crow + q));
+  uint32_t best = 0;
+  for (int r = 0; r < kth_big; ++r) {
+    const uint32_t head = float_key(tl.top[0]);
+    best = __reduce_max_sync(kFull, head);
+    const unsigned who = __ballot_sync(kFull, head == best);
+    if (lane == __ffs(who) - 1) tl.pop();
+  }
+  if (lane == 0) thresh[env] = key_float(best);
+}
+
 // ---------------------------------------------------------------- fused search kernel
 constexpr int kLSThreads = 512;                 // consumer threads
 constexpr int kLSWarps = kLSThreads / 32;
@@ -1233,6 +1279,15 @@ static int run_search(const GraphDev& g, int64_t num_envs, int64_t* vs, int ws_m
   for (int k = 0; k < num_iters; ++k) {
     RLSB_REQUIRE(h_noise_ptrs[k] != nullptr, RLSB_ERR_INVALID, "ls_search: null noise tensor %d", k);
     pipe = pipe && aligned16(h_noise_ptrs[k]);
+  }
+  // the threshold on its own (what the fused-RNG path asks for): one warp per env over the row-major counts
+  if (thresh_noise && num_iters == 0 && !finish && w.cross_rows && dc != 2 && g.n % 4 == 0 && aligned16(thresh_noise) &&
+      kth_big <= 10 && !(debug_flags() & RLSB_DEBUG_THRESH_PIPE)) {
+    ls_thresh_rows_kernel<10><<<(unsigned)((num_envs + 7) / 8), 256, 0, st>>>(g.n, g.np, w.cross_rows, w.rd_std, w.degm,
+                                                                            ws_mult, thresh_noise, kth_big, num_envs,
+                                                                            w.thresh);
+    RLSB_LAUNCH_OK();
+    return RLSB_OK;
   }
   if (thresh_noise && !pipe) {
     if (int rc = dc == 2 ? launch_thresh<uint16_t>(g, w, ws_mult, thresh_noise, kth_big, num_envs, st)

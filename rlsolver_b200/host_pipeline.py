@@ -23,6 +23,8 @@ from typing import Callable, Optional
 
 import torch as th
 
+from .graph_store import on_device
+
 TEN = th.Tensor
 
 
@@ -39,7 +41,12 @@ class HostPipeline:
         if depth < 2:
             raise ValueError("depth must be at least 2")
         self.sim, self.envs, self.layout, self.depth = sim, int(num_envs), layout, int(depth)
-        self.device = dev = sim.device
+        self.device = sim.device
+        with on_device(self.device):         # streams, graphs and events belong to the simulator's device
+            self._build(num_iters, num_spin, noise_std, pre_step, in_graph_post, eager_post)
+
+    def _build(self, num_iters, num_spin, noise_std, pre_step, in_graph_post, eager_post) -> None:
+        sim, layout, depth, dev = self.sim, self.layout, self.depth, self.device
         st = sim.store
         self.compute = th.cuda.current_stream(dev)
         self.s_in, self.s_out = th.cuda.Stream(device=dev), th.cuda.Stream(device=dev)
@@ -94,6 +101,10 @@ class HostPipeline:
         """Enqueues one batch: h_in -> device, the step, results -> h_out (same layout as h_in) and h_vs (int64 [E]).
         Returns at once; the host tensors must stay alive (and pinned, for the copies to be asynchronous) until
         `drain()`."""
+        with on_device(self.device):
+            self._submit(h_in, h_out, h_vs)
+
+    def _submit(self, h_in: TEN, h_out: TEN, h_vs: TEN) -> None:
         b = self.count % self.depth
         self.count += 1
         with th.cuda.stream(self.s_in):

@@ -595,3 +595,35 @@ def test_row_major_metropolis_same_seed_same_samples(sims, dim, repeats, num_ite
     assert th.equal(got, want)
     assert th.equal(th.cuda.get_rng_state(cuda_device), end)
     assert th.equal(start, start0)            # the start rows are not modified
+
+
+# ------------------------------------------------------------------ threshold-only pass: warp per env == tile pipeline
+@pytest.mark.parametrize("name,envs,spin,bidir", [("G22", 4096, 8, True), ("G70", 2048 + 17, 4, False), ("G14", 300, 8, True)])
+def test_threshold_rows_kernel_equals_pipelined_kernel(name, envs, spin, bidir, cuda_device):
+    """rlsb_ls_run(thresh only): the warp-per-env kernel over the row-major counts and the pipelined tile kernel
+    (RLSB_DEBUG_THRESH_PIPE) produce the same float32 thresholds, bit for bit, and they equal torch.kthvalue of the
+    reference's expression evaluated with torch ops on the same device."""
+    from rlsolver_b200 import _lib
+    from rlsolver_b200.envs.env_L2A import EnvMaxcut
+    sim = EnvMaxcut(mygraph=gset_like(name), device=cuda_device, if_bidirectional=bidir)
+    st, n = sim.store, sim.num_nodes
+    th.manual_seed(5)
+    xs = sim.generate_xs_randomly(envs)
+    ws = st.ls_workspace(envs)
+    vs = st.ls_begin(xs, None, 1, 0.3, ws)
+    noise = th.randn((envs, n), device=cuda_device)
+    got = []
+    for flag in (0, _lib.DEBUG_THRESH_PIPE):
+        _lib.debug_flags(flag, _lib.DEBUG_THRESH_PIPE ^ flag)
+        st.ls_section(ws, envs, "thresh").fill_(float("nan"))
+        st.ls_run(vs, 1, noise, spin, [], False, None, ws)
+        got.append(st.ls_section(ws, envs, "thresh").clone())
+    _lib.debug_flags(0, _lib.DEBUG_THRESH_PIPE)
+    assert th.equal(got[0], got[1]) and not bool(th.isnan(got[0]).any())
+    # the reference's expression (env_L2A.py:90-96) in torch on the same tensors
+    vs_raw = sim.calculate_obj_values_for_loop(xs, if_sum=False)
+    wsr = sim.n0_num_n1 - (2 if bidir else 1) * vs_raw
+    ws_std = wsr.max(dim=0, keepdim=True)[0] - wsr.min(dim=0, keepdim=True)[0]
+    spin_rand = wsr + noise * (ws_std.float() * 0.3)
+    want = th.kthvalue(spin_rand, k=n - spin, dim=1)[0]
+    assert th.equal(got[0], want)
