@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) ls_thresh_kernel(GraphDev g, const CrossT
 // consecutive nodes per trip: one 16-byte streaming load of noise, one word of counts, rd_std / degree words as
 // vectors (L1 resident: every warp reads the same 16 KB).
 template <int KMAX>
-__global__ void __launch_bounds__(256) ls_thresh_rows_kernel(int n, int np, const uint8_t* __restrict__ cross_rows,
+__global__ void __launch_bounds__(128) ls_thresh_rows_kernel(int n, int np, const uint8_t* __restrict__ cross_rows,
                                                              const float* __restrict__ rd_std,
                                                              const int32_t* __restrict__ degm, int mult,
                                                              const float* __restrict__ noise, int kth_big,
@@ -166,14 +166,45 @@ __global__ void __launch_bounds__(256) ls_thresh_rows_kernel(int n, int np, cons
     tl.push(spin_rand(dm.z, -mult, (int)((c >> 16) & 0xffu), z.z, rd.z));
     tl.push(spin_rand(dm.w, -mult, (int)(c >> 24), z.w, rd.w));
   };
+  // Phase 1: the first two trips (256 nodes of the row) go into the lanes' lists unconditionally; the kth largest of
+  // those is a lower bound of the row's kth largest.  Phase 2: only values above that bound can matter, and they are
+  // rare (~k ln(N / 256) per row), so the 2 x KMAX-instruction insertion all but disappears from the loop (the
+  // unconditional form spent 2800 instructions per warp, 11.4 M in all, and ran as long as the pipelined kernel).
   int q = lane;
+  for (int trip = 0; trip < 2 && q < groups; ++trip, q += 32) take(q, ldg_stream4(nrow + 4 * q), __ldg(crow + q));
+  float bound;
+  {
+    TopList<KMAX> probe = tl;
+    uint32_t best = 0;
+    for (int r = 0; r < kth_big; ++r) {
+      const uint32_t head = float_key(probe.top[0]);
+      best = __reduce_max_sync(kFull, head);
+      const unsigned who = __ballot_sync(kFull, head == best);
+      if (lane == __ffs(who) - 1) probe.pop();
+    }
+    bound = key_float(best);            // -inf while the row has fewer than kth_big values
+  }
+  auto take_above = [&](int qq, const float4& z, uint32_t c) {
+    const float4 rd = __ldg(reinterpret_cast<const float4*>(rd_std) + qq);
+    const int4 dm = __ldg(reinterpret_cast<const int4*>(degm) + qq);
+    const float s0 = spin_rand(dm.x, -mult, (int)(c & 0xffu), z.x, rd.x);
+    const float s1 = spin_rand(dm.y, -mult, (int)((c >> 8) & 0xffu), z.y, rd.y);
+    const float s2 = spin_rand(dm.z, -mult, (int)((c >> 16) & 0xffu), z.z, rd.z);
+    const float s3 = spin_rand(dm.w, -mult, (int)(c >> 24), z.w, rd.w);
+    if (fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)) > bound) {
+      if (s0 > bound) tl.push(s0);
+      if (s1 > bound) tl.push(s1);
+      if (s2 > bound) tl.push(s2);
+      if (s3 > bound) tl.push(s3);
+    }
+  };
   for (; q + 96 < groups; q += 128) {                 // four trips in flight per lane
     const float4 z0 = ldg_stream4(nrow + 4 * q), z1 = ldg_stream4(nrow + 4 * (q + 32));
     const float4 z2 = ldg_stream4(nrow + 4 * (q + 64)), z3 = ldg_stream4(nrow + 4 * (q + 96));
     const uint32_t c0 = __ldg(crow + q), c1 = __ldg(crow + q + 32), c2 = __ldg(crow + q + 64), c3 = __ldg(crow + q + 96);
-    take(q, z0, c0), take(q + 32, z1, c1), take(q + 64, z2, c2), take(q + 96, z3, c3);
+    take_above(q, z0, c0), take_above(q + 32, z1, c1), take_above(q + 64, z2, c2), take_above(q + 96, z3, c3);
   }
-  for (; q < groups; q += 32) take(q, ldg_stream4(nrow + 4 * q), __ldg(crow + q));
+  for (; q < groups; q += 32) take_above(q, ldg_stream4(nrow + 4 * q), __ldg(crow + q));
   uint32_t best = 0;
   for (int r = 0; r < kth_big; ++r) {
     const uint32_t head = float_key(tl.top[0]);
@@ -1283,7 +1314,7 @@ static int run_search(const GraphDev& g, int64_t num_envs, int64_t* vs, int ws_m
   // the threshold on its own (what the fused-RNG path asks for): one warp per env over the row-major counts
   if (thresh_noise && num_iters == 0 && !finish && w.cross_rows && dc != 2 && g.n % 4 == 0 && aligned16(thresh_noise) &&
       kth_big <= 10 && !(debug_flags() & RLSB_DEBUG_THRESH_PIPE)) {
-    ls_thresh_rows_kernel<10><<<(unsigned)((num_envs + 7) / 8), 256, 0, st>>>(g.n, g.np, w.cross_rows, w.rd_std, w.degm,
+    ls_thresh_rows_kernel<10><<<(unsigned)((num_envs + 3) / 4), 128, 0, st>>>(g.n, g.np, w.cross_rows, w.rd_std, w.degm,
                                                                             ws_mult, thresh_noise, kth_big, num_envs,
                                                                             w.thresh);
     RLSB_LAUNCH_OK();
