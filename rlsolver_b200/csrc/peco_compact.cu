@@ -172,13 +172,18 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step_kernel(PecoC 
   }
 }
 
-// Eight lanes per env (N <= 128): four envs share a warp, so four times as many dependent load chains are in flight
-// per resident warp -- the step is bound by the latency of its two dependent HBM trips, and at 10^6 envs of N = 100 a
-// warp per env leaves the memory system idle most of the time.  Lane `sub` of a group owns the 16 nodes
-// 16 sub .. 16 sub + 15: they sit in ONE word of the spin / adjacency / sign rows (word sub / 2), which the lane loads
-// itself, and their 16 byte-sized fields are one 16-byte load -- no shuffles in the node loop (the first version spent
-// 700 instructions per warp, 70 % issue-active, on 13 rounds of three shuffles).
-constexpr int kPcLpe = 8, kPcNpl = 16;       // lanes per env, nodes per lane (N <= 128)
+// A few lanes per env (N <= 128): several envs share a warp, so several times as many dependent load chains are in
+// flight per resident warp as with a warp per env.  Lane `sub` of a group owns kPcNpl consecutive nodes: they sit in ONE
+// word of the spin / adjacency / sign rows, which the lane loads itself, and their byte-sized fields are 16-byte loads --
+// no shuffles in the node loop.  History of this kernel (2^20 ER-100 envs): warp per env 0.35 ms; 8 lanes x 16 nodes
+// with shuffles 0.233; no shuffles 0.186; byte fields 0.178; four fields per word 0.1435 (ncu: 94 % issue-active before
+// that step, so instructions per env are what counts); 4 lanes x 32 nodes halves the per-env share of everything
+// outside the node loop (addresses, scalars, reward arithmetic are computed by every lane of a group).
+constexpr int kPcLpe = 4, kPcNpl = 32;       // lanes per env, nodes per lane (kPcLpe * kPcNpl = 128 >= N)
+constexpr int kPcLpw = 32 / kPcNpl;          // lanes per 32-bit word of the bit rows
+constexpr int kPcFw = kPcNpl / 4;            // 32-bit words of byte fields per lane
+constexpr uint32_t kPcGroupMask = (1u << kPcLpe) - 1u;
+static_assert(kPcLpe * kPcNpl == kPcByteFields && kPcNpl % 16 == 0 && 32 % kPcNpl == 0, "lane geometry");
 // bits 0..3 -> 0x01 in bytes 0..3 (the partial products of the multiplier land on distinct bits: no carries)
 __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return ((nib & 0xFu) * 0x00204081u) & 0x01010101u; }
 __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step8_kernel(PecoC p) {
@@ -187,13 +192,18 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step8_kernel(PecoC
   const bool live = env < p.num_envs;
   const int64_t ev = live ? env : 0;             // dead groups shadow env 0 read-only (all lanes stay in the shuffles)
   const int n = p.n, W = p.words;
-  const int myw = sub >> 1, j0 = kPcNpl * sub;   // my word, my first node
+  const int myw = sub / kPcLpw, j0 = kPcNpl * sub;   // my word, my first node
   const bool has = myw < W;                      // the lane owns nodes of this graph (np >= 32 W covers them)
   int8_t* fl = static_cast<int8_t*>(p.fields) + ev * (int64_t)p.np;        // N <= 128: byte fields
   const int64_t a_raw = p.action[ev];
   const uint32_t sp0 = has ? p.spins[ev * W + myw] : 0u;
-  uint4 fa = make_uint4(0, 0, 0, 0);
-  if (has) fa = *reinterpret_cast<const uint4*>(fl + j0);
+  uint32_t fw[kPcFw];
+#pragma unroll
+  for (int v4 = 0; v4 < kPcFw / 4; ++v4) {
+    uint4 f = make_uint4(0, 0, 0, 0);
+    if (has) f = *reinterpret_cast<const uint4*>(fl + j0 + 16 * v4);
+    fw[4 * v4] = f.x, fw[4 * v4 + 1] = f.y, fw[4 * v4 + 2] = f.z, fw[4 * v4 + 3] = f.w;
+  }
   const float score0 = p.score[ev], best_obs = p.best_score[ev];
   unsigned long long key0 = 0ull;
   if (p.hset) key0 = p.hkey[ev];
@@ -203,21 +213,21 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step8_kernel(PecoC
   const int wa = a >> 5, ba = a & 31;
   const uint32_t arow = has ? __ldg(p.adj + (ev * n + a) * W + myw) : 0u;
   const uint32_t srow = (p.sgn && has) ? __ldg(p.sgn + ev * p.sgn_stride + (int64_t)a * W + myw) : 0u;
-  const int s_old = ((__shfl_sync(kFull, sp0, base + 2 * wa) >> ba) & 1u) ? 1 : -1;
-  const uint32_t sp = (myw == wa) ? sp0 ^ (1u << ba) : sp0;      // both lanes of the word see the flipped spin
-  if (valid && sub == 2 * wa) p.spins[env * W + wa] = sp;
-  uint32_t fw[4] = {fa.x, fa.y, fa.z, fa.w};
-  const int sh = (sub & 1) * kPcNpl;             // my 16 bits inside the word
-  const uint32_t abits = (arow >> sh) & 0xFFFFu, sbits = (srow >> sh) & 0xFFFFu, pbits = (sp >> sh) & 0xFFFFu;
-  // Four byte-sized fields per 32-bit word, handled together (the kernel is issue bound: 16 nodes x ~15 instructions per
-  // lane in the one-node-at-a-time form).  spread4 turns 4 bits into 0x01 flags of 4 bytes; the update adds +2 / -2 per
-  // flagged byte with a carry-free byte-wise add; "s_j (A s)_j <= 0" per byte is zero | (negative == spin up).
+  const int s_old = ((__shfl_sync(kFull, sp0, base + kPcLpw * wa) >> ba) & 1u) ? 1 : -1;
+  const uint32_t sp = (myw == wa) ? sp0 ^ (1u << ba) : sp0;      // every lane of the word sees the flipped spin
+  if (valid && sub == kPcLpw * wa) p.spins[env * W + wa] = sp;
+  const int sh = (sub % kPcLpw) * kPcNpl;        // my bits inside the word
+  constexpr uint32_t kMine = kPcNpl == 32 ? 0xFFFFFFFFu : ((1u << (kPcNpl & 31)) - 1u);
+  const uint32_t abits = (arow >> sh) & kMine, sbits = (srow >> sh) & kMine, pbits = (sp >> sh) & kMine;
+  // Four byte-sized fields per 32-bit word, handled together.  spread4 turns 4 bits into 0x01 flags of 4 bytes; the
+  // update adds +2 / -2 per flagged byte with a carry-free byte-wise add; "s_j (A s)_j <= 0" per byte is
+  // zero | (negative == spin up).
   const uint32_t plus = s_old > 0 ? sbits : ~sbits;            // neighbours whose field moves by +2 (the others: -2)
   const int rest = n - j0;                                      // my nodes below n
-  const uint32_t vbits = rest >= kPcNpl ? 0xFFFFu : (rest > 0 ? (1u << rest) - 1u : 0u);
+  const uint32_t vbits = rest >= kPcNpl ? kMine : (rest > 0 ? (1u << rest) - 1u : 0u);
   int nonpos = 0;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < kPcFw; ++q) {
     const uint32_t a4 = (abits >> (4 * q)) & 0xFu;
     const uint32_t y = spread4(a4 & (plus >> (4 * q))) * 2u + spread4(a4 & ~(plus >> (4 * q))) * 0xFEu;
     const uint32_t w = ((fw[q] & 0x7F7F7F7Fu) + (y & 0x7F7F7F7Fu)) ^ ((fw[q] ^ y) & 0x80808080u);
@@ -230,12 +240,18 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step8_kernel(PecoC
   int delta = 0;
   const int ta = a - j0;                                         // the acted node, if it is one of mine
   if (ta >= 0 && ta < kPcNpl) {
-    const uint32_t wsel = (ta >> 2) == 0 ? fw[0] : (ta >> 2) == 1 ? fw[1] : (ta >> 2) == 2 ? fw[2] : fw[3];
+    uint32_t wsel = fw[0];
+#pragma unroll
+    for (int q = 1; q < kPcFw; ++q) wsel = (ta >> 2) == q ? fw[q] : wsel;
     const int v = (int)(int8_t)((wsel >> (8 * (ta & 3))) & 0xFFu);
     delta = ((pbits >> ta) & 1u) ? -v : v;                       // -(s_a (A s)_a) with the flipped spin
   }
-  // the lane's 16 fields go back as ONE 16-byte store (a group rewrites at most the env's 128 bytes, whole sectors)
-  if (valid && has && abits) *reinterpret_cast<uint4*>(fl + j0) = make_uint4(fw[0], fw[1], fw[2], fw[3]);
+  // the lane's fields go back as 16-byte stores (a group rewrites at most the env's 128 bytes, whole sectors)
+  if (valid && has && abits) {
+#pragma unroll
+    for (int v4 = 0; v4 < kPcFw / 4; ++v4)
+      *reinterpret_cast<uint4*>(fl + j0 + 16 * v4) = make_uint4(fw[4 * v4], fw[4 * v4 + 1], fw[4 * v4 + 2], fw[4 * v4 + 3]);
+  }
 #pragma unroll
   for (int off = kPcLpe / 2; off >= 1; off >>= 1) {
     nonpos += __shfl_xor_sync(kFull, nonpos, off);
@@ -257,11 +273,11 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step8_kernel(PecoC
     const uint32_t mask = (uint32_t)p.hcap - 1u;
     const uint32_t h = (uint32_t)(key >> 17) & mask;
     bool fresh = true, done = !valid;
-    for (int probe = 0; probe < p.hcap; probe += kPcLpe) {      // windows of 8 slots per group; groups finish on their own
+    for (int probe = 0; probe < p.hcap; probe += kPcLpe) {      // windows of kPcLpe slots per group; groups finish on their own
       const uint32_t slot = (h + probe + sub) & mask;
       const unsigned long long v = done ? ~0ull : tab[slot];
-      const uint32_t hit = (__ballot_sync(kFull, !done && v == key) >> base) & 0xFFu;
-      const uint32_t empty = (__ballot_sync(kFull, !done && v == 0ull) >> base) & 0xFFu;
+      const uint32_t hit = (__ballot_sync(kFull, !done && v == key) >> base) & kPcGroupMask;
+      const uint32_t empty = (__ballot_sync(kFull, !done && v == 0ull) >> base) & kPcGroupMask;
       const int first_empty = empty ? __ffs(empty) - 1 : kPcLpe;
       if (!done) {
         if (hit && (__ffs(hit) - 1) < first_empty) fresh = false, done = true;
@@ -275,11 +291,11 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_step8_kernel(PecoC
     if (p.use_stag && !fresh) rew = __fsub_rn(rew, p.stag);
     if (p.use_basin && nonpos == n && fresh) rew = __fadd_rn(rew, p.basin);
   }
-  const bool none_left = ((__ballot_sync(kFull, has && sp != 0u) >> base) & 0xFFu) == 0u;
+  const bool none_left = ((__ballot_sync(kFull, has && sp != 0u) >> base) & kPcGroupMask) == 0u;
   if (live && sub == 0 && p.done) p.done[env] = (uint8_t)(p.last_step || (valid && p.irreversible && none_left));
   if (!valid) return;
   const bool better = score > best_obs;
-  if (better && has && !(sub & 1)) p.best_spins[env * W + myw] = sp;
+  if (better && has && sub % kPcLpw == 0) p.best_spins[env * W + myw] = sp;
   if (sub == 0) {
     p.score[env] = score;
     p.best_score[env] = better ? score : best_obs;
