@@ -150,6 +150,8 @@ __global__ void __launch_bounds__(128) ls_thresh_rows_kernel(int n, int np, cons
                                                              const int32_t* __restrict__ degm, int mult,
                                                              const float* __restrict__ noise, int kth_big,
                                                              int64_t num_envs, float* __restrict__ thresh) {
+  constexpr int kParkDepth = 8;
+  __shared__ float sPark[4][kParkDepth * 32];
   const int lane = threadIdx.x & 31;
   const int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (env >= num_envs) return;
@@ -184,19 +186,30 @@ __global__ void __launch_bounds__(128) ls_thresh_rows_kernel(int n, int np, cons
     }
     bound = key_float(best);            // -inf while the row has fewer than kth_big values
   }
+  // A value above the bound is only PARKED in a lane-private column of shared memory (a predicated store and an add):
+  // some lane of the warp meets one in almost every trip, and the sorted insertion executed by the whole warp for it
+  // was still 2/3 of this kernel's instructions.  A lane expects ~2 of them per row; a full column is drained into the
+  // lane's sorted list.
+  float* park = sPark[threadIdx.x >> 5] + lane;
+  int parked = 0;
+  auto drain = [&]() {
+    for (int k = 0; k < parked; ++k) tl.push(park[32 * k]);
+    parked = 0;
+  };
+  auto keep = [&](float sv) {
+    if (sv > bound) {
+      if (parked == kParkDepth) drain();
+      park[32 * parked] = sv;
+      ++parked;
+    }
+  };
   auto take_above = [&](int qq, const float4& z, uint32_t c) {
     const float4 rd = __ldg(reinterpret_cast<const float4*>(rd_std) + qq);
     const int4 dm = __ldg(reinterpret_cast<const int4*>(degm) + qq);
-    const float s0 = spin_rand(dm.x, -mult, (int)(c & 0xffu), z.x, rd.x);
-    const float s1 = spin_rand(dm.y, -mult, (int)((c >> 8) & 0xffu), z.y, rd.y);
-    const float s2 = spin_rand(dm.z, -mult, (int)((c >> 16) & 0xffu), z.z, rd.z);
-    const float s3 = spin_rand(dm.w, -mult, (int)(c >> 24), z.w, rd.w);
-    if (fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)) > bound) {
-      if (s0 > bound) tl.push(s0);
-      if (s1 > bound) tl.push(s1);
-      if (s2 > bound) tl.push(s2);
-      if (s3 > bound) tl.push(s3);
-    }
+    keep(spin_rand(dm.x, -mult, (int)(c & 0xffu), z.x, rd.x));
+    keep(spin_rand(dm.y, -mult, (int)((c >> 8) & 0xffu), z.y, rd.y));
+    keep(spin_rand(dm.z, -mult, (int)((c >> 16) & 0xffu), z.z, rd.z));
+    keep(spin_rand(dm.w, -mult, (int)(c >> 24), z.w, rd.w));
   };
   for (; q + 96 < groups; q += 128) {                 // four trips in flight per lane
     const float4 z0 = ldg_stream4(nrow + 4 * q), z1 = ldg_stream4(nrow + 4 * (q + 32));
@@ -205,6 +218,7 @@ __global__ void __launch_bounds__(128) ls_thresh_rows_kernel(int n, int np, cons
     take_above(q, z0, c0), take_above(q + 32, z1, c1), take_above(q + 64, z2, c2), take_above(q + 96, z3, c3);
   }
   for (; q < groups; q += 32) take_above(q, ldg_stream4(nrow + 4 * q), __ldg(crow + q));
+  drain();
   uint32_t best = 0;
   for (int r = 0; r < kth_big; ++r) {
     const uint32_t head = float_key(tl.top[0]);
