@@ -186,22 +186,16 @@ __global__ void __launch_bounds__(128) ls_thresh_rows_kernel(int n, int np, cons
     }
     bound = key_float(best);            // -inf while the row has fewer than kth_big values
   }
-  // A value above the bound is only PARKED in a lane-private column of shared memory (a predicated store and an add):
-  // some lane of the warp meets one in almost every trip, and the sorted insertion executed by the whole warp for it
-  // was still 2/3 of this kernel's instructions.  A lane expects ~2 of them per row; a full column is drained into the
-  // lane's sorted list.
+  // A value above the bound is only PARKED in a lane-private column of shared memory (a predicated store and an add, no
+  // branch): some lane of the warp meets one in almost every trip, and the sorted insertion executed by the whole warp
+  // for it was still 2/3 of this kernel's instructions.  A lane expects ~2 of them per row; if a column overflows
+  // (kParkDepth) the row is redone with every value inserted.
   float* park = sPark[threadIdx.x >> 5] + lane;
   int parked = 0;
-  auto drain = [&]() {
-    for (int k = 0; k < parked; ++k) tl.push(park[32 * k]);
-    parked = 0;
-  };
   auto keep = [&](float sv) {
-    if (sv > bound) {
-      if (parked == kParkDepth) drain();
-      park[32 * parked] = sv;
-      ++parked;
-    }
+    const bool hit = sv > bound;
+    if (hit) park[32 * min(parked, kParkDepth - 1)] = sv;
+    parked += hit ? 1 : 0;
   };
   auto take_above = [&](int qq, const float4& z, uint32_t c) {
     const float4 rd = __ldg(reinterpret_cast<const float4*>(rd_std) + qq);
@@ -218,7 +212,12 @@ __global__ void __launch_bounds__(128) ls_thresh_rows_kernel(int n, int np, cons
     take_above(q, z0, c0), take_above(q + 32, z1, c1), take_above(q + 64, z2, c2), take_above(q + 96, z3, c3);
   }
   for (; q < groups; q += 32) take_above(q, ldg_stream4(nrow + 4 * q), __ldg(crow + q));
-  drain();
+  if (__any_sync(kFull, parked > kParkDepth)) {
+    tl.clear();
+    for (q = lane; q < groups; q += 32) take(q, ldg_stream4(nrow + 4 * q), __ldg(crow + q));
+  } else {
+    for (int k = 0; k < parked; ++k) tl.push(park[32 * k]);
+  }
   uint32_t best = 0;
   for (int r = 0; r < kth_big; ++r) {
     const uint32_t head = float_key(tl.top[0]);

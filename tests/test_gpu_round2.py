@@ -612,6 +612,9 @@ def test_threshold_rows_kernel_equals_pipelined_kernel(name, envs, spin, bidir, 
     ws = st.ls_workspace(envs)
     vs = st.ls_begin(xs, None, 1, 0.3, ws)
     noise = th.randn((envs, n), device=cuda_device)
+    # every second row ascending: all of its later values beat the bound taken from its first 256 (the kernel's
+    # parking columns overflow and the row is redone with every value inserted)
+    noise[::2] = th.arange(n, device=cuda_device, dtype=th.float32)[None, :] * 0.01 + noise[::2] * 1e-3
     got = []
     for flag in (0, _lib.DEBUG_THRESH_PIPE):
         _lib.debug_flags(flag, _lib.DEBUG_THRESH_PIPE ^ flag)
