@@ -512,6 +512,13 @@ int rlsb_peco_gen_er(uint32_t* adj, int64_t num_envs, int32_t num_spins, float p
                      uint64_t offset, uint32_t rng_threads, uint32_t rng_iters, void* stream);
 int rlsb_peco_gen_ba(uint32_t* adj, int64_t num_envs, int32_t num_spins, int32_t m_insertion_edges, uint64_t seed,
                      uint64_t offset, uint32_t rng_threads, uint32_t rng_iters, void* stream);
+/* Power-law cluster graphs (Holme-Kim growth = networkx.powerlaw_cluster_graph, the reference's third graph family:
+ * rlsolver/methods/util_generate.py:75-93 with m = 4, p = 0.05) as bit rows, one graph per env, from a Philox stream
+ * (seed, subsequence = env, offset).  The reference grows single graphs on the host from Python's `random`, so the
+ * agreement is statistical (edge count m (n - m) up to repeated picks, degree tail, clustering), not bitwise.
+ * num_spins <= 128. */
+int rlsb_peco_gen_pl(uint32_t* adj, int64_t num_envs, int32_t num_spins, int32_t m_insertion_edges, float p_triangle,
+                     uint64_t seed, uint64_t offset, void* stream);
 
 /* ---- float tail of an ISCO / PISCO Metropolis-Hastings step (csrc/isco.cu), one CTA per chain:
  * propose = get_local_dist + multinomial + the flip (rlsolver/envs/env_ISCO.py:37-63 / 394-418,

@@ -159,6 +159,7 @@ SIGNATURES = {
                                                  _i32, _i32, _f32, _i32, _i32, _vp]),
     "rlsb_peco_gen_er": (C.c_int, [_vp, _i64, _i32, _f32, _u64, _u64, _u32, _u32, _vp]),
     "rlsb_peco_gen_ba": (C.c_int, [_vp, _i64, _i32, _i32, _u64, _u64, _u32, _u32, _vp]),
+    "rlsb_peco_gen_pl": (C.c_int, [_vp, _i64, _i32, _i32, _f32, _u64, _u64, _vp]),
     "rlsb_isco_propose": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp,
                                     _i32, _i32, _i64, _vp]),
     "rlsb_isco_accept": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp,

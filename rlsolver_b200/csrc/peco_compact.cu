@@ -555,6 +555,78 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_gen_ba_kernel(uint32_t* __
   }
 }
 
+// Power-law cluster graphs (Holme-Kim), the third graph family of the reference: `nx.powerlaw_cluster_graph(n, m, p)`
+// (rlsolver/methods/util_generate.py:75-93 with m = 4, p = 0.05).  networkx grows ONE graph on the host from Python's
+// `random`; there is no device-side stream to reproduce, so this is the same growth process per env on a Philox stream
+// of its own (subsequence = env): node t >= m draws m distinct targets with probability proportional to networkx's
+// `repeated_nodes` multiplicities (one entry per initial node, one per edge end at a target, m per finished source),
+// connects to the first, and for each further edge either -- with probability p, if the previous target has a
+// neighbour that is not yet adjacent to t -- closes a triangle with a uniformly chosen such neighbour, or takes the
+// next drawn target.  One thread per env, weights in local memory, the adjacency bit rows are the output (zeroed by
+// the caller).  Statistical, not bitwise, agreement with networkx (tests: edge counts, degree tail, clustering).
+constexpr int kPlMaxNodes = 128;
+__global__ void __launch_bounds__(128) peco_gen_pl_kernel(uint32_t* __restrict__ adj, int64_t num_envs, int n, int W, int m,
+                                                          float p_tri, uint64_t seed, uint64_t offset) {
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= num_envs) return;
+  curandStatePhilox4_32_10_t rs;
+  curand_init(seed, (unsigned long long)env, offset, &rs);
+  uint32_t* rows = adj + env * (int64_t)n * W;
+  uint16_t wt[kPlMaxNodes];
+  for (int v = 0; v < n; ++v) wt[v] = v < m ? 1 : 0;
+  int total = m;
+  auto connect = [&](int u, int v) {               // networkx add_edge + repeated_nodes.append(v)
+    rows[u * W + (v >> 5)] |= 1u << (v & 31);
+    rows[v * W + (u >> 5)] |= 1u << (u & 31);
+    ++wt[v], ++total;
+  };
+  for (int src = m; src < n; ++src) {
+    int targets[32];
+    int nt = 0;
+    while (nt < m) {                                // _random_subset: draw until m distinct
+      int r = min((int)(curand_uniform(&rs) * (float)total), total - 1);
+      int v = 0;
+      while (r >= (int)wt[v]) r -= wt[v], ++v;
+      bool seen = false;
+      for (int k = 0; k < nt; ++k) seen |= targets[k] == v;
+      if (!seen) targets[nt++] = v;
+    }
+    int next = 0;
+    int target = targets[next++];
+    connect(src, target);
+    for (int count = 1; count < m; ++count) {
+      if (curand_uniform(&rs) < p_tri) {
+        int cand = 0;                               // neighbours of `target` not adjacent to src (and not src)
+        for (int w = 0; w < W; ++w) {
+          uint32_t c = rows[target * W + w] & ~rows[src * W + w];
+          if ((src >> 5) == w) c &= ~(1u << (src & 31));
+          cand += __popc(c);
+        }
+        if (cand > 0) {
+          int pick = min((int)(curand_uniform(&rs) * (float)cand), cand - 1);
+          int nbr = -1;
+          for (int w = 0; w < W && nbr < 0; ++w) {
+            uint32_t c = rows[target * W + w] & ~rows[src * W + w];
+            if ((src >> 5) == w) c &= ~(1u << (src & 31));
+            const int here = __popc(c);
+            if (pick < here) {
+              for (int k = 0; k < pick; ++k) c &= c - 1;
+              nbr = 32 * w + __ffs(c) - 1;
+            } else {
+              pick -= here;
+            }
+          }
+          connect(src, nbr);
+          continue;
+        }
+      }
+      target = targets[next++];
+      connect(src, target);
+    }
+    wt[src] += (uint16_t)m, total += m;             // repeated_nodes.extend([source] * m)
+  }
+}
+
 }  // namespace rlsb
 
 extern "C" {
@@ -717,6 +789,24 @@ int rlsb_peco_gen_ba(uint32_t* adj, int64_t num_envs, int32_t num_spins, int32_t
   if (num_spins <= 128) peco_gen_ba_kernel<4><<<grid, kPcWarps * 32, 0, st>>>(adj, num_envs, num_spins, W, m_insertion_edges, r);
   else if (num_spins <= 256) peco_gen_ba_kernel<8><<<grid, kPcWarps * 32, 0, st>>>(adj, num_envs, num_spins, W, m_insertion_edges, r);
   else peco_gen_ba_kernel<32><<<grid, kPcWarps * 32, 0, st>>>(adj, num_envs, num_spins, W, m_insertion_edges, r);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+int rlsb_peco_gen_pl(uint32_t* adj, int64_t num_envs, int32_t num_spins, int32_t m_insertion_edges, float p_triangle,
+                     uint64_t seed, uint64_t offset, void* stream) {
+  using namespace rlsb;
+  if (int rc = pc_shape_ok(num_envs, num_spins, "peco_gen_pl")) return rc;
+  if (num_envs == 0) return RLSB_OK;
+  RLSB_REQUIRE(num_spins <= kPlMaxNodes, RLSB_ERR_UNSUPPORTED, "peco_gen_pl: at most %d spins", kPlMaxNodes);
+  RLSB_REQUIRE(m_insertion_edges >= 1 && m_insertion_edges < 32 && m_insertion_edges < num_spins, RLSB_ERR_INVALID,
+               "peco_gen_pl: 1 <= m < 32 and m < n_spins");
+  RLSB_REQUIRE(adj && p_triangle >= 0.f && p_triangle <= 1.f, RLSB_ERR_INVALID, "peco_gen_pl: bad argument");
+  const int W = (num_spins + 31) / 32;
+  auto st = static_cast<cudaStream_t>(stream);
+  RLSB_CUDA_OK(cudaMemsetAsync(adj, 0, (size_t)num_envs * num_spins * W * sizeof(uint32_t), st));
+  peco_gen_pl_kernel<<<(unsigned)((num_envs + 127) / 128), 128, 0, st>>>(adj, num_envs, num_spins, W, m_insertion_edges,
+                                                                       p_triangle, seed, offset);
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }

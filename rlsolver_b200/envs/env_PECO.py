@@ -239,6 +239,30 @@ class RandomBAGraphGenerator(GraphGenerator):
         return CompactGraphs(adj, self._sign_rows(), n)
 
 
+class RandomPLGraphGenerator(GraphGenerator):
+    """Power-law cluster graphs (Holme-Kim), the reference's third graph family (`GraphType.PL`:
+    `nx.powerlaw_cluster_graph(n, m=4, p=0.05)`, rlsolver/methods/util_generate.py:75-93), one graph per env on the
+    device (csrc/peco_compact.cu peco_gen_pl_kernel).  The reference grows single graphs on the host from Python's
+    `random`, so there is no stream to reproduce: the graphs follow the same growth process from torch's CUDA
+    generator state (seed, offset; the offset moves by 64 * n_spins per call) and agree with networkx statistically."""
+
+    def __init__(self, n_spins=20, m_insertion_edges=4, p_triangle=0.05, edge_type=EdgeType.DISCRETE, num_envs=8,
+                 device="cuda"):
+        super().__init__(n_spins, edge_type, False, num_envs)
+        self.m_insertion_edges, self.p_triangle, self.device = m_insertion_edges, p_triangle, require_cuda(device)
+
+    def get_compact(self) -> CompactGraphs:
+        e, n, dev = self.num_envs, self.n_spins, self.device
+        adj = th.empty((e, n, _words(n)), dtype=th.int32, device=dev)
+        gen = rng.generator(dev)
+        seed, offset = int(gen.initial_seed()) & 0xFFFFFFFFFFFFFFFF, int(gen.get_offset())
+        with on_device(dev):
+            _lib.check(_lib.lib().rlsb_peco_gen_pl(_ptr(adj), e, n, int(self.m_insertion_edges),
+                                                   float(self.p_triangle), seed, offset, _stream_ptr(dev)), "peco_gen_pl")
+        gen.set_offset(offset + 64 * n)
+        return CompactGraphs(adj, self._sign_rows(), n)
+
+
 class SetMatrixGenerator(GraphGenerator):
     """Hands out a fixed `[E, N, N]` tensor (replaying recorded graphs)."""
 

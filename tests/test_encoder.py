@@ -46,3 +46,22 @@ def test_matches_literal_reference_code():
         z = th.zeros(n, dtype=th.bool)
         assert enc.bool_to_str(z) == _ref_bool_to_str(z, enc.base_digits, enc.string_len)
         assert th.equal(enc.str_to_bool(enc.bool_to_str(z)), z)
+
+
+def test_generate_mygraph_matches_reference():
+    """methods/util_generate.generate_mygraph == the reference's (util_generate.py:75-93) for a seeded Python `random`
+    (fixture: tools/make_goldens_generate.py)."""
+    import os
+    import random
+
+    import numpy as np
+    pytest = __import__("pytest")
+    pytest.importorskip("networkx")
+    from rlsolver_b200.methods.config import GraphType
+    from rlsolver_b200.methods.util_generate import generate_mygraph
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "genmygraph.npz"))
+    for gt in (GraphType.BA, GraphType.ER, GraphType.PL):
+        random.seed(5)
+        graph, n, m = generate_mygraph(gt, 30)
+        assert [n, m] == z[gt.value + "_nm"].tolist()
+        assert np.array_equal(np.asarray(graph, dtype=np.int64).reshape(-1, 3), z[gt.value])
