@@ -850,22 +850,34 @@ __device__ __forceinline__ MaskChunk mask_chunk_load(const uint32_t* __restrict_
 __device__ __forceinline__ void mask_chunk_apply(const MaskChunk& c, uint64_t row, int b0, int n, const uint32_t* sP,
                                                  uint32_t* sX, uint16_t* sF, int* sNF) {
   const int lane = threadIdx.x & 31;
+  // the four blocks of a chunk are independent: their transposes interleave, and ONE shared-memory atomic reserves the
+  // list slots of all four (it was one per block, each with its round trip on the warp's critical path)
+  uint32_t ball[4];
+  bool flips[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int b = b0 + u * kLSWarps;
-    if (32 * b >= n) break;                                         // warp-uniform
-    const uint32_t word = __funnelshift_r(c.lo[u], c.hi[u], (uint32_t)(row + 32u * (uint32_t)b) & 31u);
-    const uint32_t t = transpose32(word, lane);                     // lane = node 32b + lane, bit = env
-    const int i = 32 * b + lane;
-    const bool flips = i < n && t != 0u;
-    if (i < n) sX[i] = sP[i] ^ t;
-    if (sF) {
-      const uint32_t ball = __ballot_sync(kFull, flips);
-      if (ball) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(sNF, __popc(ball));
-        base = __shfl_sync(kFull, base, 0);
-        if (flips) sF[base + __popc(ball & ((1u << lane) - 1u))] = (uint16_t)i;
+    flips[u] = false;
+    if (32 * b < n) {                                               // warp-uniform
+      const uint32_t word = __funnelshift_r(c.lo[u], c.hi[u], (uint32_t)(row + 32u * (uint32_t)b) & 31u);
+      const uint32_t t = transpose32(word, lane);                   // lane = node 32b + lane, bit = env
+      const int i = 32 * b + lane;
+      flips[u] = i < n && t != 0u;
+      if (i < n) sX[i] = sP[i] ^ t;
+    }
+  }
+  if (sF) {
+    int total = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ball[u] = __ballot_sync(kFull, flips[u]), total += __popc(ball[u]);
+    if (total) {                                                    // warp-uniform
+      int base = 0;
+      if (lane == 0) base = atomicAdd(sNF, total);
+      base = __shfl_sync(kFull, base, 0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (flips[u]) sF[base + __popc(ball[u] & ((1u << lane) - 1u))] = (uint16_t)(32 * (b0 + u * kLSWarps) + lane);
+        base += __popc(ball[u]);
       }
     }
   }
