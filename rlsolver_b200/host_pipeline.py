@@ -111,12 +111,13 @@ class HostPipeline:
             self.s_in.wait_event(self.buf_free[b])           # the D2H of the batch that used this buffer last
             self.d_in[b].copy_(h_in, non_blocking=True)
             self.in_ready[b].record(self.s_in)
-        self.compute.wait_event(self.in_ready[b])
-        self.graphs[b].replay()
-        res, vs = self.outs[b]
-        if self.eager_post is not None:
-            self.eager_post(res, vs)
-        self.done[b].record(self.compute)
+        with th.cuda.stream(self.compute):                  # whatever stream the caller is on right now
+            self.compute.wait_event(self.in_ready[b])
+            self.graphs[b].replay()
+            res, vs = self.outs[b]
+            if self.eager_post is not None:
+                self.eager_post(res, vs)
+            self.done[b].record(self.compute)
         with th.cuda.stream(self.s_out):
             self.s_out.wait_event(self.done[b])
             h_out.copy_(res, non_blocking=True)
