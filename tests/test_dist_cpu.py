@@ -58,3 +58,21 @@ def test_negative_values_order_below_positive_ones():
     # saturation to the int32 range
     big = th.tensor([2 ** 40, 5])
     assert decode_key(int(local_best_key(big, 0, 2).item())) == (2 ** 31 - 1, 0)
+
+
+def test_peer_exchange_needs_cuda_devices():
+    """The peer-memory exchange is a CUDA kernel over NVLink mailboxes: on a CPU device it refuses loudly (the gloo /
+    torch path for CPU tensors is best_allreduce)."""
+    import pytest
+    from rlsolver_b200.dist import PeerBestExchange
+    with pytest.raises(RuntimeError, match="CUDA"):
+        PeerBestExchange(10, 0, 1, 4, th.device("cpu"))
+
+
+def test_host_pipeline_rejects_bad_arguments():
+    import pytest
+    from rlsolver_b200.host_pipeline import HostPipeline
+    with pytest.raises(ValueError):
+        HostPipeline(None, 4, layout="rows")
+    with pytest.raises(ValueError):
+        HostPipeline(None, 4, depth=1)
