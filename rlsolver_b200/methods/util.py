@@ -36,7 +36,7 @@ def evolutionary_replacement(xs: TEN, vs: TEN, low_k: int, if_maximize: bool):
     num_sims = xs.shape[0]
     ids = vs.argsort()
     top_ids, low_ids = (ids[:-low_k], ids[-low_k:]) if if_maximize else (ids[:low_k], ids[low_k:])
-    if top_ids.shape[0] < num_sims - low_k:
+    if not if_maximize and top_ids.shape[0] < num_sims - low_k:
         # minimising, the reference indexes its low_k-row `top_ids` with a permutation of E - low_k > low_k numbers:
         # IndexError on the CPU, a device-side assert (which poisons the CUDA context) on the GPU.  Same failure, raised
         # on the host before anything is launched.
