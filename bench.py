@@ -702,9 +702,13 @@ def run_b200(args):
             th.cuda.synchronize()
             sim.store.rng_cursor_sync()        # the captured kernels read the generator state from device memory
             g = th.cuda.CUDAGraph()
+            counted = sim.store.launch_count
             with th.cuda.graph(g):
                 out = step_body()
             th.cuda.synchronize()
+            # launches of this library inside the captured step (the threshold draw and the cursor update are this
+            # library's kernels here; in eager mode the draw is torch's own call)
+            state["graph_launches"] = sim.store.launch_count - counted
             state["graph"], state["out"] = g, out
             return "captured (local search" + (")" if world == 1 else " + peer-memory best-cut exchange)" if in_graph else
                                                "); best-cut exchange eager behind the replay")
@@ -735,7 +739,9 @@ def run_b200(args):
     barrier()
     t1 = time.time()
     log("timed steps done")
-    launches = launches_per_step * args.steps          # kernels of this library per step (counted on an eager step)
+    if state["graph"] is not None and state.get("graph_launches"):
+        launches_per_step = state["graph_launches"] + (0 if world == 1 else 1 if in_graph else 2)
+    launches = launches_per_step * args.steps          # kernels of this library per step (counted while capturing it)
     total_ms = ctx.max_over_ranks(sum(ms))
     per_call = env_steps_per_call(envs, n, NUM_ITERS, n)
     value = per_call * world * args.steps / (total_ms * 1e-3)
