@@ -508,6 +508,15 @@ int rlsb_peco_compact_expand_state(const uint32_t* spins, const uint32_t* best_s
                                    int64_t num_envs, int32_t num_spins, int32_t num_obs, const int32_t* h_obs_rows,
                                    int32_t step, int32_t binary_spins, float termination, int32_t scalar_div_as_cuda,
                                    int32_t at_reset, void* stream);
+/* expand_state with float16 rows: the inference env's use_tensor_core mode (inference_network_env.py:143-145, 212-236).
+ * state: __half [E][...] with state_env_stride counted in halves; table[k] = the k-fold accumulation of 1/max_steps as
+ * torch performs it on a half tensor (float32 add, rounded to half each time), stored as float32. */
+int rlsb_peco_compact_expand_state_half(const uint32_t* spins, const uint32_t* best_spins, const void* fields,
+                                        const uint16_t* last_flip, const float* score, const float* best_score,
+                                        const float* max_local, const float* table, void* state, int64_t state_env_stride,
+                                        int64_t num_envs, int32_t num_spins, int32_t num_obs, const int32_t* h_obs_rows,
+                                        int32_t step, int32_t binary_spins, float termination, int32_t scalar_div_as_cuda,
+                                        int32_t at_reset, void* stream);
 int rlsb_peco_gen_er(uint32_t* adj, int64_t num_envs, int32_t num_spins, float p_connection, uint64_t seed,
                      uint64_t offset, uint32_t rng_threads, uint32_t rng_iters, void* stream);
 int rlsb_peco_gen_ba(uint32_t* adj, int64_t num_envs, int32_t num_spins, int32_t m_insertion_edges, uint64_t seed,

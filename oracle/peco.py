@@ -128,6 +128,44 @@ class SpinSystem:
         return np.concatenate([state, self.m], axis=-2)
 
 
+def half_state(env: "SpinSystem", scalar_as_cuda: bool = False) -> np.ndarray:
+    """float16 `state` of the inference env's use_tensor_core mode (inference_network_env.py:143-145, 212-236) derived
+    from the float32 restatement: torch evaluates a half operation in float32 and rounds once, so every observable is
+    the float32 value rounded to half, except the greedy row (count / n, then 1 - x: two roundings) and the time rows
+    (k-fold half accumulation of 1 / max_steps; the Python scalar is rounded to half first on the CPU, kept float32 on
+    CUDA).  Valid while every integer involved is below 2048.  Pinned by tests/golden/pecoinfhalf_*.npz."""
+    f16 = np.float16
+    e, n = env.e, env.n
+    spins = env.state[:, 0, :]
+    inv = f32(1. / env.max_steps) if scalar_as_cuda else f32(f16(1. / env.max_steps))
+    tab = np.zeros(env.max_steps + 2, f32)
+    for k in range(1, tab.size):
+        tab[k] = f32(f16(f32(tab[k - 1]) + inv))
+    imm = fields(env.m, spins)
+    cnt = (imm <= 0).sum(axis=-1).astype(f32)
+    at_reset = env.current_step == 0
+    out = np.zeros((e, len(env.obs), n), f16)
+    for idx, o in env.obs:
+        if o == SPIN:
+            out[:, idx, :] = spins.astype(f16)
+        elif o == IMM:
+            out[:, idx, :] = (imm / env.max_local[:, None]).astype(f32).astype(f16)
+        elif o == TSF:
+            out[:, idx, :] = tab[np.rint(env.state[:, idx, :] * env.max_steps).astype(int)].astype(f16)
+        elif o == EPT:
+            out[:, idx, :] = f16(tab[env.current_step])
+        elif o == TERM:
+            out[:, idx, :] = f16(env.state[0, idx, 0])
+        elif o == GREEDY:
+            x = env.div_n(cnt).astype(f16)
+            out[:, idx, :] = (f32(1) - x.astype(f32)).astype(f16)[:, None]
+        elif o == DSCORE:
+            out[:, idx, :] = 0 if at_reset else (np.abs(env.score - env.best_score) / env.max_local).astype(f32).astype(f16)[:, None]
+        elif o == DSTATE:
+            out[:, idx, :] = 0 if at_reset else np.count_nonzero(env.best_spins - spins, axis=-1).astype(f16)[:, None]
+    return out
+
+
 # --------------------------------------------------------------------------- generators (torch restatement)
 def torch_edge_mask(edge_type: str, n: int, num_envs: int, device):
     """util_envs_PECO.py:21-38 / 67-84, op for op: the edge-weight mask drawn per get() call.

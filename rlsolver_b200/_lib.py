@@ -157,6 +157,8 @@ SIGNATURES = {
     "rlsb_peco_compact_expand_matrix": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _i64, _vp]),
     "rlsb_peco_compact_expand_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp,
                                                  _i32, _i32, _f32, _i32, _i32, _vp]),
+    "rlsb_peco_compact_expand_state_half": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32,
+                                                      _vp, _i32, _i32, _f32, _i32, _i32, _vp]),
     "rlsb_peco_gen_er": (C.c_int, [_vp, _i64, _i32, _f32, _u64, _u64, _u32, _u32, _vp]),
     "rlsb_peco_gen_ba": (C.c_int, [_vp, _i64, _i32, _i32, _u64, _u64, _u32, _u32, _vp]),
     "rlsb_peco_gen_pl": (C.c_int, [_vp, _i64, _i32, _i32, _f32, _u64, _u64, _vp]),

@@ -27,6 +27,8 @@
 //
 // Generators (util_envs_PECO.py:40-52 ER, 87-107 BA) write the bit rows directly from torch's Philox stream: the
 // same graphs as the reference's torch ops on the same device and seed, no [E, N, N] float tensor on the way.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -445,6 +447,56 @@ __global__ void __launch_bounds__(kPcWarps * 32) peco_compact_expand_state_kerne
   }
 }
 
+// The same state as float16 rows: the inference env's `use_tensor_core=True` mode (inference_network_env.py:143-145,
+// 212-236) keeps `state` in half precision.  torch evaluates every half operation in float32 and rounds the result to
+// half, so each observable is the float32 value of the kernel above rounded once -- except the greedy-actions row, whose
+// two operations (count / n, then 1 - x) round twice -- and the time observables, whose k-fold accumulation of
+// 1 / max_steps happens in half (the table handed in holds those values).  Integers below 2048 are exact in half; the
+// Python side admits this mode only for graphs whose sums stay below that.
+__global__ void __launch_bounds__(kPcWarps * 32) peco_compact_expand_state_half_kernel(PecoExpand p, __half* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t env = (int64_t)blockIdx.x * kPcWarps + (threadIdx.x >> 5);
+  if (env >= p.num_envs) return;
+  const int n = p.n, W = p.words;
+  const uint32_t sp = lane < W ? p.spins[env * W + lane] : 0u;
+  const uint32_t bs = lane < W ? p.best_spins[env * W + lane] : 0u;
+  const int dist = warp_sum_i(__popc(sp ^ bs));
+  const float maxl = p.max_local[env];
+  const int8_t* fl8 = static_cast<const int8_t*>(p.fields) + env * (int64_t)p.np;
+  const int16_t* fl16 = static_cast<const int16_t*>(p.fields) + env * (int64_t)p.np;
+  const uint16_t* lf = p.last_flip + env * (int64_t)p.np;
+  __half* st = out + env * p.state_env_stride;
+  int nonpos = 0;
+  for (int k = 0; k < W; ++k) {
+    const uint32_t spw = __shfl_sync(kFull, sp, k);
+    const int j = 32 * k + lane;
+    if (j < n) {
+      const bool up = (spw >> lane) & 1u;
+      const int as = n <= kPcByteFields ? (int)fl8[j] : (int)fl16[j];
+      const int f = up ? as : -as;
+      nonpos += (int)(f <= 0);
+      st[j] = __float2half_rn(p.binary_spins ? (up ? 0.f : 1.f) : (up ? 1.f : -1.f));
+      if (p.idx_imm >= 0) st[p.idx_imm * n + j] = __float2half_rn(__fdiv_rn((float)f, maxl));
+      if (p.idx_tsf >= 0) st[p.idx_tsf * n + j] = __float2half_rn(__ldg(p.table + (p.step - (int)lf[j])));
+    }
+  }
+  nonpos = warp_sum_i(nonpos);
+  const float score = p.score[env], best = p.best_score[env];
+  const __half frac = __float2half_rn(p.recip_div ? __fmul_rn((float)nonpos, p.inv_n) : __fdiv_rn((float)nonpos, (float)n));
+  const __half g_greedy = __float2half_rn(__fsub_rn(1.f, __half2float(frac)));
+  const __half g_dscore = __float2half_rn(p.at_reset ? 0.f : __fdiv_rn(fabsf(__fsub_rn(score, best)), maxl));
+  const __half g_dstate = __float2half_rn(p.at_reset ? 0.f : (float)dist);
+  const __half g_ept = __float2half_rn(__ldg(p.table + p.step));
+  const __half g_term = __float2half_rn(p.termination);
+  for (int j = lane; j < n; j += 32) {
+    if (p.idx_ept >= 0) st[p.idx_ept * n + j] = g_ept;
+    if (p.idx_term >= 0) st[p.idx_term * n + j] = g_term;
+    if (p.idx_greedy >= 0) st[p.idx_greedy * n + j] = g_greedy;
+    if (p.idx_dscore >= 0) st[p.idx_dscore * n + j] = g_dscore;
+    if (p.idx_dstate >= 0) st[p.idx_dstate * n + j] = g_dstate;
+  }
+}
+
 // ---- generators ----------------------------------------------------------------------------------------------
 // ER (util_envs_PECO.py:40-52): adj[e][i][j] = adj[e][j][i] = [rand(E, n, n)[e][i][j] < p] for i < j.  The kernel
 // keeps torch's decomposition of that ONE rand call: thread idx, round r owns elements idx + T (4 r + c), all four
@@ -763,6 +815,35 @@ int rlsb_peco_compact_expand_state(const uint32_t* spins, const uint32_t* best_s
   p.termination = termination, p.inv_n = 1.0f / (float)num_spins, p.recip_div = scalar_div_as_cuda, p.at_reset = at_reset;
   peco_compact_expand_state_kernel<<<(unsigned)((num_envs + kPcWarps - 1) / kPcWarps), kPcWarps * 32, 0,
                                      static_cast<cudaStream_t>(stream)>>>(p);
+  RLSB_LAUNCH_OK();
+  return RLSB_OK;
+}
+
+int rlsb_peco_compact_expand_state_half(const uint32_t* spins, const uint32_t* best_spins, const void* fields,
+                                        const uint16_t* last_flip, const float* score, const float* best_score,
+                                        const float* max_local, const float* table, void* state, int64_t state_env_stride,
+                                        int64_t num_envs, int32_t num_spins, int32_t num_obs, const int32_t* h_obs_rows,
+                                        int32_t step, int32_t binary_spins, float termination, int32_t scalar_div_as_cuda,
+                                        int32_t at_reset, void* stream) {
+  using namespace rlsb;
+  if (int rc = pc_shape_ok(num_envs, num_spins, "peco_compact_expand_state_half")) return rc;
+  if (num_envs == 0) return RLSB_OK;
+  RLSB_REQUIRE(spins && best_spins && fields && last_flip && score && best_score && max_local && table && state &&
+                   h_obs_rows && num_obs >= 1 && state_env_stride >= (int64_t)num_obs * num_spins,
+               RLSB_ERR_INVALID, "peco_compact_expand_state_half: bad argument");
+  PecoExpand p{};
+  p.spins = spins, p.best_spins = best_spins, p.fields = fields, p.last_flip = last_flip, p.score = score;
+  p.best_score = best_score, p.max_local = max_local, p.table = table, p.state = nullptr;
+  p.state_env_stride = state_env_stride, p.num_envs = num_envs, p.n = num_spins, p.np = (num_spins + 31) / 32 * 32;
+  p.words = (num_spins + 31) / 32, p.step = step, p.binary_spins = binary_spins;
+  for (int k = 0; k < 7; ++k)
+    RLSB_REQUIRE(h_obs_rows[k] < num_obs, RLSB_ERR_INVALID,
+                 "peco_compact_expand_state_half: observable row %d out of range", h_obs_rows[k]);
+  p.idx_imm = h_obs_rows[0], p.idx_tsf = h_obs_rows[1], p.idx_ept = h_obs_rows[2], p.idx_term = h_obs_rows[3];
+  p.idx_greedy = h_obs_rows[4], p.idx_dscore = h_obs_rows[5], p.idx_dstate = h_obs_rows[6];
+  p.termination = termination, p.inv_n = 1.0f / (float)num_spins, p.recip_div = scalar_div_as_cuda, p.at_reset = at_reset;
+  peco_compact_expand_state_half_kernel<<<(unsigned)((num_envs + kPcWarps - 1) / kPcWarps), kPcWarps * 32, 0,
+                                          static_cast<cudaStream_t>(stream)>>>(p, static_cast<__half*>(state));
   RLSB_LAUNCH_OK();
   return RLSB_OK;
 }

@@ -10,13 +10,20 @@ PECO pattern-I environment as it is used at INFERENCE time -- ONE graph shared b
 
 The step itself is the same arithmetic, so it runs on the same kernels (csrc/peco_compact.cu for {-1, 0, 1} weights,
 csrc/peco.cu otherwise) with the one graph replicated per env in the resident layout (bit rows: N * ceil(N / 32) * 4
-bytes per env).  `use_tensor_core=True` (float16 state, 143-145) is not reproduced: the reference accumulates its
-time observables in float16, which this integer-state implementation has no counterpart for.
+bytes per env).
+
+`use_tensor_core=True` (143-145, 212-236: matrix, spins and `state` in float16).  The resident state here is integers
+and bits either way; what the mode changes is the rounding of what is MATERIALISED: `state` / the observation come out
+as float16 with torch's half arithmetic reproduced (every operation evaluated in float32 and rounded to half once; the
+time observables accumulated in half), for graphs with {-1, 0, 1} weights and at most 1024 edges, where every integer the
+reference holds in a half (scores, sums of the matrix) stays below 2048 and is exact.  `score` / `best_score` /
+`best_spins` stay float32 tensors holding the same values.
 """
 from __future__ import annotations
 
 from typing import Optional
 
+import numpy as np
 import torch as th
 
 from .env_PECO import (ECO_PECO_OBSERVABLES, CompactGraphs, EdgeType, ExtraAction, GraphGenerator, Observable,  # noqa: F401
@@ -69,9 +76,7 @@ class SpinSystemUnbiased(_BatchedSpinSystem):
                  optimisation_target=OptimisationTarget.ENERGY, spin_basis=SpinBasis.SIGNED, norm_rewards=False,
                  memory_length=None, horizon_length=None, stag_punishment=None, basin_reward=None,
                  reversible_spins=False, init_snap=None, seed=None, device=None, num_envs=None, use_tensor_core=False):
-        if use_tensor_core:
-            raise NotImplementedError("use_tensor_core=True (float16 state) is not reproduced; see the module docstring")
-        self.use_tensor_core = False
+        self.use_tensor_core = bool(use_tensor_core)
         # the inference step never looks at its reward: SINGLE (rejected by the training mirror) is as good as any
         signal = RewardSignal.DENSE if reward_signal == RewardSignal.SINGLE else reward_signal
         # the reference's inference step has no history buffer: stag / basin settings are accepted and ignored (295-444)
@@ -95,6 +100,9 @@ class SpinSystemUnbiased(_BatchedSpinSystem):
                 self._compact = CompactGraphs(adj, sgn, self.n_spins)
         if self._compact is None:
             self._dense_batch = m.unsqueeze(0).expand(self.num_envs, -1, -1).contiguous()
+        if self.use_tensor_core and (self._compact is None or int((m != 0).sum()) > 2048):
+            raise NotImplementedError("use_tensor_core=True is reproduced for graphs with weights in {-1, 0, 1} and at most "
+                                      "1024 edges (beyond that the reference's float16 sums are no longer exact integers)")
 
     @property
     def matrix(self) -> TEN:
@@ -129,8 +137,48 @@ class SpinSystemUnbiased(_BatchedSpinSystem):
         self._best_is_scalar = False
         return obs, done
 
+    # ------------------------------------------------------------------ float16 materialisation (use_tensor_core)
+    def _half_table(self) -> TEN:
+        """k-fold `state[row] += 1 / max_steps` on a half tensor: float32 add, rounded to half each time.  The Python
+        scalar enters the add as float32 on CUDA (the kernel's opmath type) and rounded to half first on the CPU -- like
+        `x / n_spins`, `scalar_div_as_cuda` selects whose arithmetic is reproduced."""
+        key = bool(self.scalar_div_as_cuda)
+        cached = getattr(self, "_table16", None)
+        if cached is None or cached[0] != key:
+            inv = np.float32(1. / self.max_steps) if key else np.float32(np.float16(1. / self.max_steps))
+            tab = np.zeros(self.max_steps + 2, np.float32)
+            for k in range(1, tab.size):
+                tab[k] = np.float32(np.float16(np.float32(tab[k - 1]) + inv))
+            cached = self._table16 = (key, th.from_numpy(tab).to(self.device))
+        return cached[1]
+
+    def _expand_state_half(self, out: TEN, env_stride: int, binary: bool) -> None:
+        from .. import _lib
+        from ..graph_store import on_device
+        with on_device(self.device):
+            _lib.check(self._lib.rlsb_peco_compact_expand_state_half(
+                self._spins.data_ptr(), self._best_words.data_ptr(), self._cfields.data_ptr(), self._last_flip.data_ptr(),
+                self.score.data_ptr(), self.best_score.data_ptr(), self.max_local_reward_available_.data_ptr(),
+                self._half_table().data_ptr(), out.data_ptr(), int(env_stride), self.num_envs, self.n_spins,
+                len(self.observables), self._rows.ctypes.data, self.current_step, int(binary), self._termination(),
+                int(bool(self.scalar_div_as_cuda)), int(self.current_step == 0),
+                th.cuda.current_stream(self.device).cuda_stream), "peco_compact_expand_state_half")
+
+    @property
+    def state(self) -> TEN:
+        if not self.use_tensor_core:
+            return _BatchedSpinSystem.state.fget(self)
+        out = th.empty((self.num_envs, len(self.observables), self.n_spins), dtype=th.float16, device=self.device)
+        self._expand_state_half(out, len(self.observables) * self.n_spins, False)
+        return out
+
     def get_observation(self):
         n, k = self.n_spins, len(self.observables)
+        if self.use_tensor_core:
+            obs = th.empty((self.num_envs, k + n, n), dtype=th.float16, device=self.device)
+            self._expand_state_half(obs, (k + n) * n, self.spin_basis == SpinBasis.BINARY)
+            obs[:, k:, :] = self._shared_matrix.to(th.float16)
+            return obs
         if self._compact is None:
             state = self._dense_state.clone()
             if self.spin_basis == SpinBasis.BINARY:

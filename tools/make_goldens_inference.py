@@ -20,7 +20,7 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "g
 CPU = th.device("cpu")
 
 
-def case(name, matrix, num_envs, steps, seed, spin_basis):
+def case(name, matrix, num_envs, steps, seed, spin_basis, half=False):
     th.manual_seed(seed)
     gg = up.SetGraphGenerator(matrix, device="cpu")
     n = matrix.shape[0]
@@ -28,7 +28,7 @@ def case(name, matrix, num_envs, steps, seed, spin_basis):
         gg, 2 * n, observables=ue.ECO_PECO_OBSERVABLES, reward_signal=ue.RewardSignal.BLS, extra_action=ue.ExtraAction.NONE,
         optimisation_target=ue.OptimisationTarget.CUT, spin_basis=spin_basis, norm_rewards=True, memory_length=None,
         horizon_length=None, stag_punishment=None, basin_reward=1. / 20, reversible_spins=True, if_greedy=False,
-        use_tensor_core=False, device=CPU, num_envs=num_envs)
+        use_tensor_core=half, device=CPU, num_envs=num_envs)
     out = dict(matrix=matrix.numpy().copy(), spins0=env.state[:, 0, :].numpy().copy(), state0=env.state.numpy().copy(),
                score0=env.score.numpy().copy(), best0=np.asarray(env.get_best_cut().numpy()),
                best_spins0=env.best_spins.numpy().copy(), obs0=env.get_observation().numpy().copy(),
@@ -43,7 +43,7 @@ def case(name, matrix, num_envs, steps, seed, spin_basis):
     out.update(actions=np.stack([a.numpy() for a in acts]), states=np.stack(states), dones=np.stack(dones),
                scores=np.stack(scores), best_scores=np.stack(bests), best_spins=np.stack(best_spins),
                obs_last=obs.numpy().copy())
-    p = os.path.join(OUT, f"pecoinf_{name}.npz")
+    p = os.path.join(OUT, f"pecoinf{'half' if half else ''}_{name}.npz")
     np.savez_compressed(p, **out)
     print("wrote", p, {k: v.shape for k, v in out.items() if k in ("matrix", "states", "best0", "best_scores")})
 
@@ -62,6 +62,9 @@ def main():
     case("n40_uniform", sym(40, 0.2, 1, "01"), 13, 16, 701, ue.SpinBasis.BINARY)
     case("n150_pm1", sym(150, 0.06, 2, "pm1"), 9, 12, 702, ue.SpinBasis.SIGNED)
     case("n24_float", sym(24, 0.4, 3, "float"), 6, 10, 703, ue.SpinBasis.BINARY)
+    # use_tensor_core=True: state, scores and the observation in float16 (inference_network_env.py:143-145, 212-236)
+    case("n40_uniform", sym(40, 0.2, 1, "01"), 13, 16, 704, ue.SpinBasis.BINARY, half=True)
+    case("n100_pm1", sym(100, 0.08, 4, "pm1"), 9, 30, 705, ue.SpinBasis.SIGNED, half=True)
 
 
 if __name__ == "__main__":
